@@ -1,0 +1,343 @@
+/* locotouch_b200 -- C ABI of the B200-native LocoTouch hot path (liblocotouch_b200.so, sm_100a).
+ *
+ * Every entry point is stateless: raw DEVICE pointers + sizes + scalar parameters + the CUDA stream to launch on
+ * (passed as void* == cudaStream_t; 0 is the legacy default stream).  No allocation happens inside the library;
+ * workspaces are passed in (query the size with the matching *_workspace_bytes function).  All functions return an
+ * int status (LT_OK == 0); lt_error_string() maps it to text.  Launches are asynchronous and capturable into CUDA
+ * graphs.  All floating point is IEEE fp32 unless stated; masks are uint8 (0/1); dones uint8; episode_length int64.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repository root).
+ */
+#ifndef LOCOTOUCH_B200_H
+#define LOCOTOUCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LT_ABI_VERSION 1
+
+enum LtStatus {
+  LT_OK = 0,
+  LT_ERR_INVALID_ARG = 1,  /* null pointer, non-positive size, unsupported dimension */
+  LT_ERR_CUDA = 2,         /* kernel launch failed: see lt_last_cuda_error() */
+  LT_ERR_WORKSPACE = 3,    /* workspace too small */
+  LT_ERR_UNSUPPORTED = 4
+};
+
+int lt_abi_version(void);
+const char* lt_error_string(int status);
+/* Text of the last CUDA error seen by this thread inside the library ("" if none). */
+const char* lt_last_cuda_error(void);
+/* sizeof() of the argument structs as compiled, so that a foreign-language binding can verify its own layout:
+ * which = 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams; -1 otherwise. */
+int64_t lt_struct_size(int which);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K4  GAE returns + advantage normalisation
+ * replaces  loco_rl/loco_rl/storage/rollout_storage.py:152-174  RolloutStorage.compute_returns
+ *   rewards, values [T,N] f32 ; dones [T,N] u8 ; last_values [N] f32  ->  returns, advantages [T,N] f32
+ *   delta = r + (1-d)*gamma*V' - V ; A = delta + (1-d)*gamma*lam*A' ; R = A + V ; adv = R - V
+ *   normalize != 0:  adv = (adv - mean) / (std_unbiased + 1e-8) over all T*N elements.
+ * lt_gae = lt_gae_scan + lt_adv_normalize on the same stream.  Multi-GPU callers run lt_gae_scan, all-reduce the
+ * three doubles in `stats` (sum, sum of squares, count) and then call lt_adv_normalize.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int64_t lt_gae_workspace_bytes(int T, int N);
+int lt_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+           float* returns, float* advantages, int T, int N, float gamma, float lam, int normalize,
+           void* workspace, int64_t workspace_bytes, void* stream);
+/* stats: 4 doubles on the device = {sum(adv), sum(adv^2), count, unused}; overwritten. */
+int lt_gae_scan(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                float* returns, float* advantages, int T, int N, float gamma, float lam,
+                double* stats, void* workspace, int64_t workspace_bytes, void* stream);
+int lt_adv_normalize(float* advantages, int64_t count, const double* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K3  act epilogue + transition store
+ * replaces  loco_rl/loco_rl/modules/actor_critic.py:105-123 (Normal sample / log_prob) as used by
+ *           loco_rl/loco_rl/algorithms/ppo.py:129-141 (PPO.act), and
+ *           ppo.py:143-170 (process_env_step: timeout bootstrap) + rollout_storage.py:80-107 (add_transitions)
+ * lt_act_sample:   actions = mu + sigma*eps ; logp = sum_j[-(a-mu)^2/(2 sigma^2) - log sigma - log sqrt(2 pi)]
+ *                  and writes mu / sigma(expanded) rows; all outputs may point straight into the rollout slot.
+ *                  eps == NULL -> in-kernel Philox4x32-10 normal draws keyed by (seed, offset, sample, j).
+ * lt_store_step:   rewards_out = r + gamma*V*time_out ; dones_out = (u8) dones ; optional row copies of obs /
+ *                  critic obs (skipped when src == dst or src == NULL).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int lt_act_sample(const float* mu, const float* sigma /*[A]*/, const float* eps /*[N,A] or NULL*/,
+                  float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A,
+                  uint64_t seed, uint64_t offset, void* stream);
+int lt_store_step(const float* rewards, const int64_t* dones_i64, const uint8_t* dones_u8, const uint8_t* time_outs,
+                  const float* values, float gamma, float* rewards_out, uint8_t* dones_out,
+                  const float* obs, float* obs_out, int obs_dim,
+                  const float* critic_obs, float* critic_obs_out, int critic_obs_dim, int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K5  mini-batch gather
+ * replaces  rollout_storage.py:186-243  RolloutStorage.mini_batch_generator  (9 advanced-index gathers)
+ * Gathers `count` rows given by indices[count] (int64, into the flattened [T*N] axis) from up to LT_GATHER_MAX
+ * row-major sources in ONE launch.  The permutation is drawn once per update() (rollout_storage.py:189) and reused
+ * by every epoch, so a caller may gather the whole permuted rollout once and slice it afterwards.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define LT_GATHER_MAX 12
+typedef struct {
+  int num_tensors;
+  const float* src[LT_GATHER_MAX];
+  float* dst[LT_GATHER_MAX];
+  int row_len[LT_GATHER_MAX]; /* floats per row */
+} LtGatherArgs;
+int lt_gather_rows(const LtGatherArgs* args, const int64_t* indices, int64_t count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K6  fused PPO loss (forward + analytic backward)
+ * replaces  loco_rl/loco_rl/algorithms/ppo.py:252-302 (log-prob, entropy, KL, adaptive LR, clipped surrogate,
+ *           clipped value loss, total loss) and the autograd backward of those lines up to mu / sigma / value.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int B;                   /* mini-batch rows */
+  int A;                   /* action dim, multiple of 4, <= 64 */
+  const float* mu;         /* [B,A] actor output */
+  const float* sigma;      /* [A]   state-independent std parameter */
+  const float* value;      /* [B]   critic output */
+  const float* actions;    /* [B,A] */
+  const float* old_logp;   /* [B] */
+  const float* old_mu;     /* [B,A] */
+  const float* old_sigma;  /* [B,A] */
+  const float* advantages; /* [B] */
+  const float* returns;    /* [B] */
+  const float* old_values; /* [B] */
+  float clip_param, value_loss_coef, entropy_coef;
+  int use_clipped_value_loss;
+  float desired_kl;        /* adaptive schedule when > 0 and lr_inout != NULL (ppo.py:264-281) */
+  float grad_scale;        /* multiplies every gradient (1 for one process; 1 also for DDP: the all-reduce averages) */
+  float* grad_mu;          /* [B,A]  dLoss/dmu */
+  float* grad_value;       /* [B]    dLoss/dvalue */
+  float* grad_sigma;       /* [A]    dLoss/dsigma (overwritten, deterministic two-stage reduction) */
+  float* out;              /* [8] = {loss, surrogate, value_loss, entropy_mean, kl_mean, lr_after, 0, 0} */
+  float* lr_inout;         /* device scalar learning rate or NULL */
+  float* loss_accum;       /* optional [4] running sums {value_loss, surrogate, entropy, count} (ppo.py:361-363) or NULL */
+  void* workspace;
+  int64_t workspace_bytes;
+} LtPpoLossArgs;
+int64_t lt_ppo_loss_workspace_bytes(int B, int A);
+int lt_ppo_loss(const LtPpoLossArgs* args, void* stream);
+/* lr = max(1e-5, lr/1.5) if kl > 2*desired ; lr = min(1e-2, lr*1.5) if 0 < kl < desired/2.  kl = *kl_sum * kl_scale. */
+int lt_adaptive_lr(const float* kl_sum, float kl_scale, float desired_kl, float* lr_inout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K7  global-norm clip + Adam over one flat parameter buffer
+ * replaces  ppo.py:350-353  nn.utils.clip_grad_norm_(params, max_norm) ; optim.Adam.step()  (and AdamW for the
+ *           student, locotouch/distill/student.py:82,151, with weight_decay > 0)
+ *   g *= grad_scale ; total = ||g||_2 ; g *= min(1, max_norm/(total+1e-6)) (skipped when max_norm <= 0)
+ *   p *= 1 - lr*weight_decay ; m = m + (g-m)(1-b1) ; v = b2 v + (1-b2) g^2
+ *   p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * lr and the step counter live on the device so that a captured graph can be replayed.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int64_t lt_clip_adam_workspace_bytes(int64_t n);
+int lt_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 const float* lr, float* step_inout, float max_grad_norm, double beta1, double beta2, float eps,
+                 float weight_decay, float grad_scale, float* grad_norm_out /*or NULL*/,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K2  binary taxel synthesis (+ fused delay line)
+ * replaces  locotouch/mdp/observations.py:154-159,166-199,281-308  BinaryTactileSignals.__call__
+ *           locotouch/distill/tactile_recorder.py:4-34             TactileRecorder (lt_tactile_delay)
+ *   F_n = -(R(q_taxel)^T F_w).z ; C = F_n > thr ; C' = C & !(U_drop < p_drop) ; out = C' | (U_add < p_add)
+ *   signal [N, 2*T] f32 = (out, out) ; packed [N, ceil(T/32)] u32 warp-ballot bitmap (bit t%32 of word t/32).
+ *   u_drop / u_add == NULL -> in-kernel Philox uniforms keyed by (seed, offset, env, taxel).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int N;                      /* envs */
+  int T;                      /* taxels per env (17*13 = 221) */
+  const float* body_quat_w;   /* [N, quat_stride_bodies, 4] (w,x,y,z); taxel t is body quat_body_offset + t */
+  int quat_num_bodies;        /* bodies per env in body_quat_w */
+  int quat_body_offset;
+  const float* net_forces_w;  /* [N, T, 3] */
+  const float* thresholds;    /* [N, T] */
+  const float* u_drop;        /* [N, T] or NULL */
+  const float* u_add;         /* [N, T] or NULL */
+  float p_drop, p_add;
+  uint64_t seed, offset;
+  float* signal;              /* [N, 2T] or NULL */
+  uint32_t* packed;           /* [N, ceil(T/32)] or NULL */
+  float* normal_forces;       /* [N, T] or NULL  (original_normal_forces side buffer) */
+  uint8_t* original_contact;  /* [N, T] or NULL  (original_contact_taxels side buffer) */
+  /* fused delay line on the packed bitmap (all NULL/0 to disable): ring [N, max_delay, words] */
+  uint32_t* delay_ring;
+  uint8_t* delay_first;       /* [N] 1 = first frame after reset -> fill every slot */
+  const int64_t* delay_steps; /* [N] slot to read */
+  int max_delay;
+  float* delayed_signal;      /* [N, 2T] */
+} LtTaxelArgs;
+int lt_taxel_synth(const LtTaxelArgs* args, void* stream);
+/* Generic fp32 delay line: ring [N, max_delay, D]; shift in `signal`, first-frame fill, out[n] = ring[n, delay[n]]. */
+int lt_tactile_delay(float* ring, uint8_t* first, const int64_t* delay_steps, const float* signal, float* out,
+                     int N, int max_delay, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K1  fused MDP step: terminations -> rewards (incl. stateful gait term) -> [auto reset] -> observations
+ * replaces  locotouch/mdp/rewards.py:15-604, locotouch/mdp/terminations.py:10-23,
+ *           locotouch/mdp/observations.py:38-91 and the IsaacLab manager loops that call them
+ *           (RewardManager.compute / TerminationManager.compute / ObservationManager.compute).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define LT_MAX_REWARD_TERMS 32
+#define LT_MAX_TERMINATION_TERMS 8
+#define LT_MAX_OBS_TERMS 8
+#define LT_MAX_CONTACT_IDS 8
+
+enum LtRewardKind {
+  LT_RK_ALIVE = 0, LT_RK_TRACK_LIN_VEL_XY, LT_RK_TRACK_ANG_VEL_Z, LT_RK_FOOT_SLIP, LT_RK_FOOT_DRAG, LT_RK_GAIT,
+  LT_RK_BASE_HEIGHT, LT_RK_BASE_Z_VEL, LT_RK_BASE_RP_ANGLE, LT_RK_BASE_RP_VEL, LT_RK_JOINT_POS_LIMIT,
+  LT_RK_JOINT_POS, LT_RK_JOINT_ACC, LT_RK_JOINT_VEL, LT_RK_JOINT_TORQUE, LT_RK_ACTION_RATE,
+  LT_RK_THIGH_CALF_COLLISION, LT_RK_OBJ_XY_POS, LT_RK_OBJ_XY_VEL, LT_RK_OBJ_LOSE_CONTACT, LT_RK_OBJ_Z_VEL,
+  LT_RK_OBJ_RP_ANGLE, LT_RK_OBJ_RP_VEL, LT_RK_OBJ_ROLL_ANGLE, LT_RK_OBJ_ROLL_VEL, LT_RK_OBJ_YAW, LT_RK_OBJ_DANGER,
+  LT_RK_COUNT
+};
+enum LtTerminationKind {
+  LT_TK_TIME_OUT = 0, LT_TK_BAD_ORIENTATION, LT_TK_ROOT_HEIGHT, LT_TK_ILLEGAL_CONTACT, LT_TK_OBJECT_BELOW_ROBOT,
+  LT_TK_BAD_ROLL
+};
+enum LtObsKind {
+  LT_OK_COMMAND = 0, LT_OK_BASE_ANG_VEL, LT_OK_PROJECTED_GRAVITY, LT_OK_JOINT_POS_REL, LT_OK_JOINT_VEL_REL,
+  LT_OK_LAST_ACTION, LT_OK_OBJECT_STATE
+};
+enum LtMdpPhase { LT_PHASE_REWARDS = 1, LT_PHASE_OBS = 2 };
+
+typedef struct { int kind; float weight; float p[6]; } LtRewardTerm;
+typedef struct { int kind; int time_out; float p[2]; int num_ids; int body_ids[LT_MAX_CONTACT_IDS]; } LtTerminationTerm;
+typedef struct { int kind; int dim; float scale; int noisy; float n_min, n_max; } LtObsTerm;
+
+typedef struct {
+  /* rewards.py:168-188 parameters of AdaptiveSymmetricGaitReward */
+  float judge_time_threshold, air_time_gait_bound, contact_time_gait_bound, async_time_tolerance;
+  float stance_rwd_scale, tolerance_proportion, rwd_upper_bound, rwd_lower_bound;
+  float vel_tracking_exp_sigma, task_performance_ratio, linear_scale, two_step_dt;
+  float async_judge_time_threshold; /* float(judge_time_threshold + async_time_tolerance), rewards.py:67 */
+  int encourage_symmetricity; /* bool */
+  int with_object;            /* AdaptiveSymmetricGaitRewardwithObject */
+  float obj_x_max, obj_y_max;
+  int feet_ids[4];            /* contact-sensor body ids in gait order (pair0[0], pair0[1], pair1[0], pair1[1]) */
+} LtGaitParams;
+
+typedef struct {
+  /* rewards.py:96-105 state arrays, read AND written */
+  float* last_step_current_air_time;     /* [N,4] */
+  float* last_step_current_contact_time; /* [N,4] */
+  uint8_t* swinging_in_zero_cmd;         /* [N,4] */
+  float* valid_last_air_time;            /* [N,4] */
+  uint8_t* valid_previous_contact;       /* [N,4] */
+  float* last_velocity_cmd;              /* [N,3] */
+  float* step_from_changing_cmd;         /* [N]   */
+} LtGaitState;
+
+typedef struct {
+  int N;
+  int phases;                    /* LT_PHASE_REWARDS | LT_PHASE_OBS */
+  float step_dt;
+  int64_t max_episode_length;
+  /* ---- inputs: exactly the IsaacLab tensors the reference terms read, contiguous row-major ---- */
+  const float* command;          /* [N,3]  command_manager.get_command("base_velocity") */
+  const float* root_pos_w;       /* [N,3] */
+  const float* root_quat_w;      /* [N,4] wxyz (object tasks only) */
+  const float* root_lin_vel_w;   /* [N,3] (object tasks only) */
+  const float* root_ang_vel_w;   /* [N,3] (object tasks only) */
+  const float* root_lin_vel_b;   /* [N,3] */
+  const float* root_ang_vel_b;   /* [N,3] */
+  const float* projected_gravity_b; /* [N,3] */
+  const float* joint_pos;        /* [N,J] */
+  const float* joint_vel;        /* [N,J] */
+  const float* joint_acc;        /* [N,J] */
+  const float* applied_torque;   /* [N,J] */
+  const float* default_joint_pos;/* [N,J] */
+  const float* default_joint_vel;/* [N,J] */
+  const float* soft_joint_pos_limits; /* [N,J,2] */
+  const float* raw_actions;      /* [N,J] action_manager.get_term("joint_pos").raw_actions */
+  const float* prev_raw_actions; /* [N,J] */
+  int J;                         /* joints (12) */
+  const float* body_pos_w;       /* [N,num_bodies,3] */
+  const float* body_lin_vel_w;   /* [N,num_bodies,3] */
+  int num_bodies;
+  int feet_body_ids[4];          /* articulation body ids of ".*foot" (slip / dragging) */
+  const float* net_forces_w_history; /* [N,H,num_sensor_bodies,3] */
+  int force_history;             /* H (3) */
+  int num_sensor_bodies;         /* 17 */
+  int feet_sensor_ids[4];        /* contact-sensor ids of ".*foot" in body order */
+  int thigh_calf_sensor_ids[8];
+  int num_thigh_calf;
+  const float* current_air_time;     /* [N,num_sensor_bodies] */
+  const float* current_contact_time; /* [N,num_sensor_bodies] */
+  const float* last_air_time;        /* [N,num_sensor_bodies] */
+  const int64_t* episode_length_buf; /* [N] */
+  /* object (NULL for the locomotion task) */
+  const float* obj_root_pos_w;   /* [N,3] */
+  const float* obj_root_quat_w;  /* [N,4] */
+  const float* obj_root_lin_vel_w;   /* [N,3] */
+  const float* obj_root_ang_vel_w;   /* [N,3] */
+  const float* obj_projected_gravity_b; /* [N,3] */
+  const float* obj_last_contact_time;    /* [N] */
+  const float* obj_current_contact_time; /* [N] */
+  const float* obj_current_air_time;     /* [N] */
+  /* ---- term tables ---- */
+  int num_reward_terms;
+  LtRewardTerm reward_terms[LT_MAX_REWARD_TERMS];
+  int num_termination_terms;
+  LtTerminationTerm termination_terms[LT_MAX_TERMINATION_TERMS];
+  LtGaitParams gait;
+  LtGaitState gait_state;
+  int any_nonzero_cmd_override;  /* -1: compute torch.any(non_zero_cmd) on the device (rewards.py:190); 0/1: use this */
+  int auto_reset;                /* 1: zero gait state + episode sums of done envs after the reward pass (== the
+                                    manager .reset(env_ids) calls that follow in ManagerBasedRLEnv.step) */
+  /* ---- reward / termination outputs ---- */
+  float* reward;                 /* [N]   reward_buf */
+  float* step_reward;            /* [N,num_reward_terms]  value/dt  ([IL] RewardManager._step_reward) */
+  float* episode_sums;           /* [num_reward_terms,N]  += value  (one contiguous [N] row per term) */
+  float* term_raw;               /* [num_reward_terms,N] unweighted term values or NULL (per-term drop-in cache) */
+  uint8_t* term_masks;           /* [num_termination_terms,N] or NULL */
+  uint8_t* terminated;           /* [N] */
+  uint8_t* time_outs;            /* [N] */
+  uint8_t* dones;                /* [N] terminated | time_outs */
+  float* episode_log_sums;       /* [num_reward_terms+1] or NULL: += episode sums of reset envs, last = count */
+  /* ---- observation phase ---- */
+  int num_obs_terms;
+  LtObsTerm obs_terms[LT_MAX_OBS_TERMS];
+  int history_length;            /* 6 */
+  uint8_t* obs_fill;             /* [N] in/out or NULL.  1 = history empty: this observation pass writes the new values into
+                                    every history slot ([IL] CircularBuffer first push) and clears the flag.  A reward pass with
+                                    auto_reset sets it for done envs (or, when fused with the observation pass, applies it). */
+  const float* policy_obs_in;    /* [N, D] previous policy observation (history source) */
+  float* policy_obs_out;         /* [N, D] may alias policy_obs_in */
+  const float* critic_obs_in;
+  float* critic_obs_out;
+  const float* u_obs;            /* [N, sum(dim)] uniforms for the policy-group noise, or NULL -> Philox */
+  const float* u_obj_euler;      /* [N,3] uniforms for the object quaternion noise (observations.py:78) or NULL */
+  uint64_t seed, offset;
+  /* object_state_in_robot_frame parameters (observations.py:38-91) */
+  float os_n_min[13], os_n_max[13], os_scale[13], os_non_contact[13];
+  float os_last_contact_thr, os_current_contact_thr;
+  int* any_flag_ws;              /* [2] device ints, zero-initialised once; used for the cross-env any() */
+} LtMdpArgs;
+int lt_mdp_step(const LtMdpArgs* args, void* stream);
+/* AdaptiveSymmetricGaitReward.reset(env_ids) (rewards.py:107-114) for a mask of envs; also zeroes episode sums. */
+int lt_mdp_reset(const LtGaitState* gait_state, float* episode_sums, int num_reward_terms, const uint8_t* mask,
+                 int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K8  student batch helpers
+ * replaces  locotouch/distill/replay_buffer.py:90-112 (_prepare_padded_sequence) and
+ *           locotouch/distill/student.py:131,142-143 (per-element MSE .mean(-1), masked mean) + its backward
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Pads B trajectories stored back to back in `flat` [total_steps, D] (trajectory b = rows offsets[b]..offsets[b]+len[b])
+ * into out [L_max, B, D] (zero filled) and masks [L_max, B]. */
+int lt_pad_trajectories(const float* flat, const int64_t* offsets, const int64_t* lengths, int B, int L_max, int D,
+                        float* out, uint8_t* masks, void* stream);
+/* loss = sum_{t,b} mask * mean_a (s - t)^2 / sum(mask) ; grad_student = dloss/ds.  out[4] = {loss, mae, count, 0}. */
+int64_t lt_masked_mse_workspace_bytes(int64_t rows);
+int lt_masked_mse(const float* student, const float* teacher, const uint8_t* masks, int64_t rows, int A,
+                  float* grad_student, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCOTOUCH_B200_H */

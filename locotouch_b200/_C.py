@@ -1,0 +1,230 @@
+"""ctypes binding of ``liblocotouch_b200.so`` (the C ABI declared in include/locotouch_b200.h).
+
+The library is the product: there is NO fallback.  If the shared object is missing or a call returns a non-zero
+status this module raises -- loudly -- instead of routing around the CUDA path.
+PyTorch is used only as the owner of device memory and streams: tensors cross the ABI as raw ``data_ptr()`` values.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "liblocotouch_b200.so")
+
+LT_GATHER_MAX = 12
+LT_MAX_REWARD_TERMS = 32
+LT_MAX_TERMINATION_TERMS = 8
+LT_MAX_OBS_TERMS = 8
+LT_MAX_CONTACT_IDS = 8
+LT_PHASE_REWARDS = 1
+LT_PHASE_OBS = 2
+
+f32p = C.c_void_p  # raw device pointers are passed as void*
+
+
+class LtGatherArgs(C.Structure):
+    _fields_ = [
+        ("num_tensors", C.c_int),
+        ("src", C.c_void_p * LT_GATHER_MAX),
+        ("dst", C.c_void_p * LT_GATHER_MAX),
+        ("row_len", C.c_int * LT_GATHER_MAX),
+    ]
+
+
+class LtPpoLossArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("A", C.c_int),
+        ("mu", C.c_void_p), ("sigma", C.c_void_p), ("value", C.c_void_p), ("actions", C.c_void_p),
+        ("old_logp", C.c_void_p), ("old_mu", C.c_void_p), ("old_sigma", C.c_void_p), ("advantages", C.c_void_p),
+        ("returns", C.c_void_p), ("old_values", C.c_void_p),
+        ("clip_param", C.c_float), ("value_loss_coef", C.c_float), ("entropy_coef", C.c_float),
+        ("use_clipped_value_loss", C.c_int),
+        ("desired_kl", C.c_float), ("grad_scale", C.c_float),
+        ("grad_mu", C.c_void_p), ("grad_value", C.c_void_p), ("grad_sigma", C.c_void_p), ("out", C.c_void_p),
+        ("lr_inout", C.c_void_p), ("loss_accum", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
+class LtTaxelArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("T", C.c_int),
+        ("body_quat_w", C.c_void_p), ("quat_num_bodies", C.c_int), ("quat_body_offset", C.c_int),
+        ("net_forces_w", C.c_void_p), ("thresholds", C.c_void_p), ("u_drop", C.c_void_p), ("u_add", C.c_void_p),
+        ("p_drop", C.c_float), ("p_add", C.c_float),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("signal", C.c_void_p), ("packed", C.c_void_p), ("normal_forces", C.c_void_p), ("original_contact", C.c_void_p),
+        ("delay_ring", C.c_void_p), ("delay_first", C.c_void_p), ("delay_steps", C.c_void_p), ("max_delay", C.c_int),
+        ("delayed_signal", C.c_void_p),
+    ]
+
+
+class LtRewardTerm(C.Structure):
+    _fields_ = [("kind", C.c_int), ("weight", C.c_float), ("p", C.c_float * 6)]
+
+
+class LtTerminationTerm(C.Structure):
+    _fields_ = [("kind", C.c_int), ("time_out", C.c_int), ("p", C.c_float * 2), ("num_ids", C.c_int),
+                ("body_ids", C.c_int * LT_MAX_CONTACT_IDS)]
+
+
+class LtObsTerm(C.Structure):
+    _fields_ = [("kind", C.c_int), ("dim", C.c_int), ("scale", C.c_float), ("noisy", C.c_int),
+                ("n_min", C.c_float), ("n_max", C.c_float)]
+
+
+class LtGaitParams(C.Structure):
+    _fields_ = [
+        ("judge_time_threshold", C.c_float), ("air_time_gait_bound", C.c_float), ("contact_time_gait_bound", C.c_float),
+        ("async_time_tolerance", C.c_float), ("stance_rwd_scale", C.c_float), ("tolerance_proportion", C.c_float),
+        ("rwd_upper_bound", C.c_float), ("rwd_lower_bound", C.c_float), ("vel_tracking_exp_sigma", C.c_float),
+        ("task_performance_ratio", C.c_float), ("linear_scale", C.c_float), ("two_step_dt", C.c_float),
+        ("async_judge_time_threshold", C.c_float),
+        ("encourage_symmetricity", C.c_int), ("with_object", C.c_int),
+        ("obj_x_max", C.c_float), ("obj_y_max", C.c_float),
+        ("feet_ids", C.c_int * 4),
+    ]
+
+
+class LtGaitState(C.Structure):
+    _fields_ = [
+        ("last_step_current_air_time", C.c_void_p), ("last_step_current_contact_time", C.c_void_p),
+        ("swinging_in_zero_cmd", C.c_void_p), ("valid_last_air_time", C.c_void_p), ("valid_previous_contact", C.c_void_p),
+        ("last_velocity_cmd", C.c_void_p), ("step_from_changing_cmd", C.c_void_p),
+    ]
+
+
+class LtMdpArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("phases", C.c_int), ("step_dt", C.c_float), ("max_episode_length", C.c_int64),
+        ("command", C.c_void_p), ("root_pos_w", C.c_void_p), ("root_quat_w", C.c_void_p), ("root_lin_vel_w", C.c_void_p),
+        ("root_ang_vel_w", C.c_void_p), ("root_lin_vel_b", C.c_void_p), ("root_ang_vel_b", C.c_void_p),
+        ("projected_gravity_b", C.c_void_p), ("joint_pos", C.c_void_p), ("joint_vel", C.c_void_p), ("joint_acc", C.c_void_p),
+        ("applied_torque", C.c_void_p), ("default_joint_pos", C.c_void_p), ("default_joint_vel", C.c_void_p),
+        ("soft_joint_pos_limits", C.c_void_p), ("raw_actions", C.c_void_p), ("prev_raw_actions", C.c_void_p),
+        ("J", C.c_int),
+        ("body_pos_w", C.c_void_p), ("body_lin_vel_w", C.c_void_p), ("num_bodies", C.c_int),
+        ("feet_body_ids", C.c_int * 4),
+        ("net_forces_w_history", C.c_void_p), ("force_history", C.c_int), ("num_sensor_bodies", C.c_int),
+        ("feet_sensor_ids", C.c_int * 4), ("thigh_calf_sensor_ids", C.c_int * 8), ("num_thigh_calf", C.c_int),
+        ("current_air_time", C.c_void_p), ("current_contact_time", C.c_void_p), ("last_air_time", C.c_void_p),
+        ("episode_length_buf", C.c_void_p),
+        ("obj_root_pos_w", C.c_void_p), ("obj_root_quat_w", C.c_void_p), ("obj_root_lin_vel_w", C.c_void_p),
+        ("obj_root_ang_vel_w", C.c_void_p), ("obj_projected_gravity_b", C.c_void_p), ("obj_last_contact_time", C.c_void_p),
+        ("obj_current_contact_time", C.c_void_p), ("obj_current_air_time", C.c_void_p),
+        ("num_reward_terms", C.c_int), ("reward_terms", LtRewardTerm * LT_MAX_REWARD_TERMS),
+        ("num_termination_terms", C.c_int), ("termination_terms", LtTerminationTerm * LT_MAX_TERMINATION_TERMS),
+        ("gait", LtGaitParams), ("gait_state", LtGaitState),
+        ("any_nonzero_cmd_override", C.c_int), ("auto_reset", C.c_int),
+        ("reward", C.c_void_p), ("step_reward", C.c_void_p), ("episode_sums", C.c_void_p), ("term_raw", C.c_void_p),
+        ("term_masks", C.c_void_p), ("terminated", C.c_void_p), ("time_outs", C.c_void_p), ("dones", C.c_void_p),
+        ("episode_log_sums", C.c_void_p),
+        ("num_obs_terms", C.c_int), ("obs_terms", LtObsTerm * LT_MAX_OBS_TERMS), ("history_length", C.c_int),
+        ("obs_fill", C.c_void_p), ("policy_obs_in", C.c_void_p), ("policy_obs_out", C.c_void_p),
+        ("critic_obs_in", C.c_void_p), ("critic_obs_out", C.c_void_p), ("u_obs", C.c_void_p), ("u_obj_euler", C.c_void_p),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("os_n_min", C.c_float * 13), ("os_n_max", C.c_float * 13), ("os_scale", C.c_float * 13),
+        ("os_non_contact", C.c_float * 13), ("os_last_contact_thr", C.c_float), ("os_current_contact_thr", C.c_float),
+        ("any_flag_ws", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/locotouch_b200.h declares
+_SIGNATURES = {
+    "lt_abi_version": (C.c_int, []),
+    "lt_error_string": (C.c_char_p, [C.c_int]),
+    "lt_last_cuda_error": (C.c_char_p, []),
+    "lt_struct_size": (C.c_int64, [C.c_int]),
+    "lt_gae_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "lt_gae": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "lt_gae_scan": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "lt_adv_normalize": (C.c_int, [f32p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "lt_act_sample": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "lt_store_step": (C.c_int, [f32p, C.c_void_p, C.c_void_p, C.c_void_p, f32p, C.c_float, f32p, C.c_void_p, f32p, f32p, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_void_p]),
+    "lt_gather_rows": (C.c_int, [C.POINTER(LtGatherArgs), C.c_void_p, C.c_int64, C.c_void_p]),
+    "lt_ppo_loss_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "lt_ppo_loss": (C.c_int, [C.POINTER(LtPpoLossArgs), C.c_void_p]),
+    "lt_adaptive_lr": (C.c_int, [f32p, C.c_float, C.c_float, f32p, C.c_void_p]),
+    "lt_clip_adam_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "lt_clip_adam": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int64, f32p, f32p, C.c_float, C.c_double, C.c_double, C.c_float, C.c_float, C.c_float, f32p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "lt_taxel_synth": (C.c_int, [C.POINTER(LtTaxelArgs), C.c_void_p]),
+    "lt_tactile_delay": (C.c_int, [f32p, C.c_void_p, C.c_void_p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "lt_mdp_step": (C.c_int, [C.POINTER(LtMdpArgs), C.c_void_p]),
+    "lt_mdp_reset": (C.c_int, [C.POINTER(LtGaitState), f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "lt_pad_trajectories": (C.c_int, [f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, C.c_void_p, C.c_void_p]),
+    "lt_masked_mse_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "lt_masked_mse": (C.c_int, [f32p, f32p, C.c_void_p, C.c_int64, C.c_int, f32p, f32p, C.c_void_p, C.c_int64, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class LocoTouchLibraryError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Loads the shared object (once).  Raises if it has not been built: there is no CPU / eager fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LocoTouchLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m locotouch_b200.csrc.build` "
+            "(or __graft_entry__.build()).  locotouch_b200 has no fallback path."
+        )
+    handle = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError as e:  # pragma: no cover
+            raise LocoTouchLibraryError(f"{LIB_PATH} does not export {name}; rebuild the library") from e
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if handle.lt_abi_version() != 1:
+        raise LocoTouchLibraryError("ABI version mismatch between _C.py and liblocotouch_b200.so")
+    for which, struct in enumerate((LtGatherArgs, LtPpoLossArgs, LtTaxelArgs, LtMdpArgs, LtGaitState, LtGaitParams)):
+        if handle.lt_struct_size(which) != C.sizeof(struct):
+            raise LocoTouchLibraryError(
+                f"struct layout mismatch for {struct.__name__}: C {handle.lt_struct_size(which)} vs ctypes {C.sizeof(struct)}")
+    _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        handle = lib()
+        msg = handle.lt_error_string(status).decode()
+        cuda = handle.lt_last_cuda_error().decode()
+        raise LocoTouchLibraryError(f"{what or 'locotouch_b200 call'} failed: {msg}" + (f" [{cuda}]" if cuda and status == 2 else ""))
+
+
+def ptr(t: torch.Tensor | None, dtype: torch.dtype | None = None, name: str = "tensor") -> int | None:
+    """Raw device pointer of a contiguous CUDA tensor (``None`` passes NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise LocoTouchLibraryError(f"{name} must live on a CUDA device (got {t.device}); locotouch_b200 has no CPU path")
+    if not t.is_contiguous():
+        raise LocoTouchLibraryError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise LocoTouchLibraryError(f"{name} must be {dtype} (got {t.dtype})")
+    return t.data_ptr()
+
+
+def current_stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# launch counter: bench.py reports how many of OUR kernels-launching ABI calls ran inside the timed region
+launch_count = 0
+
+
+def count_launches(n: int = 1):
+    global launch_count
+    launch_count += n

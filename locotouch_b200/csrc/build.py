@@ -1,0 +1,87 @@
+"""Builds ``locotouch_b200/liblocotouch_b200.so`` (the C-ABI library) in-tree with nvcc for sm_100a.
+
+    python -m locotouch_b200.csrc.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU; the built .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import subprocess
+import sys
+
+CSRC = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(CSRC)
+ROOT = os.path.dirname(PKG)
+INCLUDE = os.path.join(ROOT, "include")
+LIB_PATH = os.path.join(PKG, "liblocotouch_b200.so")
+
+# Kernels whose masks must be bit-exact against the torch expression order are built without FMA contraction
+# (torch evaluates a*b+c as two rounded ops).
+PER_FILE_FLAGS = {"mdp_step.cu": ["-fmad=false"], "taxel.cu": ["-fmad=false"], "gae.cu": ["-fmad=false"]}
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fvisibility=default",
+]
+
+
+def sources() -> list[str]:
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _deps() -> list[str]:
+    return sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in _deps())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    objs = []
+    build_dir = os.path.join(CSRC, "build")
+    os.makedirs(build_dir, exist_ok=True)
+    procs = []
+    for src in sources():
+        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))):
+            continue
+        cmd = [nvcc, *NVCC_FLAGS, *PER_FILE_FLAGS.get(os.path.basename(src), []), "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, proc in procs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            failed = True
+            sys.stderr.write(f"nvcc failed for {src}:\n{out}\n")
+        elif verbose or out.strip():
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-cudart", "static"]
+    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

@@ -1,0 +1,122 @@
+// K7: global-norm gradient clip + Adam(W) over ONE flat fp32 parameter buffer.
+// Replaces reference loco_rl/loco_rl/algorithms/ppo.py:350-353 (nn.utils.clip_grad_norm_ + optim.Adam.step, ~6 foreach
+// launches per parameter group) and the AdamW step of locotouch/distill/student.py:82,151.
+//
+// Two launches, no host round trip: (1) per-block partial sums of g^2 in fp64 (fixed order, written to the workspace)
+// + step counter increment; (2) every block folds the partials in index order, derives the clip coefficient and the
+// bias corrections, and updates p / m / v with 128-bit accesses.  lr and the step counter are device scalars so the
+// pair can be captured in a CUDA graph and replayed.  After a DDP all-reduce(sum) pass grad_scale = 1/world_size.
+// Algorithmic traffic: 4 B (norm pass) + 16 B read + 12 B written per parameter.
+#include "lt_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVecPerThread = 4;  // float4 per thread per tile
+
+__global__ void __launch_bounds__(kThreads)
+grad_sqnorm_kernel(const float* __restrict__ g, int64_t n, float grad_scale, double* __restrict__ partial, float* step_inout) {
+  __shared__ double red[kThreads / 32];
+  const int64_t n4 = n >> 2;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float a = v.x * grad_scale, b = v.y * grad_scale, c = v.z * grad_scale, d = v.w * grad_scale;
+    acc += (double)(a * a + b * b) + (double)(c * c + d * d);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int64_t j = n4 << 2; j < n; ++j) {
+      const float a = g[j] * grad_scale;
+      acc += (double)(a * a);
+    }
+    *step_inout += 1.0f;  // Adam's state["step"] += 1
+  }
+  acc = lt::block_sum(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float coef, float lr, float step_size,
+                                         float sqrt_bc2, float b1, float b2, float eps, float wd) {
+  g *= coef;
+  if (wd != 0.f) p *= 1.0f - lr * wd;        // AdamW decoupled decay
+  m = m + (g - m) * (1.0f - b1);             // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * b2 + (1.0f - b2) * g * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  const float denom = sqrtf(v) / sqrt_bc2 + eps;  // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+  p = p - step_size * (m / denom);           // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+__global__ void __launch_bounds__(kThreads)
+clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                 const float* __restrict__ lr_ptr, const float* __restrict__ step_ptr, float max_norm, double b1d, double b2d,
+                 float eps, float wd, float grad_scale, const double* __restrict__ partial, int num_partials,
+                 float* grad_norm_out) {
+  __shared__ double red[kThreads / 32];
+  __shared__ float s_coef, s_step_size, s_sqrt_bc2;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < num_partials; i += kThreads) acc += partial[i];
+  acc = lt::block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float total = (float)sqrt(acc);
+    float c = 1.0f;
+    if (max_norm > 0.f) c = fminf(max_norm / (total + 1e-6f), 1.0f);  // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
+    s_coef = c * grad_scale;
+    if (blockIdx.x == 0 && grad_norm_out) *grad_norm_out = total;
+    // torch.optim.Adam evaluates the bias corrections in Python doubles
+    const double step = (double)*step_ptr;
+    const double bc1 = 1.0 - pow(b1d, step), bc2 = 1.0 - pow(b2d, step);
+    s_step_size = (float)((double)*lr_ptr / bc1);
+    s_sqrt_bc2 = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float coef = s_coef, lr = *lr_ptr, step_size = s_step_size, sqrt_bc2 = s_sqrt_bc2;
+  const float b1 = (float)b1d, b2 = (float)b2d;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
+    adam_one(pp.y, gg.y, mm.y, vv.y, coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
+    adam_one(pp.z, gg.z, mm.z, vv.z, coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
+    adam_one(pp.w, gg.w, mm.w, vv.w, coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int64_t j = n4 << 2; j < n; ++j) adam_one(p[j], g[j], m[j], v[j], coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
+  }
+}
+
+int grid_for(int64_t n) {
+  const int64_t want = lt::ceil_div(lt::ceil_div(n, 4), (int64_t)kThreads * kVecPerThread);
+  int64_t cap = 8LL * lt::sm_count();
+  if (cap > 1024) cap = 1024;  // workspace holds 1024 partials
+  const int64_t g = want < cap ? want : cap;
+  return (int)(g > 0 ? g : 1);
+}
+
+}  // namespace
+
+extern "C" int64_t lt_clip_adam_workspace_bytes(int64_t n) {
+  (void)n;
+  return 1024 * (int64_t)sizeof(double);  // one fp64 partial per block; grids are capped at 1024 blocks
+}
+
+extern "C" int lt_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
+                            float* step_inout, float max_grad_norm, double beta1, double beta2, float eps, float weight_decay,
+                            float grad_scale, float* grad_norm_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !lr || !step_inout || !workspace || n <= 0) return LT_ERR_INVALID_ARG;
+  const uintptr_t align = (uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq;
+  if (align & 15) return LT_ERR_INVALID_ARG;
+  const int grid = grid_for(n);
+  if (workspace_bytes < (int64_t)grid * (int64_t)sizeof(double)) return LT_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partial = (double*)workspace;
+  grad_sqnorm_kernel<<<grid, kThreads, 0, st>>>(grads, n, grad_scale, partial, step_inout);
+  int rc = lt::check_launch();
+  if (rc != LT_OK) return rc;
+  clip_adam_kernel<<<grid, kThreads, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, step_inout, max_grad_norm, beta1, beta2,
+                                              eps, weight_decay, grad_scale, partial, grid, grad_norm_out);
+  return lt::check_launch();
+}

@@ -1,0 +1,142 @@
+// K2: binary taxel synthesis from back-mounted contact forces (+ the tactile delay line).
+// Replaces reference locotouch/mdp/observations.py:154-159 (get_original_signals), :166-199 (get_normal_forces) and
+// :281-308 (BinaryTactileSignals.__call__) -- 385 ATen launches per step in the reference -- and
+// locotouch/distill/tactile_recorder.py:4-34 (TactileRecorder).
+//
+// One warp per env.  The 221 taxels of an env are walked in 7 rounds of 32 lanes: each lane loads its taxel's link
+// quaternion with one 128-bit access, the world force, the per-(env,taxel) threshold, rotates the force into the
+// taxel frame, thresholds it (strict '>'), applies dropout / addition, and the warp ballots the 32 verdicts into one
+// word of the packed bitmap.  The fp32 [N, 2*221] tensor the student consumes is written from the same registers;
+// the delay line is kept on the packed words (28 B/env/frame instead of 1768 B).
+// The normal force is evaluated in the reference's operation order with contraction disabled so that the comparison
+// against the threshold sees the same fp32 value as the torch expression.
+// Algorithmic traffic per env-step: 221 x (16 + 12 + 4) B read + 442 x 4 B written = 8840 B.
+#include "lt_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxWords = 32;  // T <= 1024
+
+// z component of quat_apply_inverse(q, v) ([IL] isaaclab.utils.math): v - w*t + xyz x t, t = 2 (xyz x v)
+__device__ __forceinline__ float rotate_inverse_z(float4 q /*w,x,y,z*/, float vx, float vy, float vz) {
+  const float w = q.x, x = q.y, y = q.z, z = q.w;
+  const float tx = __fmul_rn(__fsub_rn(__fmul_rn(y, vz), __fmul_rn(z, vy)), 2.0f);
+  const float ty = __fmul_rn(__fsub_rn(__fmul_rn(z, vx), __fmul_rn(x, vz)), 2.0f);
+  const float tz = __fmul_rn(__fsub_rn(__fmul_rn(x, vy), __fmul_rn(y, vx)), 2.0f);
+  const float cz = __fsub_rn(__fmul_rn(x, ty), __fmul_rn(y, tx));
+  return __fadd_rn(__fsub_rn(vz, __fmul_rn(w, tz)), cz);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) taxel_kernel(const LtTaxelArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (n >= a.N) return;  // warp-uniform
+  const int T = a.T, words = (T + 31) >> 5;
+  const float4* quat = reinterpret_cast<const float4*>(a.body_quat_w) + (size_t)n * a.quat_num_bodies + a.quat_body_offset;
+  const float* force = a.net_forces_w + (size_t)n * T * 3;
+  const size_t row = (size_t)n * T;
+  uint32_t my_word = 0;  // lane r keeps word r
+  uint4 rnd = make_uint4(0, 0, 0, 0);
+  for (int r = 0; r < words; ++r) {
+    const int t = 32 * r + lane;
+    bool contact = false;
+    if (t < T) {
+      const float4 q = __ldcs(quat + t);
+      const float fx = __ldcs(force + 3 * t), fy = __ldcs(force + 3 * t + 1), fz = __ldcs(force + 3 * t + 2);
+      const float thr = __ldcs(a.thresholds + row + t);
+      const float fn = -rotate_inverse_z(q, fx, fy, fz);  // observations.py:156-158
+      const bool original = fn > thr;                     // observations.py:159 (strict)
+      contact = original;
+      float ud, ua;
+      if (a.u_drop || a.u_add) {
+        ud = a.u_drop ? __ldcs(a.u_drop + row + t) : 1.0f;
+        ua = a.u_add ? __ldcs(a.u_add + row + t) : 1.0f;
+      } else {
+        if ((r & 1) == 0) rnd = lt::Philox::gen(a.seed, a.offset, (uint32_t)n, (uint32_t)(32 * (r >> 1) + lane));
+        ud = lt::Philox::u01((r & 1) ? rnd.z : rnd.x);
+        ua = lt::Philox::u01((r & 1) ? rnd.w : rnd.y);
+      }
+      if (a.p_drop > 0.f) contact = contact && !(ud < a.p_drop);  // observations.py:172-176
+      if (a.p_add > 0.f) contact = contact || (ua < a.p_add);     // observations.py:180-185
+      if (a.normal_forces) a.normal_forces[row + t] = fn;
+      if (a.original_contact) a.original_contact[row + t] = original ? 1 : 0;
+      if (a.signal) {
+        const float s = contact ? 1.0f : 0.0f;
+        float* out = a.signal + (size_t)n * 2 * T;
+        __stcs(out + t, s);      // channel 0
+        __stcs(out + T + t, s);  // channel 1 (observations.py:308: two identical channels)
+      }
+    }
+    const uint32_t word = __ballot_sync(LT_FULL_MASK, contact);
+    if (lane == r) my_word = word;
+  }
+  if (a.packed && lane < words) a.packed[(size_t)n * words + lane] = my_word;
+
+  if (a.delay_ring) {  // tactile_recorder.py:25-34 on the packed words
+    uint32_t* ring = a.delay_ring + (size_t)n * a.max_delay * words;
+    const bool first = a.delay_first[n] != 0;
+    const int slot = (int)a.delay_steps[n];
+    uint32_t delayed = 0;
+    if (lane < words) {
+      for (int k = a.max_delay - 1; k >= 1; --k) ring[k * words + lane] = first ? my_word : ring[(k - 1) * words + lane];
+      ring[lane] = my_word;
+      delayed = ring[slot * words + lane];
+    }
+    __syncwarp();
+    if (lane == 0) a.delay_first[n] = 0;
+    if (a.delayed_signal) {
+      float* out = a.delayed_signal + (size_t)n * 2 * T;
+      for (int r = 0; r < words; ++r) {
+        const uint32_t w = __shfl_sync(LT_FULL_MASK, delayed, r);
+        const int t = 32 * r + lane;
+        if (t < T) {
+          const float s = (w >> lane) & 1u ? 1.0f : 0.0f;
+          __stcs(out + t, s);
+          __stcs(out + T + t, s);
+        }
+      }
+    }
+  }
+}
+
+// Generic fp32 delay line, one warp per env (the `first` flag is read and cleared by the same warp).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+tactile_delay_kernel(float* __restrict__ ring, uint8_t* __restrict__ first, const int64_t* __restrict__ delay_steps,
+                     const float* __restrict__ signal, float* __restrict__ out, int N, int max_delay, int D) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const bool fill = first[n] != 0;
+  const int slot = (int)delay_steps[n];
+  float* r = ring + (size_t)n * max_delay * D;
+  for (int d = lane; d < D; d += 32) {
+    const float x = __ldcs(signal + (size_t)n * D + d);
+    for (int k = max_delay - 1; k >= 1; --k) r[(size_t)k * D + d] = fill ? x : r[(size_t)(k - 1) * D + d];
+    r[d] = x;
+    out[(size_t)n * D + d] = r[(size_t)slot * D + d];
+  }
+  __syncwarp();
+  if (lane == 0) first[n] = 0;
+}
+
+}  // namespace
+
+extern "C" int lt_taxel_synth(const LtTaxelArgs* a, void* stream) {
+  if (!a || a->N <= 0 || a->T <= 0 || a->T > 32 * kMaxWords) return LT_ERR_INVALID_ARG;
+  if (!a->body_quat_w || !a->net_forces_w || !a->thresholds) return LT_ERR_INVALID_ARG;
+  if (((uintptr_t)a->body_quat_w & 15) != 0) return LT_ERR_INVALID_ARG;
+  if (a->quat_body_offset < 0 || a->quat_body_offset + a->T > a->quat_num_bodies) return LT_ERR_INVALID_ARG;
+  if (a->delay_ring && (!a->delay_first || !a->delay_steps || a->max_delay <= 0)) return LT_ERR_INVALID_ARG;
+  const int grid = (int)lt::ceil_div(a->N, kWarpsPerBlock);
+  taxel_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(*a);
+  return lt::check_launch();
+}
+
+extern "C" int lt_tactile_delay(float* ring, uint8_t* first, const int64_t* delay_steps, const float* signal, float* out, int N,
+                                int max_delay, int D, void* stream) {
+  if (!ring || !first || !delay_steps || !signal || !out || N <= 0 || max_delay <= 0 || D <= 0) return LT_ERR_INVALID_ARG;
+  const int grid = (int)lt::ceil_div(N, kWarpsPerBlock);
+  tactile_delay_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(ring, first, delay_steps, signal, out, N, max_delay, D);
+  return lt::check_launch();
+}

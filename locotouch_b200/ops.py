@@ -1,0 +1,264 @@
+"""Functional wrappers over the C ABI: tensors in, tensors out, one ABI call each.
+
+These are the thinnest possible host side -- argument checking, workspace ownership and pointer extraction.  The
+classes that mirror the reference interfaces (``locotouch_b200.loco_rl``, ``locotouch_b200.mdp``,
+``locotouch_b200.distill``) are built on top of them.  Every function requires CUDA tensors; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _C
+from ._C import check, count_launches, current_stream, lib, ptr
+
+_workspaces: dict[tuple, torch.Tensor] = {}
+
+
+def _workspace(key: str, nbytes: int, device) -> torch.Tensor:
+    """Zero-initialised, cached device workspace (the kernels keep their counters self-cleaning)."""
+    k = (key, str(device), torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0)
+    ws = _workspaces.get(k)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _workspaces[k] = ws
+    return ws
+
+
+# ----------------------------------------------------------------------------------------------------------- K4 GAE
+def gae(rewards, values, dones, last_values, gamma: float, lam: float, normalize_advantage: bool = True,
+        returns=None, advantages=None):
+    """RolloutStorage.compute_returns (reference rollout_storage.py:152-174).  Tensors are [T,N] or [T,N,1]."""
+    T, N = rewards.shape[0], rewards.shape[1]
+    if returns is None:
+        returns = torch.empty_like(rewards)
+    if advantages is None:
+        advantages = torch.empty_like(rewards)
+    if dones.dtype != torch.uint8:
+        raise _C.LocoTouchLibraryError("dones must be uint8 (RolloutStorage stores them with .byte())")
+    nbytes = lib().lt_gae_workspace_bytes(T, N)
+    ws = _workspace("gae", nbytes, rewards.device)
+    check(lib().lt_gae(ptr(rewards, torch.float32, "rewards"), ptr(values, torch.float32, "values"), ptr(dones, torch.uint8, "dones"),
+                       ptr(last_values, torch.float32, "last_values"), ptr(returns, torch.float32), ptr(advantages, torch.float32),
+                       T, N, gamma, lam, int(normalize_advantage), ptr(ws), nbytes, current_stream()), "lt_gae")
+    count_launches(2 if normalize_advantage else 1)
+    return returns, advantages
+
+
+def gae_scan(rewards, values, dones, last_values, gamma, lam, returns, advantages, stats):
+    """First half of ``gae`` (no normalisation); ``stats`` (4 x float64) receives sum, sum of squares, count."""
+    T, N = rewards.shape[0], rewards.shape[1]
+    nbytes = lib().lt_gae_workspace_bytes(T, N)
+    ws = _workspace("gae", nbytes, rewards.device)
+    check(lib().lt_gae_scan(ptr(rewards, torch.float32), ptr(values, torch.float32), ptr(dones, torch.uint8), ptr(last_values, torch.float32),
+                            ptr(returns, torch.float32), ptr(advantages, torch.float32), T, N, gamma, lam, ptr(stats, torch.float64),
+                            ptr(ws), nbytes, current_stream()), "lt_gae_scan")
+    count_launches(1)
+
+
+def adv_normalize(advantages, stats):
+    check(lib().lt_adv_normalize(ptr(advantages, torch.float32), advantages.numel(), ptr(stats, torch.float64), current_stream()), "lt_adv_normalize")
+    count_launches(1)
+
+
+# ------------------------------------------------------------------------------------------------- K3 act / store / K5
+def act_sample(mu, sigma, eps=None, actions=None, logp=None, mu_out=None, sigma_out=None, seed: int = 0, offset: int = 0):
+    """Normal(mu, sigma).sample() + log_prob().sum(-1) (reference actor_critic.py:105-123)."""
+    N, A = mu.shape
+    if actions is None:
+        actions = torch.empty_like(mu)
+    if logp is None:
+        logp = torch.empty(N, device=mu.device, dtype=torch.float32)
+    check(lib().lt_act_sample(ptr(mu, torch.float32, "mu"), ptr(sigma, torch.float32, "sigma"), ptr(eps, torch.float32, "eps"),
+                              ptr(actions, torch.float32), ptr(logp, torch.float32), ptr(mu_out, torch.float32), ptr(sigma_out, torch.float32),
+                              N, A, seed, offset, current_stream()), "lt_act_sample")
+    count_launches(1)
+    return actions, logp
+
+
+def store_step(rewards, dones, time_outs, values, gamma, rewards_out, dones_out, obs=None, obs_out=None, critic_obs=None,
+               critic_obs_out=None):
+    """PPO.process_env_step bootstrap + RolloutStorage.add_transitions (reference ppo.py:143-170, rollout_storage.py:80-107)."""
+    N = rewards.shape[0]
+    d64 = ptr(dones, torch.int64, "dones") if dones.dtype == torch.int64 else None
+    d8 = ptr(dones.view(torch.uint8) if dones.dtype == torch.bool else dones, torch.uint8, "dones") if dones.dtype != torch.int64 else None
+    to = None
+    if time_outs is not None:
+        to = ptr(time_outs.view(torch.uint8) if time_outs.dtype == torch.bool else time_outs, torch.uint8, "time_outs")
+    check(lib().lt_store_step(ptr(rewards, torch.float32, "rewards"), d64, d8, to, ptr(values, torch.float32, "values"), gamma,
+                              ptr(rewards_out, torch.float32), ptr(dones_out, torch.uint8),
+                              ptr(obs, torch.float32), ptr(obs_out, torch.float32), obs.shape[-1] if obs is not None else 0,
+                              ptr(critic_obs, torch.float32), ptr(critic_obs_out, torch.float32),
+                              critic_obs.shape[-1] if critic_obs is not None else 0, N, current_stream()), "lt_store_step")
+    n = 1
+    if obs is not None and obs_out is not None and obs.data_ptr() != obs_out.data_ptr():
+        n += 1
+    if critic_obs is not None and critic_obs_out is not None and critic_obs.data_ptr() != critic_obs_out.data_ptr():
+        n += 1
+    count_launches(n)
+
+
+def gather_rows(sources, indices, outs=None):
+    """``[src[indices] for src in sources]`` in one launch (reference rollout_storage.py:221-231)."""
+    count = indices.numel()
+    if outs is None:
+        outs = [torch.empty((count,) + tuple(s.shape[1:]), device=s.device, dtype=s.dtype) for s in sources]
+    args = _C.LtGatherArgs()
+    args.num_tensors = len(sources)
+    if len(sources) > _C.LT_GATHER_MAX:
+        raise _C.LocoTouchLibraryError("too many tensors for one gather")
+    for i, (s, o) in enumerate(zip(sources, outs)):
+        args.src[i] = ptr(s, torch.float32, "gather source")
+        args.dst[i] = ptr(o, torch.float32, "gather destination")
+        args.row_len[i] = s[0].numel()
+    check(lib().lt_gather_rows(C.byref(args), ptr(indices, torch.int64, "indices"), count, current_stream()), "lt_gather_rows")
+    count_launches(1)
+    return outs
+
+
+# --------------------------------------------------------------------------------------------------------- K6 PPO loss
+class PpoLossBuffers:
+    """Pre-allocated outputs + workspace for ``ppo_loss`` (no allocation inside the update loop / graph capture)."""
+
+    def __init__(self, B: int, A: int, device):
+        self.B, self.A = B, A
+        self.grad_mu = torch.empty(B, A, device=device)
+        self.grad_value = torch.empty(B, device=device)
+        self.grad_sigma = torch.empty(A, device=device)
+        self.out = torch.zeros(8, device=device)
+        self.nbytes = lib().lt_ppo_loss_workspace_bytes(B, A)
+        self.ws = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+
+
+def ppo_loss(mu, sigma, value, actions, old_logp, old_mu, old_sigma, advantages, returns, old_values, *, clip_param=0.2,
+             value_loss_coef=1.0, entropy_coef=0.0, use_clipped_value_loss=True, desired_kl=None, lr=None, loss_accum=None,
+             grad_scale=1.0, buffers: PpoLossBuffers | None = None):
+    """Fused PPO loss forward + backward (reference ppo.py:252-302).  Returns the ``PpoLossBuffers`` holding
+    ``grad_mu`` [B,A], ``grad_value`` [B], ``grad_sigma`` [A] and ``out`` = (loss, surrogate, value_loss, entropy, kl, lr)."""
+    B, A = mu.shape
+    if buffers is None:
+        buffers = PpoLossBuffers(B, A, mu.device)
+    a = _C.LtPpoLossArgs()
+    a.B, a.A = B, A
+    a.mu = ptr(mu, torch.float32, "mu")
+    a.sigma = ptr(sigma, torch.float32, "sigma")
+    a.value = ptr(value, torch.float32, "value")
+    a.actions = ptr(actions, torch.float32, "actions")
+    a.old_logp = ptr(old_logp, torch.float32, "old_logp")
+    a.old_mu = ptr(old_mu, torch.float32, "old_mu")
+    a.old_sigma = ptr(old_sigma, torch.float32, "old_sigma")
+    a.advantages = ptr(advantages, torch.float32, "advantages")
+    a.returns = ptr(returns, torch.float32, "returns")
+    a.old_values = ptr(old_values, torch.float32, "old_values")
+    a.clip_param, a.value_loss_coef, a.entropy_coef = clip_param, value_loss_coef, entropy_coef
+    a.use_clipped_value_loss = int(use_clipped_value_loss)
+    a.desired_kl = float(desired_kl) if (desired_kl is not None and lr is not None) else 0.0
+    a.grad_scale = grad_scale
+    a.grad_mu, a.grad_value, a.grad_sigma = ptr(buffers.grad_mu), ptr(buffers.grad_value), ptr(buffers.grad_sigma)
+    a.out = ptr(buffers.out)
+    a.lr_inout = ptr(lr, torch.float32, "lr")
+    a.loss_accum = ptr(loss_accum, torch.float32, "loss_accum")
+    a.workspace, a.workspace_bytes = ptr(buffers.ws), buffers.nbytes
+    check(lib().lt_ppo_loss(C.byref(a), current_stream()), "lt_ppo_loss")
+    count_launches(1)
+    return buffers
+
+
+def adaptive_lr(kl_sum, kl_scale: float, desired_kl: float, lr):
+    check(lib().lt_adaptive_lr(ptr(kl_sum, torch.float32), kl_scale, desired_kl, ptr(lr, torch.float32), current_stream()), "lt_adaptive_lr")
+    count_launches(1)
+
+
+# ------------------------------------------------------------------------------------------------------- K7 clip + Adam
+def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+              grad_scale=1.0, grad_norm_out=None):
+    """clip_grad_norm_ + Adam/AdamW step over flat fp32 buffers (reference ppo.py:350-353).  ``lr``/``step`` are device scalars."""
+    n = params.numel()
+    nbytes = lib().lt_clip_adam_workspace_bytes(n)
+    ws = _workspace("adam", nbytes, params.device)
+    check(lib().lt_clip_adam(ptr(params, torch.float32, "params"), ptr(grads, torch.float32, "grads"), ptr(exp_avg, torch.float32),
+                             ptr(exp_avg_sq, torch.float32), n, ptr(lr, torch.float32, "lr"), ptr(step, torch.float32, "step"),
+                             float(max_grad_norm if max_grad_norm is not None else 0.0), betas[0], betas[1], eps, weight_decay,
+                             grad_scale, ptr(grad_norm_out, torch.float32), ptr(ws), nbytes, current_stream()), "lt_clip_adam")
+    count_launches(2)
+
+
+# ----------------------------------------------------------------------------------------------------------- K2 taxels
+def taxel_synth(body_quat_w, net_forces_w, thresholds, *, quat_body_offset=0, u_drop=None, u_add=None, p_drop=0.005, p_add=0.005,
+                seed=0, offset=0, signal=None, packed=None, normal_forces=None, original_contact=None, delay_ring=None,
+                delay_first=None, delay_steps=None, delayed_signal=None, want_signal=True, want_packed=True):
+    """Binary taxel bitmap from contact forces (reference observations.py:154-199, 281-308)."""
+    N, T = net_forces_w.shape[0], net_forces_w.shape[1]
+    dev = net_forces_w.device
+    if signal is None and want_signal:
+        signal = torch.empty(N, 2 * T, device=dev)
+    words = (T + 31) // 32
+    if packed is None and want_packed:
+        packed = torch.empty(N, words, device=dev, dtype=torch.int32)
+    a = _C.LtTaxelArgs()
+    a.N, a.T = N, T
+    a.body_quat_w = ptr(body_quat_w, torch.float32, "body_quat_w")
+    a.quat_num_bodies = body_quat_w.shape[1]
+    a.quat_body_offset = quat_body_offset
+    a.net_forces_w = ptr(net_forces_w, torch.float32, "net_forces_w")
+    a.thresholds = ptr(thresholds, torch.float32, "thresholds")
+    a.u_drop, a.u_add = ptr(u_drop, torch.float32), ptr(u_add, torch.float32)
+    a.p_drop, a.p_add = p_drop, p_add
+    a.seed, a.offset = seed, offset
+    a.signal = ptr(signal, torch.float32)
+    a.packed = ptr(packed, torch.int32)
+    a.normal_forces = ptr(normal_forces, torch.float32)
+    a.original_contact = ptr(original_contact.view(torch.uint8) if original_contact is not None and original_contact.dtype == torch.bool else original_contact, torch.uint8)
+    if delay_ring is not None:
+        a.delay_ring = ptr(delay_ring, torch.int32)
+        a.delay_first = ptr(delay_first.view(torch.uint8) if delay_first.dtype == torch.bool else delay_first, torch.uint8)
+        a.delay_steps = ptr(delay_steps, torch.int64)
+        a.max_delay = delay_ring.shape[1]
+        a.delayed_signal = ptr(delayed_signal, torch.float32)
+    check(lib().lt_taxel_synth(C.byref(a), current_stream()), "lt_taxel_synth")
+    count_launches(1)
+    return signal, packed
+
+
+def tactile_delay(ring, first, delay_steps, signal, out=None):
+    """TactileRecorder.record_new_tactile_signals + get_tactile_signals (reference tactile_recorder.py:25-34)."""
+    N, max_delay, D = ring.shape
+    if out is None:
+        out = torch.empty(N, D, device=ring.device)
+    check(lib().lt_tactile_delay(ptr(ring, torch.float32, "ring"), ptr(first.view(torch.uint8) if first.dtype == torch.bool else first, torch.uint8),
+                                 ptr(delay_steps, torch.int64, "delay_steps"), ptr(signal, torch.float32, "signal"), ptr(out, torch.float32),
+                                 N, max_delay, D, current_stream()), "lt_tactile_delay")
+    count_launches(1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ K8 student batch
+def pad_trajectories(flat, offsets, lengths, L_max: int, out=None, masks=None):
+    """ReplayBuffer._prepare_padded_sequence (reference replay_buffer.py:90-112): [sum_len, D] -> [L_max, B, D] + mask."""
+    B, D = offsets.numel(), flat.shape[1]
+    if out is None:
+        out = torch.empty(L_max, B, D, device=flat.device)
+    if masks is None:
+        masks = torch.empty(L_max, B, device=flat.device, dtype=torch.bool)
+    check(lib().lt_pad_trajectories(ptr(flat, torch.float32, "flat"), ptr(offsets, torch.int64), ptr(lengths, torch.int64), B, L_max, D,
+                                    ptr(out, torch.float32), ptr(masks.view(torch.uint8), torch.uint8), current_stream()), "lt_pad_trajectories")
+    count_launches(1)
+    return out, masks
+
+
+def masked_mse(student, teacher, masks, grad=None, out=None, want_grad=True):
+    """Masked behaviour-cloning loss + gradient (reference student.py:131,142-151).  out = (loss, mae, count, 0)."""
+    A = student.shape[-1]
+    rows = student.numel() // A
+    if grad is None and want_grad:
+        grad = torch.empty_like(student)
+    if out is None:
+        out = torch.zeros(4, device=student.device)
+    nbytes = lib().lt_masked_mse_workspace_bytes(rows)
+    ws = _workspace("mse", nbytes, student.device)
+    m = masks.view(torch.uint8) if masks.dtype == torch.bool else masks
+    check(lib().lt_masked_mse(ptr(student, torch.float32, "student"), ptr(teacher, torch.float32, "teacher"), ptr(m, torch.uint8, "masks"),
+                              rows, A, ptr(grad, torch.float32), ptr(out, torch.float32), ptr(ws), nbytes, current_stream()), "lt_masked_mse")
+    count_launches(2 if grad is not None else 1)
+    return out, grad

@@ -1,0 +1,309 @@
+"""Generates the committed golden vectors by running the UNMODIFIED reference (``/root/reference``) on seeded inputs.
+
+    PYTHONPATH=. python tests/golden/make_golden.py
+
+Only runs in the build container (the reference is mounted read-only there; it does not exist on the GPU box).  The
+inputs are NOT stored: they are regenerated from the same seeds by ``tests/helpers.py`` /
+``locotouch_b200.sim.synth``; every fixture carries an input checksum so that generator drift is detected.
+
+Fixtures (all < 1 MB):
+  mdp_locomotion.npz / mdp_teacher.npz  per-step raw values of every reward term, custom terminations, object-state
+                                        observation (clean + noisy) and the final gait state, from the reference
+                                        ``locotouch/mdp`` callables driven through the IsaacLab stub namespace.
+  ppo_c1.npz                            RolloutStorage.compute_returns outputs and one full PPO.update() (losses,
+                                        learning-rate, parameters after the update) from the reference ``loco_rl``.
+  tactile_c4.npz                        BinaryTactileSignals bitmaps (explicit dropout / addition uniforms) and
+                                        TactileRecorder outputs across resets.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from oracle.mdp import MdpOracle  # noqa: E402
+from tests import helpers as H  # noqa: E402
+from locotouch_b200.sim import synth  # noqa: E402
+from locotouch_b200.sim.scene import SceneEntityCfg  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def env_checksum(env) -> float:
+    return float(sum(t.double().abs().sum() for k, t in env.named_tensors().items() if k not in ("terminated", "time_outs")))
+
+
+class patched_rand:
+    """Feeds the reference's ``torch.rand_like`` / ``torch.rand`` calls from a queue of explicit tensors."""
+
+    def __init__(self, rand_like_queue=(), rand_queue=()):
+        self.like_q, self.rand_q = list(rand_like_queue), list(rand_queue)
+
+    def __enter__(self):
+        self._rl, self._r = torch.rand_like, torch.rand
+
+        def rand_like(x, *a, **k):
+            if self.like_q:
+                item = self.like_q.pop(0)
+                out = item(x) if callable(item) else item
+                if out is not None:
+                    assert out.shape == x.shape, (out.shape, x.shape)
+                    return out.to(x.dtype)
+            return self._rl(x, *a, **k)
+
+        def rand(*a, **k):
+            if self.rand_q:
+                return self.rand_q.pop(0)
+            return self._r(*a, **k)
+
+        torch.rand_like, torch.rand = rand_like, rand
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand_like, torch.rand = self._rl, self._r
+
+
+def reference_reward_terms(rw, env, spec, gait):
+    """{name: raw tensor} from the reference callables, in cfg order, for the non-[IL] terms with non-zero weight."""
+    sc = lambda *a, **k: SceneEntityCfg(*a, **k).resolve(env.scene)  # noqa: E731
+    feet = sc("robot", body_names=".*foot")
+    feet_s = sc("robot_contact_senosr", body_names=".*foot")
+    out = {
+        "track_lin_vel_xy": rw.track_lin_vel_xy_pst(env, 0.25, "base_velocity"),
+        "track_ang_vel_z": rw.track_ang_vel_z_pst(env, 0.25, "base_velocity"),
+        "foot_slip": rw.foot_slipping_ngt(env, 0.5, feet, feet_s),
+        "foot_dragging": rw.foot_dragging_ngt(env, feet, 0.03, 0.1),
+        "gait": gait(env, **gait.cfg.params),
+        "track_base_height": rw.track_base_height_ngt(env, 0.42),
+        "base_z_velocity": rw.base_z_velocity_ngt(env),
+        "base_roll_pitch_angle": rw.base_roll_pitch_angle_ngt(env),
+        "base_roll_pitch_velocity": rw.base_roll_pitch_velocity_ngt(env),
+        "joint_position_limit": rw.joint_position_limit_ngt(env),
+        "joint_position": rw.joint_position_ngt(env, SceneEntityCfg("robot"), 5.0, 0.3),
+        "joint_acceleration": rw.joint_acceleration_ngt(env),
+        "joint_velocity": rw.joint_velocity_ngt(env),
+        "joint_torque": rw.joint_torque_ngt(env),
+        "action_rate": rw.action_rate_ngt(env),
+        "thigh_calf_collision": rw.thigh_calf_collision_ngt(env, 0.1, sc("robot_contact_senosr", body_names=[".*thigh", ".*calf"])),
+    }
+    if spec.with_object:
+        out.update({
+            "object_xy_position": rw.object_relative_xy_position_ngt(env, work_only_when_cmd=1),
+            "object_xy_velocity": rw.object_relative_xy_velocity_ngt(env),
+            "object_z_contact": rw.object_lose_contact_ngt(env, sensor_cfg=SceneEntityCfg("object_contact_sensor")),
+            "object_z_velocity": rw.object_relative_z_velocity_ngt(env),
+            "object_roll_pitch_angle": rw.object_relative_roll_angle_ngt(env),
+            "object_roll_pitch_velocity": rw.object_relative_roll_velocity_ngt(env),
+            "object_yaw_alignment": rw.object_relative_yaw_angle_ngt(env, work_only_when_cmd=1),
+            "object_dangerous_state": rw.object_dangerous_state_ngt(env, x_max=0.125, y_max=0.097, z_min=0.095, roll_pitch_max=None, vel_xy_max=2.5),
+            # extra: the two generic (non-cylinder) variants the object task can select (weights 0 in the cylinder cfg)
+            "x_object_rp_angle": rw.object_relative_roll_pitch_angle_ngt(env),
+            "x_object_rp_velocity": rw.object_relative_roll_pitch_velocity_ngt(env),
+        })
+    return {k: v.float() for k, v in out.items()}
+
+
+def golden_mdp(scenario: str):
+    rw, ob, te, _ = ref_loader.load_reference_mdp()
+    spec, env, steps = H.make_mdp_env(scenario)
+    oracle = MdpOracle(env, spec)  # supplies the [IL] termination set that decides which envs are reset
+    cfg = H.gait_cfg(spec)
+    gait_cls = rw.AdaptiveSymmetricGaitRewardwithObject if spec.with_object else rw.AdaptiveSymmetricGaitReward
+    gait = gait_cls(cfg, env)
+    names, raws, sums = None, [], []
+    extra = {k: [] for k in ("bad_roll", "object_below_robot", "obj_state_clean", "obj_state_noisy", "done")}
+    os_ = spec.object_state
+    for step in range(steps):
+        sums.append(env_checksum(env))
+        masks, terminated, time_outs = oracle.terminations(env)
+        vals = reference_reward_terms(rw, env, spec, gait)
+        names = list(vals)
+        raws.append(torch.stack([vals[k] for k in names]))
+        done = terminated | time_outs
+        extra["done"].append(done.clone())
+        if spec.with_object:
+            extra["bad_roll"].append(te.bad_roll(env, math.pi / 3, SceneEntityCfg("object")))
+            extra["object_below_robot"].append(te.object_below_robot(env))
+            kw = dict(last_contact_time_threshold=os_.last_contact_time_threshold, current_contact_time_threshold=os_.current_contact_time_threshold,
+                      non_contact_obs=list(os_.non_contact_obs), n_min=list(os_.n_min), n_max=list(os_.n_max), scale=list(os_.scale))
+            extra["obj_state_clean"].append(ob.object_state_in_robot_frame(env, add_uniform_noise=False, **kw))
+            u_obs, u_euler = H.mdp_noise(scenario, step, env.num_envs, spec.obs_dim_per_step)
+            u_state = u_obs[:, -13:]
+            s = env.scene.sensors["object_contact_sensor"].data
+            never = torch.logical_and(s.last_contact_time < os_.last_contact_time_threshold, s.current_contact_time < os_.current_contact_time_threshold).reshape(-1)
+            with patched_rand([u_state.clone(), u_state[never].clone()], [u_euler.clone()]):
+                extra["obj_state_noisy"].append(ob.object_state_in_robot_frame(env, add_uniform_noise=True, **kw))
+        ids = done.nonzero(as_tuple=False).flatten()
+        if len(ids) > 0:
+            gait.reset(ids)
+        H.advance_mdp_env(env, step)
+    out = dict(
+        term_names=np.array(names),
+        raw=torch.stack(raws).numpy(),
+        done=torch.stack(extra["done"]).numpy(),
+        input_checksum=np.array(sums),
+        gait_valid_last_air_time=gait.valid_last_air_time.numpy(),
+        gait_swinging_in_zero_cmd=gait.swinging_in_zero_cmd.numpy(),
+        gait_valid_previous_contact=gait.valid_previous_contact.numpy(),
+        gait_last_velocity_cmd=gait.last_velocity_cmd.numpy(),
+        gait_step_from_changing_cmd=gait.step_from_changing_cmd.numpy(),
+        gait_last_step_current_air_time=gait.last_step_current_air_time.numpy(),
+        gait_last_step_current_contact_time=gait.last_step_current_contact_time.numpy(),
+    )
+    if spec.with_object:
+        for k in ("bad_roll", "object_below_robot", "obj_state_clean", "obj_state_noisy"):
+            out[k] = torch.stack(extra[k]).numpy()
+    np.savez_compressed(os.path.join(OUT, f"mdp_{scenario}.npz"), **out)
+    frac_vla = float((gait.valid_last_air_time > 0.04).float().mean())
+    print(f"mdp_{scenario}: raw {out['raw'].shape}, done rate {out['done'].mean():.3f}, gait mean {out['raw'][:, names.index('gait')].mean():.3f}, final VLA>0.04 {frac_vla:.2f}")
+
+
+PPO_SMALL = dict(T=24, N=32, obs_dim=270, A=12, hidden=[64, 48, 32], seed=5)
+
+
+def golden_ppo():
+    ref_loader.load_reference_loco_rl()
+    from loco_rl.algorithms import PPO
+    from loco_rl.modules import ActorCritic
+    from loco_rl.storage import RolloutStorage
+
+    # ---- GAE alone on C1-shaped tensors (incl. the all-done and done-at-last-step envs)
+    r = H.make_rollout(T=24, N=64, seed=0)
+    st = RolloutStorage(64, 24, [270], [270], [12])
+    st.rewards.copy_(r["rewards"])
+    st.values.copy_(r["values"])
+    st.dones.copy_(r["dones"].byte())
+    st.compute_returns(r["last_values"], 0.99, 0.95, normalize_advantage=True)
+    out = dict(gae_returns=st.returns.numpy().copy(), gae_advantages=st.advantages.numpy().copy())
+    st.compute_returns(r["last_values"], 0.99, 0.95, normalize_advantage=False)
+    out["gae_advantages_raw"] = st.advantages.numpy().copy()
+
+    # ---- act -> process_env_step -> compute_returns -> update with the LocoTouch PPO cfg (rsl_rl_ppo_cfg.py:17-30)
+    c = PPO_SMALL
+    T, N, A = c["T"], c["N"], c["A"]
+    torch.manual_seed(c["seed"])
+    ac = ActorCritic(c["obs_dim"], c["obs_dim"], A, c["hidden"], c["hidden"], "elu", 1.0)
+    init = torch.cat([p.detach().flatten() for p in ac.parameters()]).clone()
+    alg = PPO(ac, num_learning_epochs=2, num_mini_batches=2, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
+              entropy_coef=0.01, learning_rate=1.0e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
+              desired_kl=0.01, device="cpu")
+    alg.init_storage(N, T, [c["obs_dim"]], [c["obs_dim"]], [A])
+    r = H.make_rollout(T=T, N=N, obs_dim=c["obs_dim"], A=A, seed=c["seed"])
+    g = torch.Generator().manual_seed(c["seed"] + 1)
+    eps = torch.randn(T, N, A, generator=g)
+    from torch.distributions import Normal
+    orig_sample = Normal.sample
+    for t in range(T):
+        Normal.sample = lambda self, sample_shape=torch.Size(), _e=eps[t]: (self.loc + self.scale * _e).detach()
+        alg.act(r["obs"][t], r["critic_obs"][t])
+        Normal.sample = orig_sample
+        infos = {"time_outs": r["time_outs"][t, :, 0]}
+        alg.process_env_step(r["rewards"][t, :, 0].clone(), r["dones"][t, :, 0].long(), infos)
+    alg.compute_returns(r["critic_obs"][-1])
+    out.update(
+        ppo_init_params=init.numpy(),
+        ppo_eps=eps.numpy(),
+        ppo_actions=alg.storage.actions.numpy().copy(),
+        ppo_logp=alg.storage.actions_log_prob.numpy().copy(),
+        ppo_values=alg.storage.values.numpy().copy(),
+        ppo_rewards=alg.storage.rewards.numpy().copy(),
+        ppo_returns=alg.storage.returns.numpy().copy(),
+        ppo_advantages=alg.storage.advantages.numpy().copy(),
+    )
+    perms = []
+    orig_randperm = torch.randperm
+
+    def randperm(n, *a, **k):
+        p = orig_randperm(n, *a, **k)
+        perms.append(p.clone())
+        return p
+
+    torch.randperm = randperm
+    torch.manual_seed(c["seed"] + 2)
+    # record the learning rate after every mini-batch
+    lrs = []
+    orig_step = alg.optimizer.step
+
+    def step(*a, **k):
+        lrs.append(alg.optimizer.param_groups[0]["lr"])
+        return orig_step(*a, **k)
+
+    alg.optimizer.step = step
+    losses = alg.update()
+    torch.randperm = orig_randperm
+    out.update(
+        ppo_perm=perms[0].numpy(),
+        ppo_lr_sequence=np.array(lrs),
+        ppo_losses=np.array([losses[0], losses[1], losses[2]]),
+        ppo_final_params=torch.cat([p.detach().flatten() for p in ac.parameters()]).numpy(),
+        ppo_param_names=np.array([k for k, _ in ac.named_parameters()]),
+    )
+    np.savez_compressed(os.path.join(OUT, "ppo_c1.npz"), **out)
+    print(f"ppo_c1: losses {losses[:3]}, lr sequence {lrs}, |dparams| {float((torch.as_tensor(out['ppo_final_params']) - init).abs().mean()):.3e}")
+
+
+TACTILE = dict(N=48, seed=21, steps=4)
+
+
+def tactile_inputs(step: int, n: int, p_case: int):
+    g = torch.Generator().manual_seed(1000 * (p_case + 1) + step)
+    return torch.rand(n, 17, 13, generator=g), torch.rand(n, 17, 13, generator=g)
+
+
+def golden_tactile():
+    _, ob, _, _ = ref_loader.load_reference_mdp()
+    _, rec_mod, _ = ref_loader.load_reference_distill()
+    from types import SimpleNamespace
+
+    c = TACTILE
+    out = {}
+    for p_case, (p_drop, p_add, jitter) in enumerate([(0.005, 0.005, 0.0), (0.2, 0.1, 0.3)]):
+        env = synth.make_env(c["N"], seed=c["seed"] + p_case, with_object=True, with_tactile=True, tactile_jitter=jitter)
+        params = dict(
+            asset_cfg=SceneEntityCfg("robot", body_names="sensor_.*").resolve(env.scene),
+            sensor_cfg=SceneEntityCfg("tactile_contact_sensor", body_names="sensor_.*").resolve(env.scene),
+            tactile_signal_shape=(17, 13), contact_threshold=0.05, add_threshold_noise=True, threshold_n_min=-0.05 * 0.2,
+            threshold_n_max=0.05 * 0.2, contact_dropout_prob=p_drop, contact_addition_prob=p_add, add_continuous_artifact=0.0,
+            artifact_taxel_num_min=0, artifact_taxel_num_max=3, add_force_noise=True, force_n_prop_min=-0.1, force_n_prop_max=0.1,
+            maximal_force=3.0, total_levels=5, add_level_noise=True, level_n_min=-1, level_n_max=1)
+        g = torch.Generator().manual_seed(77 + p_case)
+        u_thr = torch.rand(c["N"], 17, 13, generator=g)
+        with patched_rand([u_thr.clone()]):
+            term = ob.BinaryTactileSignals(SimpleNamespace(params=params), env)
+        recorder = rec_mod.TactileRecorder("cpu", c["N"], 442, min_delay=1, max_delay=2)
+        sigs, delayed = [], []
+        for step in range(c["steps"]):
+            u_drop, u_add = tactile_inputs(step, c["N"], p_case)
+            with patched_rand([u_drop.clone(), None, u_add.clone()]):
+                sig = term(env, **params)
+            sigs.append(sig.clone())
+            if step == 2:  # reset a third of the envs before recording, like ReplayBuffer.collect_data does on dones
+                recorder.reset(torch.arange(0, c["N"], 3))
+            recorder.record_new_tactile_signals(sig)
+            delayed.append(recorder.get_tactile_signals().clone())
+            synth.advance(env, tactile_jitter=jitter)
+        out[f"thresholds_{p_case}"] = term.contact_threshold_envs_sensors.numpy().copy()
+        out[f"signal_{p_case}"] = torch.stack(sigs).numpy().astype(np.uint8)
+        out[f"delayed_{p_case}"] = torch.stack(delayed).numpy().astype(np.uint8)
+        out[f"normal_forces_last_{p_case}"] = term.original_normal_forces.numpy().copy()
+        print(f"tactile case {p_case}: contact fraction {out[f'signal_{p_case}'].mean():.4f}")
+    np.savez_compressed(os.path.join(OUT, "tactile_c4.npz"), **out)
+
+
+if __name__ == "__main__":
+    assert ref_loader.reference_available(), "the reference is not mounted"
+    torch.set_num_threads(1)
+    golden_mdp("locomotion")
+    golden_mdp("teacher")
+    golden_ppo()
+    golden_tactile()
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

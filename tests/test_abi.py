@@ -1,0 +1,78 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "locotouch_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_survey_entry_points():
+    names = declared_functions()
+    for want in ("lt_mdp_step", "lt_mdp_reset", "lt_taxel_synth", "lt_tactile_delay", "lt_store_step", "lt_gae", "lt_gather_rows",
+                 "lt_ppo_loss", "lt_clip_adam", "lt_masked_mse", "lt_act_sample", "lt_pad_trajectories"):
+        assert want in names
+
+
+def test_library_exports_every_declared_symbol(lt_lib):
+    from locotouch_b200 import _C
+
+    raw = ctypes.CDLL(_C.LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(raw, name), f"{name} is declared in include/locotouch_b200.h but not exported"
+        assert name in _C.EXPORTED_SYMBOLS, f"{name} has no ctypes signature in _C.py"
+
+
+def test_struct_layouts_match(lt_lib):
+    from locotouch_b200 import _C
+
+    for which, struct in enumerate((_C.LtGatherArgs, _C.LtPpoLossArgs, _C.LtTaxelArgs, _C.LtMdpArgs, _C.LtGaitState, _C.LtGaitParams)):
+        assert lt_lib.lt_struct_size(which) == ctypes.sizeof(struct), struct.__name__
+    assert lt_lib.lt_struct_size(99) == -1
+
+
+def test_error_strings_and_workspace_queries(lt_lib):
+    assert lt_lib.lt_abi_version() == 1
+    assert lt_lib.lt_error_string(0) == b"ok"
+    assert b"workspace" in lt_lib.lt_error_string(3)
+    assert lt_lib.lt_gae_workspace_bytes(24, 4096) >= 16 + 2 * 32 * 8
+    assert lt_lib.lt_ppo_loss_workspace_bytes(24576, 12) >= 384 * 15 * 4
+    assert lt_lib.lt_clip_adam_workspace_bytes(607641) >= 1024 * 8
+    assert lt_lib.lt_masked_mse_workspace_bytes(20000) > 0
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu(lt_lib):
+    # argument validation happens before any CUDA call, so it can be exercised on the CPU box
+    assert lt_lib.lt_gae(None, None, None, None, None, None, 24, 64, 0.99, 0.95, 1, None, 0, None) == 3  # workspace
+    assert lt_lib.lt_adv_normalize(None, 10, None, None) == 1
+    assert lt_lib.lt_ppo_loss(None, None) == 1
+    assert lt_lib.lt_taxel_synth(None, None) == 1
+    assert lt_lib.lt_mdp_step(None, None) == 1
+    assert lt_lib.lt_clip_adam(None, None, None, None, 10, None, None, 1.0, 0.9, 0.999, 1e-8, 0.0, 1.0, None, None, 0, None) == 1
+
+
+def test_product_path_refuses_cpu_tensors(lt_lib):
+    import torch
+
+    from locotouch_b200 import _C, ops
+
+    with pytest.raises(_C.LocoTouchLibraryError):
+        ops.gae(torch.zeros(4, 8), torch.zeros(4, 8), torch.zeros(4, 8, dtype=torch.uint8), torch.zeros(8), 0.99, 0.95)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under locotouch_b200/ may import it."""
+    pkg = os.path.join(ROOT, "locotouch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
