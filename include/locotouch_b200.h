@@ -67,7 +67,11 @@ int lt_adv_normalize(float* advantages, int64_t count, const double* stats, void
  * ------------------------------------------------------------------------------------------------------------------ */
 int lt_act_sample(const float* mu, const float* sigma /*[A]*/, const float* eps /*[N,A] or NULL*/,
                   float* actions, float* logp, float* mu_out, float* sigma_out, int N, int A,
-                  uint64_t seed, uint64_t offset, void* stream);
+                  uint64_t seed, uint64_t offset, const int64_t* offset_base /*device counter added to offset, or NULL*/,
+                  void* stream);
+/* *counter += inc on the stream: advances the device-resident step counter that `offset_base` arguments point at, so
+ * that a captured CUDA graph draws fresh random numbers (and hands the right step index on) at every replay. */
+int lt_counter_add(int64_t* counter, int64_t inc, void* stream);
 int lt_store_step(const float* rewards, const int64_t* dones_i64, const uint8_t* dones_u8, const uint8_t* time_outs,
                   const float* values, float gamma, float* rewards_out, uint8_t* dones_out,
                   const float* obs, float* obs_out, int obs_dim,
@@ -160,6 +164,7 @@ typedef struct {
   const float* u_add;         /* [N, T] or NULL */
   float p_drop, p_add;
   uint64_t seed, offset;
+  const int64_t* offset_base; /* optional device counter added to offset */
   float* signal;              /* [N, 2T] or NULL */
   uint32_t* packed;           /* [N, ceil(T/32)] or NULL */
   float* normal_forces;       /* [N, T] or NULL  (original_normal_forces side buffer) */
@@ -312,9 +317,12 @@ typedef struct {
   float* critic_obs_out;
   const float* u_obs;            /* [N, sum(dim)] uniforms for the policy-group noise, or NULL -> Philox */
   const float* u_obj_euler;      /* [N,3] uniforms for the object quaternion noise (observations.py:78) or NULL */
-  uint64_t seed, offset;
+  uint64_t seed, offset;         /* Philox key / counter; `offset` is also the env-step index used by the cross-env any() hand-over */
+  const int64_t* offset_base;    /* optional DEVICE counter added to `offset` (lets a captured CUDA graph advance the step) */
   /* object_state_in_robot_frame parameters (observations.py:38-91) */
-  float os_n_min[13], os_n_max[13], os_scale[13], os_non_contact[13];
+  float os_n_min[13], os_n_max[13];       /* additive noise per state slot; the 4 quaternion slots are 0 (observations.py:74-77) */
+  float os_euler_min[3], os_euler_max[3]; /* euler-angle noise composed onto the quaternion (observations.py:72-73,78-80) */
+  float os_scale[13], os_non_contact[13];
   float os_last_contact_thr, os_current_contact_thr;
   int* any_flag_ws;              /* [2] device ints, zero-initialised once; used for the cross-env any() */
 } LtMdpArgs;

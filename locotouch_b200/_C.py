@@ -55,7 +55,7 @@ class LtTaxelArgs(C.Structure):
         ("body_quat_w", C.c_void_p), ("quat_num_bodies", C.c_int), ("quat_body_offset", C.c_int),
         ("net_forces_w", C.c_void_p), ("thresholds", C.c_void_p), ("u_drop", C.c_void_p), ("u_add", C.c_void_p),
         ("p_drop", C.c_float), ("p_add", C.c_float),
-        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("seed", C.c_uint64), ("offset", C.c_uint64), ("offset_base", C.c_void_p),
         ("signal", C.c_void_p), ("packed", C.c_void_p), ("normal_forces", C.c_void_p), ("original_contact", C.c_void_p),
         ("delay_ring", C.c_void_p), ("delay_first", C.c_void_p), ("delay_steps", C.c_void_p), ("max_delay", C.c_int),
         ("delayed_signal", C.c_void_p),
@@ -125,8 +125,9 @@ class LtMdpArgs(C.Structure):
         ("num_obs_terms", C.c_int), ("obs_terms", LtObsTerm * LT_MAX_OBS_TERMS), ("history_length", C.c_int),
         ("obs_fill", C.c_void_p), ("policy_obs_in", C.c_void_p), ("policy_obs_out", C.c_void_p),
         ("critic_obs_in", C.c_void_p), ("critic_obs_out", C.c_void_p), ("u_obs", C.c_void_p), ("u_obj_euler", C.c_void_p),
-        ("seed", C.c_uint64), ("offset", C.c_uint64),
-        ("os_n_min", C.c_float * 13), ("os_n_max", C.c_float * 13), ("os_scale", C.c_float * 13),
+        ("seed", C.c_uint64), ("offset", C.c_uint64), ("offset_base", C.c_void_p),
+        ("os_n_min", C.c_float * 13), ("os_n_max", C.c_float * 13), ("os_euler_min", C.c_float * 3), ("os_euler_max", C.c_float * 3),
+        ("os_scale", C.c_float * 13),
         ("os_non_contact", C.c_float * 13), ("os_last_contact_thr", C.c_float), ("os_current_contact_thr", C.c_float),
         ("any_flag_ws", C.c_void_p),
     ]
@@ -142,7 +143,8 @@ _SIGNATURES = {
     "lt_gae": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_gae_scan": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_adv_normalize": (C.c_int, [f32p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "lt_act_sample": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "lt_act_sample": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "lt_counter_add": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_store_step": (C.c_int, [f32p, C.c_void_p, C.c_void_p, C.c_void_p, f32p, C.c_float, f32p, C.c_void_p, f32p, f32p, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_void_p]),
     "lt_gather_rows": (C.c_int, [C.POINTER(LtGatherArgs), C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_ppo_loss_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),

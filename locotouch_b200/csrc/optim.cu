@@ -36,11 +36,11 @@ grad_sqnorm_kernel(const float* __restrict__ g, int64_t n, float grad_scale, dou
 }
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float coef, float lr, float step_size,
-                                         float sqrt_bc2, float b1, float b2, float eps, float wd) {
+                                         float sqrt_bc2, float omb1, float b2, float omb2, float eps, float wd) {
   g *= coef;
   if (wd != 0.f) p *= 1.0f - lr * wd;        // AdamW decoupled decay
-  m = m + (g - m) * (1.0f - b1);             // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * b2 + (1.0f - b2) * g * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  m = m + (g - m) * omb1;                    // exp_avg.lerp_(grad, 1 - beta1)   (1 - beta evaluated in double like Python)
+  v = v * b2 + omb2 * g * g;                 // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
   const float denom = sqrtf(v) / sqrt_bc2 + eps;  // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
   p = p - step_size * (m / denom);           // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
@@ -69,22 +69,22 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
   __syncthreads();
   const float coef = s_coef, lr = *lr_ptr, step_size = s_step_size, sqrt_bc2 = s_sqrt_bc2;
-  const float b1 = (float)b1d, b2 = (float)b2d;
+  const float omb1 = (float)(1.0 - b1d), b2 = (float)b2d, omb2 = (float)(1.0 - b2d);
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = __ldcs(reinterpret_cast<const float4*>(g) + i);
     float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
-    adam_one(pp.x, gg.x, mm.x, vv.x, coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
-    adam_one(pp.y, gg.y, mm.y, vv.y, coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
-    adam_one(pp.z, gg.z, mm.z, vv.z, coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
-    adam_one(pp.w, gg.w, mm.w, vv.w, coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
+    adam_one(pp.x, gg.x, mm.x, vv.x, coef, lr, step_size, sqrt_bc2, omb1, b2, omb2, eps, wd);
+    adam_one(pp.y, gg.y, mm.y, vv.y, coef, lr, step_size, sqrt_bc2, omb1, b2, omb2, eps, wd);
+    adam_one(pp.z, gg.z, mm.z, vv.z, coef, lr, step_size, sqrt_bc2, omb1, b2, omb2, eps, wd);
+    adam_one(pp.w, gg.w, mm.w, vv.w, coef, lr, step_size, sqrt_bc2, omb1, b2, omb2, eps, wd);
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (int64_t j = n4 << 2; j < n; ++j) adam_one(p[j], g[j], m[j], v[j], coef, lr, step_size, sqrt_bc2, b1, b2, eps, wd);
+    for (int64_t j = n4 << 2; j < n; ++j) adam_one(p[j], g[j], m[j], v[j], coef, lr, step_size, sqrt_bc2, omb1, b2, omb2, eps, wd);
   }
 }
 

@@ -16,7 +16,8 @@ constexpr float kHalfLog2Pi = 0.91893853320467274178f;
 __global__ void __launch_bounds__(256)
 act_sample_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ eps,
                   float* __restrict__ actions, float* __restrict__ logp, float* __restrict__ mu_out,
-                  float* __restrict__ sigma_out, int N, int A, uint64_t seed, uint64_t offset) {
+                  float* __restrict__ sigma_out, int N, int A, uint64_t seed, uint64_t offset, const int64_t* __restrict__ offset_base) {
+  if (offset_base) offset += (uint64_t)*offset_base;
   const int chunks = A >> 2;
   const int sub = threadIdx.x & 3;
   const int base = (blockIdx.x * blockDim.x) >> 2;
@@ -116,16 +117,24 @@ gather_rows_kernel(const GatherParams p, const int64_t* __restrict__ indices, in
   }
 }
 
+__global__ void counter_add_kernel(int64_t* c, int64_t inc) { *c += inc; }
+
 }  // namespace
 
+extern "C" int lt_counter_add(int64_t* counter, int64_t inc, void* stream) {
+  if (!counter) return LT_ERR_INVALID_ARG;
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+  return lt::check_launch();
+}
+
 extern "C" int lt_act_sample(const float* mu, const float* sigma, const float* eps, float* actions, float* logp, float* mu_out,
-                             float* sigma_out, int N, int A, uint64_t seed, uint64_t offset, void* stream) {
+                             float* sigma_out, int N, int A, uint64_t seed, uint64_t offset, const int64_t* offset_base, void* stream) {
   if (!mu || !sigma || !actions || !logp || N <= 0 || A <= 0 || (A & 3)) return LT_ERR_INVALID_ARG;
   uintptr_t al = (uintptr_t)mu | (uintptr_t)sigma | (uintptr_t)actions | (uintptr_t)(eps ? eps : mu) |
                  (uintptr_t)(mu_out ? mu_out : mu) | (uintptr_t)(sigma_out ? sigma_out : mu);
   if (al & 15) return LT_ERR_INVALID_ARG;
   const int grid = (int)lt::ceil_div((int64_t)N * 4, 256);
-  act_sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mu, sigma, eps, actions, logp, mu_out, sigma_out, N, A, seed, offset);
+  act_sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mu, sigma, eps, actions, logp, mu_out, sigma_out, N, A, seed, offset, offset_base);
   return lt::check_launch();
 }
 

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) taxel_kernel(const LtTaxe
   const float4* quat = reinterpret_cast<const float4*>(a.body_quat_w) + (size_t)n * a.quat_num_bodies + a.quat_body_offset;
   const float* force = a.net_forces_w + (size_t)n * T * 3;
   const size_t row = (size_t)n * T;
+  const uint64_t rng_offset = a.offset + (a.offset_base ? (uint64_t)*a.offset_base : 0ull);
   uint32_t my_word = 0;  // lane r keeps word r
   uint4 rnd = make_uint4(0, 0, 0, 0);
   for (int r = 0; r < words; ++r) {
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) taxel_kernel(const LtTaxe
         ud = a.u_drop ? __ldcs(a.u_drop + row + t) : 1.0f;
         ua = a.u_add ? __ldcs(a.u_add + row + t) : 1.0f;
       } else {
-        if ((r & 1) == 0) rnd = lt::Philox::gen(a.seed, a.offset, (uint32_t)n, (uint32_t)(32 * (r >> 1) + lane));
+        if ((r & 1) == 0) rnd = lt::Philox::gen(a.seed, rng_offset, (uint32_t)n, (uint32_t)(32 * (r >> 1) + lane));
         ud = lt::Philox::u01((r & 1) ? rnd.z : rnd.x);
         ua = lt::Philox::u01((r & 1) ? rnd.w : rnd.y);
       }

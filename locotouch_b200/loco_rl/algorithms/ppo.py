@@ -1,0 +1,223 @@
+"""PPO with the reference's interface (reference loco_rl/loco_rl/algorithms/ppo.py:19-385).
+
+Same constructor keywords, attributes (``actor_critic``, ``optimizer``, ``storage``, ``transition``, ``learning_rate``,
+``rnd``, ``symmetry``) and methods (``init_storage``, ``test_mode`` / ``train_mode``, ``act``, ``process_env_step``,
+``compute_returns``, ``update`` returning the 5-tuple of ppo.py:385), so ``OnPolicyRunner`` drives it unchanged.
+
+What changed below the interface:
+* ``act`` writes actions / log-prob / mu / sigma / values directly into the RolloutStorage slot (K3);
+* ``process_env_step`` fuses the time-out bootstrap into the store kernel (K3);
+* ``compute_returns`` is the GAE kernel pair (K4);
+* ``update``: one fused gather of the permuted rollout (K5); per mini-batch the cuBLAS MLP forward, ONE fused loss
+  kernel (K6: log-prob, entropy, KL, adaptive learning rate on the device, clipped surrogate + value loss and their
+  analytic gradients), autograd only through the two MLPs, ONE fused clip + Adam over the flat parameter buffer (K7).
+  No ``.item()`` inside the loop: the learning rate lives on the device and the three logged means are accumulated on
+  the device and read back once per update.  With ``torch.distributed`` initialised, gradients are all-reduced as one
+  flat NCCL buffer and the KL statistic is all-reduced before the learning-rate decision.
+RND and symmetry augmentation (unused by every LocoTouch runner cfg) are not part of the hot path and raise.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from ... import ops
+from ..modules import ActorCritic
+from ..storage import RolloutStorage
+
+
+class _FusedAdam:
+    """``optimizer``-shaped facade over the fused clip + Adam kernel: keeps ``param_groups[0]['lr']`` and
+    ``state_dict`` / ``load_state_dict`` in torch.optim.Adam's format so runner checkpoints stay interchangeable."""
+
+    def __init__(self, actor_critic: ActorCritic, lr: float):
+        self.ac = actor_critic
+        self.flat, self.grads = actor_critic.flatten_parameters()
+        dev = self.flat.device
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_t = torch.zeros(1, device=dev)
+        self.lr_t = torch.full((1,), lr, device=dev)
+        self.grad_norm = torch.zeros(1, device=dev)
+        self.param_groups = [dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, params=list(range(len(list(actor_critic.parameters())))))]
+        self._host_lr = lr
+
+    def sync_lr_to_device(self):
+        lr = self.param_groups[0]["lr"]
+        if lr != self._host_lr:  # someone (runner, user) wrote param_groups[...]["lr"]
+            self.lr_t.fill_(lr)
+            self._host_lr = lr
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.grads.zero_()
+
+    def step(self, max_grad_norm=None, grad_scale: float = 1.0):
+        g = self.param_groups[0]
+        ops.clip_adam(self.flat, self.grads, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t, max_grad_norm=max_grad_norm,
+                      betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], grad_scale=grad_scale, grad_norm_out=self.grad_norm)
+
+    def state_dict(self):
+        state = {}
+        step = self.step_t.detach().cpu().clone().squeeze(0)
+        for i, (name, p) in enumerate(self.ac.named_parameters()):
+            off, n = self.ac._slices[name]
+            state[i] = dict(step=step.clone(), exp_avg=self.exp_avg[off:off + n].view(p.shape).clone(), exp_avg_sq=self.exp_avg_sq[off:off + n].view(p.shape).clone())
+        pg = dict(self.param_groups[0])
+        pg["lr"] = float(self.lr_t.item())
+        return dict(state=state, param_groups=[pg])
+
+    def load_state_dict(self, sd):
+        for i, (name, p) in enumerate(self.ac.named_parameters()):
+            if i in sd["state"]:
+                off, n = self.ac._slices[name]
+                self.exp_avg[off:off + n].copy_(sd["state"][i]["exp_avg"].flatten())
+                self.exp_avg_sq[off:off + n].copy_(sd["state"][i]["exp_avg_sq"].flatten())
+                self.step_t.fill_(float(sd["state"][i]["step"]))
+        lr = sd["param_groups"][0]["lr"]
+        self.param_groups[0]["lr"] = lr
+        self.lr_t.fill_(lr)
+        self._host_lr = lr
+
+
+class PPO:
+    """Proximal Policy Optimization algorithm (https://arxiv.org/abs/1707.06347)."""
+
+    actor_critic: ActorCritic
+
+    def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
+                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True,
+                 schedule="fixed", desired_kl=0.01, device="cpu", normalize_advantage_per_mini_batch=False,
+                 rnd_cfg: dict | None = None, symmetry_cfg: dict | None = None):
+        self.device = device
+        if torch.device(device).type != "cuda":
+            from ... import _C
+            raise _C.LocoTouchLibraryError(f"locotouch_b200 PPO runs on CUDA only (device={device!r}); there is no CPU fallback")
+        self.desired_kl = desired_kl
+        self.schedule = schedule
+        self.learning_rate = learning_rate
+        self.normalize_advantage_per_mini_batch = normalize_advantage_per_mini_batch
+        if rnd_cfg is not None:
+            raise NotImplementedError("RND is not used by any LocoTouch cfg and is outside the hot path (SURVEY.md 2, #24)")
+        self.rnd = None
+        self.rnd_optimizer = None
+        if symmetry_cfg is not None:
+            use_symmetry = symmetry_cfg["use_data_augmentation"] or symmetry_cfg["use_mirror_loss"]
+            if symmetry_cfg["use_data_augmentation"] and not callable(symmetry_cfg["data_augmentation_func"]):
+                raise ValueError("Data augmentation enabled but the function is not callable:" f" {symmetry_cfg['data_augmentation_func']}")
+            if use_symmetry:
+                raise NotImplementedError("symmetry augmentation is not used by any LocoTouch cfg and is outside the hot path")
+        self.symmetry = None
+        self.actor_critic = actor_critic
+        self.actor_critic.to(self.device)
+        self.optimizer = _FusedAdam(self.actor_critic, learning_rate)
+        self.storage: RolloutStorage = None  # type: ignore
+        self.transition = RolloutStorage.Transition()
+        self.clip_param = clip_param
+        self.num_learning_epochs = num_learning_epochs
+        self.num_mini_batches = num_mini_batches
+        self.value_loss_coef = value_loss_coef
+        self.entropy_coef = entropy_coef
+        self.gamma = gamma
+        self.lam = lam
+        self.max_grad_norm = max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self._loss_bufs = None
+        self._loss_accum = torch.zeros(4, device=self.device)
+        self._adv_stats = torch.zeros(4, device=self.device, dtype=torch.float64)
+        self.global_advantage_normalization = True  # multi-GPU: normalise over ALL ranks' envs (== the single-process reference)
+
+    # ----------------------------------------------------------------------------------------------------------- setup
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, None, self.device)
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    # --------------------------------------------------------------------------------------------------------- rollout
+    def act(self, obs, critic_obs):
+        slot = self.storage.slot()
+        t = self.transition
+        with torch.no_grad():
+            t.actions = self.actor_critic.act(obs, out=slot)
+            values = self.actor_critic.evaluate(critic_obs)
+            slot["values"].copy_(values)  # the critic GEMM's output row is the only copy left on this path
+        t.values = slot["values"]
+        t.actions_log_prob = slot["logp"]
+        t.action_mean = slot["mu"]
+        t.action_sigma = slot["sigma"]
+        t.observations = obs
+        t.critic_observations = critic_obs
+        return t.actions
+
+    def process_env_step(self, rewards, dones, infos):
+        t = self.transition
+        t.rewards = rewards
+        t.dones = dones
+        time_outs = infos["time_outs"] if "time_outs" in infos else None
+        self.storage.add_transitions(t, time_outs=time_outs, gamma=self.gamma)
+        t.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs):
+        with torch.no_grad():
+            last_values = self.actor_critic.evaluate(last_critic_obs).detach()
+        st = self.storage
+        normalize = not self.normalize_advantage_per_mini_batch
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if world == 1 or not normalize or not self.global_advantage_normalization:
+            st.compute_returns(last_values, self.gamma, self.lam, normalize_advantage=normalize)
+            return
+        # env-sharded ranks: sum / sum of squares / count are all-reduced between the scan and the normalisation
+        ops.gae_scan(st.rewards, st.values, st.dones, last_values.contiguous().view(-1), self.gamma, self.lam, st.returns, st.advantages, self._adv_stats)
+        dist.all_reduce(self._adv_stats, op=dist.ReduceOp.SUM)
+        ops.adv_normalize(st.advantages, self._adv_stats)
+
+    # ---------------------------------------------------------------------------------------------------------- update
+    def update(self, indices=None):  # noqa: C901
+        ac, opt, st = self.actor_critic, self.optimizer, self.storage
+        if ac.is_recurrent:
+            raise NotImplementedError("recurrent policies are outside the LocoTouch hot path")
+        if self.normalize_advantage_per_mini_batch:
+            raise NotImplementedError("per-mini-batch advantage normalisation is not used by the LocoTouch cfgs")
+        ac.flatten_parameters()
+        opt.sync_lr_to_device()
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._loss_accum.zero_()
+        sigma_off, sigma_n = ac._slices["std" if ac.noise_std_type == "scalar" else "log_std"]
+        if ac.noise_std_type != "scalar":
+            raise NotImplementedError("noise_std_type='log' is not used by the LocoTouch cfgs")
+        generator = st.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs, indices=indices)
+        for (obs_batch, critic_obs_batch, actions_batch, target_values_batch, advantages_batch, returns_batch, old_logp_batch,
+             old_mu_batch, old_sigma_batch, _hid, _masks, _rnd) in generator:
+            B, A = actions_batch.shape
+            if self._loss_bufs is None or self._loss_bufs.B != B:
+                self._loss_bufs = ops.PpoLossBuffers(B, A, self.device)
+            bufs = self._loss_bufs
+            mu = ac.actor(obs_batch)
+            value = ac.critic(critic_obs_batch)
+            opt.zero_grad()
+            ops.ppo_loss(mu.detach(), ac.std.detach(), value.detach().view(-1), actions_batch, old_logp_batch.view(-1), old_mu_batch, old_sigma_batch,
+                         advantages_batch.view(-1), returns_batch.view(-1), target_values_batch.view(-1), clip_param=self.clip_param,
+                         value_loss_coef=self.value_loss_coef, entropy_coef=self.entropy_coef, use_clipped_value_loss=self.use_clipped_value_loss,
+                         desired_kl=self.desired_kl if (adaptive and world == 1) else None, lr=opt.lr_t if (adaptive and world == 1) else None,
+                         loss_accum=self._loss_accum, buffers=bufs)
+            torch.autograd.backward([mu, value], [bufs.grad_mu, bufs.grad_value.view_as(value)])
+            opt.grads[sigma_off:sigma_off + sigma_n].add_(bufs.grad_sigma)
+            if world > 1:
+                dist.all_reduce(opt.grads, op=dist.ReduceOp.SUM)
+                if adaptive:  # every rank must take the same learning-rate decision
+                    kl = bufs.out[4:5]
+                    dist.all_reduce(kl, op=dist.ReduceOp.SUM)
+                    ops.adaptive_lr(kl, 1.0 / world, self.desired_kl, opt.lr_t)
+            opt.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world)
+        acc = self._loss_accum.tolist()  # the only device->host read of the update
+        n = max(acc[3], 1.0)
+        self.learning_rate = float(opt.lr_t.item())
+        opt.param_groups[0]["lr"] = self.learning_rate
+        opt._host_lr = self.learning_rate
+        st.clear()
+        return acc[0] / n, acc[1] / n, acc[2] / n, None, None

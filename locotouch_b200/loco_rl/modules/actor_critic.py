@@ -1,0 +1,186 @@
+"""ActorCritic with the reference's interface (reference loco_rl/loco_rl/modules/actor_critic.py:8-144).
+
+Same constructor signature, ``state_dict`` keys (``std`` | ``log_std``, ``actor.{0,2,4,6}.*``, ``critic.*``) and methods,
+so reference checkpoints load unchanged.  Differences are below the interface:
+
+* all parameters are views into ONE flat fp32 buffer (``flat_params``) with a matching flat gradient buffer, so that the
+  gradient all-reduce is a single NCCL call and clip + Adam is a single fused kernel (K7);
+* ``act`` / ``get_actions_log_prob`` run the fused act epilogue (K3) instead of ``torch.distributions.Normal``: no
+  distribution object, no expanded-std tensor, outputs can be written straight into a RolloutStorage slot.
+The MLP GEMMs stay cuBLAS (TF32 allowed exactly like reference locotouch/scripts/train.py:66-69).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..utils import resolve_nn_activation
+
+
+class _GaussianView:
+    """Minimal stand-in for the ``self.distribution`` attribute some callers poke at (mean / stddev / entropy)."""
+
+    def __init__(self, mean, std_rows):
+        self.mean, self.stddev = mean, std_rows
+        self.loc, self.scale = mean, std_rows
+
+    def entropy(self):
+        return 0.5 + 0.5 * math.log(2 * math.pi) + torch.log(self.stddev)
+
+    def log_prob(self, value):
+        var = self.stddev**2
+        return -((value - self.mean) ** 2) / (2 * var) - self.stddev.log() - math.log(math.sqrt(2 * math.pi))
+
+    def sample(self):
+        return torch.normal(self.mean, self.stddev)
+
+
+class ActorCritic(nn.Module):
+    is_recurrent = False
+
+    def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=[256, 256, 256], critic_hidden_dims=[256, 256, 256],
+                 activation="elu", init_noise_std=1.0, noise_std_type: str = "scalar", **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str([key for key in kwargs.keys()]))
+        super().__init__()
+        act = resolve_nn_activation(activation)
+
+        def mlp(inp, hidden, out):
+            layers, prev = [], inp
+            for h in hidden:
+                layers += [nn.Linear(prev, h), act]
+                prev = h
+            layers.append(nn.Linear(prev, out))
+            return nn.Sequential(*layers)
+
+        self.actor = mlp(num_actor_obs, actor_hidden_dims, num_actions)
+        self.critic = mlp(num_critic_obs, critic_hidden_dims, 1)
+        self.init_noise_std = init_noise_std
+        self.noise_std_type = noise_std_type
+        if noise_std_type == "scalar":
+            self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+        elif noise_std_type == "log":
+            self.log_std = nn.Parameter(torch.log(init_noise_std * torch.ones(num_actions)))
+        else:
+            raise ValueError(f"Unknown standard deviation type: {self.noise_std_type}. Should be 'scalar' or 'log'")
+        self.num_actions = num_actions
+        self.distribution = None
+        self.flat_params = None
+        self.flat_grads = None
+        self._logp = None
+        self._sampled = None
+        self.rng = "philox"  # "torch": eps = torch.randn (same generator stream as torch.normal); "philox": in-kernel
+        self.seed = 0
+        self._draws = 0
+
+    # ------------------------------------------------------------------------------------------ flat parameter storage
+    def flatten_parameters(self):
+        """Re-homes every parameter (and its .grad) as a view of one 16-byte aligned flat buffer.  Idempotent."""
+        params = list(self.parameters())
+        dev = params[0].device
+        if self.flat_params is not None and self.flat_params.device == dev and all(p.data.data_ptr() == self._offsets[i][0] for i, p in enumerate(params)):
+            return self.flat_params, self.flat_grads
+        total = sum((p.numel() + 3) // 4 * 4 for p in params)  # every tensor starts 16-byte aligned
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        off, self._offsets, self._slices = 0, [], {}
+        names = [k for k, _ in self.named_parameters()]
+        for name, p in zip(names, params):
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.flatten())
+            p.data = flat[off:off + n].view(p.shape)
+            p.grad = grads[off:off + n].view(p.shape)
+            self._offsets.append((p.data.data_ptr(), off, n))
+            self._slices[name] = (off, n)
+            off += (n + 3) // 4 * 4
+        self.flat_params, self.flat_grads = flat, grads
+        return flat, grads
+
+    def _apply(self, fn, *a, **k):  # .to(device) invalidates the views
+        out = super()._apply(fn, *a, **k)
+        self.flat_params = None
+        return out
+
+    # ---------------------------------------------------------------------------------------------- reference interface
+    @staticmethod
+    def init_weights(sequential, scales):
+        [torch.nn.init.orthogonal_(module.weight, gain=scales[idx]) for idx, module in enumerate(mod for mod in sequential if isinstance(mod, nn.Linear))]
+
+    def reset(self, dones=None):
+        pass
+
+    def forward(self):
+        raise NotImplementedError
+
+    def _std_vector(self):
+        if self.noise_std_type == "scalar":
+            return self.std
+        return torch.exp(self.log_std)
+
+    @property
+    def action_mean(self):
+        return self.distribution.mean
+
+    @property
+    def action_std(self):
+        return self.distribution.stddev
+
+    @property
+    def entropy(self):
+        return self.distribution.entropy().sum(dim=-1)
+
+    def update_distribution(self, observations):
+        mean = self.actor(observations)
+        self.distribution = _GaussianView(mean, self._std_vector().expand_as(mean))
+        self._logp = self._sampled = None
+
+    def act(self, observations, out=None, **kwargs):
+        """Samples actions.  ``out`` = dict(actions, logp, mu, sigma) of pre-allocated rows (e.g. a RolloutStorage slot)."""
+        mean = self.actor(observations)
+        std = self._std_vector()
+        if mean.requires_grad:  # training-time call (PPO.update in the reference): distribution only
+            self.distribution = _GaussianView(mean, std.expand_as(mean))
+            self._logp = self._sampled = None
+            return self.distribution.sample()
+        out = out or {}
+        if callable(self.rng):
+            eps = self.rng(mean)  # explicit standard-normal draws (parity tests)
+        else:
+            eps = torch.randn_like(mean) if self.rng == "torch" else None
+        sigma_rows = out.get("sigma")
+        if sigma_rows is None:
+            sigma_rows = torch.empty_like(mean)
+        mean = mean.contiguous()
+        actions, logp = ops.act_sample(mean, std.detach().contiguous(), eps, out.get("actions"), out.get("logp"), out.get("mu"), sigma_rows,
+                                       seed=self.seed, offset=self._draws)
+        self._draws += 1
+        self.distribution = _GaussianView(out.get("mu", mean) if out.get("mu") is not None else mean, sigma_rows)
+        self._logp, self._sampled = logp, actions
+        return actions
+
+    def get_actions_log_prob(self, actions):
+        if self._sampled is not None and actions.data_ptr() == self._sampled.data_ptr():
+            return self._logp  # computed by the same kernel that drew the sample
+        return self.distribution.log_prob(actions).sum(dim=-1)
+
+    def act_inference(self, observations):
+        return self.actor(observations)
+
+    def evaluate(self, critic_observations, **kwargs):
+        return self.critic(critic_observations)
+
+    def reset_init_std(self):
+        if self.noise_std_type == "scalar":
+            self.std.data.fill_(self.init_noise_std)
+        elif self.noise_std_type == "log":
+            self.log_std.data.fill_(math.log(self.init_noise_std))
+        else:
+            raise ValueError(f"Unknown standard deviation type: {self.noise_std_type}. Should be 'scalar' or 'log'")
+
+    def get_actor_critic_obs_from_obs_dict(self, obs_dict):
+        actor_obs = obs_dict["policy"]
+        critic_obs = obs_dict.get("critic", actor_obs)
+        return actor_obs, critic_obs

@@ -42,6 +42,8 @@ class FusedMdp:
         self.env = env
         self.spec = spec
         self.device = torch.device(env.device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         if self.device.type != "cuda":
             raise _C.LocoTouchLibraryError(f"FusedMdp needs a CUDA env (got {self.device}); locotouch_b200 has no CPU path")
         lib()  # fail loudly right away if the extension is missing
@@ -179,9 +181,14 @@ class FusedMdp:
             ot.n_min, ot.n_max = t.noise if t.noise is not None else (0.0, 0.0)
         if spec.object_state is not None:
             os_ = spec.object_state
+            # the cfg lists 12 noise bounds: pos(3) vel(3) EULER(3) ang-vel(3); the quaternion slots get no additive noise
+            n_min = tuple(os_.n_min[0:6]) + (0.0,) * 4 + tuple(os_.n_min[9:])
+            n_max = tuple(os_.n_max[0:6]) + (0.0,) * 4 + tuple(os_.n_max[9:])
             for k in range(13):
-                a.os_n_min[k], a.os_n_max[k] = os_.n_min[k], os_.n_max[k]
+                a.os_n_min[k], a.os_n_max[k] = n_min[k], n_max[k]
                 a.os_scale[k], a.os_non_contact[k] = os_.scale[k], os_.non_contact_obs[k]
+            for k in range(3):
+                a.os_euler_min[k], a.os_euler_max[k] = os_.n_min[6 + k], os_.n_max[6 + k]
             a.os_last_contact_thr = os_.last_contact_time_threshold
             a.os_current_contact_thr = os_.current_contact_time_threshold
 

@@ -62,8 +62,14 @@ def adv_normalize(advantages, stats):
     count_launches(1)
 
 
+def counter_add(counter, inc: int = 1):
+    """``counter += inc`` on the current stream (device-resident step counter for CUDA-graph replays)."""
+    check(lib().lt_counter_add(ptr(counter, torch.int64, "counter"), inc, current_stream()), "lt_counter_add")
+    count_launches(1)
+
+
 # ------------------------------------------------------------------------------------------------- K3 act / store / K5
-def act_sample(mu, sigma, eps=None, actions=None, logp=None, mu_out=None, sigma_out=None, seed: int = 0, offset: int = 0):
+def act_sample(mu, sigma, eps=None, actions=None, logp=None, mu_out=None, sigma_out=None, seed: int = 0, offset: int = 0, offset_base=None):
     """Normal(mu, sigma).sample() + log_prob().sum(-1) (reference actor_critic.py:105-123)."""
     N, A = mu.shape
     if actions is None:
@@ -72,7 +78,7 @@ def act_sample(mu, sigma, eps=None, actions=None, logp=None, mu_out=None, sigma_
         logp = torch.empty(N, device=mu.device, dtype=torch.float32)
     check(lib().lt_act_sample(ptr(mu, torch.float32, "mu"), ptr(sigma, torch.float32, "sigma"), ptr(eps, torch.float32, "eps"),
                               ptr(actions, torch.float32), ptr(logp, torch.float32), ptr(mu_out, torch.float32), ptr(sigma_out, torch.float32),
-                              N, A, seed, offset, current_stream()), "lt_act_sample")
+                              N, A, seed, offset, ptr(offset_base, torch.int64, "offset_base"), current_stream()), "lt_act_sample")
     count_launches(1)
     return actions, logp
 
@@ -186,7 +192,7 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0
 
 # ----------------------------------------------------------------------------------------------------------- K2 taxels
 def taxel_synth(body_quat_w, net_forces_w, thresholds, *, quat_body_offset=0, u_drop=None, u_add=None, p_drop=0.005, p_add=0.005,
-                seed=0, offset=0, signal=None, packed=None, normal_forces=None, original_contact=None, delay_ring=None,
+                seed=0, offset=0, offset_base=None, signal=None, packed=None, normal_forces=None, original_contact=None, delay_ring=None,
                 delay_first=None, delay_steps=None, delayed_signal=None, want_signal=True, want_packed=True):
     """Binary taxel bitmap from contact forces (reference observations.py:154-199, 281-308)."""
     N, T = net_forces_w.shape[0], net_forces_w.shape[1]
@@ -206,6 +212,7 @@ def taxel_synth(body_quat_w, net_forces_w, thresholds, *, quat_body_offset=0, u_
     a.u_drop, a.u_add = ptr(u_drop, torch.float32), ptr(u_add, torch.float32)
     a.p_drop, a.p_add = p_drop, p_add
     a.seed, a.offset = seed, offset
+    a.offset_base = ptr(offset_base, torch.int64, "offset_base")
     a.signal = ptr(signal, torch.float32)
     a.packed = ptr(packed, torch.int32)
     a.normal_forces = ptr(normal_forces, torch.float32)

@@ -1,0 +1,214 @@
+"""Per-kernel micro-benchmark: achieved algorithmic GB/s of every hand-written kernel at BASELINE sizes.
+
+    python tools/kbench.py [--envs 4096] [--reps 200] [--json out.json]
+
+Each kernel is timed with CUDA events over ``reps`` launches captured in a CUDA graph (so that Python / ctypes launch
+overhead is not what is measured), cycling through ``copies`` independent input sets whose total footprint exceeds the
+126 MB L2 ("inputs larger than L2").  Algorithmic bytes per unit are the SURVEY.md section 8(d) figures.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from locotouch_b200 import ops  # noqa: E402
+from locotouch_b200.mdp import task_spec as TS  # noqa: E402
+from locotouch_b200.mdp.fused import FusedMdp  # noqa: E402
+from locotouch_b200.sim import synth  # noqa: E402
+
+L2_BYTES = 126e6
+
+
+def peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def time_graph(launch, copies: int, reps: int, warmup: int = 3):
+    """``launch(i)`` enqueues one kernel on input set i.  Returns mean microseconds per launch."""
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for i in range(copies):
+            launch(i)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for r in range(reps):
+                launch(r % copies)
+        for _ in range(warmup):
+            graph.replay()
+        stream.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(5):
+            start.record(stream)
+            graph.replay()
+            end.record(stream)
+            end.synchronize()
+            best = min(best, start.elapsed_time(end) * 1e3 / reps)
+    return best
+
+
+def copies_for(bytes_per_set: float) -> int:
+    return max(2, int(L2_BYTES * 1.5 / max(bytes_per_set, 1)) + 1)
+
+
+def bench_mdp(task: str, n: int, reps: int, phases=("fused",)):
+    spec = TS.SPECS[task]()
+    env_kw = dict(with_object=spec.with_object)
+    per_env = {"locomotion": 5579, "teacher": 6919}[task]
+    copies = min(copies_for(per_env * n), 16)
+    mdps = []
+    for i in range(copies):
+        env = synth.make_env(n, seed=i, **env_kw).to("cuda")
+        m = FusedMdp(env, spec, seed=i)
+        m.exact_any_nonzero_cmd = True
+        m.step(True, True)  # warm: fills history, publishes the any() flag
+        mdps.append(m)
+    torch.cuda.synchronize()
+    out = {}
+
+    def fused(i):
+        mdps[i].step(True, True)
+
+    def rew(i):
+        mdps[i].compute_rewards()
+
+    def obs(i):
+        mdps[i].compute_observations()
+
+    out[f"mdp_step[{task}]"] = (time_graph(fused, copies, reps), per_env * n)
+    rew_bytes = {"locomotion": 1619, "teacher": 2015}[task] * n
+    obs_bytes = per_env * n - rew_bytes + (276 if task == "locomotion" else 420) * n
+    out[f"mdp_rewards[{task}]"] = (time_graph(rew, copies, reps), rew_bytes)
+    out[f"mdp_obs[{task}]"] = (time_graph(obs, copies, reps), obs_bytes)
+    return out
+
+
+def bench_taxel(n: int, reps: int):
+    per_env = 8840
+    copies = min(copies_for(per_env * n), 12)
+    sets = []
+    for i in range(copies):
+        g = torch.Generator().manual_seed(i)
+        q = torch.randn(n, 238, 4, generator=g)
+        q = (q / q.norm(dim=-1, keepdim=True)).cuda()
+        f = (torch.randn(n, 221, 3, generator=g) * 0.1).cuda()
+        thr = (0.05 + (torch.rand(n, 221, generator=g) - 0.5) * 0.02).cuda()
+        sets.append((q, f, thr, torch.empty(n, 442, device="cuda"), torch.empty(n, 7, device="cuda", dtype=torch.int32),
+                     torch.zeros(n, 2, 7, device="cuda", dtype=torch.int32), torch.ones(n, device="cuda", dtype=torch.uint8),
+                     torch.ones(n, device="cuda", dtype=torch.int64), torch.empty(n, 442, device="cuda")))
+
+    def plain(i):
+        q, f, thr, sig, packed, *_ = sets[i]
+        ops.taxel_synth(q, f, thr, quat_body_offset=17, seed=1, offset=i, signal=sig, packed=packed)
+
+    def delayed(i):
+        q, f, thr, sig, packed, ring, first, delay, dsig = sets[i]
+        ops.taxel_synth(q, f, thr, quat_body_offset=17, seed=1, offset=i, signal=None, packed=packed, want_signal=False, delay_ring=ring,
+                        delay_first=first, delay_steps=delay, delayed_signal=dsig)
+
+    return {"taxel_synth": (time_graph(plain, copies, reps), per_env * n),
+            "taxel_synth+delay": (time_graph(delayed, copies, reps), (per_env + 28 * 3) * n)}
+
+
+def bench_gae(n: int, reps: int, T: int = 24):
+    per = 17 * T * n + 4 * n
+    copies = min(copies_for(per), 64)
+    sets = []
+    for i in range(copies):
+        g = torch.Generator().manual_seed(i)
+        sets.append((torch.randn(T, n, generator=g).cuda(), torch.randn(T, n, generator=g).cuda(),
+                     (torch.rand(T, n, generator=g) < 0.02).byte().cuda(), torch.randn(n, generator=g).cuda(),
+                     torch.empty(T, n, device="cuda"), torch.empty(T, n, device="cuda")))
+
+    def run(i):
+        r, v, d, lv, ret, adv = sets[i]
+        ops.gae(r, v, d, lv, 0.99, 0.95, True, ret, adv)
+
+    return {"gae+normalize (2 launches)": (time_graph(run, copies, reps), per + 8 * T * n)}
+
+
+def bench_ppo_loss(b: int, reps: int, A: int = 12):
+    per = 264 * b
+    copies = min(copies_for(per), 32)
+    sets = []
+    for i in range(copies):
+        g = torch.Generator().manual_seed(i)
+        rn = lambda *s: torch.randn(*s, generator=g).cuda()  # noqa: E731
+        sets.append(dict(mu=rn(b, A), sigma=(0.5 + torch.rand(A, generator=g)).cuda(), value=rn(b), actions=rn(b, A), old_logp=rn(b),
+                         old_mu=rn(b, A), old_sigma=(0.5 + torch.rand(b, A, generator=g)).cuda(), advantages=rn(b), returns=rn(b), old_values=rn(b)))
+    bufs = [ops.PpoLossBuffers(b, A, "cuda") for _ in range(copies)]
+    lr = torch.tensor([1e-3], device="cuda")
+
+    def run(i):
+        ops.ppo_loss(**sets[i], entropy_coef=0.01, desired_kl=0.01, lr=lr, buffers=bufs[i])
+
+    return {"ppo_loss fwd+bwd": (time_graph(run, copies, reps), per)}
+
+
+def bench_adam(n: int, reps: int):
+    per = 32 * n
+    copies = min(copies_for(per), 16)
+    sets = [tuple(torch.randn(n, device="cuda") for _ in range(2)) + (torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")) for _ in range(copies)]
+    lr, step = torch.tensor([1e-3], device="cuda"), torch.zeros(1, device="cuda")
+
+    def run(i):
+        p, g, m, v = sets[i]
+        ops.clip_adam(p, g, m, v, lr, step)
+
+    return {"clip+adam (2 launches)": (time_graph(run, copies, reps), per)}
+
+
+def bench_gather(n_rows: int, count: int, reps: int, obs_dim: int = 270):
+    dims = (obs_dim, obs_dim, 12, 1, 1, 1, 1, 12, 12)
+    per = sum(dims) * 4 * 2 * count
+    src = [torch.randn(n_rows, d, device="cuda") for d in dims]
+    copies = 4
+    outs = [[torch.empty(count, d, device="cuda") for d in dims] for _ in range(copies)]
+    idx = [torch.randperm(n_rows, device="cuda")[:count].contiguous() for _ in range(copies)]
+
+    def run(i):
+        ops.gather_rows(src, idx[i], outs[i])
+
+    return {"gather_rows (9 tensors)": (time_graph(run, copies, reps), per)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--reps", type=int, default=200)
+    ap.add_argument("--json", type=str, default=None)
+    args = ap.parse_args()
+    peak, kind = peak_gbs()
+    n = args.envs
+    res = {}
+    for task in ("locomotion", "teacher"):
+        res.update(bench_mdp(task, n, args.reps))
+    res.update(bench_taxel(n, args.reps))
+    res.update(bench_gae(n, args.reps))
+    res.update(bench_ppo_loss(n * 24 // 4, args.reps))
+    res.update(bench_adam(607641 // 4 * 4, args.reps))
+    res.update(bench_gather(n * 24, n * 24 // 4, max(20, args.reps // 10)))
+    rows = []
+    print(f"envs={n}  peak={peak} GB/s ({kind})")
+    print(f"{'kernel':38s} {'us/launch':>10s} {'alg MB':>9s} {'GB/s':>9s} {'frac':>6s}")
+    for k, (us, nbytes) in res.items():
+        gbs = nbytes / us / 1e3
+        rows.append(dict(kernel=k, us=us, bytes=nbytes, gbs=gbs, frac=gbs / peak))
+        print(f"{k:38s} {us:10.2f} {nbytes / 1e6:9.2f} {gbs:9.1f} {gbs / peak:6.3f}")
+    if args.json:
+        json.dump(dict(envs=n, peak_gbs=peak, peak_kind=kind, rows=rows), open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
