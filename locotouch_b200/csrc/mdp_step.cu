@@ -37,7 +37,7 @@ constexpr int kGaitFloats = 24;  // per env: lsa[4] lsc[4] vla[4] last_cmd[3] st
 // shared-memory layout (float offsets; per-env row stride = row length), filled in on the host
 struct Layout {
   int cmd, pos, linb, angb, grav, q, qd, qdd, tau, q0, qd0, lim, act, pact, force, air, con, lair, fpos, fvel;
-  int quat, linw, angw, opos, oquat, olin, oang, ograv, octime, fmax, gait, gait_out, esum, raw, newobs, hist, map, total;
+  int quat, linw, angw, opos, oquat, olin, oang, ograv, octime, fmax, gait, gait_out, esum, raw, newobs, uscr, hist, map, total;
   int D;    // observation dim per group
   int dps;  // new values per step per group
   int hist_stride;  // floats per group in the history staging area (kEnvs * D rounded up to 4)
@@ -77,7 +77,7 @@ __device__ __noinline__ Quat quat_mul(Quat a, Quat b) {
           qq - zz + (a.z + a.y) * (b.w - b.x)};
 }
 // [IL] quat_inv: conj(q) / max(|q|^2, 1e-9)
-__device__ __forceinline__ Quat quat_inv(Quat q) {
+__device__ __noinline__ Quat quat_inv(Quat q) {
   const float n = fmaxf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z, 1e-9f);
   return {q.w / n, -q.x / n, -q.y / n, -q.z / n};
 }
@@ -218,13 +218,6 @@ __device__ __noinline__ float gait_async(const GaitP gp, float a0, float a1, flo
   return (both || (air0 && con1) || (con0 && air1)) ? 1.f : 0.f;
 }
 
-// which warp computes a reward kind
-__device__ __forceinline__ int role_of(int kind) {
-  if (kind == LT_RK_GAIT) return 0;
-  if (kind >= LT_RK_OBJ_XY_POS) return 2;
-  return 1;
-}
-
 // ---------------------------------------------------------------------------------------------------------- kernels
 __global__ void any_nonzero_cmd_kernel(const float* __restrict__ cmd, int N, int* flag_ws, int step) {
   bool nz = false;
@@ -314,9 +307,9 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
       }
     } else if (warp == 3) {
       if (A.episode_sums)
-        for (int i = lane; i < T * nvalid; i += 32) {
-          const int t = i / nvalid, e = i - t * nvalid;
-          sm[L.esum + t * kEnvs + e] = A.episode_sums[(size_t)t * A.N + e0 + e];
+        for (int i = lane; i < T * kEnvs; i += 32) {
+          const int t = i / kEnvs, e = i % kEnvs;
+          if (e < nvalid) sm[L.esum + i] = A.episode_sums[(size_t)t * A.N + e0 + e];
         }
     }
   }
@@ -361,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
   if (do_rew && tid >= 64 && tid < 64 + LT_RK_COUNT) {
     const int kind = tid - 64;
     int slot = -1;
+#pragma unroll 1
     for (int i = 0; i < T; ++i)
       if (A.reward_terms[i].kind == kind && A.reward_terms[i].weight != 0.f) slot = i;
     s_slot[kind] = (signed char)slot;
@@ -439,6 +433,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
         go[12] = g.last_cmd[0]; go[13] = g.last_cmd[1]; go[14] = g.last_cmd[2]; go[15] = g.steps;
       } else {
         // no gait term: carry the state through unchanged
+#pragma unroll 1
         for (int k = 0; k < kGaitFloats; ++k) sm[L.gait_out + e * kGaitFloats + k] = sm[L.gait + e * kGaitFloats + k];
       }
     }
@@ -449,6 +444,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
         const int e = i / S, b = i % S;
         const float* f = sm + L.force + e * (H * S * 3);
         float m = 0.f;
+#pragma unroll 1
         for (int h = 0; h < H; ++h) {
           const float* p = f + (h * S + b) * 3;
           m = fmaxf(m, sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));  // torch.max(norm(F, dim=-1), dim=1)
@@ -459,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
       if (lane < nvalid) {
         const int e = lane, n = e0 + e;
         bool terminated = false, timed_out = false;
+#pragma unroll 1
         for (int t = 0; t < A.num_termination_terms; ++t) {
           const LtTerminationTerm& tt = A.termination_terms[t];
           bool m = false;
@@ -467,6 +464,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
             case LT_TK_BAD_ORIENTATION: m = fabsf(acosf(-sm[L.grav + e * 3 + 2])) > tt.p[0]; break;
             case LT_TK_ROOT_HEIGHT: m = sm[L.pos + e * 3 + 2] < tt.p[0]; break;
             case LT_TK_ILLEGAL_CONTACT:
+#pragma unroll 1
               for (int k = 0; k < tt.num_ids; ++k) m = m || sm[L.fmax + e * S + tt.body_ids[k]] > tt.p[0];
               break;
             case LT_TK_OBJECT_BELOW_ROBOT: m = sm[L.opos + e * 3 + 2] < sm[L.pos + e * 3 + 2]; break;
@@ -484,72 +482,76 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
           if (do_obs) s_fill[e] = 1;
           else if (A.obs_fill) A.obs_fill[n] = 1;
         }
-        // robot reward terms
+        // robot reward terms, straight-line: every value is computed, stored only when the task lists the term
+        auto put = [&](int kind, float v) {
+          const int i = s_slot[kind];
+          if (i >= 0) s_raw[i * kEnvs + e] = v;
+        };
+        auto par = [&](int kind, int k) -> float {
+          const int i = s_slot[kind];
+          return A.reward_terms[i < 0 ? 0 : i].p[k];
+        };
         const Vec3 cmd = ld3(sm + L.cmd + e * 3), vb = ld3(sm + L.linb + e * 3), wb = ld3(sm + L.angb + e * 3);
         const Vec3 grav = ld3(sm + L.grav + e * 3);
         const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
         const float* fmx = sm + L.fmax + e * S;
         const float* fpos = sm + L.fpos + e * 12;
         const float* fvel = sm + L.fvel + e * 12;
-        float foot_speed[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) foot_speed[k] = sqrtf(fvel[3 * k] * fvel[3 * k] + fvel[3 * k + 1] * fvel[3 * k + 1]);
+        put(LT_RK_ALIVE, terminated ? 0.f : 1.f);
+        {
+          const float dx = cmd.x - vb.x, dy = cmd.y - vb.y;
+          put(LT_RK_TRACK_LIN_VEL_XY, exp_neg_over(sqrtf(dx * dx + dy * dy), par(LT_RK_TRACK_LIN_VEL_XY, 0)));
+          put(LT_RK_TRACK_ANG_VEL_Z, exp_neg_over(fabsf(cmd.z - wb.z), par(LT_RK_TRACK_ANG_VEL_Z, 0)));
+        }
+        {
+          const float slip_thr = par(LT_RK_FOOT_SLIP, 0), drag_h = par(LT_RK_FOOT_DRAG, 0), drag_v = par(LT_RK_FOOT_DRAG, 1);
+          float slip = 0.f, drag = 0.f;
 #pragma unroll 1
-        for (int i = 0; i < T; ++i) {
-          const LtRewardTerm& rt = A.reward_terms[i];
-          if (rt.weight == 0.f || role_of(rt.kind) != 1) continue;
-          float raw = 0.f;
-          switch (rt.kind) {
-            case LT_RK_ALIVE: raw = terminated ? 0.f : 1.f; break;
-            case LT_RK_TRACK_LIN_VEL_XY: {
-              const float dx = cmd.x - vb.x, dy = cmd.y - vb.y;
-              raw = exp_neg_over(sqrtf(dx * dx + dy * dy), rt.p[0]);
-            } break;
-            case LT_RK_TRACK_ANG_VEL_Z: raw = exp_neg_over(fabsf(cmd.z - wb.z), rt.p[0]); break;
-            case LT_RK_FOOT_SLIP:
-#pragma unroll
-              for (int k = 0; k < 4; ++k) raw += (fmx[A.feet_sensor_ids[k]] > rt.p[0] ? 1.f : 0.f) * foot_speed[k];
-              break;
-            case LT_RK_FOOT_DRAG:
-#pragma unroll
-              for (int k = 0; k < 4; ++k) raw += (fpos[3 * k + 2] <= rt.p[0] && foot_speed[k] > rt.p[1]) ? 1.f : 0.f;
-              break;
-            case LT_RK_BASE_HEIGHT: { const float d = sm[L.pos + e * 3 + 2] - rt.p[0]; raw = d * d; } break;
-            case LT_RK_BASE_Z_VEL: raw = vb.z * vb.z; break;
-            case LT_RK_BASE_RP_ANGLE: raw = grav.x * grav.x + grav.y * grav.y; break;
-            case LT_RK_BASE_RP_VEL: raw = fabsf(wb.x) + fabsf(wb.y); break;
-            case LT_RK_JOINT_POS_LIMIT: {
-              const float* qq = sm + L.q + e * J; const float* lim = sm + L.lim + e * 2 * J;
-#pragma unroll 1
-              for (int j = 0; j < J; ++j) raw += -fminf(qq[j] - lim[2 * j], 0.f) + fmaxf(qq[j] - lim[2 * j + 1], 0.f);
-            } break;
-            case LT_RK_JOINT_POS: {
-              const float* qq = sm + L.q + e * J; const float* q0 = sm + L.q0 + e * J;
-              float s = 0.f;
-#pragma unroll 1
-              for (int j = 0; j < J; ++j) { const float d = qq[j] - q0[j]; s += d * d; }
-              const float dev = sqrtf(s);
-              const float bv = sqrtf(vb.x * vb.x + vb.y * vb.y);
-              raw = (cmd_norm > 0.f || bv > rt.p[1]) ? dev : rt.p[0] * dev;
-            } break;
-            case LT_RK_JOINT_ACC: case LT_RK_JOINT_VEL: case LT_RK_JOINT_TORQUE: {
-              const float* x = sm + (rt.kind == LT_RK_JOINT_ACC ? L.qdd : (rt.kind == LT_RK_JOINT_VEL ? L.qd : L.tau)) + e * J;
-              float s = 0.f;
-#pragma unroll 1
-              for (int j = 0; j < J; ++j) s += x[j] * x[j];
-              raw = sqrtf(s);
-            } break;
-            case LT_RK_ACTION_RATE: {
-              const float* a = sm + L.act + e * J; const float* pa = sm + L.pact + e * J;
-#pragma unroll 1
-              for (int j = 0; j < J; ++j) { const float d = a[j] - pa[j]; raw += d * d; }
-            } break;
-            case LT_RK_THIGH_CALF_COLLISION:
-              for (int k = 0; k < A.num_thigh_calf; ++k) raw += fmx[A.thigh_calf_sensor_ids[k]] > rt.p[0] ? 1.f : 0.f;
-              break;
-            default: break;
+          for (int k = 0; k < 4; ++k) {
+            const float sp = sqrtf(fvel[3 * k] * fvel[3 * k] + fvel[3 * k + 1] * fvel[3 * k + 1]);
+            slip += (fmx[A.feet_sensor_ids[k]] > slip_thr ? 1.f : 0.f) * sp;
+            drag += (fpos[3 * k + 2] <= drag_h && sp > drag_v) ? 1.f : 0.f;
           }
-          s_raw[i * kEnvs + e] = raw;
+          put(LT_RK_FOOT_SLIP, slip);
+          put(LT_RK_FOOT_DRAG, drag);
+        }
+        {
+          const float d = sm[L.pos + e * 3 + 2] - par(LT_RK_BASE_HEIGHT, 0);
+          put(LT_RK_BASE_HEIGHT, d * d);
+          put(LT_RK_BASE_Z_VEL, vb.z * vb.z);
+          put(LT_RK_BASE_RP_ANGLE, grav.x * grav.x + grav.y * grav.y);
+          put(LT_RK_BASE_RP_VEL, fabsf(wb.x) + fabsf(wb.y));
+        }
+        {
+          const float* qq = sm + L.q + e * J; const float* q0 = sm + L.q0 + e * J; const float* lim = sm + L.lim + e * 2 * J;
+          const float* qd = sm + L.qd + e * J; const float* qdd = sm + L.qdd + e * J; const float* tau = sm + L.tau + e * J;
+          const float* ac = sm + L.act + e * J; const float* pa = sm + L.pact + e * J;
+          float s_lim = 0.f, s_dev = 0.f, s_acc = 0.f, s_vel = 0.f, s_tau = 0.f, s_rate = 0.f;
+#pragma unroll 2
+          for (int j = 0; j < J; ++j) {
+            s_lim += -fminf(qq[j] - lim[2 * j], 0.f) + fmaxf(qq[j] - lim[2 * j + 1], 0.f);
+            const float d = qq[j] - q0[j];
+            s_dev += d * d;
+            s_acc += qdd[j] * qdd[j];
+            s_vel += qd[j] * qd[j];
+            s_tau += tau[j] * tau[j];
+            const float da = ac[j] - pa[j];
+            s_rate += da * da;
+          }
+          put(LT_RK_JOINT_POS_LIMIT, s_lim);
+          const float dev = sqrtf(s_dev), bv = sqrtf(vb.x * vb.x + vb.y * vb.y);
+          put(LT_RK_JOINT_POS, (cmd_norm > 0.f || bv > par(LT_RK_JOINT_POS, 1)) ? dev : par(LT_RK_JOINT_POS, 0) * dev);
+          put(LT_RK_JOINT_ACC, sqrtf(s_acc));
+          put(LT_RK_JOINT_VEL, sqrtf(s_vel));
+          put(LT_RK_JOINT_TORQUE, sqrtf(s_tau));
+          put(LT_RK_ACTION_RATE, s_rate);
+        }
+        {
+          const float thr = par(LT_RK_THIGH_CALF_COLLISION, 0);
+          float c = 0.f;
+#pragma unroll 1
+          for (int k = 0; k < A.num_thigh_calf; ++k) c += fmx[A.thigh_calf_sensor_ids[k]] > thr ? 1.f : 0.f;
+          put(LT_RK_THIGH_CALF_COLLISION, c);
         }
       }
     }
@@ -565,44 +567,46 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
       const Vec3 rel_vel = rot_inv(q, sub3(ld3(sm + L.olin + e * 3), ld3(sm + L.linw + e * 3)));
       const Vec3 rel_ang = rot_inv(q, sub3(ld3(sm + L.oang + e * 3), ld3(sm + L.angw + e * 3)));
       const Vec3 g_obj = rot_inv(q, rot(ld4(sm + L.oquat + e * 4), ld3(sm + L.ograv + e * 3)));
-#pragma unroll 1
-      for (int i = 0; i < T; ++i) {
-        const LtRewardTerm& rt = A.reward_terms[i];
-        if (rt.weight == 0.f || role_of(rt.kind) != 2) continue;
-        float raw = 0.f;
-        switch (rt.kind) {
-          case LT_RK_OBJ_XY_POS:
-            raw = sqrtf(rel_pos_w.x * rel_pos_w.x + rel_pos_w.y * rel_pos_w.y);
-            if (rt.p[0] != 0.f) raw *= (cmd_norm > 0.f) ? 1.f : 0.f;
-            break;
-          case LT_RK_OBJ_XY_VEL: raw = rel_vel.x * rel_vel.x + rel_vel.y * rel_vel.y; break;
-          case LT_RK_OBJ_LOSE_CONTACT: raw = (sm[L.octime + e * 3 + 0] > 0.f && sm[L.octime + e * 3 + 2] > 0.f) ? 1.f : 0.f; break;
-          case LT_RK_OBJ_Z_VEL: raw = rel_vel.z * rel_vel.z; break;
-          case LT_RK_OBJ_RP_ANGLE: raw = g_obj.x * g_obj.x + g_obj.y * g_obj.y; break;
-          case LT_RK_OBJ_RP_VEL: raw = fabsf(rel_ang.x) + fabsf(rel_ang.y); break;
-          case LT_RK_OBJ_ROLL_ANGLE: raw = g_obj.y * g_obj.y; break;
-          case LT_RK_OBJ_ROLL_VEL: raw = rel_ang.x * rel_ang.x; break;
-          case LT_RK_OBJ_YAW: {  // rewards.py:545-567
-            const Quat qr = yaw_quat(yaw_of(q)), qo = yaw_quat(yaw_of(ld4(sm + L.oquat + e * 4)));
-            float d = yaw_of(quat_mul(quat_inv(qr), qo));
-            const float pi = 3.14159274101257324f;  // float32(torch.pi)
-            if (d > pi) d -= 2.f * pi;
-            if (d > 0.5f * pi) d -= pi;
-            if (d <= -0.5f * pi) d += pi;
-            raw = d * d;
-            if (rt.p[0] != 0.f) raw *= (cmd_norm > 0.f) ? 1.f : 0.f;
-          } break;
-          case LT_RK_OBJ_DANGER: {  // rewards.py:569-594
-            bool bad = fabsf(rel_pos.x) > rt.p[0];
-            bad = bad || fabsf(rel_pos.y) > rt.p[1];
-            bad = bad || rel_pos.z < rt.p[2];
-            if (rt.p[3] >= 0.f) bad = bad || fabsf(acosf(-sm[L.ograv + e * 3 + 2])) > rt.p[3] * 3.14159265358979323846f / 180.f;
-            if (rt.p[4] >= 0.f) bad = bad || sqrtf(rel_vel.x * rel_vel.x + rel_vel.y * rel_vel.y) > rt.p[4];
-            raw = bad ? 1.f : 0.f;
-          } break;
-          default: break;
-        }
-        s_raw[i * kEnvs + e] = raw;
+      auto put = [&](int kind, float v) {
+        const int i = s_slot[kind];
+        if (i >= 0) s_raw[i * kEnvs + e] = v;
+      };
+      auto par = [&](int kind, int k) -> float {
+        const int i = s_slot[kind];
+        return A.reward_terms[i < 0 ? 0 : i].p[k];
+      };
+      const float moving = cmd_norm > 0.f ? 1.f : 0.f;
+      {
+        float v = sqrtf(rel_pos_w.x * rel_pos_w.x + rel_pos_w.y * rel_pos_w.y);
+        if (par(LT_RK_OBJ_XY_POS, 0) != 0.f) v *= moving;
+        put(LT_RK_OBJ_XY_POS, v);
+      }
+      put(LT_RK_OBJ_XY_VEL, rel_vel.x * rel_vel.x + rel_vel.y * rel_vel.y);
+      put(LT_RK_OBJ_LOSE_CONTACT, (sm[L.octime + e * 3 + 0] > 0.f && sm[L.octime + e * 3 + 2] > 0.f) ? 1.f : 0.f);
+      put(LT_RK_OBJ_Z_VEL, rel_vel.z * rel_vel.z);
+      put(LT_RK_OBJ_RP_ANGLE, g_obj.x * g_obj.x + g_obj.y * g_obj.y);
+      put(LT_RK_OBJ_RP_VEL, fabsf(rel_ang.x) + fabsf(rel_ang.y));
+      put(LT_RK_OBJ_ROLL_ANGLE, g_obj.y * g_obj.y);
+      put(LT_RK_OBJ_ROLL_VEL, rel_ang.x * rel_ang.x);
+      if (s_slot[LT_RK_OBJ_YAW] >= 0) {  // rewards.py:545-567
+        const Quat qr = yaw_quat(yaw_of(q)), qo = yaw_quat(yaw_of(ld4(sm + L.oquat + e * 4)));
+        float d = yaw_of(quat_mul(quat_inv(qr), qo));
+        const float pi = 3.14159274101257324f;  // float32(torch.pi)
+        if (d > pi) d -= 2.f * pi;
+        if (d > 0.5f * pi) d -= pi;
+        if (d <= -0.5f * pi) d += pi;
+        float v = d * d;
+        if (par(LT_RK_OBJ_YAW, 0) != 0.f) v *= moving;
+        put(LT_RK_OBJ_YAW, v);
+      }
+      if (s_slot[LT_RK_OBJ_DANGER] >= 0) {  // rewards.py:569-594
+        bool bad = fabsf(rel_pos.x) > par(LT_RK_OBJ_DANGER, 0);
+        bad = bad || fabsf(rel_pos.y) > par(LT_RK_OBJ_DANGER, 1);
+        bad = bad || rel_pos.z < par(LT_RK_OBJ_DANGER, 2);
+        const float rp = par(LT_RK_OBJ_DANGER, 3), vmax = par(LT_RK_OBJ_DANGER, 4);
+        if (rp >= 0.f) bad = bad || fabsf(acosf(-sm[L.ograv + e * 3 + 2])) > rp * 3.14159265358979323846f / 180.f;
+        if (vmax >= 0.f) bad = bad || sqrtf(rel_vel.x * rel_vel.x + rel_vel.y * rel_vel.y) > vmax;
+        put(LT_RK_OBJ_DANGER, bad ? 1.f : 0.f);
       }
     }
   } else if (warp == 3) {
@@ -626,9 +630,9 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
 #pragma unroll
         for (int k = 0; k < 13; ++k) cst[k] = A.os_non_contact[k];
         if (grp == 0) {  // policy group: add_uniform_noise=True
-          float u13[13];
+          float* u13 = sm + L.uscr + e * 16;  // 13 uniforms of this env (one policy-group lane per env)
           if (A.u_obs) {
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < 13; ++k) u13[k] = __ldcs(A.u_obs + (size_t)n * dps + jb + k);
           } else {  // the same (env, quad) counter stream the proprioceptive values use: value j takes word j & 3 of quad j >> 2
 #pragma unroll 1
@@ -638,9 +642,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
                 const int k = 4 * qd + c4 - jb;
-#pragma unroll
-                for (int kk = 0; kk < 13; ++kk)
-                  if (kk == k) u13[kk] = lt::Philox::u01(rw[c4]);
+                if (k >= 0 && k < 13) u13[k] = lt::Philox::u01(rw[c4]);
               }
             }
           }
@@ -718,8 +720,9 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
   if (do_rew) {
     const float dt = A.step_dt;
     // [IL] RewardManager.compute: value = f * weight * dt ; episode_sums += value ; step_reward = value / dt
-    for (int i = tid; i < T * nvalid; i += kThreads) {
-      const int t = i / nvalid, e = i - t * nvalid, n = e0 + e;
+    for (int i = tid; i < T * kEnvs; i += kThreads) {
+      const int t = i / kEnvs, e = i % kEnvs, n = e0 + e;
+      if (e >= nvalid) continue;
       const LtRewardTerm& rt = A.reward_terms[t];
       if (rt.weight == 0.f) {  // skipped terms: step_reward column is zero, sums untouched
         if (A.step_reward) A.step_reward[(size_t)n * T + t] = 0.f;
@@ -739,6 +742,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
     if (warp == kWarps - 1 && lane < nvalid) {  // reward_buf: sequential fp32 sum in term order
       const int e = lane;
       float reward = 0.f;
+#pragma unroll 1
       for (int t = 0; t < T; ++t) {
         const LtRewardTerm& rt = A.reward_terms[t];
         if (rt.weight != 0.f) reward = reward + (s_raw[t * kEnvs + e] * rt.weight) * dt;
@@ -891,6 +895,7 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   L.fmax = take(S); L.gait = take(kGaitFloats); L.gait_out = take(kGaitFloats);
   L.esum = take(T); L.raw = take(T);
   L.newobs = take(2 * dps);
+  L.uscr = take(16);
   off = (off + 3) & ~3;
   L.hist_stride = ((kEnvs * L.D + 3) & ~3) + 4;  // +4: the shifted read of the last element may touch one slot past the block
   L.hist = off; off += 2 * L.hist_stride;
