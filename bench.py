@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the LocoTouch hot path (BASELINE.json metric: env-steps/s, MDP + tactile + GAE + PPO, 4096 envs/GPU).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                       # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1       # the reference algorithm on the host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one PPO iteration at 4096 envs per GPU: 24 x [actor-critic act, action pre-processing, fused MDP step of
+the RandCylinderTransportTeacher task (23 active rewards incl. the gait term, 6 terminations, 2 x 348-D observations),
+binary taxel synthesis + delay line, transition store] + GAE + 5 epochs x 4 mini-batches of PPO update.  Synthetic state
+tensors stand in for PhysX (6 pre-generated state sets per rank, ~200 MB, cycled through).
+value = (N_gpus * 4096 * 24) / seconds per step, device-timed (CUDA events, max over ranks), inputs resident in HBM,
+the whole step replayed from CUDA graphs.  e2e = the same metric through the public drop-in classes (eager calls) with
+every env step's state set copied host->device from pinned memory and the iteration's metrics read back.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+T_STEPS = 24
+METRIC = "env-steps/s (MDP+tactile+GAE+PPO) at 4096 envs/GPU"
+WORKLOAD = ("PPO iteration, Isaac-RandCylinderTransportTeacher-LocoTouch-v1 terms (23 rewards incl. gait, 6 terminations, 2x348 obs) "
+            "+ binary taxels (221) + GAE + PPO update (5 epochs x 4 mini-batches, MLP [512,256,128]), 4096 envs x 24 steps per GPU")
+
+# algorithmic bytes per unit (SURVEY.md 8d / DESIGN.md section 4)
+ALG_BYTES = {"mdp_step[teacher]": 6919, "mdp_step[locomotion]": 5579, "taxel_synth": 8840}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p["hbm_gbs"], p.get("bf16_tflops_sustained", 1363.9), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int = 0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_sample(envs: int = ENVS_PER_GPU, env_steps: int = 2, minibatches: int = 2, threads: int | None = None):
+    """Times the reference algorithm (oracle port, torch CPU fp32) on the host cores over a bounded sample of one step and
+    extrapolates to the full iteration: T x env-step + GAE + 20 x mini-batch.  Returns (env_steps_per_s, detail dict)."""
+    from oracle import ppo as OP
+    from oracle import tactile as OT
+    from oracle.mdp import MdpOracle
+    from locotouch_b200.mdp import task_spec as TS
+    from locotouch_b200.sim import synth
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    spec = TS.teacher_spec()
+    env = synth.make_env(envs, seed=0, with_object=True, with_tactile=True)
+    oracle = MdpOracle(env, spec)
+    D, A = spec.obs_dim, 12
+    g = torch.Generator().manual_seed(0)
+    shapes = OP.actor_critic_shapes(D, D, A, [512, 256, 128], [512, 256, 128])
+    n_params = sum(int(torch.tensor(s).prod()) for _, s in shapes)
+    flat = torch.randn(n_params, generator=g) * 0.05
+    flat[:A] = 1.0
+    params = OP.unflatten(flat, shapes)
+    aw, ab, cw, cb = OP._split(params)
+    thr = 0.05 + (torch.rand(envs, 221, generator=g) * 0.02 - 0.01)
+    delay = OT.TactileDelayOracle(envs, 442, 1, 2)
+    obs = torch.zeros(envs, D)
+    # ---- env-step sample
+    t_env = []
+    for i in range(env_steps + 1):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            mu = OP.mlp_forward(obs, aw, ab)
+            actions, logp = OP.act_sample(mu, params["std"], torch.randn(envs, A, generator=g))
+            values = OP.mlp_forward(obs, cw, cb)
+            out = oracle.step(env)
+            obs, cobs = oracle.observe(env, u_noise=torch.rand(envs, spec.obs_dim_per_step, generator=g), u_obj_euler=torch.rand(envs, 3, generator=g))
+            tac = OT.binary_taxels(env.scene["robot"].data.body_quat_w[:, 17:], env.scene.sensors["tactile_contact_sensor"].data.net_forces_w, thr,
+                                   torch.rand(envs, 221, generator=g), torch.rand(envs, 221, generator=g))
+            delay.record(tac["signal"])
+            delay.get()
+            OP.bootstrap_rewards(out["reward"], values, out["time_outs"], 0.99)
+        if i > 0:
+            t_env.append(time.perf_counter() - t0)
+    # ---- GAE
+    r = torch.randn(T_STEPS, envs, 1, generator=g) * 0.02
+    v = torch.randn(T_STEPS, envs, 1, generator=g)
+    d = (torch.rand(T_STEPS, envs, 1, generator=g) < 0.02).byte()
+    t0 = time.perf_counter()
+    OP.gae_returns(r, v, d, torch.randn(envs, 1, generator=g), 0.99, 0.95, True)
+    t_gae = time.perf_counter() - t0
+    # ---- mini-batch sample
+    B = envs * T_STEPS // 4
+    st = dict(obs=torch.randn(B, D, generator=g), critic_obs=torch.randn(B, D, generator=g), actions=torch.randn(B, A, generator=g),
+              values=torch.randn(B, 1, generator=g), returns=torch.randn(B, 1, generator=g), logp=torch.randn(B, 1, generator=g) - 12,
+              advantages=torch.randn(B, 1, generator=g), mu=torch.randn(B, A, generator=g), sigma=torch.ones(B, A))
+    t0 = time.perf_counter()
+    OP.ppo_update(flat, shapes, st, torch.arange(B), num_learning_epochs=minibatches, num_mini_batches=1, clip_param=0.2, value_loss_coef=1.0,
+                  entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0, desired_kl=0.01)
+    t_mb = (time.perf_counter() - t0) / minibatches
+    t_env_mean = sum(t_env) / len(t_env)
+    iteration = T_STEPS * t_env_mean + t_gae + 20 * t_mb
+    detail = dict(env_step_s=t_env_mean, gae_s=t_gae, minibatch_s=t_mb, iteration_s=iteration,
+                  sample=f"{env_steps} env steps (act+MDP+taxels+store) + 1 GAE + {minibatches} of 20 PPO mini-batches at {envs} envs, extrapolated to 24 steps + 20 mini-batches")
+    return envs * T_STEPS / iteration, detail
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_sample(env_steps=1, minibatches=1, threads=cores)
+    vals, details = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, details = cpu_reference_sample(threads=cores)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    value = statistics.median(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * ENVS_PER_GPU * T_STEPS / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "inputs": "host memory (torch CPU tensors)"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": details["sample"],
+                         "detail": {k: details[k] for k in ("env_step_s", "gae_s", "minibatch_s", "iteration_s")}},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "sample_wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ kernel roofline
+def kernel_rooflines(engine, reps: int = 96):
+    """Per-launch duration of the two streaming kernels of the rollout, measured live: `reps` launches captured in one CUDA
+    graph on the timing stream, cycling through the engine's state sets (6 x ~33 MB > L2), CUDA events around the replay."""
+    from locotouch_b200 import ops
+    from locotouch_b200.sim import synth
+
+    st = engine.alg.storage
+    stream = torch.cuda.current_stream()
+    out = {}
+
+    def timed(launch, name, bytes_per_launch):
+        for k in range(engine.K):
+            launch(k)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for r in range(reps):
+                launch(r % engine.K)
+        for _ in range(3):
+            g.replay()
+        best = 1e30
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(5):
+            e0.record()
+            g.replay()
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+        out[name] = (best, bytes_per_launch)
+
+    def mdp(k):
+        engine._bind(k)
+        t = k % engine.T
+        engine.mdp.step(True, True, policy_in=st._obs_buf[t], critic_in=st._priv_buf[t], policy_out=st._obs_buf[t + 1], critic_out=st._priv_buf[t + 1],
+                        step_offset=k, offset_base=engine.step_counter)
+
+    timed(mdp, "mdp_step[teacher]", ALG_BYTES["mdp_step[teacher]"] * engine.N)
+    if engine.tactile:
+        def tax(k):
+            env = engine.envs[k]
+            ops.taxel_synth(env.scene["robot"].data.body_quat_w, env.scene.sensors["tactile_contact_sensor"].data.net_forces_w, engine.taxel_thr,
+                            quat_body_offset=synth.NUM_ROBOT_BODIES, seed=1, offset=k, offset_base=engine.step_counter, signal=None, want_signal=False,
+                            packed=engine.taxel_packed, delay_ring=engine.taxel_ring, delay_first=engine.taxel_first, delay_steps=engine.taxel_delay,
+                            delayed_signal=engine.tactile_obs)
+        timed(tax, "taxel_synth", ALG_BYTES["taxel_synth"] * engine.N)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the locotouch_b200 product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=device)
+    from locotouch_b200 import _C
+    from locotouch_b200.engine import HotPathEngine
+
+    N = args.envs_per_gpu
+    engine = HotPathEngine(num_envs=N, task="teacher", tactile=True, device=device, seed=0, num_state_sets=6, pin_host=True)
+    launches_before = _C.launch_count
+    engine.capture()
+    # ABI launches recorded into the graphs = launches of one iteration (2 warm-up iterations + 1 captured)
+    launches_per_step = (_C.launch_count - launches_before) // 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        engine.replay()
+    barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        start.record()
+        for _ in range(args.steps):
+            engine.replay()
+        end.record()
+        barrier()
+    ms = torch.tensor([start.elapsed_time(end)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = world * N * T_STEPS / (ms_per_step * 1e-3)
+    metrics = engine.read_results()
+
+    # ---- end to end through the public drop-in classes, host buffers, copies inside the timed region
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    engine.iteration(upload=True)
+    engine.read_results()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        engine.iteration(upload=True)
+        engine.read_results()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * T_STEPS / float(e2e_s.item())
+    h2d = T_STEPS * engine.state_bytes
+    d2h = 4 * 6
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core GEMMs, as the reference)",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "steps_per_env": T_STEPS, "parallelism": f"env-sharded dp{world}, NCCL all-reduce of flat PPO gradients" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (6 state sets ~200 MB + 290 MB rollout storage per rank)", "timing": "CUDA events on the launch stream around K graph replays, max over ranks"},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "how": "eager public API (PPO/RolloutStorage/FusedMdp), per env step one pinned-host -> device copy of the state set, metrics read back per iteration"},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks.summary(),
+        "iteration_metrics": metrics,
+    }
+    if rank == 0:
+        hbm, tf, kind = peaks()
+        rl = kernel_rooflines(engine)
+        rows = []
+        for name, (us, nbytes) in rl.items():
+            gbs = nbytes / us / 1e3
+            rows.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "us_per_launch": us,
+                         "alg_bytes_per_launch": nbytes})
+        top = max(rows, key=lambda r: r["us_per_launch"])
+        line["roofline"] = {"bound": "hbm", "achieved": top["achieved"], "peak": hbm, "unit": "GB/s", "frac": top["frac"], "traffic": None,
+                            "kernel": top["kernel"], "us_per_launch": top["us_per_launch"], "peak_kind": kind,
+                            "how": "96 launches in one CUDA graph cycling 6 state sets (> L2), CUDA events on the launch stream"}
+        line["kernels"] = rows
+        if world == 1 and not args.no_cpu_baseline:
+            v, detail = cpu_reference_sample()
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": detail["sample"],
+                                    "detail": {k: detail[k] for k in ("env_step_s", "gae_s", "minibatch_s", "iteration_s")}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

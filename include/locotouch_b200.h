@@ -78,6 +78,18 @@ int lt_store_step(const float* rewards, const int64_t* dones_i64, const uint8_t*
                   const float* critic_obs, float* critic_obs_out, int critic_obs_dim, int N, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * K0  action pre-processing
+ * replaces  locotouch/mdp/actions.py:30-44  JointPositionActionPrevPrev.process_actions (+ [IL] JointPositionAction):
+ *   prev_prev_raw = prev_raw ; prev_raw = raw ; prev_prev_processed = prev_processed ; prev_processed = processed
+ *   raw = clamp(actions, -clip, clip) * raw_scale   (clip <= 0: no clipping)
+ *   processed = raw * scale + offset[N,J]
+ * All state tensors are [N,J]; the two "processed" history buffers may be NULL.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int lt_process_actions(const float* actions, float clip, float raw_scale, float scale, const float* offset,
+                       float* raw, float* prev_raw, float* prev_prev_raw,
+                       float* processed, float* prev_processed, float* prev_prev_processed, int64_t count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * K5  mini-batch gather
  * replaces  rollout_storage.py:186-243  RolloutStorage.mini_batch_generator  (9 advanced-index gathers)
  * Gathers `count` rows given by indices[count] (int64, into the flattened [T*N] axis) from up to LT_GATHER_MAX

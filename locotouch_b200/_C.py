@@ -144,6 +144,7 @@ _SIGNATURES = {
     "lt_gae_scan": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_adv_normalize": (C.c_int, [f32p, C.c_int64, C.c_void_p, C.c_void_p]),
     "lt_act_sample": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "lt_process_actions": (C.c_int, [f32p, C.c_float, C.c_float, C.c_float, f32p, f32p, f32p, f32p, f32p, f32p, f32p, C.c_int64, C.c_void_p]),
     "lt_counter_add": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_store_step": (C.c_int, [f32p, C.c_void_p, C.c_void_p, C.c_void_p, f32p, C.c_float, f32p, C.c_void_p, f32p, f32p, C.c_int, f32p, f32p, C.c_int, C.c_int, C.c_void_p]),
     "lt_gather_rows": (C.c_int, [C.POINTER(LtGatherArgs), C.c_void_p, C.c_int64, C.c_void_p]),

@@ -117,6 +117,28 @@ gather_rows_kernel(const GatherParams p, const int64_t* __restrict__ indices, in
   }
 }
 
+__global__ void __launch_bounds__(256)
+process_actions_kernel(const float* __restrict__ actions, float clip, float raw_scale, float scale, const float* __restrict__ offset,
+                       float* __restrict__ raw, float* __restrict__ prev_raw, float* __restrict__ prev_prev_raw,
+                       float* __restrict__ processed, float* __restrict__ prev_processed, float* __restrict__ prev_prev_processed,
+                       int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float old_raw = raw[i];
+  if (prev_prev_raw) prev_prev_raw[i] = prev_raw[i];
+  prev_raw[i] = old_raw;
+  if (processed) {
+    const float old_p = processed[i];
+    if (prev_prev_processed && prev_processed) prev_prev_processed[i] = prev_processed[i];
+    if (prev_processed) prev_processed[i] = old_p;
+  }
+  float a = actions[i];
+  if (clip > 0.f) a = fminf(fmaxf(a, -clip), clip);  // torch.clamp
+  a = __fmul_rn(a, raw_scale);
+  raw[i] = a;
+  if (processed) processed[i] = __fadd_rn(__fmul_rn(a, scale), offset ? offset[i] : 0.f);
+}
+
 __global__ void counter_add_kernel(int64_t* c, int64_t inc) { *c += inc; }
 
 }  // namespace
@@ -124,6 +146,15 @@ __global__ void counter_add_kernel(int64_t* c, int64_t inc) { *c += inc; }
 extern "C" int lt_counter_add(int64_t* counter, int64_t inc, void* stream) {
   if (!counter) return LT_ERR_INVALID_ARG;
   counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+  return lt::check_launch();
+}
+
+extern "C" int lt_process_actions(const float* actions, float clip, float raw_scale, float scale, const float* offset, float* raw,
+                                  float* prev_raw, float* prev_prev_raw, float* processed, float* prev_processed,
+                                  float* prev_prev_processed, int64_t count, void* stream) {
+  if (!actions || !raw || !prev_raw || count <= 0) return LT_ERR_INVALID_ARG;
+  process_actions_kernel<<<(unsigned)lt::ceil_div(count, 256), 256, 0, (cudaStream_t)stream>>>(
+      actions, clip, raw_scale, scale, offset, raw, prev_raw, prev_prev_raw, processed, prev_processed, prev_prev_processed, count);
   return lt::check_launch();
 }
 

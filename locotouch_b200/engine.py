@@ -1,0 +1,229 @@
+"""Hot-path engine: one PPO iteration of the LocoTouch learning path on one GPU (one process per GPU).
+
+Sequence of reference ``OnPolicyRunner.learn`` (loco_rl/loco_rl/runners/on_policy_runner.py:150-222), with IsaacLab's
+PhysX stepping replaced by pre-generated synthetic state sets (BASELINE.json north_star):
+
+    for t in range(num_steps_per_env):                       HOT LOOP A
+        actions = alg.act(obs, critic_obs)                   cuBLAS MLPs + K3 act epilogue -> rollout slot t
+        [ env.step(actions) ]                                K0 action pre-processing, synthetic state set t % K,
+                                                             K1 fused MDP step (obs written straight into slot t+1),
+                                                             K2 binary taxels + packed delay line
+        alg.process_env_step(rewards, dones, infos)          K3 store (time-out bootstrap fused)
+    alg.compute_returns(critic_obs)                          K4 GAE + advantage normalisation
+    alg.update()                                             HOT LOOP B: K5 gather, cuBLAS MLPs, K6 loss, K7 clip+Adam
+
+``iteration()`` runs it through the public drop-in classes (PPO / RolloutStorage / ActorCritic / FusedMdp);
+``capture()`` records the same calls into CUDA graphs so that ``replay()`` has no Python or launch overhead.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .loco_rl import PPO, ActorCritic
+from .mdp import task_spec as TS
+from .mdp.fused import FusedMdp
+from .sim import synth
+from .sim.scene import ActionTermState
+
+# reference locotouch/config/locotouch/agents/rsl_rl_ppo_cfg.py:6-30
+PPO_CFG = dict(num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0, entropy_coef=0.01,
+               learning_rate=1.0e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01)
+NUM_STEPS_PER_ENV = 24
+HIDDEN = (512, 256, 128)
+# reference locotouch/config/base/locomotion_base_env_cfg.py:127-135
+ACTION_CLIP, ACTION_RAW_SCALE = 100.0, 0.25
+
+
+def pack_env(env, device, pin: bool = False):
+    """Re-homes every state tensor of a SynthEnv as a view of ONE contiguous device buffer (256-byte aligned slices),
+    returning (device_env, flat_device_buffer, flat_host_buffer).  One H2D copy then refreshes the whole state."""
+    tensors = env.named_tensors()
+    skip = {k for k in tensors if k.startswith("action.") or k in ("terminated", "time_outs")}
+    layout, off = [], 0
+    for name, t in tensors.items():
+        if name in skip:
+            continue
+        nbytes = t.numel() * t.element_size()
+        layout.append((name, off, nbytes, t.dtype, tuple(t.shape)))
+        off += (nbytes + 255) // 256 * 256
+    host = torch.empty(off, dtype=torch.uint8, pin_memory=pin)
+    for name, o, nbytes, dtype, shape in layout:
+        host[o:o + nbytes].view(dtype).view(shape).copy_(tensors[name])
+    flat = host.to(device)
+    denv = env.to(device)
+    views = {name: flat[o:o + nbytes].view(dtype).view(shape) for name, o, nbytes, dtype, shape in layout}
+    denv.load_named_tensors(views)
+    return denv, flat, host
+
+
+class HotPathEngine:
+    def __init__(self, num_envs: int = 4096, task: str = "teacher", tactile: bool = True, device="cuda:0", seed: int = 0,
+                 num_state_sets: int = 6, num_steps: int = NUM_STEPS_PER_ENV, hidden=HIDDEN, ppo_cfg: dict | None = None,
+                 pin_host: bool = False, tf32: bool = True):
+        self.device = torch.device(device)
+        self.N, self.T, self.K = num_envs, num_steps, num_state_sets
+        self.spec = TS.SPECS[task]()
+        self.tactile = tactile
+        self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if tf32:  # reference locotouch/scripts/train.py:66-69
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+        # ---- synthetic state sets (stand-in for PhysX), one packed buffer each
+        self.envs, self.dev_flat, self.host_flat = [], [], []
+        base = synth.make_env(num_envs, seed=seed * 1000 + self.rank, with_object=self.spec.with_object, with_tactile=tactile,
+                              max_episode_length=self.spec.max_episode_length)
+        self.action_term = ActionTermState(num_envs, synth.NUM_JOINTS, self.device)
+        for k in range(num_state_sets):
+            if k > 0:
+                synth.advance(base, keep_cmd_prob=0.9)
+            denv, flat, host = pack_env(base, self.device, pin=pin_host)
+            denv.action_manager._terms["joint_pos"] = self.action_term  # actions come from the policy, not from the set
+            self.envs.append(denv)
+            self.dev_flat.append(flat)
+            self.host_flat.append(host)
+        self.state_bytes = int(self.dev_flat[0].numel())
+        self.default_joint_pos = self.envs[0].scene["robot"].data.default_joint_pos.clone()
+        # ---- learner
+        D = self.spec.obs_dim
+        torch.manual_seed(seed)  # every rank starts from the same parameters
+        ac = ActorCritic(D, D, synth.NUM_JOINTS, list(hidden), list(hidden), "elu", 1.0)
+        cfg = dict(PPO_CFG)
+        cfg.update(ppo_cfg or {})
+        self.alg = PPO(ac, device=str(self.device), **cfg)
+        self.alg.init_storage(num_envs, num_steps, [D], [D], [synth.NUM_JOINTS])
+        ac.seed = seed * 7919 + self.rank
+        self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int64)  # device-resident env-step index
+        # ---- fused MDP: one instance, re-bound to the state set of each step
+        self.mdp = FusedMdp(self.envs[0], self.spec, seed=seed * 104729 + self.rank)
+        self.mdp_args = []  # per state set: a frozen copy of the argument block (pointers never change afterwards)
+        # ---- tactile
+        if tactile:
+            g = torch.Generator().manual_seed(seed + 17)
+            # contact_threshold 0.05 + U(-0.01, 0.01) per (env, taxel), sampled once (reference observations.py:121-126)
+            self.taxel_thr = (0.05 + (torch.rand(num_envs, 221, generator=g) * 0.02 - 0.01)).to(self.device)
+            self.taxel_ring = torch.zeros(num_envs, 2, 7, device=self.device, dtype=torch.int32)
+            self.taxel_first = torch.ones(num_envs, device=self.device, dtype=torch.uint8)
+            self.taxel_delay = torch.ones(num_envs, device=self.device, dtype=torch.int64)  # randint(1, 2) == 1
+            self.tactile_obs = torch.zeros(num_envs, 442, device=self.device)
+            self.taxel_packed = torch.zeros(num_envs, 7, device=self.device, dtype=torch.int32)
+        self.perm = torch.zeros(num_envs * num_steps // cfg["num_mini_batches"] * cfg["num_mini_batches"], device=self.device, dtype=torch.int64)
+        self.results = torch.zeros(8, device=self.device)  # mean reward, losses ... read back by the caller
+        self._graphs = None
+        self._initial_observation()
+
+    # ------------------------------------------------------------------------------------------------------- pieces
+    def _bind(self, k: int):
+        self.mdp.env = self.envs[k]
+        self.mdp._bound_ptrs = None
+
+    def _initial_observation(self):
+        st = self.alg.storage
+        self._bind(0)
+        self.mdp.compute_observations(policy_in=st._obs_buf[0], critic_in=st._priv_buf[0], policy_out=st._obs_buf[0], critic_out=st._priv_buf[0])
+
+    def upload_state(self, k: int):
+        """H2D refresh of state set k from (pinned) host memory: what an env living on the host would have to do."""
+        self.dev_flat[k].copy_(self.host_flat[k], non_blocking=True)
+
+    def env_step(self, t: int, actions: torch.Tensor):
+        """Stand-in for ``env.step(actions)``: everything IsaacLab's managers would compute around PhysX."""
+        k = t % self.K
+        st = self.alg.storage
+        a = self.action_term
+        ops.process_actions(actions, a.raw_actions, a.prev_raw_actions, a.prev_prev_raw_actions, a.processed_actions,
+                            clip=ACTION_CLIP, raw_scale=ACTION_RAW_SCALE, scale=1.0, offset=self.default_joint_pos)
+        self._bind(k)
+        self.mdp.step(True, True, policy_in=st._obs_buf[t], critic_in=st._priv_buf[t], policy_out=st._obs_buf[t + 1],
+                      critic_out=st._priv_buf[t + 1], step_offset=t, offset_base=self.step_counter)
+        if self.tactile:
+            env = self.envs[k]
+            ops.taxel_synth(env.scene["robot"].data.body_quat_w, env.scene.sensors["tactile_contact_sensor"].data.net_forces_w,
+                            self.taxel_thr, quat_body_offset=synth.NUM_ROBOT_BODIES, p_drop=0.005, p_add=0.005, seed=self.mdp.seed + 1,
+                            offset=t, offset_base=self.step_counter, signal=None, want_signal=False, packed=self.taxel_packed,
+                            delay_ring=self.taxel_ring, delay_first=self.taxel_first, delay_steps=self.taxel_delay,
+                            delayed_signal=self.tactile_obs)
+            # envs that were reset start a fresh delay line (reference replay_buffer.py:61 -> tactile_recorder.py:18-22)
+            torch.logical_or(self.taxel_first, self.mdp.dones, out=self.taxel_first.view(torch.bool))
+        return st._obs_buf[t + 1], self.mdp.reward_buf, self.mdp.dones, {"time_outs": self.mdp.time_outs, "observations": {"critic": st._priv_buf[t + 1]}}
+
+    def rollout(self, upload: bool = False):
+        alg, st = self.alg, self.alg.storage
+        ac = alg.actor_critic
+        ac._offset_base = self.step_counter
+        for t in range(self.T):
+            if upload:
+                self.upload_state(t % self.K)
+            ac._graph_slot = t
+            actions = alg.act(st._obs_buf[t], st._priv_buf[t])
+            obs, rewards, dones, infos = self.env_step(t, actions)
+            alg.process_env_step(rewards, dones, infos)
+        ops.counter_add(self.step_counter, self.T)
+        alg.compute_returns(st._priv_buf[self.T])
+        torch.sum(st.rewards, dim=(0, 1, 2), out=self.results[0])
+
+    def finish_iteration(self):
+        """Observation after the last transition becomes the first observation of the next rollout."""
+        st = self.alg.storage
+        st._obs_buf[0].copy_(st._obs_buf[self.T])
+        st._priv_buf[0].copy_(st._priv_buf[self.T])
+
+    def draw_permutation(self):
+        torch.randperm(self.perm.numel(), device=self.device, out=self.perm)
+
+    # --------------------------------------------------------------------------------------------------- public API
+    def iteration(self, upload: bool = False):
+        """One PPO iteration through the drop-in classes (eager).  ``upload``: refresh every step's state set from host
+        memory inside the step (the end-to-end measurement)."""
+        self.rollout(upload=upload)
+        self.draw_permutation()
+        losses = self.alg.update(indices=self.perm)
+        self.finish_iteration()
+        return losses
+
+    def capture(self):
+        """Records rollout and update into CUDA graphs (single process: update in one graph; multi-process: the NCCL
+        all-reduces stay eager between per-mini-batch graphs)."""
+        alg = self.alg
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):  # warm-up on the side stream (cuBLAS workspaces, autograd buffers)
+                self.rollout()
+                self.draw_permutation()
+                alg.update_body(self.perm)
+                self.finish_iteration()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g_roll = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_roll):
+            self.rollout()
+        if self.world == 1:
+            g_upd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_upd):
+                alg.update_body(self.perm)
+                self.finish_iteration()
+            self._graphs = (g_roll, g_upd)
+        else:
+            self._graphs = (g_roll, None)
+        torch.cuda.synchronize()
+        return self
+
+    def replay(self):
+        g_roll, g_upd = self._graphs
+        g_roll.replay()
+        self.draw_permutation()
+        if g_upd is not None:
+            g_upd.replay()
+        else:
+            self.alg.update_body(self.perm)
+            self.finish_iteration()
+        self.alg.storage.clear()
+
+    def read_results(self):
+        """Device -> host read of the iteration's metrics (mean step reward, mean losses, learning rate)."""
+        losses = self.alg.update_epilogue()
+        return dict(mean_reward=float(self.results[0].item()) / (self.T * self.N), value_loss=losses[0], surrogate_loss=losses[1], entropy=losses[2],
+                    learning_rate=self.alg.learning_rate)

@@ -176,20 +176,27 @@ class PPO:
         ops.adv_normalize(st.advantages, self._adv_stats)
 
     # ---------------------------------------------------------------------------------------------------------- update
-    def update(self, indices=None):  # noqa: C901
+    def update(self, indices=None):
+        """reference ppo.py:179-385.  ``indices``: optional explicit permutation (the reference draws it with randperm)."""
+        self.optimizer.sync_lr_to_device()
+        self.update_body(indices)
+        return self.update_epilogue()
+
+    def update_body(self, indices=None):  # noqa: C901
+        """The device work of ``update()``: no host synchronisation, capturable in a CUDA graph (``indices`` must then be
+        a persistent tensor that is refilled before each replay)."""
         ac, opt, st = self.actor_critic, self.optimizer, self.storage
         if ac.is_recurrent:
             raise NotImplementedError("recurrent policies are outside the LocoTouch hot path")
         if self.normalize_advantage_per_mini_batch:
             raise NotImplementedError("per-mini-batch advantage normalisation is not used by the LocoTouch cfgs")
+        if ac.noise_std_type != "scalar":
+            raise NotImplementedError("noise_std_type='log' is not used by the LocoTouch cfgs")
         ac.flatten_parameters()
-        opt.sync_lr_to_device()
         adaptive = self.desired_kl is not None and self.schedule == "adaptive"
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._loss_accum.zero_()
-        sigma_off, sigma_n = ac._slices["std" if ac.noise_std_type == "scalar" else "log_std"]
-        if ac.noise_std_type != "scalar":
-            raise NotImplementedError("noise_std_type='log' is not used by the LocoTouch cfgs")
+        sigma_off, sigma_n = ac._slices["std"]
         generator = st.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs, indices=indices)
         for (obs_batch, critic_obs_batch, actions_batch, target_values_batch, advantages_batch, returns_batch, old_logp_batch,
              old_mu_batch, old_sigma_batch, _hid, _masks, _rnd) in generator:
@@ -214,10 +221,15 @@ class PPO:
                     dist.all_reduce(kl, op=dist.ReduceOp.SUM)
                     ops.adaptive_lr(kl, 1.0 / world, self.desired_kl, opt.lr_t)
             opt.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world)
-        acc = self._loss_accum.tolist()  # the only device->host read of the update
+        st.clear()
+
+    def update_epilogue(self):
+        """The only device->host read of an update: the three logged means (reference ppo.py:361-363 reads them with
+        ``.item()`` after every mini-batch) and the learning rate."""
+        acc = self._loss_accum.tolist()
         n = max(acc[3], 1.0)
+        opt = self.optimizer
         self.learning_rate = float(opt.lr_t.item())
         opt.param_groups[0]["lr"] = self.learning_rate
         opt._host_lr = self.learning_rate
-        st.clear()
         return acc[0] / n, acc[1] / n, acc[2] / n, None, None

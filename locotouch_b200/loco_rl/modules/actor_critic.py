@@ -75,6 +75,8 @@ class ActorCritic(nn.Module):
         self.rng = "philox"  # "torch": eps = torch.randn (same generator stream as torch.normal); "philox": in-kernel
         self.seed = 0
         self._draws = 0
+        self._offset_base = None  # optional device int64 counter added to the Philox offset (CUDA-graph replays)
+        self._graph_slot = 0
 
     # ------------------------------------------------------------------------------------------ flat parameter storage
     def flatten_parameters(self):
@@ -155,7 +157,8 @@ class ActorCritic(nn.Module):
             sigma_rows = torch.empty_like(mean)
         mean = mean.contiguous()
         actions, logp = ops.act_sample(mean, std.detach().contiguous(), eps, out.get("actions"), out.get("logp"), out.get("mu"), sigma_rows,
-                                       seed=self.seed, offset=self._draws)
+                                       seed=self.seed, offset=self._graph_slot if self._offset_base is not None else self._draws,
+                                       offset_base=self._offset_base)
         self._draws += 1
         self.distribution = _GaussianView(out.get("mu", mean) if out.get("mu") is not None else mean, sigma_rows)
         self._logp, self._sampled = logp, actions

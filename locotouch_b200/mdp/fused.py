@@ -241,18 +241,29 @@ class FusedMdp:
 
     # --------------------------------------------------------------------------------------------------------- launch
     def step(self, rewards: bool = True, observations: bool = True, *, auto_reset: bool = True, u_obs=None, u_obj_euler=None,
-             policy_out=None, critic_out=None, policy_in=None, critic_in=None, any_nonzero_cmd: bool | None = None):
+             policy_out=None, critic_out=None, policy_in=None, critic_in=None, any_nonzero_cmd: bool | None = None,
+             step_offset: int | None = None, offset_base: torch.Tensor | None = None):
         """One fused pass.  ``rewards``: terminations + rewards (+ reset of done envs when ``auto_reset``);
         ``observations``: policy / critic observation rows (history source ``*_in`` defaults to this object's buffers,
-        destination ``*_out`` likewise; they may alias, or point into RolloutStorage slots for a zero-copy rollout)."""
+        destination ``*_out`` likewise; they may alias, or point into RolloutStorage slots for a zero-copy rollout).
+        ``offset_base`` (device int64 scalar) + ``step_offset``: the env-step index lives on the device, so that the call can
+        be captured in a CUDA graph and replayed (fresh noise, correct any(non_zero_cmd) hand-over) -- the caller then
+        guarantees that the previous step's observation pass ran with the same counter."""
         self.bind()
         a = self._args
         a.phases = (_C.LT_PHASE_REWARDS if rewards else 0) | (_C.LT_PHASE_OBS if observations else 0)
         a.auto_reset = int(auto_reset)
         # an observation-only pass belongs to the step whose reward pass already ran (IsaacLab order: rewards -> reset -> obs)
         step = self.step_index if rewards else self.step_index - 1
+        if offset_base is not None:
+            step = int(step_offset or 0)
+            a.offset_base = _C.ptr(offset_base, torch.int64, "offset_base")
+        else:
+            a.offset_base = None
         a.seed, a.offset = self.seed, step & 0xFFFFFFFFFFFFFFFF
-        if any_nonzero_cmd is not None:
+        if offset_base is not None and any_nonzero_cmd is None:
+            a.any_nonzero_cmd_override = -1
+        elif any_nonzero_cmd is not None:
             a.any_nonzero_cmd_override = int(bool(any_nonzero_cmd))
         elif not self.exact_any_nonzero_cmd:
             a.any_nonzero_cmd_override = 1
@@ -273,10 +284,11 @@ class FusedMdp:
             a.u_obj_euler = _C.ptr(u_obj_euler, torch.float32, "u_obj_euler")
         check(lib().lt_mdp_step(C.byref(a), current_stream()), "lt_mdp_step")
         count_launches(n_launch)
-        if observations:
-            self._published_step = step + 1
-        if rewards:
-            self.step_index += 1
+        if offset_base is None:
+            if observations:
+                self._published_step = step + 1
+            if rewards:
+                self.step_index += 1
         return self
 
     def compute_rewards(self, **kw):

@@ -62,6 +62,16 @@ def adv_normalize(advantages, stats):
     count_launches(1)
 
 
+def process_actions(actions, raw, prev_raw, prev_prev_raw=None, processed=None, prev_processed=None, prev_prev_processed=None, *,
+                    clip: float = 0.0, raw_scale: float = 1.0, scale: float = 1.0, offset=None):
+    """JointPositionActionPrevPrev.process_actions (reference mdp/actions.py:30-44) on [N,J] state tensors, in place."""
+    check(lib().lt_process_actions(ptr(actions, torch.float32, "actions"), clip, raw_scale, scale, ptr(offset, torch.float32, "offset"),
+                                   ptr(raw, torch.float32, "raw"), ptr(prev_raw, torch.float32), ptr(prev_prev_raw, torch.float32),
+                                   ptr(processed, torch.float32), ptr(prev_processed, torch.float32), ptr(prev_prev_processed, torch.float32),
+                                   actions.numel(), current_stream()), "lt_process_actions")
+    count_launches(1)
+
+
 def counter_add(counter, inc: int = 1):
     """``counter += inc`` on the current stream (device-resident step counter for CUDA-graph replays)."""
     check(lib().lt_counter_add(ptr(counter, torch.int64, "counter"), inc, current_stream()), "lt_counter_add")
