@@ -233,8 +233,9 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-lite", action="store_true", help="for ncu launch lists: skip e2e / roofline / cpu legs")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, 3) if (args.impl == "ours" and not args.profile_lite) else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -284,6 +285,10 @@ def main():
     value = world * N * T_STEPS / (ms_per_step * 1e-3)
     metrics = engine.read_results()
 
+    if args.profile_lite:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms_per_step, "profile_lite": True}), flush=True)
+        return
     # ---- end to end through the public drop-in classes, host buffers, copies inside the timed region
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     engine.iteration(upload=True)

@@ -21,6 +21,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from ... import dist as D
 from ... import ops
 from ..modules import ActorCritic
 from ..storage import RolloutStorage
@@ -172,7 +173,7 @@ class PPO:
             return
         # env-sharded ranks: sum / sum of squares / count are all-reduced between the scan and the normalisation
         ops.gae_scan(st.rewards, st.values, st.dones, last_values.contiguous().view(-1), self.gamma, self.lam, st.returns, st.advantages, self._adv_stats)
-        dist.all_reduce(self._adv_stats, op=dist.ReduceOp.SUM)
+        D.reduce_adv_stats_(self._adv_stats)
         ops.adv_normalize(st.advantages, self._adv_stats)
 
     # ---------------------------------------------------------------------------------------------------------- update
@@ -214,13 +215,14 @@ class PPO:
                          loss_accum=self._loss_accum, buffers=bufs)
             torch.autograd.backward([mu, value], [bufs.grad_mu, bufs.grad_value.view_as(value)])
             opt.grads[sigma_off:sigma_off + sigma_n].add_(bufs.grad_sigma)
+            grad_scale = 1.0
             if world > 1:
-                dist.all_reduce(opt.grads, op=dist.ReduceOp.SUM)
+                grad_scale = D.average_gradients_(opt.grads)  # one flat NCCL all-reduce; the 1/W is applied inside K7
                 if adaptive:  # every rank must take the same learning-rate decision
                     kl = bufs.out[4:5]
-                    dist.all_reduce(kl, op=dist.ReduceOp.SUM)
+                    D.allreduce_sum_(kl)
                     ops.adaptive_lr(kl, 1.0 / world, self.desired_kl, opt.lr_t)
-            opt.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world)
+            opt.step(max_grad_norm=self.max_grad_norm, grad_scale=grad_scale)
         st.clear()
 
     def update_epilogue(self):

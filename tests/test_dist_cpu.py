@@ -1,0 +1,87 @@
+"""world_size-2 gloo tests (CPU) of the env-sharding logic of SURVEY.md 8e: averaged shard gradients == gradient on the
+concatenated mini-batch, all-reduced advantage statistics == statistics of the concatenated rollout, and identical
+learning-rate decisions on every rank."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ppo as OP
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _batch(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    A = 12
+    old_mu = torch.randn(B, A, generator=g)
+    old_sigma = (0.5 + torch.rand(A, generator=g)).expand(B, A).contiguous()
+    actions = old_mu + old_sigma * torch.randn(B, A, generator=g)
+    old_logp = (-((actions - old_mu) ** 2) / (2 * old_sigma**2) - old_sigma.log() - 0.9189385332046727).sum(-1, keepdim=True)
+    return dict(mu=old_mu + 0.2 * torch.randn(B, A, generator=g), sigma=old_sigma[0] * 1.05, value=torch.randn(B, 1, generator=g), actions=actions,
+                old_logp=old_logp, old_mu=old_mu, old_sigma=old_sigma, adv=torch.randn(B, 1, generator=g), returns=torch.randn(B, 1, generator=g),
+                old_values=torch.randn(B, 1, generator=g))
+
+
+def _grads(b):
+    mu, sigma, value = b["mu"].clone().requires_grad_(True), b["sigma"].clone().requires_grad_(True), b["value"].clone().requires_grad_(True)
+    res = OP.ppo_loss(mu, sigma, value, b["actions"], b["old_logp"], b["old_mu"], b["old_sigma"], b["adv"], b["returns"], b["old_values"])
+    res["loss"].backward()
+    return res, sigma.grad, mu.grad, value.grad
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from locotouch_b200 import dist as D
+
+        assert D.world_info() == (rank, world)
+        start, count = D.shard_envs(4096 * world)
+        assert (start, count) == (rank * 4096, 4096)
+        with pytest.raises(ValueError):
+            D.shard_envs(4097)
+        # (1) gradient of the shared parameter (sigma): mean over ranks of shard gradients == gradient on the union batch
+        B = 512
+        full = _batch(B * world, seed=1)
+        shard = {k: (v[rank * B:(rank + 1) * B] if v.dim() == 2 and v.shape[0] == B * world else v) for k, v in full.items()}
+        res, g_sigma, _, _ = _grads(shard)
+        flat = g_sigma.clone()
+        scale = D.average_gradients_(flat)
+        _, g_full, _, _ = _grads(full)
+        torch.testing.assert_close(flat * scale, g_full, rtol=1e-5, atol=1e-7)
+        D.assert_same_on_all_ranks(flat, "all-reduced gradient")
+        # (2) KL statistic -> identical learning-rate decision
+        kl = res["kl_mean"].detach().clone().view(1)
+        D.global_kl_mean_(kl)
+        res_full, *_ = _grads(full)
+        torch.testing.assert_close(kl[0], res_full["kl_mean"], rtol=1e-5, atol=1e-8)
+        lr = torch.tensor([OP.adaptive_lr(1e-3, float(kl[0]), 0.01)])
+        D.assert_same_on_all_ranks(lr, "learning rate")
+        # (3) advantage statistics
+        g = torch.Generator().manual_seed(7)
+        adv_full = torch.randn(24, 64 * world, generator=g) * 3 + 0.5
+        adv = adv_full[:, rank * 64:(rank + 1) * 64].double()
+        stats = torch.tensor([adv.sum(), (adv * adv).sum(), adv.numel(), 0.0], dtype=torch.float64)
+        D.reduce_adv_stats_(stats)
+        mean, std = D.mean_and_unbiased_std(stats)
+        assert abs(mean - float(adv_full.double().mean())) < 1e-9
+        assert abs(std - float(adv_full.double().std())) < 1e-9
+        with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_env_sharding_world_size_2(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
