@@ -149,7 +149,8 @@ class HotPathEngine:
             torch.logical_or(self.taxel_first, self.mdp.dones, out=self.taxel_first.view(torch.bool))
         return st._obs_buf[t + 1], self.mdp.reward_buf, self.mdp.dones, {"time_outs": self.mdp.time_outs, "observations": {"critic": st._priv_buf[t + 1]}}
 
-    def rollout(self, upload: bool = False):
+    def rollout_steps(self, upload: bool = False):
+        """HOT LOOP A: the T env steps (no collective inside: capturable for any world size)."""
         alg, st = self.alg, self.alg.storage
         ac = alg.actor_critic
         ac._offset_base = self.step_counter
@@ -161,8 +162,16 @@ class HotPathEngine:
             obs, rewards, dones, infos = self.env_step(t, actions)
             alg.process_env_step(rewards, dones, infos)
         ops.counter_add(self.step_counter, self.T)
-        alg.compute_returns(st._priv_buf[self.T])
+
+    def rollout_finish(self):
+        """GAE (+ the 3-double advantage-statistics all-reduce when several ranks train together)."""
+        st = self.alg.storage
+        self.alg.compute_returns(st._priv_buf[self.T])
         torch.sum(st.rewards, dim=(0, 1, 2), out=self.results[0])
+
+    def rollout(self, upload: bool = False):
+        self.rollout_steps(upload)
+        self.rollout_finish()
 
     def finish_iteration(self):
         """Observation after the last transition becomes the first observation of the next rollout."""
@@ -183,10 +192,12 @@ class HotPathEngine:
         self.finish_iteration()
         return losses
 
-    def capture(self):
-        """Records rollout and update into CUDA graphs (single process: update in one graph; multi-process: the NCCL
-        all-reduces stay eager between per-mini-batch graphs)."""
+    def capture(self, split: bool | None = None):
+        """Records the iteration into CUDA graphs.  One process: rollout + GAE in one graph, the whole update in another.
+        Several processes (``split``): NCCL collectives stay OUTSIDE the graphs -- graphs are the T env steps, the gather,
+        and one forward/loss/backward graph per mini-batch slice; GAE, the all-reduces and clip+Adam run eagerly between."""
         alg = self.alg
+        split = (self.world > 1) if split is None else split
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -199,28 +210,47 @@ class HotPathEngine:
         torch.cuda.synchronize()
         g_roll = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_roll):
-            self.rollout()
-        if self.world == 1:
+            self.rollout_steps()
+            if not split:
+                self.rollout_finish()
+        if not split:
             g_upd = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_upd):
                 alg.update_body(self.perm)
                 self.finish_iteration()
-            self._graphs = (g_roll, g_upd)
+            self._graphs = dict(split=False, roll=g_roll, update=g_upd)
         else:
-            self._graphs = (g_roll, None)
+            g_begin = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_begin):
+                alg.update_begin(self.perm)
+            g_mb = []
+            for i in range(alg.num_mini_batches):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    alg.minibatch_grads(i)
+                g_mb.append(g)
+            self._graphs = dict(split=True, roll=g_roll, begin=g_begin, mb=g_mb)
+        alg.storage.clear()
         torch.cuda.synchronize()
         return self
 
     def replay(self):
-        g_roll, g_upd = self._graphs
-        g_roll.replay()
-        self.draw_permutation()
-        if g_upd is not None:
-            g_upd.replay()
+        g = self._graphs
+        alg = self.alg
+        g["roll"].replay()
+        if not g["split"]:
+            self.draw_permutation()
+            g["update"].replay()
         else:
-            self.alg.update_body(self.perm)
+            self.rollout_finish()
+            self.draw_permutation()
+            g["begin"].replay()
+            for _epoch in range(alg.num_learning_epochs):
+                for i in range(alg.num_mini_batches):
+                    g["mb"][i].replay()
+                    alg.reduce_and_step()
             self.finish_iteration()
-        self.alg.storage.clear()
+        alg.storage.clear()
 
     def read_results(self):
         """Device -> host read of the iteration's metrics (mean step reward, mean losses, learning rate)."""

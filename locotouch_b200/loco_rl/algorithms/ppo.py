@@ -183,10 +183,21 @@ class PPO:
         self.update_body(indices)
         return self.update_epilogue()
 
-    def update_body(self, indices=None):  # noqa: C901
-        """The device work of ``update()``: no host synchronisation, capturable in a CUDA graph (``indices`` must then be
-        a persistent tensor that is refilled before each replay)."""
-        ac, opt, st = self.actor_critic, self.optimizer, self.storage
+    def update_body(self, indices=None):
+        """The device work of ``update()``: no host synchronisation, capturable in a CUDA graph when no process group is
+        active (``indices`` must then be a persistent tensor that is refilled before each replay)."""
+        self.update_begin(indices)
+        for _epoch in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                self.minibatch_grads(i)
+                self.reduce_and_step()
+        self.storage.clear()
+
+    # The three stages below are public so that a caller can capture them separately (CUDA graphs must not contain the
+    # NCCL collectives of ``reduce_and_step`` when several processes train together).
+    def update_begin(self, indices=None):
+        """Draws / takes the permutation (rollout_storage.py:189) and gathers the permuted rollout once (K5)."""
+        ac, st = self.actor_critic, self.storage
         if ac.is_recurrent:
             raise NotImplementedError("recurrent policies are outside the LocoTouch hot path")
         if self.normalize_advantage_per_mini_batch:
@@ -194,36 +205,52 @@ class PPO:
         if ac.noise_std_type != "scalar":
             raise NotImplementedError("noise_std_type='log' is not used by the LocoTouch cfgs")
         ac.flatten_parameters()
-        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._loss_accum.zero_()
-        sigma_off, sigma_n = ac._slices["std"]
-        generator = st.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs, indices=indices)
-        for (obs_batch, critic_obs_batch, actions_batch, target_values_batch, advantages_batch, returns_batch, old_logp_batch,
-             old_mu_batch, old_sigma_batch, _hid, _masks, _rnd) in generator:
-            B, A = actions_batch.shape
-            if self._loss_bufs is None or self._loss_bufs.B != B:
-                self._loss_bufs = ops.PpoLossBuffers(B, A, self.device)
-            bufs = self._loss_bufs
-            mu = ac.actor(obs_batch)
-            value = ac.critic(critic_obs_batch)
-            opt.zero_grad()
-            ops.ppo_loss(mu.detach(), ac.std.detach(), value.detach().view(-1), actions_batch, old_logp_batch.view(-1), old_mu_batch, old_sigma_batch,
-                         advantages_batch.view(-1), returns_batch.view(-1), target_values_batch.view(-1), clip_param=self.clip_param,
-                         value_loss_coef=self.value_loss_coef, entropy_coef=self.entropy_coef, use_clipped_value_loss=self.use_clipped_value_loss,
-                         desired_kl=self.desired_kl if (adaptive and world == 1) else None, lr=opt.lr_t if (adaptive and world == 1) else None,
-                         loss_accum=self._loss_accum, buffers=bufs)
-            torch.autograd.backward([mu, value], [bufs.grad_mu, bufs.grad_value.view_as(value)])
-            opt.grads[sigma_off:sigma_off + sigma_n].add_(bufs.grad_sigma)
-            grad_scale = 1.0
-            if world > 1:
-                grad_scale = D.average_gradients_(opt.grads)  # one flat NCCL all-reduce; the 1/W is applied inside K7
-                if adaptive:  # every rank must take the same learning-rate decision
-                    kl = bufs.out[4:5]
-                    D.allreduce_sum_(kl)
-                    ops.adaptive_lr(kl, 1.0 / world, self.desired_kl, opt.lr_t)
-            opt.step(max_grad_norm=self.max_grad_norm, grad_scale=grad_scale)
-        st.clear()
+        batch_size = st.num_envs * st.num_transitions_per_env
+        self._mb_size = batch_size // self.num_mini_batches
+        if indices is None:
+            indices = torch.randperm(self.num_mini_batches * self._mb_size, requires_grad=False, device=self.device)
+        bufs, has_priv = st.gather_permuted(indices)
+        it = iter(bufs)
+        obs = next(it)
+        cobs = next(it) if has_priv else obs
+        self._mb = (obs, cobs) + tuple(next(it) for _ in range(7))
+
+    def minibatch_grads(self, i: int):
+        """Forward of both MLPs on mini-batch slice ``i``, fused loss (K6), backward into the flat gradient buffer."""
+        ac, opt = self.actor_critic, self.optimizer
+        sl = slice(i * self._mb_size, (i + 1) * self._mb_size)
+        obs, cobs, actions, values, returns, logp, adv, mu_old, sigma_old = (t[sl] for t in self._mb)
+        B, A = actions.shape
+        if self._loss_bufs is None or self._loss_bufs.B != B:
+            self._loss_bufs = ops.PpoLossBuffers(B, A, self.device)
+        bufs = self._loss_bufs
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        _, world = D.world_info()
+        local_lr = adaptive and world == 1  # one process: the learning-rate decision is taken inside the loss kernel
+        mu = ac.actor(obs)
+        value = ac.critic(cobs)
+        opt.zero_grad()
+        ops.ppo_loss(mu.detach(), ac.std.detach(), value.detach().view(-1), actions, logp.view(-1), mu_old, sigma_old, adv.view(-1),
+                     returns.view(-1), values.view(-1), clip_param=self.clip_param, value_loss_coef=self.value_loss_coef,
+                     entropy_coef=self.entropy_coef, use_clipped_value_loss=self.use_clipped_value_loss,
+                     desired_kl=self.desired_kl if local_lr else None, lr=opt.lr_t if local_lr else None, loss_accum=self._loss_accum, buffers=bufs)
+        torch.autograd.backward([mu, value], [bufs.grad_mu, bufs.grad_value.view_as(value)])
+        off, n = ac._slices["std"]
+        opt.grads[off:off + n].add_(bufs.grad_sigma)
+
+    def reduce_and_step(self):
+        """[NCCL: flat gradient all-reduce + KL all-reduce + learning-rate decision] then fused clip + Adam (K7)."""
+        opt = self.optimizer
+        _, world = D.world_info()
+        grad_scale = 1.0
+        if world > 1:
+            grad_scale = D.average_gradients_(opt.grads)  # one flat all-reduce; the 1/W is applied inside K7
+            if self.desired_kl is not None and self.schedule == "adaptive":  # every rank must take the same decision (SURVEY.md 8e)
+                kl = self._loss_bufs.out[4:5]
+                D.allreduce_sum_(kl)
+                ops.adaptive_lr(kl, 1.0 / world, self.desired_kl, opt.lr_t)
+        opt.step(max_grad_norm=self.max_grad_norm, grad_scale=grad_scale)
 
     def update_epilogue(self):
         """The only device->host read of an update: the three logged means (reference ppo.py:361-363 reads them with
