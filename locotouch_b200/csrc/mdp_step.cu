@@ -24,7 +24,10 @@
 
 namespace {
 
-constexpr int kEnvs = 8;
+#ifndef LT_MDP_ENVS
+#define LT_MDP_ENVS 8
+#endif
+constexpr int kEnvs = LT_MDP_ENVS;  // envs per block (multiple of 8 so that every staged span is 16-byte aligned; <= 16)
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxObsDim = 512;
@@ -37,7 +40,8 @@ constexpr int kGaitFloats = 24;  // per env: lsa[4] lsc[4] vla[4] last_cmd[3] st
 // shared-memory layout (float offsets; per-env row stride = row length), filled in on the host
 struct Layout {
   int cmd, pos, linb, angb, grav, q, qd, qdd, tau, q0, qd0, lim, act, pact, force, air, con, lair, fpos, fvel;
-  int quat, linw, angw, opos, oquat, olin, oang, ograv, octime, fmax, gait, gait_out, esum, raw, newobs, uscr, hist, map, total;
+  int quat, linw, angw, opos, oquat, olin, oang, ograv, oc_last, oc_cur, oc_air, fmax, g_lsa, g_lsc, g_vla, g_cmd, g_steps, g_sz, g_vpc, eplen, gait_out,
+      esum, raw, newobs, uscr, hist, map, total;
   int D;    // observation dim per group
   int dps;  // new values per step per group
   int hist_stride;  // floats per group in the history staging area (kEnvs * D rounded up to 4)
@@ -49,6 +53,7 @@ struct StageTable {
   const float* src[kMaxStage];
   int row[kMaxStage];
   int off[kMaxStage];
+  int vec[kMaxStage];  // 1: tensor base is 16-byte aligned
 };
 
 struct Vec3 { float x, y, z; };
@@ -229,9 +234,10 @@ __global__ void any_nonzero_cmd_kernel(const float* __restrict__ cmd, int N, int
   if (threadIdx.x == 0) flag_ws[step & 1] = any ? step : -1;
 }
 
-__global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A, const Layout L, const StageTable ST) {
+__global__ void __launch_bounds__(kThreads, kEnvs <= 8 ? 4 : 2) mdp_step_kernel(const LtMdpArgs A, const Layout L, const StageTable ST) {
   extern __shared__ __align__(16) float sm[];
   __shared__ unsigned char s_done[kEnvs], s_fill[kEnvs];
+  __shared__ int s_step, s_any_nz;
   __shared__ signed char s_slot[LT_RK_COUNT];  // reward kind -> index in the term table (-1: absent or zero weight)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int e0 = blockIdx.x * kEnvs;
@@ -239,11 +245,63 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
   const bool do_rew = A.phases & LT_PHASE_REWARDS, do_obs = A.phases & LT_PHASE_OBS;
   const bool has_obj = A.obj_root_pos_w != nullptr;
   const int J = A.J, S = A.num_sensor_bodies, H = A.force_history;
-  const int step = (int)(A.offset + (A.offset_base ? (uint64_t)*A.offset_base : 0ull));
-  const uint64_t rng_offset = (uint64_t)(int64_t)step;
   const int D = L.D, dps = L.dps, T = A.num_reward_terms;
 
   // ------------------------------------------------------------------------------------------------ stage 0: loads
+  // (b) plain [N, row] tensors, one descriptor per warp and round; full blocks move 16 bytes per lane (8 envs x row floats is
+  //     a multiple of 16 bytes and the span starts 16-byte aligned whenever the tensor itself does)
+#pragma unroll 1
+  for (int t = warp; t < ST.n; t += kWarps) {
+    const int row = ST.row[t];
+    const float* src = ST.src[t] + (size_t)e0 * row;
+    float* dst = sm + ST.off[t];
+    const int count = nvalid * row;
+    if (ST.vec[t] && nvalid == kEnvs) {
+      for (int i = lane; i < (count >> 2); i += 32) __pipeline_memcpy_async(dst + 4 * i, src + 4 * i, 16);
+    } else {
+      for (int i = lane; i < count; i += 32) __pipeline_memcpy_async(dst + i, src + i, 4);
+    }
+  }
+  // (c) gathers with arbitrary body ids / non-float types: ONE pass, every thread issues at most a few independent
+  //     4-byte cp.async (no load sits inside a loop-carried chain, so the block pays a single DRAM round trip)
+  if (do_rew) {
+    if (tid < nvalid * 4) {  // feet rows of the contact timers
+      const int e = tid >> 2, k = tid & 3;
+      const size_t r = (size_t)(e0 + e) * S + A.gait.feet_ids[k];
+      __pipeline_memcpy_async(sm + L.air + tid, A.current_air_time + r, 4);
+      __pipeline_memcpy_async(sm + L.con + tid, A.current_contact_time + r, 4);
+      __pipeline_memcpy_async(sm + L.lair + tid, A.last_air_time + r, 4);
+    }
+    if (tid >= 32 && tid < 32 + nvalid * 12) {  // feet rows of body_pos_w / body_lin_vel_w
+      const int i = tid - 32;
+      const int e = i / 12, k = (i % 12) / 3, c = i % 3;
+      const size_t r = ((size_t)(e0 + e) * A.num_bodies + A.feet_body_ids[k]) * 3 + c;
+      __pipeline_memcpy_async(sm + L.fpos + i, A.body_pos_w + r, 4);
+      __pipeline_memcpy_async(sm + L.fvel + i, A.body_lin_vel_w + r, 4);
+    }
+    if (A.episode_sums && tid >= 128 && tid < 128 + T) {  // [terms][N]: kEnvs contiguous floats per term
+      const int t = tid - 128;
+      const float* src = A.episode_sums + (size_t)t * A.N + e0;
+      for (int e = 0; e < nvalid; ++e) __pipeline_memcpy_async(sm + L.esum + t * kEnvs + e, src + e, 4);
+    }
+    if (tid >= 192 && tid < 192 + nvalid * 4) {  // bool gait state -> float
+      const int i = tid - 192;
+      sm[L.g_sz + i] = (float)A.gait_state.swinging_in_zero_cmd[(size_t)e0 * 4 + i];
+      sm[L.g_vpc + i] = (float)A.gait_state.valid_previous_contact[(size_t)e0 * 4 + i];
+    }
+    if (tid >= 224 && tid < 224 + nvalid) {
+      reinterpret_cast<long long*>(sm + L.eplen)[tid - 224] = A.episode_length_buf[e0 + tid - 224];
+    }
+  }
+  if (tid == 255) {  // env-step index and the cross-env any(non_zero_cmd) flag (one dependent pair of loads, one thread)
+    const int st = (int)(A.offset + (A.offset_base ? (uint64_t)*A.offset_base : 0ull));
+    s_step = st;
+    int any_nz = 1;
+    if (A.any_nonzero_cmd_override >= 0) any_nz = A.any_nonzero_cmd_override != 0;
+    else if (A.any_flag_ws) any_nz = A.any_flag_ws[st & 1] == st;
+    s_any_nz = any_nz;
+  }
+  __pipeline_commit();
   // (a) observation history blocks: the block's kEnvs rows of each group are one 16-byte aligned contiguous span
   if (do_obs) {
     const int total = nvalid * D;
@@ -262,63 +320,6 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
       }
     }
     __pipeline_commit();
-  }
-  // (b) plain [N, row] tensors, one descriptor per warp and round
-#pragma unroll 1
-  for (int t = warp; t < ST.n; t += kWarps) {
-    const int row = ST.row[t];
-    const float* src = ST.src[t] + (size_t)e0 * row;
-    float* dst = sm + ST.off[t];
-    const int count = nvalid * row;
-    for (int i = lane; i < count; i += 32) dst[i] = __ldcs(src + i);
-  }
-  // (c) gathers with arbitrary body ids / non-float types
-  if (do_rew) {
-    if (warp == 0) {
-      for (int i = lane; i < nvalid * 4; i += 32) {
-        const int e = i >> 2, k = i & 3;
-        const size_t r = (size_t)(e0 + e) * S + A.gait.feet_ids[k];
-        sm[L.air + i] = __ldcs(A.current_air_time + r);
-        sm[L.con + i] = __ldcs(A.current_contact_time + r);
-        sm[L.lair + i] = __ldcs(A.last_air_time + r);
-      }
-    } else if (warp == 1) {
-      for (int i = lane; i < nvalid * 12; i += 32) {
-        const int e = i / 12, k = (i % 12) / 3, c = i % 3;
-        const size_t r = ((size_t)(e0 + e) * A.num_bodies + A.feet_body_ids[k]) * 3 + c;
-        sm[L.fpos + i] = __ldcs(A.body_pos_w + r);
-        sm[L.fvel + i] = __ldcs(A.body_lin_vel_w + r);
-      }
-    } else if (warp == 2) {
-      const LtGaitState& G = A.gait_state;
-      float* gs = sm + L.gait;
-      for (int i = lane; i < nvalid * kGaitFloats; i += 32) {
-        const int e = i / kGaitFloats, k = i % kGaitFloats;
-        const int n = e0 + e;
-        float v;
-        if (k < 4) v = G.last_step_current_air_time[n * 4 + k];
-        else if (k < 8) v = G.last_step_current_contact_time[n * 4 + k - 4];
-        else if (k < 12) v = G.valid_last_air_time[n * 4 + k - 8];
-        else if (k < 15) v = G.last_velocity_cmd[n * 3 + k - 12];
-        else if (k == 15) v = G.step_from_changing_cmd[n];
-        else if (k < 20) v = (float)G.swinging_in_zero_cmd[n * 4 + k - 16];
-        else v = (float)G.valid_previous_contact[n * 4 + k - 20];
-        gs[i] = v;
-      }
-    } else if (warp == 3) {
-      if (A.episode_sums)
-        for (int i = lane; i < T * kEnvs; i += 32) {
-          const int t = i / kEnvs, e = i % kEnvs;
-          if (e < nvalid) sm[L.esum + i] = A.episode_sums[(size_t)t * A.N + e0 + e];
-        }
-    }
-  }
-  if (warp == 4 && has_obj) {
-    for (int i = lane; i < nvalid * 3; i += 32) {
-      const int e = i / 3, k = i % 3;
-      const float* src = k == 0 ? A.obj_last_contact_time : (k == 1 ? A.obj_current_contact_time : A.obj_current_air_time);
-      sm[L.octime + i] = src ? __ldcs(src + e0 + e) : 0.f;
-    }
   }
   // Observation layout tables (built once per block):
   //   s_map[k]  for column k of the flattened [term][history][dim] row: low 16 bits = index j of the per-step value that
@@ -359,11 +360,14 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
       if (A.reward_terms[i].kind == kind && A.reward_terms[i].weight != 0.f) slot = i;
     s_slot[kind] = (signed char)slot;
   }
+  __pipeline_wait_prior(do_obs ? 1 : 0);  // the state tensors have landed; the history blocks may still be in flight
   if (tid < kEnvs) {
     s_fill[tid] = (do_obs && A.obs_fill && tid < nvalid) ? A.obs_fill[e0 + tid] : 0;
     s_done[tid] = 0;
   }
   __syncthreads();
+  const int step = s_step;
+  const uint64_t rng_offset = (uint64_t)(int64_t)step;
 
   // ------------------------------------------------------------------------------------------------ stage 1: roles
   float* s_raw = sm + L.raw;  // [T][kEnvs]
@@ -390,19 +394,17 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
         const float wz = sm[L.angb + e * 3 + 2];
         const bool nz = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) > 0.f;
         GaitRegs g;
-        const float* gs = sm + L.gait + e * kGaitFloats;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          g.lsa[k] = gs[k]; g.lsc[k] = gs[4 + k]; g.vla[k] = gs[8 + k];
-          g.sz[k] = gs[16 + k] != 0.f; g.vpc[k] = gs[20 + k] != 0.f;
+          g.lsa[k] = sm[L.g_lsa + e * 4 + k]; g.lsc[k] = sm[L.g_lsc + e * 4 + k]; g.vla[k] = sm[L.g_vla + e * 4 + k];
+          g.sz[k] = sm[L.g_sz + e * 4 + k] != 0.f; g.vpc[k] = sm[L.g_vpc + e * 4 + k] != 0.f;
         }
-        g.last_cmd[0] = gs[12]; g.last_cmd[1] = gs[13]; g.last_cmd[2] = gs[14]; g.steps = gs[15];
+        g.last_cmd[0] = sm[L.g_cmd + e * 3]; g.last_cmd[1] = sm[L.g_cmd + e * 3 + 1]; g.last_cmd[2] = sm[L.g_cmd + e * 3 + 2];
+        g.steps = sm[L.g_steps + e];
         float a[4], c[4], la[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { a[k] = sm[L.air + e * 4 + k]; c[k] = sm[L.con + e * 4 + k]; la[k] = sm[L.lair + e * 4 + k]; }
-        bool any_nz = true;
-        if (A.any_nonzero_cmd_override >= 0) any_nz = A.any_nonzero_cmd_override != 0;
-        else if (A.any_flag_ws) any_nz = A.any_flag_ws[step & 1] == step;
+        const bool any_nz = s_any_nz != 0;
         gait_update(g, a, c, la, cmd, nz, any_nz, th);
         float score = 0.f;  // rewards.py:202-216 / 372-392
         if (gp.encourage_symmetricity) {
@@ -433,8 +435,13 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
         go[12] = g.last_cmd[0]; go[13] = g.last_cmd[1]; go[14] = g.last_cmd[2]; go[15] = g.steps;
       } else {
         // no gait term: carry the state through unchanged
+        float* go = sm + L.gait_out + e * kGaitFloats;
 #pragma unroll 1
-        for (int k = 0; k < kGaitFloats; ++k) sm[L.gait_out + e * kGaitFloats + k] = sm[L.gait + e * kGaitFloats + k];
+        for (int k = 0; k < 4; ++k) {
+          go[k] = sm[L.g_lsa + e * 4 + k]; go[4 + k] = sm[L.g_lsc + e * 4 + k]; go[8 + k] = sm[L.g_vla + e * 4 + k];
+          go[16 + k] = sm[L.g_sz + e * 4 + k]; go[20 + k] = sm[L.g_vpc + e * 4 + k];
+        }
+        go[12] = sm[L.g_cmd + e * 3]; go[13] = sm[L.g_cmd + e * 3 + 1]; go[14] = sm[L.g_cmd + e * 3 + 2]; go[15] = sm[L.g_steps + e];
       }
     }
   } else if (warp == 1) {
@@ -460,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
           const LtTerminationTerm& tt = A.termination_terms[t];
           bool m = false;
           switch (tt.kind) {
-            case LT_TK_TIME_OUT: m = A.episode_length_buf[n] >= A.max_episode_length; break;
+            case LT_TK_TIME_OUT: m = reinterpret_cast<const long long*>(sm + L.eplen)[e] >= A.max_episode_length; break;
             case LT_TK_BAD_ORIENTATION: m = fabsf(acosf(-sm[L.grav + e * 3 + 2])) > tt.p[0]; break;
             case LT_TK_ROOT_HEIGHT: m = sm[L.pos + e * 3 + 2] < tt.p[0]; break;
             case LT_TK_ILLEGAL_CONTACT:
@@ -582,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
         put(LT_RK_OBJ_XY_POS, v);
       }
       put(LT_RK_OBJ_XY_VEL, rel_vel.x * rel_vel.x + rel_vel.y * rel_vel.y);
-      put(LT_RK_OBJ_LOSE_CONTACT, (sm[L.octime + e * 3 + 0] > 0.f && sm[L.octime + e * 3 + 2] > 0.f) ? 1.f : 0.f);
+      put(LT_RK_OBJ_LOSE_CONTACT, (sm[L.oc_last + e] > 0.f && sm[L.oc_air + e] > 0.f) ? 1.f : 0.f);
       put(LT_RK_OBJ_Z_VEL, rel_vel.z * rel_vel.z);
       put(LT_RK_OBJ_RP_ANGLE, g_obj.x * g_obj.x + g_obj.y * g_obj.y);
       put(LT_RK_OBJ_RP_VEL, fabsf(rel_ang.x) + fabsf(rel_ang.y));
@@ -664,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 4) mdp_step_kernel(const LtMdpArgs A
           const Quat b = quat_mul({cst[6], cst[7], cst[8], cst[9]}, nq);
           cst[6] = b.w; cst[7] = b.x; cst[8] = b.y; cst[9] = b.z;
         }
-        const bool never = sm[L.octime + e * 3 + 0] < A.os_last_contact_thr && sm[L.octime + e * 3 + 1] < A.os_current_contact_thr;
+        const bool never = sm[L.oc_last + e] < A.os_last_contact_thr && sm[L.oc_cur + e] < A.os_current_contact_thr;
         const float term_scale = A.obs_terms[tobj].scale;
 #pragma unroll
         for (int k = 0; k < 13; ++k) nv[(grp * kEnvs + e) * dps + jb + k] = ((never ? cst[k] : st[k]) * A.os_scale[k]) * term_scale;
@@ -891,8 +898,11 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   L.force = take(do_rew ? H * S * 3 : 0);
   L.air = take(4); L.con = take(4); L.lair = take(4); L.fpos = take(12); L.fvel = take(12);
   L.quat = take(4); L.linw = take(3); L.angw = take(3); L.opos = take(3); L.oquat = take(4); L.olin = take(3); L.oang = take(3);
-  L.ograv = take(3); L.octime = take(3);
-  L.fmax = take(S); L.gait = take(kGaitFloats); L.gait_out = take(kGaitFloats);
+  L.ograv = take(3); L.oc_last = take(1); L.oc_cur = take(1); L.oc_air = take(1);
+  L.fmax = take(S);
+  L.g_lsa = take(4); L.g_lsc = take(4); L.g_vla = take(4); L.g_cmd = take(3); L.g_steps = take(1); L.g_sz = take(4); L.g_vpc = take(4);
+  L.eplen = take(2);  // int64 per env
+  L.gait_out = take(kGaitFloats);
   L.esum = take(T); L.raw = take(T);
   L.newobs = take(2 * dps);
   L.uscr = take(16);
@@ -902,13 +912,15 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   L.map = off; off += ((L.D + 3) & ~3) + dps;  // s_map[D] + s_jinfo[dps]
   L.total = off;
   const size_t smem = (size_t)L.total * sizeof(float);
-  if (smem > 96 * 1024) return LT_ERR_UNSUPPORTED;
+  if (smem > 200 * 1024) return LT_ERR_UNSUPPORTED;
 
   StageTable ST;
   memset(&ST, 0, sizeof(ST));
   auto add = [&](const float* src, int row, int dst_off) {
     if (!src || row <= 0) return;
-    ST.src[ST.n] = src; ST.row[ST.n] = row; ST.off[ST.n] = dst_off; ++ST.n;
+    ST.src[ST.n] = src; ST.row[ST.n] = row; ST.off[ST.n] = dst_off;
+    ST.vec[ST.n] = ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (kEnvs * row) % 4 == 0 && (dst_off % 4) == 0) ? 1 : 0;
+    ++ST.n;
   };
   if (do_rew) add(a->net_forces_w_history, H * S * 3, L.force);  // biggest first
   add(a->command, 3, L.cmd); add(a->root_pos_w, 3, L.pos); add(a->root_ang_vel_b, 3, L.angb); add(a->projected_gravity_b, 3, L.grav);
@@ -918,7 +930,14 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
     add(a->root_lin_vel_b, 3, L.linb); add(a->joint_acc, J, L.qdd); add(a->applied_torque, J, L.tau);
     add(a->soft_joint_pos_limits, 2 * J, L.lim); add(a->prev_raw_actions, J, L.pact);
   }
+  if (do_rew) {
+    const LtGaitState& gs = a->gait_state;
+    add(gs.last_step_current_air_time, 4, L.g_lsa); add(gs.last_step_current_contact_time, 4, L.g_lsc); add(gs.valid_last_air_time, 4, L.g_vla);
+    add(gs.last_velocity_cmd, 3, L.g_cmd); add(gs.step_from_changing_cmd, 1, L.g_steps);
+  }
   if (has_obj) {
+    if (!a->obj_last_contact_time || !a->obj_current_contact_time || !a->obj_current_air_time) return LT_ERR_INVALID_ARG;
+    add(a->obj_last_contact_time, 1, L.oc_last); add(a->obj_current_contact_time, 1, L.oc_cur); add(a->obj_current_air_time, 1, L.oc_air);
     add(a->root_quat_w, 4, L.quat); add(a->root_lin_vel_w, 3, L.linw); add(a->root_ang_vel_w, 3, L.angw);
     add(a->obj_root_pos_w, 3, L.opos); add(a->obj_root_quat_w, 4, L.oquat); add(a->obj_root_lin_vel_w, 3, L.olin);
     add(a->obj_root_ang_vel_w, 3, L.oang); add(a->obj_projected_gravity_b, 3, L.ograv);
@@ -927,7 +946,7 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mdp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(mdp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return lt::check(e);
     attr_set = true;
   }

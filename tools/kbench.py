@@ -188,17 +188,26 @@ def main():
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=200)
     ap.add_argument("--json", type=str, default=None)
+    ap.add_argument("--only", type=str, default="")
     args = ap.parse_args()
     peak, kind = peak_gbs()
     n = args.envs
     res = {}
-    for task in ("locomotion", "teacher"):
-        res.update(bench_mdp(task, n, args.reps))
-    res.update(bench_taxel(n, args.reps))
-    res.update(bench_gae(n, args.reps))
-    res.update(bench_ppo_loss(n * 24 // 4, args.reps))
-    res.update(bench_adam(607641 // 4 * 4, args.reps))
-    res.update(bench_gather(n * 24, n * 24 // 4, max(20, args.reps // 10)))
+    only = set(args.only.split(",")) if args.only else None
+    want = lambda k: only is None or k in only  # noqa: E731
+    if want("mdp"):
+        for task in ("locomotion", "teacher"):
+            res.update(bench_mdp(task, n, args.reps))
+    if want("taxel"):
+        res.update(bench_taxel(n, args.reps))
+    if want("gae"):
+        res.update(bench_gae(n, args.reps))
+    if want("ppo"):
+        res.update(bench_ppo_loss(n * 24 // 4, args.reps))
+    if want("adam"):
+        res.update(bench_adam(607641 // 4 * 4, args.reps))
+    if want("gather"):
+        res.update(bench_gather(n * 24, n * 24 // 4, max(20, args.reps // 10)))
     rows = []
     print(f"envs={n}  peak={peak} GB/s ({kind})")
     print(f"{'kernel':38s} {'us/launch':>10s} {'alg MB':>9s} {'GB/s':>9s} {'frac':>6s}")
