@@ -157,6 +157,18 @@ int lt_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
                  void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * K9  fused ELU backward + bias gradient (one pass over the [B, n] layer gradient)
+ * replaces  the autograd kernels behind every Linear+ELU layer of loco_rl/loco_rl/modules/actor_critic.py:33-56 and
+ *           loco_rl/loco_rl/models/mlp.py:4-25: elu_backward and the bias-gradient column sum.
+ *   grad_pre = grad_out * (act_out > 0 ? 1 : act_out + alpha)   (act_out == NULL: no activation, grad_pre = grad_out)
+ *   bias_grad[j] = sum_b grad_pre[b, j]                          (deterministic two-stage reduction)
+ * grad_pre may alias grad_out (in place) or be NULL when only the column sums are wanted.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int64_t lt_bias_act_bwd_workspace_bytes(int B, int n);
+int lt_bias_act_bwd(const float* grad_out, const float* act_out, float* grad_pre, float* bias_grad, int B, int n, float alpha,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * K2  binary taxel synthesis (+ fused delay line)
  * replaces  locotouch/mdp/observations.py:154-159,166-199,281-308  BinaryTactileSignals.__call__
  *           locotouch/distill/tactile_recorder.py:4-34             TactileRecorder (lt_tactile_delay)

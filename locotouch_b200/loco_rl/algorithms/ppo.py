@@ -228,16 +228,24 @@ class PPO:
         adaptive = self.desired_kl is not None and self.schedule == "adaptive"
         _, world = D.world_info()
         local_lr = adaptive and world == 1  # one process: the learning-rate decision is taken inside the loss kernel
-        mu = ac.actor(obs)
-        value = ac.critic(cobs)
-        opt.zero_grad()
+        explicit = ac.supports_explicit_backward
+        if explicit:
+            mu, value = ac.train_forward(obs, cobs)
+        else:  # non-ELU activations: autograd through the torch modules
+            mu = ac.actor(obs)
+            value = ac.critic(cobs)
+            opt.zero_grad()
         ops.ppo_loss(mu.detach(), ac.std.detach(), value.detach().view(-1), actions, logp.view(-1), mu_old, sigma_old, adv.view(-1),
                      returns.view(-1), values.view(-1), clip_param=self.clip_param, value_loss_coef=self.value_loss_coef,
                      entropy_coef=self.entropy_coef, use_clipped_value_loss=self.use_clipped_value_loss,
                      desired_kl=self.desired_kl if local_lr else None, lr=opt.lr_t if local_lr else None, loss_accum=self._loss_accum, buffers=bufs)
-        torch.autograd.backward([mu, value], [bufs.grad_mu, bufs.grad_value.view_as(value)])
         off, n = ac._slices["std"]
-        opt.grads[off:off + n].add_(bufs.grad_sigma)
+        if explicit:
+            ac.train_backward(bufs.grad_mu, bufs.grad_value.view(-1, 1))
+            opt.grads[off:off + n].copy_(bufs.grad_sigma)  # every gradient slot is overwritten: no zero_grad pass
+        else:
+            torch.autograd.backward([mu, value], [bufs.grad_mu, bufs.grad_value.view_as(value)])
+            opt.grads[off:off + n].add_(bufs.grad_sigma)
 
     def reduce_and_step(self):
         """[NCCL: flat gradient all-reduce + KL all-reduce + learning-rate decision] then fused clip + Adam (K7)."""

@@ -200,6 +200,20 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0
     count_launches(2)
 
 
+# ------------------------------------------------------------------------------------------------- K9 MLP backward helper
+def bias_act_bwd(grad_out, act_out, bias_grad, grad_pre=None, alpha: float = 1.0):
+    """grad_pre = grad_out * elu'(act_out) (in place when ``grad_pre`` is None) and bias_grad = grad_pre.sum(0), one pass."""
+    B, n = grad_out.shape
+    if grad_pre is None:
+        grad_pre = grad_out
+    nbytes = lib().lt_bias_act_bwd_workspace_bytes(B, n)
+    ws = _workspace("biasbwd", nbytes, grad_out.device)
+    check(lib().lt_bias_act_bwd(ptr(grad_out, torch.float32, "grad_out"), ptr(act_out, torch.float32, "act_out"), ptr(grad_pre, torch.float32),
+                                ptr(bias_grad, torch.float32, "bias_grad"), B, n, alpha, ptr(ws), nbytes, current_stream()), "lt_bias_act_bwd")
+    count_launches(1)
+    return grad_pre
+
+
 # ----------------------------------------------------------------------------------------------------------- K2 taxels
 def taxel_synth(body_quat_w, net_forces_w, thresholds, *, quat_body_offset=0, u_drop=None, u_add=None, p_drop=0.005, p_add=0.005,
                 seed=0, offset=0, offset_base=None, signal=None, packed=None, normal_forces=None, original_contact=None, delay_ring=None,

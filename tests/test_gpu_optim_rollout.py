@@ -101,3 +101,26 @@ def test_store_step_and_gather(cuda, lt_lib):
     outs = ops.gather_rows([s.to(cuda) for s in srcs], idx.to(cuda))
     for s, o in zip(srcs, outs):
         H.assert_equal(o, s[idx], "gathered rows")
+
+
+@pytest.mark.parametrize("B,n", [(24576, 512), (1000, 256), (333, 128), (4097, 12), (500, 1), (7, 6)])
+def test_bias_act_bwd_matches_autograd(cuda, lt_lib, B, n):
+    from locotouch_b200 import ops
+
+    g = torch.Generator().manual_seed(B + n)
+    z = torch.randn(B, n, generator=g, requires_grad=True)
+    h = torch.nn.functional.elu(z)
+    go = torch.randn(B, n, generator=g)
+    (h * go).sum().backward()
+    bias = torch.empty(n, device=cuda)
+    gd = go.to(cuda).clone()
+    out = ops.bias_act_bwd(gd, h.detach().to(cuda), bias)
+    assert out.data_ptr() == gd.data_ptr()
+    H.assert_close(out, z.grad, "grad wrt pre-activation", rtol=1e-5, atol=1e-7)
+    H.assert_close(bias, z.grad.sum(0), "bias gradient", rtol=2e-5, atol=1e-5 * (B ** 0.5))
+    bias2 = torch.empty(n, device=cuda)
+    ops.bias_act_bwd(go.to(cuda), None, bias2)  # activation-free last layer: column sums only
+    H.assert_close(bias2, go.sum(0), "column sums", rtol=2e-5, atol=1e-5 * (B ** 0.5))
+    bias3 = torch.empty(n, device=cuda)
+    ops.bias_act_bwd(go.to(cuda), h.detach().to(cuda), bias3)
+    H.assert_equal(bias3, bias, "deterministic reduction")

@@ -91,3 +91,12 @@ for (m, k, n) in ((B, 348, 512), (B, 512, 256), (B, 256, 128)):
     print(f"bias grad {m}x{n}: {t * 1e3:7.1f} us")
 x = torch.randn(B, 512, device="cuda")
 print(f"elu {B}x512: {timed(lambda: torch.nn.functional.elu(x), reps=50) * 1e3:7.1f} us")
+# wgrad alternatives: explicit split-K through bmm
+for (m, k, n) in ((B, 348, 512), (B, 512, 256), (B, 256, 128)):
+    gy, x = torch.randn(m, n, device="cuda"), torch.randn(m, k, device="cuda")
+    for S in (4, 8, 16):
+        gs, xs = gy.view(S, m // S, n), x.view(S, m // S, k)
+        t = timed(lambda: torch.bmm(gs.transpose(1, 2), xs).sum(0), reps=50)
+        print(f"wgrad split-{S:2d} {n}x{m}x{k}: {t * 1e3:7.1f} us  {2 * m * k * n / t / 1e9:7.1f} TFLOP/s")
+    t = timed(lambda: torch.mm(x.t(), gy), reps=50)
+    print(f"wgrad (x^T g) {k}x{m}x{n}: {t * 1e3:7.1f} us")
