@@ -35,8 +35,31 @@ bias_act_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict_
   for (int cg = cg0; cg < cols; cg += col_threads) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     if (active) {
-      for (int r = row0 + rl; r < row1; r += row_lanes) {
-        if constexpr (VEC4) {
+      if constexpr (VEC4) {
+        // 4 independent rows per trip: 8 x 16-byte loads in flight per thread
+        int r = row0 + rl;
+        for (; r + 3 * row_lanes < row1; r += 4 * row_lanes) {
+          float4 g[4], h[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const size_t i = (size_t)(r + u * row_lanes) * cols + cg;
+            g[u] = __ldcs(reinterpret_cast<const float4*>(grad_out) + i);
+            h[u] = act_out ? __ldcs(reinterpret_cast<const float4*>(act_out) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const size_t i = (size_t)(r + u * row_lanes) * cols + cg;
+            if (act_out) {
+              g[u].x *= h[u].x > 0.f ? 1.f : h[u].x + alpha;
+              g[u].y *= h[u].y > 0.f ? 1.f : h[u].y + alpha;
+              g[u].z *= h[u].z > 0.f ? 1.f : h[u].z + alpha;
+              g[u].w *= h[u].w > 0.f ? 1.f : h[u].w + alpha;
+            }
+            if (grad_pre && (act_out || grad_pre != grad_out)) reinterpret_cast<float4*>(grad_pre)[i] = g[u];
+            a0 += g[u].x; a1 += g[u].y; a2 += g[u].z; a3 += g[u].w;
+          }
+        }
+        for (; r < row1; r += row_lanes) {
           const size_t i = (size_t)r * cols + cg;
           float4 g = __ldcs(reinterpret_cast<const float4*>(grad_out) + i);
           if (act_out) {
@@ -48,7 +71,9 @@ bias_act_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict_
           }
           if (grad_pre && (act_out || grad_pre != grad_out)) reinterpret_cast<float4*>(grad_pre)[i] = g;
           a0 += g.x; a1 += g.y; a2 += g.z; a3 += g.w;
-        } else {
+        }
+      } else {
+        for (int r = row0 + rl; r < row1; r += row_lanes) {
           const size_t i = (size_t)r * n + cg;
           float g = grad_out[i];
           if (act_out) {
@@ -100,9 +125,9 @@ bias_act_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict_
 }
 
 int blocks_for(int B) {
-  int blocks = 2 * lt::sm_count();
+  int blocks = 4 * lt::sm_count();
   if (blocks > B) blocks = B;
-  if (blocks > 512) blocks = 512;
+  if (blocks > 1024) blocks = 1024;
   return blocks < 1 ? 1 : blocks;
 }
 

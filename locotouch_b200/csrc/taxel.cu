@@ -28,6 +28,12 @@ __device__ __forceinline__ float rotate_inverse_z(float4 q /*w,x,y,z*/, float vx
   return __fadd_rn(__fsub_rn(vz, __fmul_rn(w, tz)), cz);
 }
 
+constexpr int kMaxDelay = 8;
+
+// R = number of 32-taxel rounds held in registers (R == 0: generic loop for any T).  With R fixed every global load of
+// the env (quaternion, force, threshold, uniforms, old delay-ring words) is issued before the first ballot, so a warp pays
+// one DRAM round trip instead of one per round.
+template <int R>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) taxel_kernel(const LtTaxelArgs a) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -36,55 +42,114 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) taxel_kernel(const LtTaxe
   const float4* quat = reinterpret_cast<const float4*>(a.body_quat_w) + (size_t)n * a.quat_num_bodies + a.quat_body_offset;
   const float* force = a.net_forces_w + (size_t)n * T * 3;
   const size_t row = (size_t)n * T;
+  const bool explicit_u = a.u_drop || a.u_add;
+  // ---- delay line state, fetched up front (tactile_recorder.py:25-34 on the packed words)
+  uint32_t old_ring[kMaxDelay - 1];
+  bool first = false;
+  int slot = 0;
+  if (a.delay_ring) {
+    const uint32_t* ring = a.delay_ring + (size_t)n * a.max_delay * words;
+#pragma unroll
+    for (int k = 0; k < kMaxDelay - 1; ++k) old_ring[k] = (k < a.max_delay - 1 && lane < words) ? ring[k * words + lane] : 0u;
+    first = a.delay_first[n] != 0;
+    slot = (int)a.delay_steps[n];
+  }
   const uint64_t rng_offset = a.offset + (a.offset_base ? (uint64_t)*a.offset_base : 0ull);
   uint32_t my_word = 0;  // lane r keeps word r
-  uint4 rnd = make_uint4(0, 0, 0, 0);
-  for (int r = 0; r < words; ++r) {
-    const int t = 32 * r + lane;
-    bool contact = false;
-    if (t < T) {
-      const float4 q = __ldcs(quat + t);
-      const float fx = __ldcs(force + 3 * t), fy = __ldcs(force + 3 * t + 1), fz = __ldcs(force + 3 * t + 2);
-      const float thr = __ldcs(a.thresholds + row + t);
-      const float fn = -rotate_inverse_z(q, fx, fy, fz);  // observations.py:156-158
-      const bool original = fn > thr;                     // observations.py:159 (strict)
-      contact = original;
-      float ud, ua;
-      if (a.u_drop || a.u_add) {
-        ud = a.u_drop ? __ldcs(a.u_drop + row + t) : 1.0f;
-        ua = a.u_add ? __ldcs(a.u_add + row + t) : 1.0f;
-      } else {
-        if ((r & 1) == 0) rnd = lt::Philox::gen(a.seed, rng_offset, (uint32_t)n, (uint32_t)(32 * (r >> 1) + lane));
-        ud = lt::Philox::u01((r & 1) ? rnd.z : rnd.x);
-        ua = lt::Philox::u01((r & 1) ? rnd.w : rnd.y);
-      }
-      if (a.p_drop > 0.f) contact = contact && !(ud < a.p_drop);  // observations.py:172-176
-      if (a.p_add > 0.f) contact = contact || (ua < a.p_add);     // observations.py:180-185
-      if (a.normal_forces) a.normal_forces[row + t] = fn;
-      if (a.original_contact) a.original_contact[row + t] = original ? 1 : 0;
-      if (a.signal) {
-        const float s = contact ? 1.0f : 0.0f;
-        float* out = a.signal + (size_t)n * 2 * T;
-        __stcs(out + t, s);      // channel 0
-        __stcs(out + T + t, s);  // channel 1 (observations.py:308: two identical channels)
+
+  auto decide = [&](int t, float4 q, float fx, float fy, float fz, float thr, float ud, float ua) -> bool {
+    const float fn = -rotate_inverse_z(q, fx, fy, fz);  // observations.py:156-158
+    const bool original = fn > thr;                     // observations.py:159 (strict)
+    bool contact = original;
+    if (a.p_drop > 0.f) contact = contact && !(ud < a.p_drop);  // observations.py:172-176
+    if (a.p_add > 0.f) contact = contact || (ua < a.p_add);     // observations.py:180-185
+    if (a.normal_forces) a.normal_forces[row + t] = fn;
+    if (a.original_contact) a.original_contact[row + t] = original ? 1 : 0;
+    if (a.signal) {
+      const float s = contact ? 1.0f : 0.0f;
+      float* out = a.signal + (size_t)n * 2 * T;
+      __stcs(out + t, s);      // channel 0
+      __stcs(out + T + t, s);  // channel 1 (observations.py:308: two identical channels)
+    }
+    return contact;
+  };
+
+  if constexpr (R > 0) {
+    float4 q[R];
+    float fx[R], fy[R], fz[R], thr[R], ud[R], ua[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = 32 * r + lane;
+      q[r] = make_float4(1.f, 0.f, 0.f, 0.f);
+      fx[r] = fy[r] = fz[r] = 0.f;
+      thr[r] = 0.f;
+      ud[r] = ua[r] = 1.f;
+      if (t < T) {
+        q[r] = __ldcs(quat + t);
+        fx[r] = __ldcs(force + 3 * t); fy[r] = __ldcs(force + 3 * t + 1); fz[r] = __ldcs(force + 3 * t + 2);
+        thr[r] = __ldcs(a.thresholds + row + t);
+        if (explicit_u) {
+          if (a.u_drop) ud[r] = __ldcs(a.u_drop + row + t);
+          if (a.u_add) ua[r] = __ldcs(a.u_add + row + t);
+        }
       }
     }
-    const uint32_t word = __ballot_sync(LT_FULL_MASK, contact);
-    if (lane == r) my_word = word;
+    if (!explicit_u) {
+#pragma unroll
+      for (int r = 0; r < R; r += 2) {
+        const uint4 rnd = lt::Philox::gen(a.seed, rng_offset, (uint32_t)n, (uint32_t)(32 * (r >> 1) + lane));
+        ud[r] = lt::Philox::u01(rnd.x); ua[r] = lt::Philox::u01(rnd.y);
+        if (r + 1 < R) { ud[r + 1] = lt::Philox::u01(rnd.z); ua[r + 1] = lt::Philox::u01(rnd.w); }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = 32 * r + lane;
+      const bool contact = (t < T) && decide(t, q[r], fx[r], fy[r], fz[r], thr[r], ud[r], ua[r]);
+      const uint32_t word = __ballot_sync(LT_FULL_MASK, contact);
+      if (lane == r) my_word = word;
+    }
+  } else {
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    for (int r = 0; r < words; ++r) {
+      const int t = 32 * r + lane;
+      bool contact = false;
+      if (t < T) {
+        const float4 q = __ldcs(quat + t);
+        const float fx = __ldcs(force + 3 * t), fy = __ldcs(force + 3 * t + 1), fz = __ldcs(force + 3 * t + 2);
+        const float thr = __ldcs(a.thresholds + row + t);
+        float ud, ua;
+        if (explicit_u) {
+          ud = a.u_drop ? __ldcs(a.u_drop + row + t) : 1.0f;
+          ua = a.u_add ? __ldcs(a.u_add + row + t) : 1.0f;
+        } else {
+          if ((r & 1) == 0) rnd = lt::Philox::gen(a.seed, rng_offset, (uint32_t)n, (uint32_t)(32 * (r >> 1) + lane));
+          ud = lt::Philox::u01((r & 1) ? rnd.z : rnd.x);
+          ua = lt::Philox::u01((r & 1) ? rnd.w : rnd.y);
+        }
+        contact = decide(t, q, fx, fy, fz, thr, ud, ua);
+      }
+      const uint32_t word = __ballot_sync(LT_FULL_MASK, contact);
+      if (lane == r) my_word = word;
+    }
   }
   if (a.packed && lane < words) a.packed[(size_t)n * words + lane] = my_word;
 
-  if (a.delay_ring) {  // tactile_recorder.py:25-34 on the packed words
+  if (a.delay_ring) {
+    // shifted ring: ring'[0] = new, ring'[k] = first ? new : ring[k-1]; output slot = ring'[delay]  (all from registers)
     uint32_t* ring = a.delay_ring + (size_t)n * a.max_delay * words;
-    const bool first = a.delay_first[n] != 0;
-    const int slot = (int)a.delay_steps[n];
-    uint32_t delayed = 0;
+    uint32_t delayed = my_word;
     if (lane < words) {
-      for (int k = a.max_delay - 1; k >= 1; --k) ring[k * words + lane] = first ? my_word : ring[(k - 1) * words + lane];
       ring[lane] = my_word;
-      delayed = ring[slot * words + lane];
+#pragma unroll
+      for (int k = 1; k < kMaxDelay; ++k) {
+        if (k < a.max_delay) {
+          const uint32_t v = first ? my_word : old_ring[k - 1];
+          ring[k * words + lane] = v;
+          if (k == slot) delayed = v;
+        }
+      }
     }
-    __syncwarp();
     if (lane == 0) a.delay_first[n] = 0;
     if (a.delayed_signal) {
       float* out = a.delayed_signal + (size_t)n * 2 * T;
@@ -128,9 +193,12 @@ extern "C" int lt_taxel_synth(const LtTaxelArgs* a, void* stream) {
   if (!a->body_quat_w || !a->net_forces_w || !a->thresholds) return LT_ERR_INVALID_ARG;
   if (((uintptr_t)a->body_quat_w & 15) != 0) return LT_ERR_INVALID_ARG;
   if (a->quat_body_offset < 0 || a->quat_body_offset + a->T > a->quat_num_bodies) return LT_ERR_INVALID_ARG;
-  if (a->delay_ring && (!a->delay_first || !a->delay_steps || a->max_delay <= 0)) return LT_ERR_INVALID_ARG;
+  if (a->delay_ring && (!a->delay_first || !a->delay_steps || a->max_delay <= 0 || a->max_delay > kMaxDelay)) return LT_ERR_INVALID_ARG;
   const int grid = (int)lt::ceil_div(a->N, kWarpsPerBlock);
-  taxel_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(*a);
+  if (a->T > 192 && a->T <= 224)
+    taxel_kernel<7><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(*a);  // 17 x 13 = 221 taxels
+  else
+    taxel_kernel<0><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(*a);
   return lt::check_launch();
 }
 

@@ -297,6 +297,57 @@ def golden_tactile():
     np.savez_compressed(os.path.join(OUT, "tactile_c4.npz"), **out)
 
 
+STUDENT_SMALL = dict(rnn_hidden=32, enc_hidden=[32, 16], pol_hidden=[32, 16], cnn_channels=(4, 4, 4), L=11, B=4, lengths=[11, 3, 7, 1], seed=31)
+
+
+def student_batch(c=STUDENT_SMALL):
+    g = torch.Generator().manual_seed(c["seed"])
+    L, B = c["L"], c["B"]
+    masks = torch.zeros(L, B, dtype=torch.bool)
+    for b, n in enumerate(c["lengths"]):
+        masks[:n, b] = True
+    batch = dict(proprioceptions=torch.randn(L, B, 270, generator=g), teacher_encoder_obses=torch.randn(L, B, 78, generator=g),
+                 tactile_signals=(torch.rand(L, B, 442, generator=g) < 0.15).float(), masks=masks)
+    for k in ("proprioceptions", "teacher_encoder_obses", "tactile_signals"):
+        batch[k] = batch[k] * masks.unsqueeze(-1)  # padded region is zero, as _prepare_padded_sequence leaves it
+    teacher_w = torch.randn(12, 348, generator=g) * 0.05
+    teacher_b = torch.randn(12, generator=g) * 0.05
+    return batch, teacher_w, teacher_b
+
+
+def shrink_student_cfg(cfg, c=STUDENT_SMALL):
+    cfg.device = "cpu"
+    cfg.tactile_encoder.rnn_hidden_size = c["rnn_hidden"]
+    cfg.tactile_encoder.hidden_dims = list(c["enc_hidden"])
+    cfg.student_policy.hidden_dims = list(c["pol_hidden"])
+    cfg.pre_encoder.cnn_channels = tuple(c["cnn_channels"])
+    return cfg
+
+
+def golden_student():
+    student_mod, _, cfg_mod = ref_loader.load_reference_distill()
+    cfg = shrink_student_cfg(cfg_mod.DistillationRandCylinderCNNRNNMonCfg())
+    batch, tw, tb = student_batch()
+    teacher = lambda x: torch.nn.functional.linear(x, tw, tb)  # noqa: E731
+    torch.manual_seed(STUDENT_SMALL["seed"])
+    ref = student_mod.Student(cfg, 270, 442, 12, teacher_policy_inference=teacher)
+    names = list(ref.state_dict().keys())
+    init = torch.cat([v.flatten() for v in ref.state_dict().values()]).clone()
+    # one step of the loop body of Student.train_on_data (reference student.py:121-151)
+    ref._optimizer.zero_grad()
+    actions = ref.forward(batch["proprioceptions"], batch["tactile_signals"])
+    teacher_actions = teacher(torch.cat((batch["proprioceptions"], batch["teacher_encoder_obses"]), dim=-1))
+    loss = ref._criterion(actions, teacher_actions).mean(dim=-1)
+    loss = (loss * batch["masks"]).sum() / batch["masks"].sum()
+    loss.backward()
+    grad_norms = torch.stack([p.grad.norm() for p in ref.parameters()])
+    ref._optimizer.step()
+    after = torch.cat([v.flatten() for v in ref.state_dict().values()])
+    np.savez_compressed(os.path.join(OUT, "student_c4.npz"), names=np.array(names), init=init.numpy(), actions=actions.detach().numpy(),
+                        loss=np.array(float(loss)), grad_norms=grad_norms.numpy(), after=after.detach().numpy())
+    print(f"student_c4: {init.numel()} params, loss {float(loss):.6f}")
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "the reference is not mounted"
     torch.set_num_threads(1)
@@ -304,6 +355,8 @@ if __name__ == "__main__":
     golden_mdp("teacher")
     golden_ppo()
     golden_tactile()
+    golden_student()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
