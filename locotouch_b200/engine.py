@@ -36,32 +36,61 @@ HIDDEN = (512, 256, 128)
 ACTION_CLIP, ACTION_RAW_SCALE = 100.0, 0.25
 
 
-def pack_env(env, device, pin: bool = False):
-    """Re-homes every state tensor of a SynthEnv as a view of ONE contiguous device buffer (256-byte aligned slices),
-    returning (device_env, flat_device_buffer, flat_host_buffer).  One H2D copy then refreshes the whole state."""
+# State tensors the hot path never reads (not uploaded), and [N, num_bodies, 3] tensors of which it reads the four feet rows only
+# (uploaded as compact [N, 4, 3] tensors and scattered into place on the device).  Everything else is uploaded whole.
+UNREAD = ("robot_contact_senosr.last_contact_time", "robot_contact_senosr.net_forces_w", "object_contact_sensor.last_air_time")
+FEET_ROWS_ONLY = ("robot.body_pos_w", "robot.body_lin_vel_w")
+FEET = ("a_FR_foot", "b_FL_foot", "c_RR_foot", "d_RL_foot")
+
+
+def pack_host(env, pin: bool = False):
+    """Lays every state tensor of a SynthEnv out in ONE contiguous host buffer (256-byte aligned slices) so that a single
+    H2D copy of the first ``upload_bytes`` refreshes everything the hot path reads.  Returns (layout, compact, upload_bytes,
+    flat_host_buffer); ``compact`` = [(full_name, offset, nbytes, shape)] of the feet-row tensors."""
     tensors = env.named_tensors()
     skip = {k for k in tensors if k.startswith("action.") or k in ("terminated", "time_outs")}
-    layout, off = [], 0
-    for name, t in tensors.items():
-        if name in skip:
-            continue
+    feet = torch.tensor(env.scene["robot"].find_bodies(list(FEET))[0], dtype=torch.int64)
+    layout, compact, off = [], [], 0
+
+    def place(name, t, into):
+        nonlocal off
         nbytes = t.numel() * t.element_size()
-        layout.append((name, off, nbytes, t.dtype, tuple(t.shape)))
+        into.append((name, off, nbytes, t.dtype, tuple(t.shape)))
         off += (nbytes + 255) // 256 * 256
+
+    for name, t in tensors.items():  # uploaded whole
+        if name not in skip and name not in UNREAD and name not in FEET_ROWS_ONLY:
+            place(name, t, layout)
+    rows = {name: tensors[name][:, feet].contiguous() for name in FEET_ROWS_ONLY if name in tensors}
+    for name, t in rows.items():
+        place(name, t, compact)
+    upload_bytes = off
+    for name, t in tensors.items():  # device-resident only
+        if name in UNREAD or name in FEET_ROWS_ONLY:
+            place(name, t, layout)
     host = torch.empty(off, dtype=torch.uint8, pin_memory=pin)
     for name, o, nbytes, dtype, shape in layout:
         host[o:o + nbytes].view(dtype).view(shape).copy_(tensors[name])
+    for name, o, nbytes, dtype, shape in compact:
+        host[o:o + nbytes].view(dtype).view(shape).copy_(rows[name])
+    return layout, compact, upload_bytes, host
+
+
+def device_set(env, layout, compact, host, device):
+    """A device copy of the packed state set: (device_env whose tensors are views of the flat buffer, flat_device_buffer,
+    [(full tensor, compact feet rows)] to scatter after an upload)."""
     flat = host.to(device)
     denv = env.to(device)
     views = {name: flat[o:o + nbytes].view(dtype).view(shape) for name, o, nbytes, dtype, shape in layout}
     denv.load_named_tensors(views)
-    return denv, flat, host
+    scatter = [(views[name], flat[o:o + nbytes].view(dtype).view(shape)) for name, o, nbytes, dtype, shape in compact]
+    return denv, flat, scatter
 
 
 class HotPathEngine:
     def __init__(self, num_envs: int = 4096, task: str = "teacher", tactile: bool = True, device="cuda:0", seed: int = 0,
                  num_state_sets: int = 6, num_steps: int = NUM_STEPS_PER_ENV, hidden=HIDDEN, ppo_cfg: dict | None = None,
-                 pin_host: bool = False, tf32: bool = True):
+                 pin_host: bool = False, tf32: bool = True, prefetch: bool = False):
         self.device = torch.device(device)
         self.N, self.T, self.K = num_envs, num_steps, num_state_sets
         self.spec = TS.SPECS[task]()
@@ -76,14 +105,29 @@ class HotPathEngine:
         base = synth.make_env(num_envs, seed=seed * 1000 + self.rank, with_object=self.spec.with_object, with_tactile=tactile,
                               max_episode_length=self.spec.max_episode_length)
         self.action_term = ActionTermState(num_envs, synth.NUM_JOINTS, self.device)
-        for k in range(num_state_sets):
-            if k > 0:
-                synth.advance(base, keep_cmd_prob=0.9)
-            denv, flat, host = pack_env(base, self.device, pin=pin_host)
+        # ``prefetch``: two banks of T device-resident sets, so that the H2D upload of the NEXT iteration's T state sets runs on
+        # a copy stream while this iteration computes (the host keeps ``num_state_sets`` distinct pinned sets, cycled)
+        self.prefetch = prefetch
+        self.banks = 2 if prefetch else 1
+        num_device_sets = 2 * num_steps if prefetch else num_state_sets
+        layout = compact = None
+        self.scatter = []
+        self.feet_idx = torch.tensor(base.scene["robot"].find_bodies(list(FEET))[0], dtype=torch.int64, device=self.device)
+        for k in range(num_device_sets):
+            if k < num_state_sets:
+                if k > 0:
+                    synth.advance(base, keep_cmd_prob=0.9)
+                layout, compact, self.upload_bytes, host = pack_host(base, pin=pin_host)
+                self.host_flat.append(host)
+            denv, flat, scatter = device_set(base, layout, compact, self.host_flat[k % num_state_sets], self.device)
+            self.scatter.append(scatter)
             denv.action_manager._terms["joint_pos"] = self.action_term  # actions come from the policy, not from the set
             self.envs.append(denv)
             self.dev_flat.append(flat)
-            self.host_flat.append(host)
+        self._iter = 0
+        self._copy_stream = None
+        self._upload_done = [None, None]
+        self._rollout_done = [None, None]
         self.state_bytes = int(self.dev_flat[0].numel())
         self.default_joint_pos = self.envs[0].scene["robot"].data.default_joint_pos.clone()
         # ---- learner
@@ -124,13 +168,35 @@ class HotPathEngine:
         self._bind(0)
         self.mdp.compute_observations(policy_in=st._obs_buf[0], critic_in=st._priv_buf[0], policy_out=st._obs_buf[0], critic_out=st._priv_buf[0])
 
-    def upload_state(self, k: int):
-        """H2D refresh of state set k from (pinned) host memory: what an env living on the host would have to do."""
-        self.dev_flat[k].copy_(self.host_flat[k], non_blocking=True)
+    def set_index(self, t: int, bank: int = 0) -> int:
+        """Device state set read by env step t (of the iteration that uses ``bank``)."""
+        return bank * self.T + t if self.prefetch else t % self.K
 
-    def env_step(self, t: int, actions: torch.Tensor):
+    def upload_state(self, k: int):
+        """H2D refresh of device state set k from (pinned) host memory: what an env living on the host would have to do."""
+        n = self.upload_bytes  # the tensors the path reads; of body_pos_w / body_lin_vel_w only the feet rows travel
+        self.dev_flat[k][:n].copy_(self.host_flat[k % self.K][:n], non_blocking=True)
+        for full, rows in self.scatter[k]:
+            full.index_copy_(1, self.feet_idx, rows)
+
+    def prefetch_bank(self, bank: int):
+        """Enqueues, on the copy stream, the H2D upload of the T state sets of ``bank``; it starts once the rollout that last
+        read the bank has finished and overlaps whatever the compute stream is doing."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        if self._rollout_done[bank] is not None:
+            cs.wait_event(self._rollout_done[bank])
+        with torch.cuda.stream(cs):
+            for t in range(self.T):
+                self.upload_state(self.set_index(t, bank))
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._upload_done[bank] = ev
+
+    def env_step(self, t: int, actions: torch.Tensor, bank: int = 0):
         """Stand-in for ``env.step(actions)``: everything IsaacLab's managers would compute around PhysX."""
-        k = t % self.K
+        k = self.set_index(t, bank)
         st = self.alg.storage
         a = self.action_term
         ops.process_actions(actions, a.raw_actions, a.prev_raw_actions, a.prev_prev_raw_actions, a.processed_actions,
@@ -149,17 +215,17 @@ class HotPathEngine:
             torch.logical_or(self.taxel_first, self.mdp.dones, out=self.taxel_first.view(torch.bool))
         return st._obs_buf[t + 1], self.mdp.reward_buf, self.mdp.dones, {"time_outs": self.mdp.time_outs, "observations": {"critic": st._priv_buf[t + 1]}}
 
-    def rollout_steps(self, upload: bool = False):
+    def rollout_steps(self, upload: bool = False, bank: int = 0):
         """HOT LOOP A: the T env steps (no collective inside: capturable for any world size)."""
         alg, st = self.alg, self.alg.storage
         ac = alg.actor_critic
         ac._offset_base = self.step_counter
         for t in range(self.T):
             if upload:
-                self.upload_state(t % self.K)
+                self.upload_state(self.set_index(t, bank))
             ac._graph_slot = t
             actions = alg.act(st._obs_buf[t], st._priv_buf[t])
-            obs, rewards, dones, infos = self.env_step(t, actions)
+            obs, rewards, dones, infos = self.env_step(t, actions, bank)
             alg.process_env_step(rewards, dones, infos)
         ops.counter_add(self.step_counter, self.T)
 
@@ -208,11 +274,15 @@ class HotPathEngine:
                 self.finish_iteration()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        g_roll = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_roll):
-            self.rollout_steps()
-            if not split:
-                self.rollout_finish()
+        g_roll = []
+        for bank in range(self.banks):
+            alg.storage.clear()  # host-side slot counter: every bank records the same T slots
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.rollout_steps(bank=bank)
+                if not split:
+                    self.rollout_finish()
+            g_roll.append(g)
         if not split:
             g_upd = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_upd):
@@ -234,10 +304,27 @@ class HotPathEngine:
         torch.cuda.synchronize()
         return self
 
-    def replay(self):
+    def replay(self, upload: bool = False):
+        """One iteration from the captured graphs.  ``upload`` (prefetch engines): this iteration's T state sets come from
+        pinned host memory -- they were enqueued on the copy stream during the previous iteration -- and the next
+        iteration's upload is enqueued before this iteration's kernels, so copies and compute overlap."""
         g = self._graphs
         alg = self.alg
-        g["roll"].replay()
+        bank = self._iter % self.banks
+        self._iter += 1
+        if upload:
+            if not self.prefetch:
+                raise RuntimeError("replay(upload=True) needs an engine built with prefetch=True")
+            if self._upload_done[bank] is None:  # first call: nothing in flight yet
+                self.prefetch_bank(bank)
+            torch.cuda.current_stream().wait_event(self._upload_done[bank])
+            self._upload_done[bank] = None
+            self.prefetch_bank(1 - bank)
+        g["roll"][bank].replay()
+        if self.prefetch:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._rollout_done[bank] = ev
         if not g["split"]:
             self.draw_permutation()
             g["update"].replay()

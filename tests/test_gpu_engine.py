@@ -44,3 +44,35 @@ def test_graph_replay_matches_eager_iteration(cuda, lt_lib, split):
     ra, rb = a.read_results(), b.read_results()
     assert abs(ra["mean_reward"] - rb["mean_reward"]) <= 1e-5 * max(1.0, abs(ra["mean_reward"]))
     assert abs(ra["learning_rate"] - rb["learning_rate"]) <= 1e-9
+
+
+def test_prefetched_upload_replay_matches_eager_iteration(cuda, lt_lib):
+    """replay(upload=True): the state sets arrive over the copy stream (two device banks, uploads overlapping compute) and
+    the result is the one the eager iteration over device-resident sets produces."""
+    from locotouch_b200.engine import HotPathEngine
+
+    cfg = dict(num_envs=256, task="teacher", tactile=True, device=cuda, seed=5, num_state_sets=3, hidden=(64, 32), tf32=False)
+    a = HotPathEngine(**cfg)
+    b = HotPathEngine(**cfg, prefetch=True, pin_host=True)  # 24 % 3 == 0: both banks cycle the same host sets as `a`
+    assert len(b.dev_flat) == 2 * b.T and len(b.host_flat) == 3
+    perms = []
+    for it in range(5):
+        torch.manual_seed(200 + it)
+        a.iteration()
+        perms.append(a.perm.clone())
+    calls = {"n": 0}
+
+    def fixed_perm():
+        b.perm.copy_(perms[min(calls["n"], 4)])
+        calls["n"] += 1
+
+    b.draw_permutation = fixed_perm
+    b.capture(split=False)
+    # scribble over the device banks: replay(upload=True) must restore every set from the host before it is read
+    for flat in b.dev_flat:
+        flat.fill_(0x7f)
+    for _ in range(3):
+        b.replay(upload=True)
+    torch.cuda.synchronize()
+    H.assert_close(_params(b), _params(a), "parameters after 5 iterations (prefetched uploads vs eager)", rtol=1e-4, atol=1e-5)
+    H.assert_equal(b.step_counter, a.step_counter, "device step counter")
