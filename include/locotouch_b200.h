@@ -349,8 +349,15 @@ typedef struct {
   float os_scale[13], os_non_contact[13];
   float os_last_contact_thr, os_current_contact_thr;
   int* any_flag_ws;              /* [2] device ints, zero-initialised once; used for the cross-env any() */
+  const int32_t* tables;         /* optional DEVICE copy (16-byte aligned) of lt_mdp_build_tables() output for this term
+                                    configuration; NULL: every block rebuilds the tables in shared memory */
 } LtMdpArgs;
 int lt_mdp_step(const LtMdpArgs* args, void* stream);
+/* Launch-constant lookup tables (observation column map, per-value term info, reward kind -> slot); host-side, no CUDA call.
+ * They depend on obs_terms / history_length / reward_terms (kinds and zero weights) only.  lt_mdp_tables_len: ints needed
+ * (-1 on an invalid table); lt_mdp_build_tables fills `out` (host memory, `len` ints). */
+int lt_mdp_tables_len(const LtMdpArgs* args);
+int lt_mdp_build_tables(const LtMdpArgs* args, int32_t* out, int len);
 /* AdaptiveSymmetricGaitReward.reset(env_ids) (rewards.py:107-114) for a mask of envs; also zeroes episode sums. */
 int lt_mdp_reset(const LtGaitState* gait_state, float* episode_sums, int num_reward_terms, const uint8_t* mask,
                  int N, void* stream);

@@ -129,7 +129,7 @@ class LtMdpArgs(C.Structure):
         ("os_n_min", C.c_float * 13), ("os_n_max", C.c_float * 13), ("os_euler_min", C.c_float * 3), ("os_euler_max", C.c_float * 3),
         ("os_scale", C.c_float * 13),
         ("os_non_contact", C.c_float * 13), ("os_last_contact_thr", C.c_float), ("os_current_contact_thr", C.c_float),
-        ("any_flag_ws", C.c_void_p),
+        ("any_flag_ws", C.c_void_p), ("tables", C.c_void_p),
     ]
 
 
@@ -158,6 +158,8 @@ _SIGNATURES = {
     "lt_taxel_synth": (C.c_int, [C.POINTER(LtTaxelArgs), C.c_void_p]),
     "lt_tactile_delay": (C.c_int, [f32p, C.c_void_p, C.c_void_p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "lt_mdp_step": (C.c_int, [C.POINTER(LtMdpArgs), C.c_void_p]),
+    "lt_mdp_tables_len": (C.c_int, [C.POINTER(LtMdpArgs)]),
+    "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),
     "lt_mdp_reset": (C.c_int, [C.POINTER(LtGaitState), f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "lt_pad_trajectories": (C.c_int, [f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, C.c_void_p, C.c_void_p]),
     "lt_masked_mse_workspace_bytes": (C.c_int64, [C.c_int64]),

@@ -4,18 +4,25 @@
 // observations.py:38-91 and the IsaacLab manager loops around it (several thousand ATen launches per env step,
 // SURVEY.md 2.1) with one launch that reads exactly the IsaacLab tensors the reference terms read.
 //
-// Block = 256 threads = kEnvs (8) consecutive envs; the rows of 8 consecutive envs are ONE contiguous span in every
-// [N, row] input tensor, so all global traffic is coalesced and the per-env arithmetic runs out of shared memory.
-//   stage 0  table-driven staging: warp w copies input tensors w, w+8, ... (global -> shared); the two observation
-//            history blocks (the bulk of the bytes) are fetched with 16-byte cp.async and land while stage 1 computes.
-//   stage 1  warp roles, one lane per env, concurrently:
-//              warp 0  gait reward (state update, task score, sync / async / stance)        rewards.py:60-392
-//              warp 1  contact maxima, terminations, robot reward terms                      rewards.py:15-56, 398-466
-//              warp 2  object-transport reward terms                                         rewards.py:469-604
-//              warp 3  object_state_in_robot_frame for both observation groups               observations.py:38-91
-//              warps 4-7  new observation values (noise, scale) of the proprioceptive terms  [IL] ObservationManager
+// Block = 1024 threads = 32 consecutive envs: LANE == ENV in every per-env computation, WARP == TASK.  The rows of 32
+// consecutive envs are ONE contiguous span of every [N, row] input tensor, so all global traffic is coalesced and the
+// per-env arithmetic runs out of shared memory.  Every task is a serial dependent chain (measured: ~5 us each, cold or warm),
+// so the kernel is organised to run as many short chains side by side as an SM holds (32 warps, one block per SM).
+//   stage 0  one bulk async copy (cp.async.bulk, the TMA 1-D path; mbarrier completion) per state tensor, issued by the first
+//            lanes of every warp; gathers (feet rows, [terms, N] episode sums) one 4-byte cp.async per thread; launch-constant
+//            lookup tables arrive prebuilt (lt_mdp_build_tables).  The two observation history blocks (the bulk of the bytes)
+//            are requested after the state has landed and arrive while stage 1 runs.  Tail block / unaligned callers: per
+//            element cp.async.
+//   stage 1  18 fixed tasks + one task per 4 new observation values; first round task == warp, then a shared queue:
+//              0,1    gait state update + swing bonus of one synced pair            rewards.py:158-346
+//              2      gait task score, async / stance parts, final gait term        rewards.py:202-216, 348-392
+//              3,4    terminations (even / odd terms), alive                        terminations.py:10-23, rewards.py:15-22
+//              5-10   robot reward terms                                            rewards.py:24-56, 398-466
+//              11-13  object-transport reward terms                                 rewards.py:469-604
+//              14-17  object_state_in_robot_frame: policy pos+vel / ang-vel / quat (noise), critic   observations.py:38-91
+//              18+    proprioceptive observation values (noise, scale)              [IL] ObservationManager
 //   stage 2  all threads: weighted accumulation in manager order, episode sums, per-term outputs, gait state write back
-//            (zeroed for reset envs), and the history shift: shared -> global with 16-byte stores.
+//            (zeroed for reset envs), and the history shift: shared -> global, one warp per env row, 8-byte stores.
 // Floating point follows the reference's fp32 expression order (file is built with -fmad=false); masks are bit-exact.
 #include <cuda_pipeline.h>
 #include <string.h>
@@ -24,36 +31,43 @@
 
 namespace {
 
-#ifndef LT_MDP_ENVS
-#define LT_MDP_ENVS 8
-#endif
-constexpr int kEnvs = LT_MDP_ENVS;  // envs per block (multiple of 8 so that every staged span is 16-byte aligned; <= 16)
-constexpr int kThreads = 256;
+constexpr int kEnvs = 32;  // envs per block == lanes per warp
+constexpr int kThreads = 1024;  // 32 warps: the per-warp work is a serial dependent chain, so more (shorter) chains per SM
+                                          // is what hides latency; one block per SM
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxObsDim = 512;
 constexpr int kMaxNew = 96;
 constexpr int kMaxJ = 16;
 constexpr int kMaxSensorBodies = 32;
-constexpr int kMaxStage = 40;
+constexpr int kMaxStage = 36;
 constexpr int kGaitFloats = 24;  // per env: lsa[4] lsc[4] vla[4] last_cmd[3] steps sz[4] vpc[4]
+constexpr int kGaitStride = 25;
+constexpr int kFixedTasks = 18;
+constexpr int kS3 = 3, kS4 = 4;    // per-env strides of the bulk-copied 3- and 4-float rows (= row length)
+constexpr int kP4 = 5, kS12 = 13;  // padded strides of the rows the kernel gathers element by element
 
-// shared-memory layout (float offsets; per-env row stride = row length), filled in on the host
+// shared-memory layout (float offsets), filled in on the host.  Bulk-copied rows keep their row length as per-env stride.
 struct Layout {
   int cmd, pos, linb, angb, grav, q, qd, qdd, tau, q0, qd0, lim, act, pact, force, air, con, lair, fpos, fvel;
-  int quat, linw, angw, opos, oquat, olin, oang, ograv, oc_last, oc_cur, oc_air, fmax, g_lsa, g_lsc, g_vla, g_cmd, g_steps, g_sz, g_vpc, eplen, gait_out,
-      esum, raw, newobs, uscr, hist, map, total;
-  int D;    // observation dim per group
-  int dps;  // new values per step per group
-  int hist_stride;  // floats per group in the history staging area (kEnvs * D rounded up to 4)
+  int quat, linw, angw, opos, oquat, olin, oang, ograv, oc_last, oc_cur, oc_air, g_lsa, g_lsc, g_vla, g_cmd, g_steps, g_sz, g_vpc, eplen, gait_out,
+      esum, raw, gtmp, newobs, hist, map, total;
+  int sJ, sLim, sF;  // strides of the [J], [J, 2] and [H, S, 3] rows
+  int D;             // observation dim per group
+  int dps;           // new values per step per group
+  int sNew;          // stride of the new-value rows (dps | 1)
+  int hist_stride;   // floats per group in the history staging area (kEnvs * D rounded up to 4, + 4)
+  int tables_len;    // ints in the table block (see tables_len())
+  int bulk_ok;       // every [N, row] tensor base is 16-byte aligned: full blocks stage with cp.async.bulk
+  int hist_bulk_ok;  // likewise for the two history sources
+  unsigned tx_state; // bytes the state barrier of a full block waits for
 };
 
-// global -> shared copy descriptors for the plain [N, row] float tensors
+// global -> shared copy descriptors for the plain [N, row] float tensors (the block's kEnvs rows are one contiguous span)
 struct StageTable {
   int n;
   const float* src[kMaxStage];
-  int row[kMaxStage];
   int off[kMaxStage];
-  int vec[kMaxStage];  // 1: tensor base is 16-byte aligned
+  int row[kMaxStage];
 };
 
 struct Vec3 { float x, y, z; };
@@ -106,11 +120,8 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 __device__ __forceinline__ Vec3 ld3(const float* p) { return {p[0], p[1], p[2]}; }
 __device__ __forceinline__ Quat ld4(const float* p) { return {p[0], p[1], p[2], p[3]}; }
 __device__ __forceinline__ Vec3 sub3(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-__device__ __noinline__ float uniform_at(uint64_t seed, uint64_t offset, uint32_t n, uint32_t j) {
-  const uint4 r = lt::Philox::gen(seed, offset, n, j >> 2);
-  const uint32_t w = (j & 3) == 0 ? r.x : ((j & 3) == 1 ? r.y : ((j & 3) == 2 ? r.z : r.w));
-  return lt::Philox::u01(w);
-}
+// one shared copy of the generator: the kernel is bound by instruction fetch (every warp runs different code), so code size matters
+__device__ __noinline__ uint4 philox4(uint64_t seed, uint64_t offset, uint32_t a, uint32_t b) { return lt::Philox::gen(seed, offset, a, b); }
 
 // ---------------------------------------------------------------------------------------------- gait (rewards.py:60-392)
 struct GaitRegs {
@@ -196,24 +207,6 @@ __device__ __noinline__ float gait_swing_bonus(const GaitP gp, float a0, float a
   return e ? r : 0.f;
 }
 
-// rewards.py:218-241 for the pair of gait feet (f0, f0+1)
-__device__ __forceinline__ float gait_sync(const GaitP gp, const GaitRegs& g, const float a[4], const float c[4], int pair, float score) {
-  const float th = gp.judge_time_threshold;
-  const int f0 = pair ? 2 : 0, f1 = f0 + 1, o0 = pair ? 0 : 2;
-  const bool both_air = a[f0] > th && a[f0] < gp.air_time_gait_bound && a[f1] > th && a[f1] < gp.air_time_gait_bound;
-  const bool c0 = c[f0] > th && c[f0] < gp.contact_time_gait_bound;
-  const bool c1 = c[f1] > th && c[f1] < gp.contact_time_gait_bound;
-  const bool both_contact = c0 && c1;
-  if (gp.encourage_symmetricity) {
-    float bonus = gait_swing_bonus(gp, a[f0], a[f1], g.vla[f0], g.vla[f1], g.vla[o0], g.vla[o0 + 1]);
-    const float scale = 1.f - gp.task_performance_ratio + gp.task_performance_ratio * score;
-    if (bonus > 0.f) bonus *= scale;
-    bonus += 1.f;
-    return both_air ? bonus : (both_contact ? 1.f : 0.f);
-  }
-  return (both_air || both_contact) ? 1.f : 0.f;
-}
-
 // rewards.py:348-363
 __device__ __noinline__ float gait_async(const GaitP gp, float a0, float a1, float c0t, float c1t) {
   const float th = gp.judge_time_threshold, tha = gp.async_judge_time_threshold;
@@ -234,11 +227,55 @@ __global__ void any_nonzero_cmd_kernel(const float* __restrict__ cmd, int N, int
   if (threadIdx.x == 0) flag_ws[step & 1] = any ? step : -1;
 }
 
-__global__ void __launch_bounds__(kThreads, kEnvs <= 8 ? 4 : 2) mdp_step_kernel(const LtMdpArgs A, const Layout L, const StageTable ST) {
+// Optional in-kernel timeline (profiling builds only: LT_MDP_PROF=1 python -m locotouch_b200.csrc.build --force; tools/mdp_timeline.py)
+#ifdef LT_MDP_PROF
+__device__ long long* g_mdp_prof = nullptr;  // [blocks][kWarps][32] clock64 stamps
+#define PROF_STAMP(slot)                                                                                   \
+  do {                                                                                                     \
+    if (g_mdp_prof && lane == 0) g_mdp_prof[((size_t)blockIdx.x * kWarps + warp) * 32 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define PROF_STAMP(slot) do { } while (0)
+#endif
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// global -> shared bulk async copy (TMA 1-D): 16-byte aligned addresses, size a multiple of 16; completion on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void named_barrier(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// max over the history of |F| of one sensor body: torch.max(torch.norm(net_forces_w_history[:, :, ids], dim=-1), dim=1)[0]
+__device__ __noinline__ float body_force_max(const float* force_env, int H, int S, int b) {
+  float m = 0.f;
+#pragma unroll 1
+  for (int h = 0; h < H; ++h) {
+    const float* p = force_env + (h * S + b) * 3;
+    m = fmaxf(m, sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A, const Layout L, const StageTable ST) {
   extern __shared__ __align__(16) float sm[];
-  __shared__ unsigned char s_done[kEnvs], s_fill[kEnvs];
-  __shared__ int s_step, s_any_nz;
-  __shared__ signed char s_slot[LT_RK_COUNT];  // reward kind -> index in the term table (-1: absent or zero weight)
+  __shared__ unsigned char s_done[kEnvs], s_fill[kEnvs], s_tflag[kEnvs];
+  __shared__ int s_step, s_any_nz, s_next_task;
+  __shared__ __align__(8) unsigned long long s_bar[2];  // mbarriers: [0] state tensors + tables, [1] observation history
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int e0 = blockIdx.x * kEnvs;
   const int nvalid = min(kEnvs, A.N - e0);
@@ -246,54 +283,72 @@ __global__ void __launch_bounds__(kThreads, kEnvs <= 8 ? 4 : 2) mdp_step_kernel(
   const bool has_obj = A.obj_root_pos_w != nullptr;
   const int J = A.J, S = A.num_sensor_bodies, H = A.force_history;
   const int D = L.D, dps = L.dps, T = A.num_reward_terms;
+  const int sJ = L.sJ, sNew = L.sNew;
 
+  PROF_STAMP(0);
   // ------------------------------------------------------------------------------------------------ stage 0: loads
-  // (b) plain [N, row] tensors, one descriptor per warp and round; full blocks move 16 bytes per lane (8 envs x row floats is
-  //     a multiple of 16 bytes and the span starts 16-byte aligned whenever the tensor itself does)
+  // Full blocks with 16-byte aligned tensors: ONE bulk async copy (cp.async.bulk, the TMA 1-D path) per tensor, issued by
+  // the lanes of warp 0 and tracked by an mbarrier -- a few dozen instructions instead of one cp.async per element.  The tail
+  // block (nvalid < kEnvs) and unaligned callers take the per-element path below.
+  const bool bulk = L.bulk_ok && nvalid == kEnvs;
+  const bool bulk_hist = do_obs && L.hist_bulk_ok && nvalid == kEnvs;
+  int* s_map = reinterpret_cast<int*>(sm + L.map);
+  int* s_jinfo = s_map + ((D + 3) & ~3);
+  int* s_slot = s_jinfo + dps;  // reward kind -> index in the term table (-1: absent or zero weight)
+  const float* s_kpar = reinterpret_cast<const float*>(s_slot + LT_RK_COUNT);  // [kind][6] parameters of the active term of each kind
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    s_next_task = kWarps;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // every warp issues the copies of tensors warp, warp + 16, ... from its first lanes (a bulk copy is one instruction per lane);
+  // thread 0 posts the expected byte count -- the barrier cannot complete before that arrival, whatever order the copies finish in
+  if (bulk) {
+    if (tid == 0) mbar_expect_tx(&s_bar[0], L.tx_state);
+    const int t = warp + kWarps * lane;
+    if (t < ST.n) bulk_g2s(sm + ST.off[t], ST.src[t] + (size_t)e0 * ST.row[t], (unsigned)(kEnvs * 4) * ST.row[t], &s_bar[0]);
+    if (tid == kThreads - 32 && A.tables) bulk_g2s(s_map, A.tables, (unsigned)L.tables_len * 4u, &s_bar[0]);
+  }
+  if (!bulk) {
 #pragma unroll 1
-  for (int t = warp; t < ST.n; t += kWarps) {
-    const int row = ST.row[t];
-    const float* src = ST.src[t] + (size_t)e0 * row;
-    float* dst = sm + ST.off[t];
-    const int count = nvalid * row;
-    if (ST.vec[t] && nvalid == kEnvs) {
-      for (int i = lane; i < (count >> 2); i += 32) __pipeline_memcpy_async(dst + 4 * i, src + 4 * i, 16);
-    } else {
-      for (int i = lane; i < count; i += 32) __pipeline_memcpy_async(dst + i, src + i, 4);
+    for (int t = 0; t < ST.n; ++t) {
+      const float* src = ST.src[t] + (size_t)e0 * ST.row[t];
+      float* dst = sm + ST.off[t];
+      const int count = nvalid * ST.row[t];
+#pragma unroll 1
+      for (int i = tid; i < count; i += kThreads) __pipeline_memcpy_async(dst + i, src + i, 4);
+    }
+    if (A.tables) {
+#pragma unroll 1
+      for (int i = tid; i < L.tables_len; i += kThreads) s_map[i] = A.tables[i];
     }
   }
-  // (c) gathers with arbitrary body ids / non-float types: ONE pass, every thread issues at most a few independent
-  //     4-byte cp.async (no load sits inside a loop-carried chain, so the block pays a single DRAM round trip)
+  // gathers with arbitrary body ids / non-float types: ONE pass, every thread issues a few independent copies
   if (do_rew) {
-    if (tid < nvalid * 4) {  // feet rows of the contact timers
-      const int e = tid >> 2, k = tid & 3;
+    if (tid >= 384 && tid < 384 + nvalid * 4) {  // feet rows of the contact timers
+      const int i = tid - 384, e = i >> 2, k = i & 3;
       const size_t r = (size_t)(e0 + e) * S + A.gait.feet_ids[k];
-      __pipeline_memcpy_async(sm + L.air + tid, A.current_air_time + r, 4);
-      __pipeline_memcpy_async(sm + L.con + tid, A.current_contact_time + r, 4);
-      __pipeline_memcpy_async(sm + L.lair + tid, A.last_air_time + r, 4);
+      __pipeline_memcpy_async(sm + L.air + e * kP4 + k, A.current_air_time + r, 4);
+      __pipeline_memcpy_async(sm + L.con + e * kP4 + k, A.current_contact_time + r, 4);
+      __pipeline_memcpy_async(sm + L.lair + e * kP4 + k, A.last_air_time + r, 4);
     }
-    if (tid >= 32 && tid < 32 + nvalid * 12) {  // feet rows of body_pos_w / body_lin_vel_w
-      const int i = tid - 32;
-      const int e = i / 12, k = (i % 12) / 3, c = i % 3;
+    if (tid < nvalid * 12) {  // feet rows of body_pos_w / body_lin_vel_w
+      const int e = tid / 12, rc = tid - e * 12, k = rc / 3, c = rc - k * 3;
       const size_t r = ((size_t)(e0 + e) * A.num_bodies + A.feet_body_ids[k]) * 3 + c;
-      __pipeline_memcpy_async(sm + L.fpos + i, A.body_pos_w + r, 4);
-      __pipeline_memcpy_async(sm + L.fvel + i, A.body_lin_vel_w + r, 4);
+      __pipeline_memcpy_async(sm + L.fpos + e * kS12 + rc, A.body_pos_w + r, 4);
+      __pipeline_memcpy_async(sm + L.fvel + e * kS12 + rc, A.body_lin_vel_w + r, 4);
     }
-    if (A.episode_sums && tid >= 128 && tid < 128 + T) {  // [terms][N]: kEnvs contiguous floats per term
-      const int t = tid - 128;
-      const float* src = A.episode_sums + (size_t)t * A.N + e0;
-      for (int e = 0; e < nvalid; ++e) __pipeline_memcpy_async(sm + L.esum + t * kEnvs + e, src + e, 4);
-    }
-    if (tid >= 192 && tid < 192 + nvalid * 4) {  // bool gait state -> float
-      const int i = tid - 192;
-      sm[L.g_sz + i] = (float)A.gait_state.swinging_in_zero_cmd[(size_t)e0 * 4 + i];
-      sm[L.g_vpc + i] = (float)A.gait_state.valid_previous_contact[(size_t)e0 * 4 + i];
-    }
-    if (tid >= 224 && tid < 224 + nvalid) {
-      reinterpret_cast<long long*>(sm + L.eplen)[tid - 224] = A.episode_length_buf[e0 + tid - 224];
+    if (A.episode_sums) {  // [terms][N]: kEnvs contiguous floats per term
+#pragma unroll 1
+      for (int i = tid; i < T * kEnvs; i += kThreads) {
+        const int t = i >> 5, e = i & 31;
+        if (e < nvalid) __pipeline_memcpy_async(sm + L.esum + i, A.episode_sums + (size_t)t * A.N + e0 + e, 4);
+      }
     }
   }
-  if (tid == 255) {  // env-step index and the cross-env any(non_zero_cmd) flag (one dependent pair of loads, one thread)
+  if (tid == kThreads - 1) {  // env-step index and the cross-env any(non_zero_cmd) flag (one dependent pair of loads, one thread)
     const int st = (int)(A.offset + (A.offset_base ? (uint64_t)*A.offset_base : 0ull));
     s_step = st;
     int any_nz = 1;
@@ -302,8 +357,7 @@ __global__ void __launch_bounds__(kThreads, kEnvs <= 8 ? 4 : 2) mdp_step_kernel(
     s_any_nz = any_nz;
   }
   __pipeline_commit();
-  // (a) observation history blocks: the block's kEnvs rows of each group are one 16-byte aligned contiguous span
-  if (do_obs) {
+  if (do_obs && !bulk_hist) {  // observation history blocks, per-element path
     const int total = nvalid * D;
 #pragma unroll 1
     for (int grp = 0; grp < 2; ++grp) {
@@ -311,292 +365,542 @@ __global__ void __launch_bounds__(kThreads, kEnvs <= 8 ? 4 : 2) mdp_step_kernel(
       if (!in) continue;
       const float* src = in + (size_t)e0 * D;
       float* dst = sm + L.hist + grp * L.hist_stride;
-      if ((((uintptr_t)src) & 15) == 0) {
-        const int n4 = total >> 2;
-        for (int i = tid; i < n4; i += kThreads) __pipeline_memcpy_async(dst + 4 * i, src + 4 * i, 16);
-        for (int i = (n4 << 2) + tid; i < total; i += kThreads) __pipeline_memcpy_async(dst + i, src + i, 4);
-      } else {
-        for (int i = tid; i < total; i += kThreads) __pipeline_memcpy_async(dst + i, src + i, 4);
-      }
-    }
-    __pipeline_commit();
-  }
-  // Observation layout tables (built once per block):
-  //   s_map[k]  for column k of the flattened [term][history][dim] row: low 16 bits = index j of the per-step value that
-  //             feeds the column (used when the history is (re)filled), high 16 bits = k + d, the column one history
-  //             slot later of the same term (the shift source), or 0xffff when k is the newest slot
-  //   s_jinfo[j] for per-step value j: term index | component << 8
-  int* s_map = reinterpret_cast<int*>(sm + L.map);
-  int* s_jinfo = s_map + ((D + 3) & ~3);
-  if (do_obs && warp >= 5) {
-    for (int k = tid - 5 * 32; k < D + dps; k += 3 * 32) {
-      int col = 0, jbase = 0;
-      if (k < D) {
-        int entry = 0;
-        for (int t = 0; t < A.num_obs_terms; ++t) {
-          const int d = A.obs_terms[t].dim, span = d * A.history_length;
-          if (k < col + span) {
-            const int h = (k - col) / d, i = (k - col) % d;
-            entry = (jbase + i) | ((h == A.history_length - 1 ? 0xffff : k + d) << 16);
-            break;
-          }
-          col += span;
-          jbase += d;
-        }
-        s_map[k] = entry;
-      } else {
-        const int j = k - D;
-        int t = 0;
-        while (j >= jbase + A.obs_terms[t].dim) { jbase += A.obs_terms[t].dim; ++t; }
-        s_jinfo[j] = t | ((j - jbase) << 8);
-      }
-    }
-  }
-  if (do_rew && tid >= 64 && tid < 64 + LT_RK_COUNT) {
-    const int kind = tid - 64;
-    int slot = -1;
 #pragma unroll 1
-    for (int i = 0; i < T; ++i)
-      if (A.reward_terms[i].kind == kind && A.reward_terms[i].weight != 0.f) slot = i;
-    s_slot[kind] = (signed char)slot;
+      for (int i = tid; i < total; i += kThreads) __pipeline_memcpy_async(dst + i, src + i, 4);
+    }
   }
-  __pipeline_wait_prior(do_obs ? 1 : 0);  // the state tensors have landed; the history blocks may still be in flight
-  if (tid < kEnvs) {
-    s_fill[tid] = (do_obs && A.obs_fill && tid < nvalid) ? A.obs_fill[e0 + tid] : 0;
-    s_done[tid] = 0;
+  __pipeline_commit();
+  // non-float state: plain loads, issued after every asynchronous copy is in flight
+  if (do_rew) {
+    if (tid < nvalid * 4) {
+      const float sz = (float)A.gait_state.swinging_in_zero_cmd[(size_t)e0 * 4 + tid];
+      const float vpc = (float)A.gait_state.valid_previous_contact[(size_t)e0 * 4 + tid];
+      sm[L.g_sz + (tid >> 2) * kP4 + (tid & 3)] = sz;
+      sm[L.g_vpc + (tid >> 2) * kP4 + (tid & 3)] = vpc;
+    }
+    if (tid >= 128 && tid < 128 + nvalid) reinterpret_cast<long long*>(sm + L.eplen)[tid - 128] = A.episode_length_buf[e0 + tid - 128];
   }
+  if (tid >= 160 && tid < 160 + kEnvs) {
+    const int i = tid - 160;
+    s_fill[i] = (i < nvalid && do_obs && A.obs_fill) ? A.obs_fill[e0 + i] : 0;
+    s_done[i] = 0;
+  }
+  if (!A.tables) {
+    // Observation layout tables built in the kernel (callers that do not pass lt_mdp_build_tables() output):
+    //   s_map[k]  for column k of the flattened [term][history][dim] row: low 16 bits = index j of the per-step value that
+    //             feeds the column (used when the history is (re)filled), high 16 bits = k + d, the column one history
+    //             slot later of the same term (the shift source), or 0xffff when k is the newest slot
+    //   s_jinfo[j] for per-step value j: term index | component << 8
+    if (do_obs) {
+#pragma unroll 1
+      for (int k = tid; k < D + dps; k += kThreads) {
+        int col = 0, jbase = 0;
+        if (k < D) {
+          int entry = 0;
+#pragma unroll 1
+          for (int t = 0; t < A.num_obs_terms; ++t) {
+            const int d = A.obs_terms[t].dim, span = d * A.history_length;
+            if (k < col + span) {
+              const int h = (k - col) / d, i = (k - col) % d;
+              entry = (jbase + i) | ((h == A.history_length - 1 ? 0xffff : k + d) << 16);
+              break;
+            }
+            col += span;
+            jbase += d;
+          }
+          s_map[k] = entry;
+        } else {
+          const int j = k - D;
+          int t = 0;
+          while (j >= jbase + A.obs_terms[t].dim) { jbase += A.obs_terms[t].dim; ++t; }
+          s_jinfo[j] = t | ((j - jbase) << 8);
+        }
+      }
+    }
+    if (tid >= 256 && tid < 256 + LT_RK_COUNT) {
+      const int kind = tid - 256;
+      int slot = -1;
+#pragma unroll 1
+      for (int i = 0; i < T; ++i)
+        if (A.reward_terms[i].kind == kind && A.reward_terms[i].weight != 0.f) slot = i;
+      s_slot[kind] = slot;
+#pragma unroll 1
+      for (int k = 0; k < 6; ++k) reinterpret_cast<float*>(s_slot + LT_RK_COUNT)[kind * 6 + k] = slot >= 0 ? A.reward_terms[slot].p[k] : 0.f;
+    }
+  }
+  PROF_STAMP(1);
+  __pipeline_wait_prior(1);  // gathers (and the per-element state copies) have landed; the history may still be in flight
+  if (bulk) mbar_wait(&s_bar[0], 0);
+  PROF_STAMP(2);
   __syncthreads();
+  PROF_STAMP(3);
+  // the history blocks (the bulk of the bytes) are requested only now: they are not needed before stage 2 and would otherwise
+  // compete with the state tensors for the bandwidth of the very first microseconds
+  if (bulk_hist && warp == kWarps - 2) {
+    const unsigned bytes = (unsigned)(kEnvs * 4) * D;
+    if (lane == 0) mbar_expect_tx(&s_bar[1], (A.policy_obs_in ? bytes : 0u) + (A.critic_obs_in ? bytes : 0u));
+    if (lane < 2) {
+      const float* in = lane ? A.critic_obs_in : A.policy_obs_in;
+      if (in) bulk_g2s(sm + L.hist + lane * L.hist_stride, in + (size_t)e0 * D, bytes, &s_bar[1]);
+    }
+  }
   const int step = s_step;
   const uint64_t rng_offset = (uint64_t)(int64_t)step;
 
-  // ------------------------------------------------------------------------------------------------ stage 1: roles
-  float* s_raw = sm + L.raw;  // [T][kEnvs]
-  if (warp == 0) {
-    // ---- gait reward
-    if (do_rew && lane < nvalid) {
-      const int e = lane;
+  // ------------------------------------------------------------------------------------------------ stage 1: tasks
+  float* s_raw = sm + L.raw;  // [LT_RK_COUNT][kEnvs]: unweighted value of every reward kind (stage 2a picks the task's terms)
+  float* nv = sm + L.newobs;  // [2 groups][kEnvs][sNew]
+  const int e = lane, n = e0 + e;
+  const bool live = e < nvalid;
+  const int quads = do_obs ? (dps + 3) >> 2 : 0;
+  auto put = [&](int kind, float v) { s_raw[kind * kEnvs + e] = v; };
+  auto par = [&](int kind, int k) -> float { return s_kpar[kind * 6 + k]; };
+  // publish any(non_zero_cmd) for the reward pass of the NEXT step (it sees the same command tensor)
+  if (do_obs && A.any_flag_ws && warp == kWarps - 1 && live) {
+    const float* c = sm + L.cmd + e * kS3;
+    if (sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) > 0.f) A.any_flag_ws[(step + 1) & 1] = step + 1;
+  }
+  // first round static (task == warp: the three gait tasks meet at a named barrier), then a shared queue: warps whose fixed
+  // task was short pick up the per-quad observation tasks while the long ones are still running
+  auto next_task = [&]() -> int {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&s_next_task, 1);
+    return __shfl_sync(LT_FULL_MASK, t, 0);
+  };
+#ifdef LT_MDP_TWICE  // experiment: run the (idempotent) task phase twice; the second pass sees warm instruction / constant caches
+  for (int pass = 0; pass < 2; ++pass) {
+  if (pass) {
+    __syncthreads();
+    if (tid == 0) s_next_task = kWarps;
+    __syncthreads();
+    PROF_STAMP(12);
+  }
+#endif
+#pragma unroll 1
+  for (int task = warp; task < kFixedTasks + quads; task = next_task()) {
+    PROF_STAMP(task < kWarps ? 8 : 10);
+    if (task <= 2) {
+      // ---------------------------------------------------------------------------------------------- gait reward
+      if (!do_rew) continue;
       const int gi = s_slot[LT_RK_GAIT];
-      if (gi >= 0) {
-        GaitP gp;
-        gp.judge_time_threshold = A.gait.judge_time_threshold;
-        gp.async_judge_time_threshold = A.gait.async_judge_time_threshold;
-        gp.air_time_gait_bound = A.gait.air_time_gait_bound;
-        gp.contact_time_gait_bound = A.gait.contact_time_gait_bound;
-        gp.tolerance_proportion = A.gait.tolerance_proportion;
-        gp.rwd_upper_bound = A.gait.rwd_upper_bound;
-        gp.rwd_lower_bound = A.gait.rwd_lower_bound;
-        gp.linear_scale = A.gait.linear_scale;
-        gp.two_step_dt = A.gait.two_step_dt;
-        gp.task_performance_ratio = A.gait.task_performance_ratio;
-        gp.encourage_symmetricity = A.gait.encourage_symmetricity;
-        const float th = gp.judge_time_threshold;
-        const Vec3 cmd = ld3(sm + L.cmd + e * 3), vb = ld3(sm + L.linb + e * 3);
-        const float wz = sm[L.angb + e * 3 + 2];
-        const bool nz = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) > 0.f;
-        GaitRegs g;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          g.lsa[k] = sm[L.g_lsa + e * 4 + k]; g.lsc[k] = sm[L.g_lsc + e * 4 + k]; g.vla[k] = sm[L.g_vla + e * 4 + k];
-          g.sz[k] = sm[L.g_sz + e * 4 + k] != 0.f; g.vpc[k] = sm[L.g_vpc + e * 4 + k] != 0.f;
-        }
-        g.last_cmd[0] = sm[L.g_cmd + e * 3]; g.last_cmd[1] = sm[L.g_cmd + e * 3 + 1]; g.last_cmd[2] = sm[L.g_cmd + e * 3 + 2];
-        g.steps = sm[L.g_steps + e];
-        float a[4], c[4], la[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { a[k] = sm[L.air + e * 4 + k]; c[k] = sm[L.con + e * 4 + k]; la[k] = sm[L.lair + e * 4 + k]; }
-        const bool any_nz = s_any_nz != 0;
-        gait_update(g, a, c, la, cmd, nz, any_nz, th);
-        float score = 0.f;  // rewards.py:202-216 / 372-392
-        if (gp.encourage_symmetricity) {
-          const float dx = cmd.x - vb.x, dy = cmd.y - vb.y;
-          const float e_lin = nz ? sqrtf(dx * dx + dy * dy) : 0.f;
-          const float e_ang = nz ? fabsf(cmd.z - wz) : 0.f;
-          score = (exp_neg_over(e_lin, A.gait.vel_tracking_exp_sigma) + exp_neg_over(e_ang, A.gait.vel_tracking_exp_sigma)) / 2.f;
-          if (A.gait.with_object) {
-            const Vec3 rel_w = sub3(ld3(sm + L.opos + e * 3), ld3(sm + L.pos + e * 3));
-            const Vec3 r = rot_inv(yaw_quat(yaw_of(ld4(sm + L.quat + e * 4))), rel_w);
-            const float bx = clampf(1.f - fabsf(r.x) / A.gait.obj_x_max, 0.f, 1.f);
-            const float by = clampf(1.f - fabsf(r.y) / A.gait.obj_y_max, 0.f, 1.f);
-            score = clampf((score * 2.f + (bx + by) / 2.f) / 3.f, 0.f, 1.f);
-          }
-        }
-        const float sync = (gait_sync(gp, g, a, c, 0, score) + gait_sync(gp, g, a, c, 1, score)) / 2.f;
-        const float asyn = (gait_async(gp, a[0], a[2], c[0], c[2]) + gait_async(gp, a[1], a[3], c[1], c[3]) +
-                            gait_async(gp, a[0], a[3], c[0], c[3]) + gait_async(gp, a[2], a[1], c[2], c[1])) / 4.f;
-        const float stepping = (sync + asyn) / 2.f;
-        const float stance = ((c[0] > th && c[1] > th && c[2] > th && c[3] > th) ? 1.f : 0.f) * A.gait.stance_rwd_scale;
-        s_raw[gi * kEnvs + e] = nz ? stepping : stance;
-        float* go = sm + L.gait_out + e * kGaitFloats;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          go[k] = g.lsa[k]; go[4 + k] = g.lsc[k]; go[8 + k] = g.vla[k];
-          go[16 + k] = g.sz[k] ? 1.f : 0.f; go[20 + k] = g.vpc[k] ? 1.f : 0.f;
-        }
-        go[12] = g.last_cmd[0]; go[13] = g.last_cmd[1]; go[14] = g.last_cmd[2]; go[15] = g.steps;
-      } else {
-        // no gait term: carry the state through unchanged
-        float* go = sm + L.gait_out + e * kGaitFloats;
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-          go[k] = sm[L.g_lsa + e * 4 + k]; go[4 + k] = sm[L.g_lsc + e * 4 + k]; go[8 + k] = sm[L.g_vla + e * 4 + k];
-          go[16 + k] = sm[L.g_sz + e * 4 + k]; go[20 + k] = sm[L.g_vpc + e * 4 + k];
-        }
-        go[12] = sm[L.g_cmd + e * 3]; go[13] = sm[L.g_cmd + e * 3 + 1]; go[14] = sm[L.g_cmd + e * 3 + 2]; go[15] = sm[L.g_steps + e];
-      }
-    }
-  } else if (warp == 1) {
-    // ---- contact maxima, terminations, robot terms
-    if (do_rew) {
-      for (int i = lane; i < nvalid * S; i += 32) {
-        const int e = i / S, b = i % S;
-        const float* f = sm + L.force + e * (H * S * 3);
-        float m = 0.f;
-#pragma unroll 1
-        for (int h = 0; h < H; ++h) {
-          const float* p = f + (h * S + b) * 3;
-          m = fmaxf(m, sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));  // torch.max(norm(F, dim=-1), dim=1)
-        }
-        sm[L.fmax + i] = m;
-      }
-      __syncwarp();
-      if (lane < nvalid) {
-        const int e = lane, n = e0 + e;
-        bool terminated = false, timed_out = false;
-#pragma unroll 1
-        for (int t = 0; t < A.num_termination_terms; ++t) {
-          const LtTerminationTerm& tt = A.termination_terms[t];
-          bool m = false;
-          switch (tt.kind) {
-            case LT_TK_TIME_OUT: m = reinterpret_cast<const long long*>(sm + L.eplen)[e] >= A.max_episode_length; break;
-            case LT_TK_BAD_ORIENTATION: m = fabsf(acosf(-sm[L.grav + e * 3 + 2])) > tt.p[0]; break;
-            case LT_TK_ROOT_HEIGHT: m = sm[L.pos + e * 3 + 2] < tt.p[0]; break;
-            case LT_TK_ILLEGAL_CONTACT:
-#pragma unroll 1
-              for (int k = 0; k < tt.num_ids; ++k) m = m || sm[L.fmax + e * S + tt.body_ids[k]] > tt.p[0];
-              break;
-            case LT_TK_OBJECT_BELOW_ROBOT: m = sm[L.opos + e * 3 + 2] < sm[L.pos + e * 3 + 2]; break;
-            case LT_TK_BAD_ROLL: m = fabsf(asinf(sm[L.ograv + e * 3 + 1])) > tt.p[0]; break;
-          }
-          if (A.term_masks) A.term_masks[(size_t)t * A.N + n] = m;
-          if (tt.time_out) timed_out = timed_out || m; else terminated = terminated || m;
-        }
-        const bool done = terminated || timed_out;
-        s_done[e] = done;
-        A.terminated[n] = terminated;
-        A.time_outs[n] = timed_out;
-        A.dones[n] = done;
-        if (A.auto_reset && done) {  // history of a reset env is refilled by its next observation
-          if (do_obs) s_fill[e] = 1;
-          else if (A.obs_fill) A.obs_fill[n] = 1;
-        }
-        // robot reward terms, straight-line: every value is computed, stored only when the task lists the term
-        auto put = [&](int kind, float v) {
-          const int i = s_slot[kind];
-          if (i >= 0) s_raw[i * kEnvs + e] = v;
-        };
-        auto par = [&](int kind, int k) -> float {
-          const int i = s_slot[kind];
-          return A.reward_terms[i < 0 ? 0 : i].p[k];
-        };
-        const Vec3 cmd = ld3(sm + L.cmd + e * 3), vb = ld3(sm + L.linb + e * 3), wb = ld3(sm + L.angb + e * 3);
-        const Vec3 grav = ld3(sm + L.grav + e * 3);
-        const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
-        const float* fmx = sm + L.fmax + e * S;
-        const float* fpos = sm + L.fpos + e * 12;
-        const float* fvel = sm + L.fvel + e * 12;
-        put(LT_RK_ALIVE, terminated ? 0.f : 1.f);
-        {
-          const float dx = cmd.x - vb.x, dy = cmd.y - vb.y;
-          put(LT_RK_TRACK_LIN_VEL_XY, exp_neg_over(sqrtf(dx * dx + dy * dy), par(LT_RK_TRACK_LIN_VEL_XY, 0)));
-          put(LT_RK_TRACK_ANG_VEL_Z, exp_neg_over(fabsf(cmd.z - wb.z), par(LT_RK_TRACK_ANG_VEL_Z, 0)));
-        }
-        {
-          const float slip_thr = par(LT_RK_FOOT_SLIP, 0), drag_h = par(LT_RK_FOOT_DRAG, 0), drag_v = par(LT_RK_FOOT_DRAG, 1);
-          float slip = 0.f, drag = 0.f;
+      if (gi < 0) {  // no gait term: carry the state through unchanged
+        if (task == 0 && live) {
+          float* go = sm + L.gait_out + e * kGaitStride;
 #pragma unroll 1
           for (int k = 0; k < 4; ++k) {
-            const float sp = sqrtf(fvel[3 * k] * fvel[3 * k] + fvel[3 * k + 1] * fvel[3 * k + 1]);
-            slip += (fmx[A.feet_sensor_ids[k]] > slip_thr ? 1.f : 0.f) * sp;
-            drag += (fpos[3 * k + 2] <= drag_h && sp > drag_v) ? 1.f : 0.f;
+            go[k] = sm[L.g_lsa + e * kS4 + k]; go[4 + k] = sm[L.g_lsc + e * kS4 + k]; go[8 + k] = sm[L.g_vla + e * kS4 + k];
+            go[16 + k] = sm[L.g_sz + e * kP4 + k]; go[20 + k] = sm[L.g_vpc + e * kP4 + k];
           }
-          put(LT_RK_FOOT_SLIP, slip);
-          put(LT_RK_FOOT_DRAG, drag);
+          go[12] = sm[L.g_cmd + e * kS3]; go[13] = sm[L.g_cmd + e * kS3 + 1]; go[14] = sm[L.g_cmd + e * kS3 + 2]; go[15] = sm[L.g_steps + e];
         }
-        {
-          const float d = sm[L.pos + e * 3 + 2] - par(LT_RK_BASE_HEIGHT, 0);
-          put(LT_RK_BASE_HEIGHT, d * d);
-          put(LT_RK_BASE_Z_VEL, vb.z * vb.z);
-          put(LT_RK_BASE_RP_ANGLE, grav.x * grav.x + grav.y * grav.y);
-          put(LT_RK_BASE_RP_VEL, fabsf(wb.x) + fabsf(wb.y));
-        }
-        {
-          const float* qq = sm + L.q + e * J; const float* q0 = sm + L.q0 + e * J; const float* lim = sm + L.lim + e * 2 * J;
-          const float* qd = sm + L.qd + e * J; const float* qdd = sm + L.qdd + e * J; const float* tau = sm + L.tau + e * J;
-          const float* ac = sm + L.act + e * J; const float* pa = sm + L.pact + e * J;
-          float s_lim = 0.f, s_dev = 0.f, s_acc = 0.f, s_vel = 0.f, s_tau = 0.f, s_rate = 0.f;
-#pragma unroll 2
-          for (int j = 0; j < J; ++j) {
-            s_lim += -fminf(qq[j] - lim[2 * j], 0.f) + fmaxf(qq[j] - lim[2 * j + 1], 0.f);
-            const float d = qq[j] - q0[j];
-            s_dev += d * d;
-            s_acc += qdd[j] * qdd[j];
-            s_vel += qd[j] * qd[j];
-            s_tau += tau[j] * tau[j];
-            const float da = ac[j] - pa[j];
-            s_rate += da * da;
+        continue;
+      }
+      GaitP gp;
+      gp.judge_time_threshold = A.gait.judge_time_threshold;
+      gp.async_judge_time_threshold = A.gait.async_judge_time_threshold;
+      gp.air_time_gait_bound = A.gait.air_time_gait_bound;
+      gp.contact_time_gait_bound = A.gait.contact_time_gait_bound;
+      gp.tolerance_proportion = A.gait.tolerance_proportion;
+      gp.rwd_upper_bound = A.gait.rwd_upper_bound;
+      gp.rwd_lower_bound = A.gait.rwd_lower_bound;
+      gp.linear_scale = A.gait.linear_scale;
+      gp.two_step_dt = A.gait.two_step_dt;
+      gp.task_performance_ratio = A.gait.task_performance_ratio;
+      gp.encourage_symmetricity = A.gait.encourage_symmetricity;
+      const float th = gp.judge_time_threshold;
+      float* gtmp = sm + L.gtmp;  // [pair][bonus, code][kEnvs]
+      const Vec3 cmd = ld3(sm + L.cmd + e * kS3);
+      const bool nz = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) > 0.f;
+      float a[4], c[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k] = sm[L.air + e * kP4 + k]; c[k] = sm[L.con + e * kP4 + k]; }
+      if (task < 2) {
+        // tasks 0 / 1: state update (rewards.py:158-200; both warps compute it, task 0 stores it) + one synced pair (:218-241)
+        if (live) {
+          GaitRegs g;
+          float la[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            g.lsa[k] = sm[L.g_lsa + e * kS4 + k]; g.lsc[k] = sm[L.g_lsc + e * kS4 + k]; g.vla[k] = sm[L.g_vla + e * kS4 + k];
+            g.sz[k] = sm[L.g_sz + e * kP4 + k] != 0.f; g.vpc[k] = sm[L.g_vpc + e * kP4 + k] != 0.f;
+            la[k] = sm[L.lair + e * kP4 + k];
           }
-          put(LT_RK_JOINT_POS_LIMIT, s_lim);
-          const float dev = sqrtf(s_dev), bv = sqrtf(vb.x * vb.x + vb.y * vb.y);
-          put(LT_RK_JOINT_POS, (cmd_norm > 0.f || bv > par(LT_RK_JOINT_POS, 1)) ? dev : par(LT_RK_JOINT_POS, 0) * dev);
-          put(LT_RK_JOINT_ACC, sqrtf(s_acc));
-          put(LT_RK_JOINT_VEL, sqrtf(s_vel));
-          put(LT_RK_JOINT_TORQUE, sqrtf(s_tau));
-          put(LT_RK_ACTION_RATE, s_rate);
+          g.last_cmd[0] = sm[L.g_cmd + e * kS3]; g.last_cmd[1] = sm[L.g_cmd + e * kS3 + 1]; g.last_cmd[2] = sm[L.g_cmd + e * kS3 + 2];
+          g.steps = sm[L.g_steps + e];
+          gait_update(g, a, c, la, cmd, nz, s_any_nz != 0, th);
+          if (task == 0) {
+            float* go = sm + L.gait_out + e * kGaitStride;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              go[k] = g.lsa[k]; go[4 + k] = g.lsc[k]; go[8 + k] = g.vla[k];
+              go[16 + k] = g.sz[k] ? 1.f : 0.f; go[20 + k] = g.vpc[k] ? 1.f : 0.f;
+            }
+            go[12] = g.last_cmd[0]; go[13] = g.last_cmd[1]; go[14] = g.last_cmd[2]; go[15] = g.steps;
+          }
+          // pair 0 = gait feet (0, 1), pair 1 = (2, 3); selects instead of indexing keep the arrays in registers
+          const float af0 = task ? a[2] : a[0], af1 = task ? a[3] : a[1], cf0 = task ? c[2] : c[0], cf1 = task ? c[3] : c[1];
+          const float vt0 = task ? g.vla[2] : g.vla[0], vt1 = task ? g.vla[3] : g.vla[1];
+          const float vo0 = task ? g.vla[0] : g.vla[2], vo1 = task ? g.vla[1] : g.vla[3];
+          const bool both_air = af0 > th && af0 < gp.air_time_gait_bound && af1 > th && af1 < gp.air_time_gait_bound;
+          const bool c0 = cf0 > th && cf0 < gp.contact_time_gait_bound;
+          const bool c1 = cf1 > th && cf1 < gp.contact_time_gait_bound;
+          float bonus = 0.f;
+          if (gp.encourage_symmetricity) bonus = gait_swing_bonus(gp, af0, af1, vt0, vt1, vo0, vo1);
+          gtmp[(task * 2 + 0) * kEnvs + e] = bonus;
+          gtmp[(task * 2 + 1) * kEnvs + e] = both_air ? 2.f : ((c0 && c1) ? 1.f : 0.f);
         }
-        {
-          const float thr = par(LT_RK_THIGH_CALF_COLLISION, 0);
-          float c = 0.f;
-#pragma unroll 1
-          for (int k = 0; k < A.num_thigh_calf; ++k) c += fmx[A.thigh_calf_sensor_ids[k]] > thr ? 1.f : 0.f;
-          put(LT_RK_THIGH_CALF_COLLISION, c);
+        named_barrier(1, 96);
+      } else {
+        // task 2: task score (rewards.py:202-216 / 372-392), async pairs (:348-363), stance; then the final combination
+        float score = 0.f, asyn = 0.f, stance = 0.f;
+        if (live) {
+          if (gp.encourage_symmetricity) {
+            const Vec3 vb = ld3(sm + L.linb + e * kS3);
+            const float wz = sm[L.angb + e * kS3 + 2];
+            const float dx = cmd.x - vb.x, dy = cmd.y - vb.y;
+            const float e_lin = nz ? sqrtf(dx * dx + dy * dy) : 0.f;
+            const float e_ang = nz ? fabsf(cmd.z - wz) : 0.f;
+            score = (exp_neg_over(e_lin, A.gait.vel_tracking_exp_sigma) + exp_neg_over(e_ang, A.gait.vel_tracking_exp_sigma)) / 2.f;
+            if (A.gait.with_object) {
+              const Vec3 rel_w = sub3(ld3(sm + L.opos + e * kS3), ld3(sm + L.pos + e * kS3));
+              const Vec3 r = rot_inv(yaw_quat(yaw_of(ld4(sm + L.quat + e * kS4))), rel_w);
+              const float bx = clampf(1.f - fabsf(r.x) / A.gait.obj_x_max, 0.f, 1.f);
+              const float by = clampf(1.f - fabsf(r.y) / A.gait.obj_y_max, 0.f, 1.f);
+              score = clampf((score * 2.f + (bx + by) / 2.f) / 3.f, 0.f, 1.f);
+            }
+          }
+          asyn = (gait_async(gp, a[0], a[2], c[0], c[2]) + gait_async(gp, a[1], a[3], c[1], c[3]) +
+                  gait_async(gp, a[0], a[3], c[0], c[3]) + gait_async(gp, a[2], a[1], c[2], c[1])) / 4.f;
+          stance = ((c[0] > th && c[1] > th && c[2] > th && c[3] > th) ? 1.f : 0.f) * A.gait.stance_rwd_scale;
+        }
+        named_barrier(1, 96);
+        if (live) {
+          float v[2];
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const float code = gtmp[(p * 2 + 1) * kEnvs + e];
+            if (gp.encourage_symmetricity) {
+              float bonus = gtmp[(p * 2 + 0) * kEnvs + e];
+              const float scale = 1.f - gp.task_performance_ratio + gp.task_performance_ratio * score;
+              if (bonus > 0.f) bonus *= scale;
+              bonus += 1.f;
+              v[p] = code == 2.f ? bonus : (code == 1.f ? 1.f : 0.f);
+            } else {
+              v[p] = code != 0.f ? 1.f : 0.f;
+            }
+          }
+          const float sync = (v[0] + v[1]) / 2.f;
+          const float stepping = (sync + asyn) / 2.f;
+          s_raw[LT_RK_GAIT * kEnvs + e] = nz ? stepping : stance;
         }
       }
+      continue;
     }
-  } else if (warp == 2) {
-    // ---- object-transport terms
-    if (do_rew && has_obj && lane < nvalid) {
-      const int e = lane;
-      const Vec3 cmd = ld3(sm + L.cmd + e * 3);
-      const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
-      const Quat q = ld4(sm + L.quat + e * 4);
-      const Vec3 rel_pos_w = sub3(ld3(sm + L.opos + e * 3), ld3(sm + L.pos + e * 3));
-      const Vec3 rel_pos = rot_inv(q, rel_pos_w);
-      const Vec3 rel_vel = rot_inv(q, sub3(ld3(sm + L.olin + e * 3), ld3(sm + L.linw + e * 3)));
-      const Vec3 rel_ang = rot_inv(q, sub3(ld3(sm + L.oang + e * 3), ld3(sm + L.angw + e * 3)));
-      const Vec3 g_obj = rot_inv(q, rot(ld4(sm + L.oquat + e * 4), ld3(sm + L.ograv + e * 3)));
-      auto put = [&](int kind, float v) {
-        const int i = s_slot[kind];
-        if (i >= 0) s_raw[i * kEnvs + e] = v;
-      };
-      auto par = [&](int kind, int k) -> float {
-        const int i = s_slot[kind];
-        return A.reward_terms[i < 0 ? 0 : i].p[k];
-      };
-      const float moving = cmd_norm > 0.f ? 1.f : 0.f;
-      {
-        float v = sqrtf(rel_pos_w.x * rel_pos_w.x + rel_pos_w.y * rel_pos_w.y);
-        if (par(LT_RK_OBJ_XY_POS, 0) != 0.f) v *= moving;
-        put(LT_RK_OBJ_XY_POS, v);
+    if (task >= kFixedTasks) {
+      // -------------------------------------------------- new observation values of the proprioceptive terms, 4 per task
+      if (!live) continue;
+      const int qd = task - kFixedTasks;
+      uint4 rnd = make_uint4(0, 0, 0, 0);
+      if (!A.u_obs) rnd = philox4(A.seed, rng_offset, (uint32_t)n, (uint32_t)qd);
+      const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int j = 4 * qd + c4;
+        if (j >= dps) break;
+        const int info = s_jinfo[j];
+        const LtObsTerm& ot = A.obs_terms[info & 0xff];
+        if (ot.kind == LT_OK_OBJECT_STATE) continue;
+        const int c = info >> 8;
+        float raw;
+        switch (ot.kind) {
+          case LT_OK_COMMAND: raw = sm[L.cmd + e * kS3 + c]; break;
+          case LT_OK_BASE_ANG_VEL: raw = sm[L.angb + e * kS3 + c]; break;
+          case LT_OK_PROJECTED_GRAVITY: raw = sm[L.grav + e * kS3 + c]; break;
+          case LT_OK_JOINT_POS_REL: raw = sm[L.q + e * sJ + c] - sm[L.q0 + e * sJ + c]; break;
+          case LT_OK_JOINT_VEL_REL: raw = sm[L.qd + e * sJ + c] - sm[L.qd0 + e * sJ + c]; break;
+          default: raw = sm[L.act + e * sJ + c]; break;  // LT_OK_LAST_ACTION
+        }
+        float noisy = raw;
+        if (ot.noisy) {
+          const float u = A.u_obs ? __ldcs(A.u_obs + (size_t)n * dps + j) : lt::Philox::u01(rw[c4]);
+          noisy = (raw + u * (ot.n_max - ot.n_min)) + ot.n_min;  // [IL] data + rand*(max-min) + min
+        }
+        nv[(0 * kEnvs + e) * sNew + j] = noisy * ot.scale;
+        nv[(1 * kEnvs + e) * sNew + j] = raw * ot.scale;
       }
-      put(LT_RK_OBJ_XY_VEL, rel_vel.x * rel_vel.x + rel_vel.y * rel_vel.y);
-      put(LT_RK_OBJ_LOSE_CONTACT, (sm[L.oc_last + e] > 0.f && sm[L.oc_air + e] > 0.f) ? 1.f : 0.f);
-      put(LT_RK_OBJ_Z_VEL, rel_vel.z * rel_vel.z);
-      put(LT_RK_OBJ_RP_ANGLE, g_obj.x * g_obj.x + g_obj.y * g_obj.y);
-      put(LT_RK_OBJ_RP_VEL, fabsf(rel_ang.x) + fabsf(rel_ang.y));
-      put(LT_RK_OBJ_ROLL_ANGLE, g_obj.y * g_obj.y);
-      put(LT_RK_OBJ_ROLL_VEL, rel_ang.x * rel_ang.x);
-      if (s_slot[LT_RK_OBJ_YAW] >= 0) {  // rewards.py:545-567
-        const Quat qr = yaw_quat(yaw_of(q)), qo = yaw_quat(yaw_of(ld4(sm + L.oquat + e * 4)));
+      continue;
+    }
+    if (task >= 14) {
+      // ------------------------------------------- object_state_in_robot_frame (observations.py:38-91)
+      // 14: policy group, position + linear velocity slots; 15: policy group, angular velocity; 16: policy group, quaternion;
+      // 17: critic group (all slots, no noise)
+      if (!do_obs || !has_obj) continue;
+      int jb = 0, tobj = -1;
+#pragma unroll 1
+      for (int t = 0; t < A.num_obs_terms; ++t) {
+        if (A.obs_terms[t].kind == LT_OK_OBJECT_STATE) { tobj = t; break; }
+        jb += A.obs_terms[t].dim;
+      }
+      if (tobj < 0 || !live) continue;
+      const int grp = task == 17 ? 1 : 0;
+      const bool do_pv = task == 14 || task == 17, do_w = task == 15 || task == 17, do_q = task == 16 || task == 17;
+      const Quat q = ld4(sm + L.quat + e * kS4);
+      const bool never = sm[L.oc_last + e] < A.os_last_contact_thr && sm[L.oc_cur + e] < A.os_current_contact_thr;
+      const float term_scale = A.obs_terms[tobj].scale;
+      float* out = nv + (grp * kEnvs + e) * sNew + jb;
+      const bool noise = grp == 0;  // add_uniform_noise=True for the policy group only
+      if (do_pv || do_w) {
+        // position / linear velocity / angular velocity slots: raw values first, then one pass per Philox quad
+        if (do_pv) {
+          const Vec3 p = rot_inv(q, sub3(ld3(sm + L.opos + e * kS3), ld3(sm + L.pos + e * kS3)));
+          const Vec3 v = rot_inv(q, sub3(ld3(sm + L.olin + e * kS3), ld3(sm + L.linw + e * kS3)));
+          out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = v.x; out[4] = v.y; out[5] = v.z;
+        }
+        if (do_w) {
+          const Vec3 w = rot_inv(q, sub3(ld3(sm + L.oang + e * kS3), ld3(sm + L.angw + e * kS3)));
+          out[10] = w.x; out[11] = w.y; out[12] = w.z;
+        }
+#pragma unroll 1
+        for (int qd = jb >> 2; qd <= (jb + 12) >> 2; ++qd) {
+          const int k0 = 4 * qd - jb;  // slots k0 .. k0+3 of this quad
+          const bool any_mine = (do_pv && k0 <= 5 && k0 + 3 >= 0) || (do_w && k0 <= 12 && k0 + 3 >= 10);
+          if (!any_mine) continue;
+          uint4 r4 = make_uint4(0, 0, 0, 0);
+          if (noise && !A.u_obs) r4 = philox4(A.seed, rng_offset, (uint32_t)n, (uint32_t)qd);
+          const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int k = k0 + c4;
+            const bool mine = (do_pv && k >= 0 && k <= 5) || (do_w && k >= 10 && k <= 12);
+            if (!mine) continue;
+            float st = out[k], cst = A.os_non_contact[k];
+            if (noise) {
+              const float u = A.u_obs ? __ldcs(A.u_obs + (size_t)n * dps + jb + k) : lt::Philox::u01(rw[c4]);
+              const float add = u * (A.os_n_max[k] - A.os_n_min[k]) + A.os_n_min[k];  // observations.py:77
+              st = st + add;
+              cst = cst + add;  // observations.py:82 (same draw)
+            }
+            out[k] = ((never ? cst : st) * A.os_scale[k]) * term_scale;
+          }
+        }
+      }
+      if (do_q) {
+        const Quat qr = quat_mul(quat_inv(q), ld4(sm + L.oquat + e * kS4));
+        float st[4] = {qr.w, qr.x, qr.y, qr.z};
+        float cst[4] = {A.os_non_contact[6], A.os_non_contact[7], A.os_non_contact[8], A.os_non_contact[9]};
+        if (noise) {  // additive slots, then euler-angle noise composed onto the quaternion
+          float u[4];
+          if (A.u_obs) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = __ldcs(A.u_obs + (size_t)n * dps + jb + 6 + k);
+          } else {  // value j takes word j & 3 of quad j >> 2: the four quaternion slots straddle at most two quads
+            const int j0 = jb + 6;
+            const uint4 ra = philox4(A.seed, rng_offset, (uint32_t)n, (uint32_t)(j0 >> 2));
+            uint4 rb = ra;
+            if (j0 & 3) rb = philox4(A.seed, rng_offset, (uint32_t)n, (uint32_t)((j0 >> 2) + 1));
+            const uint32_t w8[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            const int sh = j0 & 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t wv = sh == 0 ? w8[k] : (sh == 1 ? w8[k + 1] : (sh == 2 ? w8[k + 2] : w8[k + 3]));
+              u[k] = lt::Philox::u01(wv);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float add = u[k] * (A.os_n_max[6 + k] - A.os_n_min[6 + k]) + A.os_n_min[6 + k];
+            st[k] = st[k] + add;
+            cst[k] = cst[k] + add;
+          }
+          float de[3];
+          uint4 er = make_uint4(0, 0, 0, 0);
+          if (!A.u_obj_euler) er = philox4(A.seed, rng_offset, (uint32_t)n, 0x1000u >> 2);  // values 0x1000 + {0,1,2}
+          const uint32_t ew[3] = {er.x, er.y, er.z};
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float uu = A.u_obj_euler ? A.u_obj_euler[n * 3 + k] : lt::Philox::u01(ew[k]);
+            de[k] = uu * (A.os_euler_max[k] - A.os_euler_min[k]) + A.os_euler_min[k];
+          }
+          const Quat nq = quat_from_euler(de[0], de[1], de[2]);  // observations.py:78-79
+          const Quat a = quat_mul({st[0], st[1], st[2], st[3]}, nq);
+          st[0] = a.w; st[1] = a.x; st[2] = a.y; st[3] = a.z;
+          const Quat b = quat_mul({cst[0], cst[1], cst[2], cst[3]}, nq);
+          cst[0] = b.w; cst[1] = b.x; cst[2] = b.y; cst[3] = b.z;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[6 + k] = ((never ? cst[k] : st[k]) * A.os_scale[6 + k]) * term_scale;
+      }
+      continue;
+    }
+    // ------------------------------------------------------------------------ tasks 3..13: terminations, reward terms
+    if (!do_rew) continue;
+    if (task >= 5 && !live) continue;
+    if (task >= 11 && !has_obj) continue;
+    const float* force_env = sm + L.force + e * L.sF;
+    switch (task) {
+      case 3:
+      case 4: {  // terminations (terminations.py:10-23 + [IL] terms): task 3 takes the even terms, task 4 the odd ones; is_alive
+        bool terminated = false, timed_out = false;
+        if (live) {
+#pragma unroll 1
+          for (int t = task - 3; t < A.num_termination_terms; t += 2) {
+            const LtTerminationTerm& tt = A.termination_terms[t];
+            bool m = false;
+            switch (tt.kind) {
+              case LT_TK_TIME_OUT: m = reinterpret_cast<const long long*>(sm + L.eplen)[e] >= A.max_episode_length; break;
+              case LT_TK_BAD_ORIENTATION: m = fabsf(acosf(-sm[L.grav + e * kS3 + 2])) > tt.p[0]; break;
+              case LT_TK_ROOT_HEIGHT: m = sm[L.pos + e * kS3 + 2] < tt.p[0]; break;
+              case LT_TK_ILLEGAL_CONTACT:
+#pragma unroll 1
+                for (int k = 0; k < tt.num_ids; ++k) m = m || body_force_max(force_env, H, S, tt.body_ids[k]) > tt.p[0];
+                break;
+              case LT_TK_OBJECT_BELOW_ROBOT: m = sm[L.opos + e * kS3 + 2] < sm[L.pos + e * kS3 + 2]; break;
+              case LT_TK_BAD_ROLL: m = fabsf(asinf(sm[L.ograv + e * kS3 + 1])) > tt.p[0]; break;
+            }
+            if (A.term_masks) A.term_masks[(size_t)t * A.N + n] = m;
+            if (tt.time_out) timed_out = timed_out || m; else terminated = terminated || m;
+          }
+          if (task == 4) s_tflag[e] = (unsigned char)((terminated ? 1 : 0) | (timed_out ? 2 : 0));
+        }
+        named_barrier(2, 64);
+        if (task == 3 && live) {
+          const unsigned char other = s_tflag[e];
+          terminated = terminated || (other & 1);
+          timed_out = timed_out || (other & 2);
+          const bool done = terminated || timed_out;
+          s_done[e] = done;
+          A.terminated[n] = terminated;
+          A.time_outs[n] = timed_out;
+          A.dones[n] = done;
+          if (A.auto_reset && done) {  // history of a reset env is refilled by its next observation
+            if (do_obs) s_fill[e] = 1;
+            else if (A.obs_fill) A.obs_fill[n] = 1;
+          }
+          put(LT_RK_ALIVE, terminated ? 0.f : 1.f);
+        }
+        break;
+      }
+      case 5: {  // velocity tracking, base terms
+        const Vec3 cmd = ld3(sm + L.cmd + e * kS3), vb = ld3(sm + L.linb + e * kS3), wb = ld3(sm + L.angb + e * kS3);
+        const Vec3 grav = ld3(sm + L.grav + e * kS3);
+        const float dx = cmd.x - vb.x, dy = cmd.y - vb.y;
+        put(LT_RK_TRACK_LIN_VEL_XY, exp_neg_over(sqrtf(dx * dx + dy * dy), par(LT_RK_TRACK_LIN_VEL_XY, 0)));
+        put(LT_RK_TRACK_ANG_VEL_Z, exp_neg_over(fabsf(cmd.z - wb.z), par(LT_RK_TRACK_ANG_VEL_Z, 0)));
+        const float d = sm[L.pos + e * kS3 + 2] - par(LT_RK_BASE_HEIGHT, 0);
+        put(LT_RK_BASE_HEIGHT, d * d);
+        put(LT_RK_BASE_Z_VEL, vb.z * vb.z);
+        put(LT_RK_BASE_RP_ANGLE, grav.x * grav.x + grav.y * grav.y);
+        put(LT_RK_BASE_RP_VEL, fabsf(wb.x) + fabsf(wb.y));
+        break;
+      }
+      case 6: {  // foot slipping / dragging
+        const float* fpos = sm + L.fpos + e * kS12;
+        const float* fvel = sm + L.fvel + e * kS12;
+        const float slip_thr = par(LT_RK_FOOT_SLIP, 0), drag_h = par(LT_RK_FOOT_DRAG, 0), drag_v = par(LT_RK_FOOT_DRAG, 1);
+        float slip = 0.f, drag = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const float sp = sqrtf(fvel[3 * k] * fvel[3 * k] + fvel[3 * k + 1] * fvel[3 * k + 1]);
+          slip += (body_force_max(force_env, H, S, A.feet_sensor_ids[k]) > slip_thr ? 1.f : 0.f) * sp;
+          drag += (fpos[3 * k + 2] <= drag_h && sp > drag_v) ? 1.f : 0.f;
+        }
+        put(LT_RK_FOOT_SLIP, slip);
+        put(LT_RK_FOOT_DRAG, drag);
+        break;
+      }
+      case 7: {  // joint position limits / deviation
+        const float* qq = sm + L.q + e * sJ; const float* q0 = sm + L.q0 + e * sJ; const float* lim = sm + L.lim + e * L.sLim;
+        float s_lim = 0.f, s_dev = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < J; ++j) {
+          s_lim += -fminf(qq[j] - lim[2 * j], 0.f) + fmaxf(qq[j] - lim[2 * j + 1], 0.f);
+          const float d = qq[j] - q0[j];
+          s_dev += d * d;
+        }
+        put(LT_RK_JOINT_POS_LIMIT, s_lim);
+        const Vec3 cmd = ld3(sm + L.cmd + e * kS3), vb = ld3(sm + L.linb + e * kS3);
+        const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
+        const float dev = sqrtf(s_dev), bv = sqrtf(vb.x * vb.x + vb.y * vb.y);
+        put(LT_RK_JOINT_POS, (cmd_norm > 0.f || bv > par(LT_RK_JOINT_POS, 1)) ? dev : par(LT_RK_JOINT_POS, 0) * dev);
+        break;
+      }
+      case 8: {  // joint acceleration / velocity
+        const float* qd = sm + L.qd + e * sJ; const float* qdd = sm + L.qdd + e * sJ;
+        float s_acc = 0.f, s_vel = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < J; ++j) {
+          s_acc += qdd[j] * qdd[j];
+          s_vel += qd[j] * qd[j];
+        }
+        put(LT_RK_JOINT_ACC, sqrtf(s_acc));
+        put(LT_RK_JOINT_VEL, sqrtf(s_vel));
+        break;
+      }
+      case 9: {  // joint torque, action rate
+        const float* tau = sm + L.tau + e * sJ; const float* ac = sm + L.act + e * sJ; const float* pa = sm + L.pact + e * sJ;
+        float s_tau = 0.f, s_rate = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < J; ++j) {
+          s_tau += tau[j] * tau[j];
+          const float da = ac[j] - pa[j];
+          s_rate += da * da;
+        }
+        put(LT_RK_JOINT_TORQUE, sqrtf(s_tau));
+        put(LT_RK_ACTION_RATE, s_rate);
+        break;
+      }
+      case 10: {  // thigh / calf collisions
+        const float thr = par(LT_RK_THIGH_CALF_COLLISION, 0);
+        float c = 0.f;
+        if (s_slot[LT_RK_THIGH_CALF_COLLISION] >= 0) {
+#pragma unroll 1
+          for (int k = 0; k < A.num_thigh_calf; ++k) c += body_force_max(force_env, H, S, A.thigh_calf_sensor_ids[k]) > thr ? 1.f : 0.f;
+        }
+        put(LT_RK_THIGH_CALF_COLLISION, c);
+        break;
+      }
+      case 11: {  // object position / linear velocity terms, dangerous state (rewards.py:469-503, 569-594)
+        const Vec3 cmd = ld3(sm + L.cmd + e * kS3);
+        const float cmd_norm = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z);
+        const float moving = cmd_norm > 0.f ? 1.f : 0.f;
+        const Quat q = ld4(sm + L.quat + e * kS4);
+        const Vec3 rel_pos_w = sub3(ld3(sm + L.opos + e * kS3), ld3(sm + L.pos + e * kS3));
+        const Vec3 rel_vel = rot_inv(q, sub3(ld3(sm + L.olin + e * kS3), ld3(sm + L.linw + e * kS3)));
+        {
+          float v = sqrtf(rel_pos_w.x * rel_pos_w.x + rel_pos_w.y * rel_pos_w.y);
+          if (par(LT_RK_OBJ_XY_POS, 0) != 0.f) v *= moving;
+          put(LT_RK_OBJ_XY_POS, v);
+        }
+        put(LT_RK_OBJ_XY_VEL, rel_vel.x * rel_vel.x + rel_vel.y * rel_vel.y);
+        put(LT_RK_OBJ_LOSE_CONTACT, (sm[L.oc_last + e] > 0.f && sm[L.oc_air + e] > 0.f) ? 1.f : 0.f);
+        put(LT_RK_OBJ_Z_VEL, rel_vel.z * rel_vel.z);
+        if (s_slot[LT_RK_OBJ_DANGER] >= 0) {
+          const Vec3 rel_pos = rot_inv(q, rel_pos_w);
+          bool bad = fabsf(rel_pos.x) > par(LT_RK_OBJ_DANGER, 0);
+          bad = bad || fabsf(rel_pos.y) > par(LT_RK_OBJ_DANGER, 1);
+          bad = bad || rel_pos.z < par(LT_RK_OBJ_DANGER, 2);
+          const float rp = par(LT_RK_OBJ_DANGER, 3), vmax = par(LT_RK_OBJ_DANGER, 4);
+          if (rp >= 0.f) bad = bad || fabsf(acosf(-sm[L.ograv + e * kS3 + 2])) > rp * 3.14159265358979323846f / 180.f;
+          if (vmax >= 0.f) bad = bad || sqrtf(rel_vel.x * rel_vel.x + rel_vel.y * rel_vel.y) > vmax;
+          put(LT_RK_OBJ_DANGER, bad ? 1.f : 0.f);
+        }
+        break;
+      }
+      case 12: {  // object orientation / angular velocity terms (rewards.py:505-543)
+        const Quat q = ld4(sm + L.quat + e * kS4);
+        const Vec3 rel_ang = rot_inv(q, sub3(ld3(sm + L.oang + e * kS3), ld3(sm + L.angw + e * kS3)));
+        const Vec3 g_obj = rot_inv(q, rot(ld4(sm + L.oquat + e * kS4), ld3(sm + L.ograv + e * kS3)));
+        put(LT_RK_OBJ_RP_ANGLE, g_obj.x * g_obj.x + g_obj.y * g_obj.y);
+        put(LT_RK_OBJ_RP_VEL, fabsf(rel_ang.x) + fabsf(rel_ang.y));
+        put(LT_RK_OBJ_ROLL_ANGLE, g_obj.y * g_obj.y);
+        put(LT_RK_OBJ_ROLL_VEL, rel_ang.x * rel_ang.x);
+        break;
+      }
+      case 13: {  // object yaw alignment (rewards.py:545-567)
+        if (s_slot[LT_RK_OBJ_YAW] < 0) break;
+        const Vec3 cmd = ld3(sm + L.cmd + e * kS3);
+        const float moving = sqrtf(cmd.x * cmd.x + cmd.y * cmd.y + cmd.z * cmd.z) > 0.f ? 1.f : 0.f;
+        const Quat qr = yaw_quat(yaw_of(ld4(sm + L.quat + e * kS4))), qo = yaw_quat(yaw_of(ld4(sm + L.oquat + e * kS4)));
         float d = yaw_of(quat_mul(quat_inv(qr), qo));
         const float pi = 3.14159274101257324f;  // float32(torch.pi)
         if (d > pi) d -= 2.f * pi;
@@ -605,191 +909,96 @@ __global__ void __launch_bounds__(kThreads, kEnvs <= 8 ? 4 : 2) mdp_step_kernel(
         float v = d * d;
         if (par(LT_RK_OBJ_YAW, 0) != 0.f) v *= moving;
         put(LT_RK_OBJ_YAW, v);
+        break;
       }
-      if (s_slot[LT_RK_OBJ_DANGER] >= 0) {  // rewards.py:569-594
-        bool bad = fabsf(rel_pos.x) > par(LT_RK_OBJ_DANGER, 0);
-        bad = bad || fabsf(rel_pos.y) > par(LT_RK_OBJ_DANGER, 1);
-        bad = bad || rel_pos.z < par(LT_RK_OBJ_DANGER, 2);
-        const float rp = par(LT_RK_OBJ_DANGER, 3), vmax = par(LT_RK_OBJ_DANGER, 4);
-        if (rp >= 0.f) bad = bad || fabsf(acosf(-sm[L.ograv + e * 3 + 2])) > rp * 3.14159265358979323846f / 180.f;
-        if (vmax >= 0.f) bad = bad || sqrtf(rel_vel.x * rel_vel.x + rel_vel.y * rel_vel.y) > vmax;
-        put(LT_RK_OBJ_DANGER, bad ? 1.f : 0.f);
-      }
-    }
-  } else if (warp == 3) {
-    // ---- object_state_in_robot_frame (observations.py:38-91): lane = 2*env + group
-    if (do_obs && has_obj && lane < nvalid * 2) {
-      int jb = 0, tobj = -1;
-      for (int t = 0; t < A.num_obs_terms; ++t) {
-        if (A.obs_terms[t].kind == LT_OK_OBJECT_STATE) { tobj = t; break; }
-        jb += A.obs_terms[t].dim;
-      }
-      if (tobj >= 0) {
-        const int e = lane >> 1, grp = lane & 1, n = e0 + e;
-        float* nv = sm + L.newobs;
-        const Quat q = ld4(sm + L.quat + e * 4);
-        const Vec3 p = rot_inv(q, sub3(ld3(sm + L.opos + e * 3), ld3(sm + L.pos + e * 3)));
-        const Vec3 v = rot_inv(q, sub3(ld3(sm + L.olin + e * 3), ld3(sm + L.linw + e * 3)));
-        const Quat qr = quat_mul(quat_inv(q), ld4(sm + L.oquat + e * 4));
-        const Vec3 w = rot_inv(q, sub3(ld3(sm + L.oang + e * 3), ld3(sm + L.angw + e * 3)));
-        float st[13] = {p.x, p.y, p.z, v.x, v.y, v.z, qr.w, qr.x, qr.y, qr.z, w.x, w.y, w.z};
-        float cst[13];
-#pragma unroll
-        for (int k = 0; k < 13; ++k) cst[k] = A.os_non_contact[k];
-        if (grp == 0) {  // policy group: add_uniform_noise=True
-          float* u13 = sm + L.uscr + e * 16;  // 13 uniforms of this env (one policy-group lane per env)
-          if (A.u_obs) {
-#pragma unroll 1
-            for (int k = 0; k < 13; ++k) u13[k] = __ldcs(A.u_obs + (size_t)n * dps + jb + k);
-          } else {  // the same (env, quad) counter stream the proprioceptive values use: value j takes word j & 3 of quad j >> 2
-#pragma unroll 1
-            for (int qd = jb >> 2; qd <= (jb + 12) >> 2; ++qd) {
-              const uint4 r = lt::Philox::gen(A.seed, rng_offset, (uint32_t)n, (uint32_t)qd);
-              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                const int k = 4 * qd + c4 - jb;
-                if (k >= 0 && k < 13) u13[k] = lt::Philox::u01(rw[c4]);
-              }
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 13; ++k) {
-            const float add = u13[k] * (A.os_n_max[k] - A.os_n_min[k]) + A.os_n_min[k];  // observations.py:77
-            st[k] = st[k] + add;
-            cst[k] = cst[k] + add;  // observations.py:82 (same draw)
-          }
-          float de[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float u = A.u_obj_euler ? A.u_obj_euler[n * 3 + k] : uniform_at(A.seed, rng_offset, (uint32_t)n, 0x1000u + k);
-            de[k] = u * (A.os_euler_max[k] - A.os_euler_min[k]) + A.os_euler_min[k];
-          }
-          const Quat nq = quat_from_euler(de[0], de[1], de[2]);  // observations.py:78-79
-          const Quat a = quat_mul({st[6], st[7], st[8], st[9]}, nq);
-          st[6] = a.w; st[7] = a.x; st[8] = a.y; st[9] = a.z;
-          const Quat b = quat_mul({cst[6], cst[7], cst[8], cst[9]}, nq);
-          cst[6] = b.w; cst[7] = b.x; cst[8] = b.y; cst[9] = b.z;
-        }
-        const bool never = sm[L.oc_last + e] < A.os_last_contact_thr && sm[L.oc_cur + e] < A.os_current_contact_thr;
-        const float term_scale = A.obs_terms[tobj].scale;
-#pragma unroll
-        for (int k = 0; k < 13; ++k) nv[(grp * kEnvs + e) * dps + jb + k] = ((never ? cst[k] : st[k]) * A.os_scale[k]) * term_scale;
-      }
-    }
-  } else {
-    // ---- warps 4..7: new observation values of the proprioceptive terms; one thread per (env, 4 consecutive values)
-    if (do_obs) {
-      float* nv = sm + L.newobs;  // [2 groups][kEnvs][dps]
-      const int quads = (dps + 3) >> 2;
-      for (int i = tid - 4 * 32; i < nvalid * quads; i += 4 * 32) {
-        const int e = i / quads, qd = i - e * quads, n = e0 + e;
-        uint4 rnd = make_uint4(0, 0, 0, 0);
-        if (!A.u_obs) rnd = lt::Philox::gen(A.seed, rng_offset, (uint32_t)n, (uint32_t)qd);
-        const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const int j = 4 * qd + c4;
-          if (j >= dps) break;
-          const int info = s_jinfo[j];
-          const LtObsTerm& ot = A.obs_terms[info & 0xff];
-          if (ot.kind == LT_OK_OBJECT_STATE) continue;
-          const int c = info >> 8;
-          float raw;
-          switch (ot.kind) {
-            case LT_OK_COMMAND: raw = sm[L.cmd + e * 3 + c]; break;
-            case LT_OK_BASE_ANG_VEL: raw = sm[L.angb + e * 3 + c]; break;
-            case LT_OK_PROJECTED_GRAVITY: raw = sm[L.grav + e * 3 + c]; break;
-            case LT_OK_JOINT_POS_REL: raw = sm[L.q + e * J + c] - sm[L.q0 + e * J + c]; break;
-            case LT_OK_JOINT_VEL_REL: raw = sm[L.qd + e * J + c] - sm[L.qd0 + e * J + c]; break;
-            default: raw = sm[L.act + e * J + c]; break;  // LT_OK_LAST_ACTION
-          }
-          float noisy = raw;
-          if (ot.noisy) {
-            const float u = A.u_obs ? __ldcs(A.u_obs + (size_t)n * dps + j) : lt::Philox::u01(rw[c4]);
-            noisy = (raw + u * (ot.n_max - ot.n_min)) + ot.n_min;  // [IL] data + rand*(max-min) + min
-          }
-          nv[(0 * kEnvs + e) * dps + j] = noisy * ot.scale;
-          nv[(1 * kEnvs + e) * dps + j] = raw * ot.scale;
-        }
-      }
-      // publish any(non_zero_cmd) for the reward pass of the NEXT step (it sees the same command tensor)
-      if (A.any_flag_ws && warp == 4 && lane < nvalid) {
-        const float* c = sm + L.cmd + lane * 3;
-        if (sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) > 0.f) A.any_flag_ws[(step + 1) & 1] = step + 1;
-      }
+      default: break;
     }
   }
-  if (do_obs) __pipeline_wait_prior(0);
+#ifdef LT_MDP_TWICE
+  if (pass == 0) PROF_STAMP(13);
+  }
+#endif
+  PROF_STAMP(4);
+  if (do_obs) {
+    __pipeline_wait_prior(0);
+    if (bulk_hist) mbar_wait(&s_bar[1], 0);
+  }
+  PROF_STAMP(5);
   __syncthreads();
+  PROF_STAMP(6);
 
   // ---------------------------------------------------------------------------- stage 2a: reward accumulation + outputs
-  if (do_rew) {
+  const int a_warps = kWarps, b_first = 0;
+  if (do_rew && warp < a_warps) {
     const float dt = A.step_dt;
+    const int a_threads = a_warps * 32;
     // [IL] RewardManager.compute: value = f * weight * dt ; episode_sums += value ; step_reward = value / dt
-    for (int i = tid; i < T * kEnvs; i += kThreads) {
-      const int t = i / kEnvs, e = i % kEnvs, n = e0 + e;
-      if (e >= nvalid) continue;
+#pragma unroll 1
+    for (int i = tid; i < T * kEnvs; i += a_threads) {
+      const int t = i >> 5, ee = i & 31, nn = e0 + ee;
+      if (ee >= nvalid) continue;
       const LtRewardTerm& rt = A.reward_terms[t];
       if (rt.weight == 0.f) {  // skipped terms: step_reward column is zero, sums untouched
-        if (A.step_reward) A.step_reward[(size_t)n * T + t] = 0.f;
+        if (A.step_reward) A.step_reward[(size_t)nn * T + t] = 0.f;
         continue;
       }
-      const float raw = s_raw[t * kEnvs + e];
+      const float raw = s_raw[rt.kind * kEnvs + ee];
       const float value = (raw * rt.weight) * dt;
-      if (A.term_raw) A.term_raw[(size_t)t * A.N + n] = raw;
-      if (A.step_reward) A.step_reward[(size_t)n * T + t] = value / dt;
+      if (A.term_raw) A.term_raw[(size_t)t * A.N + nn] = raw;
+      if (A.step_reward) A.step_reward[(size_t)nn * T + t] = value / dt;
       if (A.episode_sums) {
-        const float total = sm[L.esum + t * kEnvs + e] + value;
-        const bool rst = A.auto_reset && s_done[e];
+        const float total = sm[L.esum + i] + value;
+        const bool rst = A.auto_reset && s_done[ee];
         if (rst && A.episode_log_sums) atomicAdd(A.episode_log_sums + t, total);
-        A.episode_sums[(size_t)t * A.N + n] = rst ? 0.f : total;
+        A.episode_sums[(size_t)t * A.N + nn] = rst ? 0.f : total;
       }
     }
-    if (warp == kWarps - 1 && lane < nvalid) {  // reward_buf: sequential fp32 sum in term order
-      const int e = lane;
+    if (warp == a_warps - 1 && live) {  // reward_buf: sequential fp32 sum in term order
       float reward = 0.f;
-#pragma unroll 1
-      for (int t = 0; t < T; ++t) {
+#pragma unroll 8
+      for (int t = 0; t < T; ++t) {  // the products are independent (loads overlap); the additions keep the term order
         const LtRewardTerm& rt = A.reward_terms[t];
-        if (rt.weight != 0.f) reward = reward + (s_raw[t * kEnvs + e] * rt.weight) * dt;
+        const float value = rt.weight != 0.f ? (s_raw[rt.kind * kEnvs + e] * rt.weight) * dt : 0.f;
+        reward = reward + value;
       }
-      A.reward[e0 + e] = reward;
+      A.reward[n] = reward;
       if (A.auto_reset && s_done[e] && A.episode_log_sums) atomicAdd(A.episode_log_sums + T, 1.0f);
     }
     // gait state write back; zeroed when the env is being reset (the manager's reset(env_ids) follows, rewards.py:107-114)
     {
       const LtGaitState& G = A.gait_state;
-      const float* go = sm + L.gait_out;
-      for (int i = tid; i < nvalid * kGaitFloats; i += kThreads) {
-        const int e = i / kGaitFloats, k = i % kGaitFloats, n = e0 + e;
-        const float v = (A.auto_reset && s_done[e]) ? 0.f : go[i];
-        if (k < 4) G.last_step_current_air_time[n * 4 + k] = v;
-        else if (k < 8) G.last_step_current_contact_time[n * 4 + k - 4] = v;
-        else if (k < 12) G.valid_last_air_time[n * 4 + k - 8] = v;
-        else if (k < 15) G.last_velocity_cmd[n * 3 + k - 12] = v;
-        else if (k == 15) G.step_from_changing_cmd[n] = v;
-        else if (k < 20) G.swinging_in_zero_cmd[n * 4 + k - 16] = v != 0.f;
-        else G.valid_previous_contact[n * 4 + k - 20] = v != 0.f;
+#pragma unroll 1
+      for (int i = tid; i < nvalid * kGaitFloats; i += a_threads) {
+        const int ee = i / kGaitFloats, k = i - ee * kGaitFloats, nn = e0 + ee;
+        const float v = (A.auto_reset && s_done[ee]) ? 0.f : sm[L.gait_out + ee * kGaitStride + k];
+        if (k < 4) G.last_step_current_air_time[nn * 4 + k] = v;
+        else if (k < 8) G.last_step_current_contact_time[nn * 4 + k - 4] = v;
+        else if (k < 12) G.valid_last_air_time[nn * 4 + k - 8] = v;
+        else if (k < 15) G.last_velocity_cmd[nn * 3 + k - 12] = v;
+        else if (k == 15) G.step_from_changing_cmd[nn] = v;
+        else if (k < 20) G.swinging_in_zero_cmd[nn * 4 + k - 16] = v != 0.f;
+        else G.valid_previous_contact[nn * 4 + k - 20] = v != 0.f;
       }
     }
   }
 
+  PROF_STAMP(7);
   // --------------------------------------------------------------------------------- stage 2b: observation history shift
-  // warp w owns env row w: rows are 8-byte aligned (D is even), so every lane moves float2 pairs
-  if (do_obs) {
-    const float* nv = sm + L.newobs;
-    for (int e = warp; e < nvalid; e += kWarps) {
-      const bool fill = s_fill[e] != 0;
+  // one warp per env row: rows are 8-byte aligned (D is even), so every lane moves float2 pairs
+  if (do_obs && warp >= b_first) {
+#pragma unroll 1
+    for (int ee = warp - b_first; ee < nvalid; ee += kWarps - b_first) {
+      const bool fill = s_fill[ee] != 0;
 #pragma unroll 1
       for (int grp = 0; grp < 2; ++grp) {
         float* out = grp ? A.critic_obs_out : A.policy_obs_out;
         if (!out) continue;
         const bool refill = fill || (grp ? A.critic_obs_in : A.policy_obs_in) == nullptr;
-        const float* hist = sm + L.hist + grp * L.hist_stride + e * D;
-        const float* nve = nv + (grp * kEnvs + e) * dps;
-        float* dst = out + (size_t)(e0 + e) * D;
+        const float* hist = sm + L.hist + grp * L.hist_stride + ee * D;
+        const float* nve = nv + (grp * kEnvs + ee) * sNew;
+        float* dst = out + (size_t)(e0 + ee) * D;
         if ((D & 1) == 0 && (((uintptr_t)dst) & 7) == 0) {
+#pragma unroll 4
           for (int p = lane; p < (D >> 1); p += 32) {
             const uint2 m = *reinterpret_cast<const uint2*>(s_map + 2 * p);
             float2 v;
@@ -798,15 +1007,17 @@ __global__ void __launch_bounds__(kThreads, kEnvs <= 8 ? 4 : 2) mdp_step_kernel(
             __stcs(reinterpret_cast<float2*>(dst) + p, v);
           }
         } else {
+#pragma unroll 1
           for (int k = lane; k < D; k += 32) {
             const unsigned m = (unsigned)s_map[k];
             __stcs(dst + k, (refill || (m >> 16) == 0xffff) ? nve[m & 0xffff] : hist[m >> 16]);
           }
         }
       }
-      if (A.obs_fill && lane == 0) A.obs_fill[e0 + e] = 0;
+      if (A.obs_fill && lane == 0) A.obs_fill[e0 + ee] = 0;
     }
   }
+  PROF_STAMP(15);
 }
 
 __global__ void mdp_reset_kernel(const LtGaitState G, float* episode_sums, int num_terms, const uint8_t* mask, int N) {
@@ -825,7 +1036,79 @@ __global__ void mdp_reset_kernel(const LtGaitState G, float* episode_sums, int n
     for (int i = 0; i < num_terms; ++i) episode_sums[(size_t)i * N + n] = 0.f;
 }
 
+// ints in the table block: s_map[D rounded up to 4] + s_jinfo[dps] + s_slot[LT_RK_COUNT] + s_kpar[LT_RK_COUNT][6] (floats), rounded
+// up to a multiple of 4
+int tables_len(int D, int dps) { return ((((D + 3) & ~3) + dps + LT_RK_COUNT * 7) + 3) & ~3; }
+
+// validates the observation term table; *dps = new values per step and group
+int obs_dims(const LtMdpArgs* a, int* dps_out, bool pointers_bound) {
+  const bool has_obj = !pointers_bound || a->obj_root_pos_w != nullptr;  // table builders run before the tensors are bound
+  if (a->num_obs_terms <= 0 || a->num_obs_terms > LT_MAX_OBS_TERMS || a->history_length <= 0) return LT_ERR_INVALID_ARG;
+  int dps = 0;
+  for (int t = 0; t < a->num_obs_terms; ++t) {
+    const LtObsTerm& ot = a->obs_terms[t];
+    if (ot.dim <= 0 || ot.dim > 255) return LT_ERR_INVALID_ARG;
+    if (ot.kind == LT_OK_OBJECT_STATE && (!has_obj || ot.dim != 13)) return LT_ERR_INVALID_ARG;
+    if ((ot.kind == LT_OK_JOINT_POS_REL || ot.kind == LT_OK_JOINT_VEL_REL || ot.kind == LT_OK_LAST_ACTION) && ot.dim != a->J)
+      return LT_ERR_INVALID_ARG;
+    if ((ot.kind == LT_OK_COMMAND || ot.kind == LT_OK_BASE_ANG_VEL || ot.kind == LT_OK_PROJECTED_GRAVITY) && ot.dim != 3)
+      return LT_ERR_INVALID_ARG;
+    dps += ot.dim;
+  }
+  if (dps > kMaxNew || dps * a->history_length > kMaxObsDim || dps > 255) return LT_ERR_UNSUPPORTED;
+  *dps_out = dps;
+  return LT_OK;
+}
+
 }  // namespace
+
+// Launch-constant lookup tables of the fused MDP kernel (observation column map, per-value term info, reward kind -> slot),
+// computed once on the host; upload the ints to the device and pass them as LtMdpArgs.tables.  Without them every block of
+// every launch rebuilds the tables in shared memory.
+extern "C" int lt_mdp_tables_len(const LtMdpArgs* a) {
+  if (!a) return -1;
+  int dps = 0;
+  if (a->num_obs_terms > 0 && obs_dims(a, &dps, false) != LT_OK) return -1;
+  return tables_len(dps * a->history_length, dps);
+}
+
+extern "C" int lt_mdp_build_tables(const LtMdpArgs* a, int32_t* out, int len) {
+  if (!a || !out) return LT_ERR_INVALID_ARG;
+  int dps = 0;
+  if (a->num_obs_terms > 0) {
+    const int rc = obs_dims(a, &dps, false);
+    if (rc != LT_OK) return rc;
+  }
+  const int D = dps * a->history_length;
+  if (len < tables_len(D, dps)) return LT_ERR_INVALID_ARG;
+  memset(out, 0, sizeof(int32_t) * (size_t)len);
+  int32_t* map = out;
+  int32_t* jinfo = out + ((D + 3) & ~3);
+  int32_t* slot = jinfo + dps;
+  int col = 0, jbase = 0;
+  for (int t = 0; t < a->num_obs_terms; ++t) {  // flattened [term][history][dim] row
+    const int d = a->obs_terms[t].dim;
+    for (int h = 0; h < a->history_length; ++h)
+      for (int i = 0; i < d; ++i) {
+        const int k = col + h * d + i;
+        map[k] = (jbase + i) | ((h == a->history_length - 1 ? 0xffff : k + d) << 16);
+      }
+    for (int i = 0; i < d; ++i) jinfo[jbase + i] = t | (i << 8);
+    col += d * a->history_length;
+    jbase += d;
+  }
+  for (int kind = 0; kind < LT_RK_COUNT; ++kind) {
+    int sl = -1;
+    for (int i = 0; i < a->num_reward_terms && i < LT_MAX_REWARD_TERMS; ++i)
+      if (a->reward_terms[i].kind == kind && a->reward_terms[i].weight != 0.f) sl = i;
+    slot[kind] = sl;
+    for (int k = 0; k < 6; ++k) {
+      const float v = sl >= 0 ? a->reward_terms[sl].p[k] : 0.f;
+      memcpy(slot + LT_RK_COUNT + kind * 6 + k, &v, sizeof(float));
+    }
+  }
+  return LT_OK;
+}
 
 extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   if (!a || a->N <= 0 || !(a->phases & (LT_PHASE_REWARDS | LT_PHASE_OBS))) return LT_ERR_INVALID_ARG;
@@ -871,82 +1154,90 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   memset(&L, 0, sizeof(L));
   int dps = 0;
   if (do_obs) {
-    if (a->num_obs_terms <= 0 || a->num_obs_terms > LT_MAX_OBS_TERMS || a->history_length <= 0 || !a->default_joint_vel)
-      return LT_ERR_INVALID_ARG;
+    if (a->num_obs_terms <= 0 || !a->default_joint_vel) return LT_ERR_INVALID_ARG;
     if (!a->policy_obs_out && !a->critic_obs_out) return LT_ERR_INVALID_ARG;
-    for (int t = 0; t < a->num_obs_terms; ++t) {
-      const LtObsTerm& ot = a->obs_terms[t];
-      if (ot.dim <= 0 || ot.dim > 255) return LT_ERR_INVALID_ARG;
-      if (ot.kind == LT_OK_OBJECT_STATE && (!has_obj || ot.dim != 13)) return LT_ERR_INVALID_ARG;
-      if ((ot.kind == LT_OK_JOINT_POS_REL || ot.kind == LT_OK_JOINT_VEL_REL || ot.kind == LT_OK_LAST_ACTION) && ot.dim != a->J)
-        return LT_ERR_INVALID_ARG;
-      if ((ot.kind == LT_OK_COMMAND || ot.kind == LT_OK_BASE_ANG_VEL || ot.kind == LT_OK_PROJECTED_GRAVITY) && ot.dim != 3)
-        return LT_ERR_INVALID_ARG;
-      dps += ot.dim;
-    }
+  }
+  if (a->num_obs_terms > 0) {  // the table block is laid out for the full configuration, whichever phases this launch runs
+    const int rc = obs_dims(a, &dps, true);
+    if (rc != LT_OK) return rc;
     L.D = dps * a->history_length;
     L.dps = dps;
-    if (dps > kMaxNew || L.D > kMaxObsDim || dps > 255) return LT_ERR_UNSUPPORTED;
   }
   const int J = a->J, S = a->num_sensor_bodies > 0 ? a->num_sensor_bodies : 1, H = a->force_history > 0 ? a->force_history : 1;
   const int T = do_rew ? a->num_reward_terms : 0;
+  L.sJ = J; L.sLim = 2 * J; L.sF = H * S * 3;
+  L.sNew = (dps > 0 ? dps : 1) | 1;
   int off = 0;
   auto take = [&](int per_env) { const int o = off; off += kEnvs * per_env; return o; };
-  L.cmd = take(3); L.pos = take(3); L.linb = take(3); L.angb = take(3); L.grav = take(3);
-  L.q = take(J); L.qd = take(J); L.qdd = take(J); L.tau = take(J); L.q0 = take(J); L.qd0 = take(J); L.lim = take(2 * J);
-  L.act = take(J); L.pact = take(J);
-  L.force = take(do_rew ? H * S * 3 : 0);
-  L.air = take(4); L.con = take(4); L.lair = take(4); L.fpos = take(12); L.fvel = take(12);
-  L.quat = take(4); L.linw = take(3); L.angw = take(3); L.opos = take(3); L.oquat = take(4); L.olin = take(3); L.oang = take(3);
-  L.ograv = take(3); L.oc_last = take(1); L.oc_cur = take(1); L.oc_air = take(1);
-  L.fmax = take(S);
-  L.g_lsa = take(4); L.g_lsc = take(4); L.g_vla = take(4); L.g_cmd = take(3); L.g_steps = take(1); L.g_sz = take(4); L.g_vpc = take(4);
+  L.cmd = take(kS3); L.pos = take(kS3); L.linb = take(kS3); L.angb = take(kS3); L.grav = take(kS3);
+  L.q = take(L.sJ); L.qd = take(L.sJ); L.qdd = take(L.sJ); L.tau = take(L.sJ); L.q0 = take(L.sJ); L.qd0 = take(L.sJ); L.lim = take(L.sLim);
+  L.act = take(L.sJ); L.pact = take(L.sJ);
+  L.force = take(do_rew ? L.sF : 0);
+  L.air = take(kP4); L.con = take(kP4); L.lair = take(kP4); L.fpos = take(kS12); L.fvel = take(kS12);
+  L.quat = take(kS4); L.linw = take(kS3); L.angw = take(kS3); L.opos = take(kS3); L.oquat = take(kS4); L.olin = take(kS3); L.oang = take(kS3);
+  L.ograv = take(kS3); L.oc_last = take(1); L.oc_cur = take(1); L.oc_air = take(1);
+  L.g_lsa = take(kS4); L.g_lsc = take(kS4); L.g_vla = take(kS4); L.g_cmd = take(kS3); L.g_steps = take(1); L.g_sz = take(kP4); L.g_vpc = take(kP4);
   L.eplen = take(2);  // int64 per env
-  L.gait_out = take(kGaitFloats);
-  L.esum = take(T); L.raw = take(T);
-  L.newobs = take(2 * dps);
-  L.uscr = take(16);
-  off = (off + 3) & ~3;
+  L.gait_out = take(kGaitStride);
+  L.esum = take(T); L.raw = take(LT_RK_COUNT);  // [T][kEnvs], [kinds][kEnvs]
+  L.gtmp = take(4);
+  L.newobs = take(2 * L.sNew);
   L.hist_stride = ((kEnvs * L.D + 3) & ~3) + 4;  // +4: the shifted read of the last element may touch one slot past the block
-  L.hist = off; off += 2 * L.hist_stride;
-  L.map = off; off += ((L.D + 3) & ~3) + dps;  // s_map[D] + s_jinfo[dps]
+  L.hist = off; off += do_obs ? 2 * L.hist_stride : 0;
+  L.tables_len = tables_len(L.D, dps);
+  L.map = off; off += L.tables_len;
   L.total = off;
   const size_t smem = (size_t)L.total * sizeof(float);
-  if (smem > 200 * 1024) return LT_ERR_UNSUPPORTED;
+  if (smem > 220 * 1024) return LT_ERR_UNSUPPORTED;
 
   StageTable ST;
   memset(&ST, 0, sizeof(ST));
+  bool overflow = false, aligned = true;
+  unsigned tx = 0;
   auto add = [&](const float* src, int row, int dst_off) {
     if (!src || row <= 0) return;
-    ST.src[ST.n] = src; ST.row[ST.n] = row; ST.off[ST.n] = dst_off;
-    ST.vec[ST.n] = ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (kEnvs * row) % 4 == 0 && (dst_off % 4) == 0) ? 1 : 0;
-    ++ST.n;
+    if (ST.n >= kMaxStage) { overflow = true; return; }
+    const int t = ST.n++;
+    ST.src[t] = src; ST.row[t] = row; ST.off[t] = dst_off;
+    aligned = aligned && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    tx += (unsigned)(kEnvs * 4) * (unsigned)row;
   };
   if (do_rew) add(a->net_forces_w_history, H * S * 3, L.force);  // biggest first
-  add(a->command, 3, L.cmd); add(a->root_pos_w, 3, L.pos); add(a->root_ang_vel_b, 3, L.angb); add(a->projected_gravity_b, 3, L.grav);
   add(a->joint_pos, J, L.q); add(a->joint_vel, J, L.qd); add(a->default_joint_pos, J, L.q0); add(a->raw_actions, J, L.act);
   if (do_obs) add(a->default_joint_vel, J, L.qd0);
   if (do_rew) {
-    add(a->root_lin_vel_b, 3, L.linb); add(a->joint_acc, J, L.qdd); add(a->applied_torque, J, L.tau);
-    add(a->soft_joint_pos_limits, 2 * J, L.lim); add(a->prev_raw_actions, J, L.pact);
+    add(a->soft_joint_pos_limits, 2 * J, L.lim); add(a->joint_acc, J, L.qdd); add(a->applied_torque, J, L.tau);
+    add(a->prev_raw_actions, J, L.pact);
   }
+  add(a->command, 3, L.cmd); add(a->root_pos_w, 3, L.pos); add(a->root_ang_vel_b, 3, L.angb); add(a->projected_gravity_b, 3, L.grav);
   if (do_rew) {
+    add(a->root_lin_vel_b, 3, L.linb);
     const LtGaitState& gs = a->gait_state;
     add(gs.last_step_current_air_time, 4, L.g_lsa); add(gs.last_step_current_contact_time, 4, L.g_lsc); add(gs.valid_last_air_time, 4, L.g_vla);
     add(gs.last_velocity_cmd, 3, L.g_cmd); add(gs.step_from_changing_cmd, 1, L.g_steps);
   }
   if (has_obj) {
     if (!a->obj_last_contact_time || !a->obj_current_contact_time || !a->obj_current_air_time) return LT_ERR_INVALID_ARG;
+    add(a->root_quat_w, 4, L.quat); add(a->obj_root_quat_w, 4, L.oquat);
     add(a->obj_last_contact_time, 1, L.oc_last); add(a->obj_current_contact_time, 1, L.oc_cur); add(a->obj_current_air_time, 1, L.oc_air);
-    add(a->root_quat_w, 4, L.quat); add(a->root_lin_vel_w, 3, L.linw); add(a->root_ang_vel_w, 3, L.angw);
-    add(a->obj_root_pos_w, 3, L.opos); add(a->obj_root_quat_w, 4, L.oquat); add(a->obj_root_lin_vel_w, 3, L.olin);
+    add(a->root_lin_vel_w, 3, L.linw); add(a->root_ang_vel_w, 3, L.angw);
+    add(a->obj_root_pos_w, 3, L.opos); add(a->obj_root_lin_vel_w, 3, L.olin);
     add(a->obj_root_ang_vel_w, 3, L.oang); add(a->obj_projected_gravity_b, 3, L.ograv);
   }
+  if (overflow) return LT_ERR_UNSUPPORTED;
+  if (a->tables) {
+    aligned = aligned && (reinterpret_cast<uintptr_t>(a->tables) & 15) == 0;
+    tx += (unsigned)L.tables_len * 4u;
+  }
+  L.bulk_ok = aligned ? 1 : 0;
+  L.tx_state = tx;
+  L.hist_bulk_ok = do_obs && (!a->policy_obs_in || (reinterpret_cast<uintptr_t>(a->policy_obs_in) & 15) == 0) &&
+                   (!a->critic_obs_in || (reinterpret_cast<uintptr_t>(a->critic_obs_in) & 15) == 0) && ((size_t)L.D * kEnvs * 4) % 16 == 0;
 
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mdp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(mdp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return lt::check(e);
     attr_set = true;
   }
@@ -962,6 +1253,10 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   mdp_step_kernel<<<grid, kThreads, smem, st>>>(args, L, ST);
   return lt::check_launch();
 }
+
+#ifdef LT_MDP_PROF
+extern "C" int lt_debug_mdp_prof(void* buf) { return lt::check(cudaMemcpyToSymbol(g_mdp_prof, &buf, sizeof(buf))); }
+#endif
 
 extern "C" int lt_mdp_reset(const LtGaitState* g, float* episode_sums, int num_reward_terms, const uint8_t* mask, int N, void* stream) {
   if (!g || !mask || N <= 0) return LT_ERR_INVALID_ARG;

@@ -191,6 +191,19 @@ class FusedMdp:
                 a.os_euler_min[k], a.os_euler_max[k] = os_.n_min[6 + k], os_.n_max[6 + k]
             a.os_last_contact_thr = os_.last_contact_time_threshold
             a.os_current_contact_thr = os_.current_contact_time_threshold
+        self._build_tables()
+
+    def _build_tables(self):
+        """Launch-constant lookup tables (lt_mdp_build_tables), computed once on the host and kept on the device; must be
+        rebuilt whenever the term tables change (kinds, dims, zero weights)."""
+        a = self._args
+        n = lib().lt_mdp_tables_len(C.byref(a))
+        if n <= 0:
+            raise _C.LocoTouchLibraryError("lt_mdp_tables_len: invalid term tables")
+        host = (C.c_int32 * n)()
+        check(lib().lt_mdp_build_tables(C.byref(a), host, n), "lt_mdp_build_tables")
+        self._tables = torch.tensor(list(host), dtype=torch.int32).to(self.device)
+        a.tables = self._tables.data_ptr()
 
     # --------------------------------------------------------------------------------------- per-step pointer binding
     def _tensor_fields(self):
