@@ -26,6 +26,7 @@ from .mdp import task_spec as TS
 from .mdp.fused import FusedMdp
 from .sim import synth
 from .sim.scene import ActionTermState
+from .streams import SideStream
 
 # reference locotouch/config/locotouch/agents/rsl_rl_ppo_cfg.py:6-30
 PPO_CFG = dict(num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0, entropy_coef=0.01,
@@ -125,6 +126,7 @@ class HotPathEngine:
             self.envs.append(denv)
             self.dev_flat.append(flat)
         self._iter = 0
+        self._taxel_stream = SideStream(self.device)
         self._copy_stream = None
         self._upload_done = [None, None]
         self._rollout_done = [None, None]
@@ -199,18 +201,21 @@ class HotPathEngine:
         k = self.set_index(t, bank)
         st = self.alg.storage
         a = self.action_term
+        if self.tactile:  # the taxel kernel reads nothing the policy or the MDP step writes: it runs next to them
+            with self._taxel_stream.forked():
+                env = self.envs[k]
+                ops.taxel_synth(env.scene["robot"].data.body_quat_w, env.scene.sensors["tactile_contact_sensor"].data.net_forces_w,
+                                self.taxel_thr, quat_body_offset=synth.NUM_ROBOT_BODIES, p_drop=0.005, p_add=0.005, seed=self.mdp.seed + 1,
+                                offset=t, offset_base=self.step_counter, signal=None, want_signal=False, packed=self.taxel_packed,
+                                delay_ring=self.taxel_ring, delay_first=self.taxel_first, delay_steps=self.taxel_delay,
+                                delayed_signal=self.tactile_obs)
         ops.process_actions(actions, a.raw_actions, a.prev_raw_actions, a.prev_prev_raw_actions, a.processed_actions,
                             clip=ACTION_CLIP, raw_scale=ACTION_RAW_SCALE, scale=1.0, offset=self.default_joint_pos)
         self._bind(k)
         self.mdp.step(True, True, policy_in=st._obs_buf[t], critic_in=st._priv_buf[t], policy_out=st._obs_buf[t + 1],
                       critic_out=st._priv_buf[t + 1], step_offset=t, offset_base=self.step_counter)
         if self.tactile:
-            env = self.envs[k]
-            ops.taxel_synth(env.scene["robot"].data.body_quat_w, env.scene.sensors["tactile_contact_sensor"].data.net_forces_w,
-                            self.taxel_thr, quat_body_offset=synth.NUM_ROBOT_BODIES, p_drop=0.005, p_add=0.005, seed=self.mdp.seed + 1,
-                            offset=t, offset_base=self.step_counter, signal=None, want_signal=False, packed=self.taxel_packed,
-                            delay_ring=self.taxel_ring, delay_first=self.taxel_first, delay_steps=self.taxel_delay,
-                            delayed_signal=self.tactile_obs)
+            self._taxel_stream.join()
             # envs that were reset start a fresh delay line (reference replay_buffer.py:61 -> tactile_recorder.py:18-22)
             torch.logical_or(self.taxel_first, self.mdp.dones, out=self.taxel_first.view(torch.bool))
         return st._obs_buf[t + 1], self.mdp.reward_buf, self.mdp.dones, {"time_outs": self.mdp.time_outs, "observations": {"critic": st._priv_buf[t + 1]}}

@@ -142,9 +142,12 @@ class PPO:
         slot = self.storage.slot()
         t = self.transition
         with torch.no_grad():
+            side = self.actor_critic.side_streams(obs.device)[0]
+            with side.forked():  # the critic runs next to the actor (two independent chains of small GEMMs)
+                values = self.actor_critic.evaluate(critic_obs)
+                slot["values"].copy_(values)  # the critic GEMM's output row is the only copy left on this path
             t.actions = self.actor_critic.act(obs, out=slot)
-            values = self.actor_critic.evaluate(critic_obs)
-            slot["values"].copy_(values)  # the critic GEMM's output row is the only copy left on this path
+            side.join()
         t.values = slot["values"]
         t.actions_log_prob = slot["logp"]
         t.action_mean = slot["mu"]

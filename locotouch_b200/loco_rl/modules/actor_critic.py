@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import ops
+from ...streams import SideStream
 from ..utils import resolve_nn_activation
 
 
@@ -116,47 +117,102 @@ class ActorCritic(nn.Module):
     def supports_explicit_backward(self) -> bool:
         return self.flat_params is not None and self._elu_stack(self.actor) and self._elu_stack(self.critic)
 
+    def side_streams(self, device):
+        """(critic chain, actor wgrad, critic wgrad) side streams, created on first use."""
+        if getattr(self, "_side", None) is None or self._side[0].device != torch.device(device):
+            self._side = tuple(SideStream(device) for _ in range(3))
+        return self._side
+
+    def _train_buffers(self, batch: int, device):
+        """Persistent activation / gradient buffers of the explicit training pass (keyed by batch size): nothing is allocated
+        inside the two concurrently running chains, so stream-ordered reuse by the caching allocator cannot alias them."""
+        key = (batch, str(device))
+        if getattr(self, "_train_buf_key", None) != key:
+            bufs = []
+            for net in (self.actor, self.critic):
+                linears = [m for m in net if isinstance(m, nn.Linear)]
+                hs = [torch.empty(batch, lin.out_features, device=device) for lin in linears]
+                gs = [None] + [torch.empty(batch, lin.in_features, device=device) for lin in linears[1:]]
+                for lin in linears:  # split-K partial products of the weight gradients
+                    lin._wgrad_part = (torch.empty(self._WGRAD_SPLIT, lin.out_features, lin.in_features, device=device)
+                                       if self._wgrad_split_ok(batch, lin.out_features) else None)
+                bufs.append((linears, hs, gs))
+            self._train_bufs, self._train_buf_key = bufs, key
+        return self._train_bufs
+
     @torch.no_grad()
     def train_forward(self, observations, critic_observations):
         """Forward of both MLPs keeping the post-activation tensors (cuBLAS GEMM with fused bias, ELU in place); no autograd
         graph is built -- ``train_backward`` produces the parameter gradients explicitly."""
+        bufs = self._train_buffers(observations.shape[0], observations.device)
         self._saved = []
         outs = []
-        for net, x in ((self.actor, observations), (self.critic, critic_observations)):
-            linears = [m for m in net if isinstance(m, nn.Linear)]
-            hs, h = [x], x
+
+        def chain(linears, hs, x):
+            acts, h = [x], x
             for i, lin in enumerate(linears):
-                h = F.linear(h, lin.weight, lin.bias)
+                h = torch.addmm(lin.bias, h, lin.weight.t(), out=hs[i])
                 if i < len(linears) - 1:
-                    h = F.elu_(h)
-                hs.append(h)
-            self._saved.append((linears, hs))
-            outs.append(h)
+                    F.elu_(h)
+                acts.append(h)
+            return acts
+
+        # the critic chain runs on a side stream next to the actor chain (eagerly and as a parallel branch of a captured graph):
+        # the GEMMs of one network overlap the memory-bound ELU passes of the other
+        side = self.side_streams(observations.device)[0]
+        for k, ((linears, hs, gs), x) in enumerate(zip(bufs, (observations, critic_observations))):
+            if k == 0:
+                acts = chain(linears, hs, x)
+            else:
+                with side.forked():
+                    acts = chain(linears, hs, x)
+            self._saved.append((linears, acts, gs))
+            outs.append(acts[-1])
+        side.join()
         return outs[0], outs[1]
 
     @torch.no_grad()
     def train_backward(self, grad_mu, grad_value):
         """Writes dLoss/dW and dLoss/db of every layer straight into the flat gradient buffer: per layer one fused
         ELU-backward + bias-gradient pass (K9), one wgrad GEMM (out = the gradient view) and one dgrad GEMM."""
-        for (linears, hs), g in zip(self._saved, (grad_mu, grad_value)):
+
+        def chain(linears, acts, gs, g, wstream):
+            # dgrad feeds the next layer; the weight gradients only have to be complete before the optimizer step, so they
+            # trail on their own stream
             last = len(linears) - 1
             for i in range(last, -1, -1):
                 lin = linears[i]
-                ops.bias_act_bwd(g, hs[i + 1] if i < last else None, lin.bias.grad)  # in place on g
-                self._wgrad(g, hs[i], lin.weight.grad)
+                ops.bias_act_bwd(g, acts[i + 1] if i < last else None, lin.bias.grad)  # in place on g
+                with wstream.forked():
+                    self._wgrad(g, acts[i], lin.weight.grad, lin._wgrad_part)
                 if i > 0:
-                    g = torch.mm(g, lin.weight)
+                    g = torch.mm(g, lin.weight, out=gs[i])
+
+        side, w_actor, w_critic = self.side_streams(grad_mu.device)
+        for k, ((linears, acts, gs), g) in enumerate(zip(self._saved, (grad_mu, grad_value))):
+            if k == 0:
+                chain(linears, acts, gs, g, w_actor)
+            else:
+                with side.forked():
+                    chain(linears, acts, gs, g, w_critic)
+                    w_critic.join()
+        w_actor.join()
+        side.join()
         self._saved = None
 
     _WGRAD_SPLIT = 8
 
-    def _wgrad(self, g, x, out):
+    def _wgrad_split_ok(self, batch: int, out_features: int) -> bool:
+        S = self._WGRAD_SPLIT
+        return batch % S == 0 and batch // S >= 512 and out_features >= 64
+
+    def _wgrad(self, g, x, out, part=None):
         """out[n,k] = g[B,n]^T x[B,k].  For the tall-skinny shapes of a PPO mini-batch (B = 24576, n*k <= 512*348) cuBLAS'
         own split-K choice leaves most SMs idle; an explicit 8-way split through one batched GEMM + a sum is ~2x faster."""
         B = g.shape[0]
         S = self._WGRAD_SPLIT
-        if B % S == 0 and B // S >= 512 and g.shape[1] >= 64:
-            part = torch.bmm(g.view(S, B // S, -1).transpose(1, 2), x.view(S, B // S, -1))
+        if self._wgrad_split_ok(B, g.shape[1]):
+            part = torch.bmm(g.view(S, B // S, -1).transpose(1, 2), x.view(S, B // S, -1), out=part)
             torch.sum(part, dim=0, out=out)
         else:
             torch.mm(g.t(), x, out=out)

@@ -1,0 +1,38 @@
+"""Fork / join of a side CUDA stream next to the caller's current stream.
+
+The hot loops are chains of small kernels whose neighbours are often independent (actor vs. critic MLP, fused MDP step vs.
+taxel synthesis, dgrad vs. wgrad GEMM).  Issuing the independent chain on a side stream lets the GPU overlap them -- eagerly
+and, because event record / wait are capturable, as parallel branches of a CUDA graph."""
+from __future__ import annotations
+
+import contextlib
+import os
+
+import torch
+
+
+class SideStream:
+    def __init__(self, device):
+        self.device = torch.device(device)
+        enabled = os.environ.get("LT_SIDE_STREAMS", "1") != "0"  # LT_SIDE_STREAMS=0: everything on the caller's stream
+        self.stream = torch.cuda.Stream(device=self.device) if (self.device.type == "cuda" and enabled) else None
+
+    @contextlib.contextmanager
+    def forked(self):
+        """``with side.forked(): ...`` enqueues the body on the side stream, ordered after everything already enqueued on the
+        current stream.  Call ``join()`` before the current stream consumes what the body produced."""
+        if self.stream is None:
+            yield
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            yield
+
+    def join(self):
+        if self.stream is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        torch.cuda.current_stream().wait_event(ev)

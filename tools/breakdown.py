@@ -26,7 +26,7 @@ def timed(fn, reps=20, warm=3):
 
 eng = HotPathEngine(num_envs=4096, task="teacher", tactile=True, device="cuda:0")
 eng.capture()
-g_roll, g_upd = eng._graphs['roll'], eng._graphs['update']
+g_roll, g_upd = eng._graphs['roll'][0], eng._graphs['update']
 print(f"rollout graph  {timed(g_roll.replay):8.3f} ms")
 print(f"update graph   {timed(g_upd.replay):8.3f} ms")
 print(f"randperm       {timed(eng.draw_permutation):8.3f} ms")
