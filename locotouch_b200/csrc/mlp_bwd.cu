@@ -3,20 +3,22 @@
 // the two autograd kernels `elu_backward` (grad * (h > 0 ? 1 : h + alpha)) and the bias-gradient column reduction
 // (sum over the batch), which together read the [B, n] gradient three times; here it is read once, written once, and the
 // column sums fall out of the same pass.  The GEMMs themselves (dgrad / wgrad) stay cuBLAS.
-// Column sums: each block folds its rows in a fixed order in shared memory and adds its partial to a float64 accumulator
-// per column (L2 atomics; the fp64 sum is order-independent to ~1e-16, i.e. the fp32 result is reproducible); the last
-// block to finish rounds the accumulators to fp32 and clears them.
+// Column sums: each block folds its rows in a fixed order in shared memory and adds its partial to one of kSub float64
+// accumulators per column (L2 atomics; the fp64 sum is order-independent to ~1e-16, i.e. the fp32 result is reproducible --
+// spreading the blocks over kSub accumulator rows keeps the same-address atomic chains short: with one row, 592 serial atomics
+// per column cost ~25 us); the last block to finish folds the kSub rows, rounds to fp32 and clears them.
 // Traffic per element: 8 B read (+0 for the last, activation-free layer: 4 B) + 4 B written.
 #include "lt_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kSub = 16;  // accumulator rows
 
 struct BwdWs {
   unsigned int counter;
   unsigned int pad[3];
-  double acc[1];  // [n] column accumulators, zero between calls
+  double acc[1];  // [kSub][n] column accumulators, zero between calls
 };
 
 template <bool VEC4>
@@ -96,7 +98,7 @@ bias_act_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict_
           const float4 u = sa[k * col_threads + cg0];
           t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
         }
-        double* acc = ws->acc + 4 * cg;
+        double* acc = ws->acc + (size_t)(blockIdx.x % kSub) * n + 4 * cg;
         atomicAdd(acc, (double)t.x); atomicAdd(acc + 1, (double)t.y); atomicAdd(acc + 2, (double)t.z); atomicAdd(acc + 3, (double)t.w);
       }
       __syncthreads();
@@ -106,7 +108,7 @@ bias_act_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict_
       if (rl == 0) {
         float t = s_acc[cg0];
         for (int k = 1; k < row_lanes; ++k) t += s_acc[k * col_threads + cg0];
-        atomicAdd(ws->acc + cg, (double)t);
+        atomicAdd(ws->acc + (size_t)(blockIdx.x % kSub) * n + cg, (double)t);
       }
       __syncthreads();
     }
@@ -118,8 +120,13 @@ bias_act_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict_
   if (!is_last) return;
   __threadfence();
   for (int j = threadIdx.x; j < n; j += kThreads) {
-    bias_grad[j] = (float)__ldcg(ws->acc + j);
-    ws->acc[j] = 0.0;
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kSub; ++k) {
+      t += __ldcg(ws->acc + (size_t)k * n + j);
+      ws->acc[(size_t)k * n + j] = 0.0;
+    }
+    bias_grad[j] = (float)t;
   }
   if (threadIdx.x == 0) ws->counter = 0;
 }
@@ -135,7 +142,7 @@ int blocks_for(int B) {
 
 extern "C" int64_t lt_bias_act_bwd_workspace_bytes(int B, int n) {
   (void)B;
-  return 16 + (int64_t)(n > 0 ? n : 1) * (int64_t)sizeof(double);
+  return 16 + (int64_t)kSub * (int64_t)(n > 0 ? n : 1) * (int64_t)sizeof(double);
 }
 
 extern "C" int lt_bias_act_bwd(const float* grad_out, const float* act_out, float* grad_pre, float* bias_grad, int B, int n, float alpha,

@@ -169,6 +169,21 @@ def bench_adam(n: int, reps: int):
     return {"clip+adam (2 launches)": (time_graph(run, copies, reps), per)}
 
 
+def bench_k9(b: int, reps: int):
+    out = {}
+    for n in (512, 256, 128):
+        per = 12 * b * n
+        copies = min(copies_for(per), 8)
+        sets = [(torch.randn(b, n, device="cuda"), torch.randn(b, n, device="cuda"), torch.empty(n, device="cuda")) for _ in range(copies)]
+
+        def run(i, sets=sets):
+            g, h, bg = sets[i]
+            ops.bias_act_bwd(g, h, bg)
+
+        out[f"bias_act_bwd [{b}x{n}]"] = (time_graph(run, copies, max(20, reps // 4)), per)
+    return out
+
+
 def bench_gather(n_rows: int, count: int, reps: int, obs_dim: int = 270):
     dims = (obs_dim, obs_dim, 12, 1, 1, 1, 1, 12, 12)
     per = sum(dims) * 4 * 2 * count
@@ -206,6 +221,8 @@ def main():
         res.update(bench_ppo_loss(n * 24 // 4, args.reps))
     if want("adam"):
         res.update(bench_adam(607641 // 4 * 4, args.reps))
+    if want("k9"):
+        res.update(bench_k9(n * 24 // 4, args.reps))
     if want("gather"):
         res.update(bench_gather(n * 24, n * 24 // 4, max(20, args.reps // 10)))
     rows = []

@@ -1,0 +1,31 @@
+"""One launch of each streaming kernel at BASELINE size (for one `ncu --set full` capture: DRAM bytes per launch).
+
+    ncu --set full --clock-control none -k regex:"mdp_step_kernel|taxel_kernel" -c 6 -o out python tools/prof_traffic.py
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from locotouch_b200 import ops  # noqa: E402
+from locotouch_b200.mdp import task_spec as TS  # noqa: E402
+from locotouch_b200.mdp.fused import FusedMdp  # noqa: E402
+from locotouch_b200.sim import synth  # noqa: E402
+
+n = 4096
+spec = TS.SPECS["teacher"]()
+env = synth.make_env(n, seed=1, with_object=True).to("cuda")
+m = FusedMdp(env, spec, seed=1)
+for _ in range(3):  # launches 0-2: the fused teacher step (the first fills the history)
+    m.step(True, True)
+g = torch.Generator().manual_seed(0)
+q = torch.randn(n, 238, 4, generator=g)
+q = (q / q.norm(dim=-1, keepdim=True)).cuda()
+f = (torch.randn(n, 221, 3, generator=g) * 0.1).cuda()
+thr = (0.05 + (torch.rand(n, 221, generator=g) - 0.5) * 0.02).cuda()
+for i in range(3):
+    ops.taxel_synth(q, f, thr, quat_body_offset=17, seed=1, offset=i)
+torch.cuda.synchronize()
+print("ok")
