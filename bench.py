@@ -175,6 +175,23 @@ def run_reference(args, rank: int):
 
 
 # ------------------------------------------------------------------------------------------------------ kernel roofline
+def ncu_traffic_bytes(kernel_substr: str):
+    """DRAM bytes per launch (read + write) of the committed `ncu --set full` capture, or None."""
+    path = os.path.join(ROOT, "profiles", "r1_k1_k2_ncu_full_summary.json")
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = []
+    for rec in json.load(open(path)):
+        if kernel_substr in rec.get("kernel", ""):
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, u = rec[key].split()
+                tot += float(v) * unit[u]
+            vals.append(tot)
+    return sum(vals) / len(vals) if vals else None
+
+
 def kernel_rooflines(engine, reps: int = 96):
     """Per-launch duration of the two streaming kernels of the rollout, measured live: `reps` launches captured in one CUDA
     graph on the timing stream, cycling through the engine's state sets (6 x ~33 MB > L2), CUDA events around the replay."""
@@ -350,7 +367,9 @@ def main():
             rows.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "us_per_launch": us,
                          "alg_bytes_per_launch": nbytes})
         top = max(rows, key=lambda r: r["us_per_launch"])
-        line["roofline"] = {"bound": "hbm", "achieved": top["achieved"], "peak": hbm, "unit": "GB/s", "frac": top["frac"], "traffic": None,
+        line["roofline"] = {"bound": "hbm", "achieved": top["achieved"], "peak": hbm, "unit": "GB/s", "frac": top["frac"], "traffic": ncu_traffic_bytes("mdp_step_kernel"),
+                            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1_k1_k2_ncu_full_summary.json (one ncu --set full capture; "
+                                            "the kernel's 12.6 MB of writes are still in L2 when it ends, ncu counts 0 written)",
                             "kernel": top["kernel"], "us_per_launch": top["us_per_launch"], "peak_kind": kind,
                             "how": "96 launches in one CUDA graph cycling 6 state sets (> L2), CUDA events on the launch stream"}
         line["kernels"] = rows

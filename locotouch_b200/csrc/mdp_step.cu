@@ -50,7 +50,7 @@ constexpr int kP4 = 5, kS12 = 13;  // padded strides of the rows the kernel gath
 struct Layout {
   int cmd, pos, linb, angb, grav, q, qd, qdd, tau, q0, qd0, lim, act, pact, force, air, con, lair, fpos, fvel;
   int quat, linw, angw, opos, oquat, olin, oang, ograv, oc_last, oc_cur, oc_air, g_lsa, g_lsc, g_vla, g_cmd, g_steps, g_sz, g_vpc, eplen, gait_out,
-      esum, raw, gtmp, newobs, hist, map, total;
+      esum, raw, gtmp, fmax, oframe, newobs, hist, map, total;
   int sJ, sLim, sF;  // strides of the [J], [J, 2] and [H, S, 3] rows
   int D;             // observation dim per group
   int dps;           // new values per step per group
@@ -261,10 +261,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 __device__ __forceinline__ void named_barrier(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // max over the history of |F| of one sensor body: torch.max(torch.norm(net_forces_w_history[:, :, ids], dim=-1), dim=1)[0]
-__device__ __noinline__ float body_force_max(const float* force_env, int H, int S, int b) {
+// The H norms are independent chains (three in flight for the usual H == 3); the max is order-independent.
+__device__ __forceinline__ float body_force_max(const float* force_env, int H, int S, int b) {
   float m = 0.f;
+  int h = 0;
+  for (; h + 3 <= H; h += 3) {
+    const float* p0 = force_env + (h * S + b) * 3;
+    const float* p1 = p0 + S * 3;
+    const float* p2 = p1 + S * 3;
+    const float n0 = sqrtf(p0[0] * p0[0] + p0[1] * p0[1] + p0[2] * p0[2]);
+    const float n1 = sqrtf(p1[0] * p1[0] + p1[1] * p1[1] + p1[2] * p1[2]);
+    const float n2 = sqrtf(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
+    m = fmaxf(m, fmaxf(n0, fmaxf(n1, n2)));
+  }
 #pragma unroll 1
-  for (int h = 0; h < H; ++h) {
+  for (; h < H; ++h) {
     const float* p = force_env + (h * S + b) * 3;
     m = fmaxf(m, sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
   }
@@ -446,6 +457,33 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
   }
   const int step = s_step;
   const uint64_t rng_offset = (uint64_t)(int64_t)step;
+  // Wide pre-phase (warps run the same short code side by side; everything below only combines these values):
+  //  * contact-force maxima of every sensor body, one warp per body -- the terminations and the slip / collision terms compare
+  //    them against their thresholds;
+  //  * the object's state in the robot frame (rewards.py:469-543, observations.py:55-58), five warps: position, linear velocity,
+  //    angular velocity, gravity direction, relative quaternion -- shared by the object reward terms and both observation groups.
+  float* s_of = sm + L.oframe;  // [16][kEnvs]
+  if (do_rew && lane < nvalid) {
+#pragma unroll 1
+    for (int b = warp; b < S; b += kWarps) sm[L.fmax + b * kEnvs + lane] = body_force_max(sm + L.force + lane * L.sF, H, S, b);
+  }
+  if (has_obj && warp >= kWarps - 5 && lane < nvalid) {
+    const int job = kWarps - 1 - warp, e = lane;
+    const Quat q = ld4(sm + L.quat + e * kS4);
+    if (job < 4) {
+      Vec3 d;
+      if (job == 0) d = sub3(ld3(sm + L.opos + e * kS3), ld3(sm + L.pos + e * kS3));
+      else if (job == 1) d = sub3(ld3(sm + L.olin + e * kS3), ld3(sm + L.linw + e * kS3));
+      else if (job == 2) d = sub3(ld3(sm + L.oang + e * kS3), ld3(sm + L.angw + e * kS3));
+      else d = rot(ld4(sm + L.oquat + e * kS4), ld3(sm + L.ograv + e * kS3));
+      const Vec3 r = rot_inv(q, d);
+      s_of[(3 * job + 0) * kEnvs + e] = r.x; s_of[(3 * job + 1) * kEnvs + e] = r.y; s_of[(3 * job + 2) * kEnvs + e] = r.z;
+    } else {
+      const Quat qr = quat_mul(quat_inv(q), ld4(sm + L.oquat + e * kS4));
+      s_of[12 * kEnvs + e] = qr.w; s_of[13 * kEnvs + e] = qr.x; s_of[14 * kEnvs + e] = qr.y; s_of[15 * kEnvs + e] = qr.z;
+    }
+  }
+  if (do_rew || has_obj) __syncthreads();
 
   // ------------------------------------------------------------------------------------------------ stage 1: tasks
   float* s_raw = sm + L.raw;  // [LT_RK_COUNT][kEnvs]: unweighted value of every reward kind (stage 2a picks the task's terms)
@@ -479,6 +517,10 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
 #pragma unroll 1
   for (int task = warp; task < kFixedTasks + quads; task = next_task()) {
     PROF_STAMP(task < kWarps ? 8 : 10);
+#ifdef LT_MDP_ONETASK  // experiment: every warp runs the same (barrier-free) task -> isolates instruction-supply effects
+    if (task >= kWarps) continue;
+    task = LT_MDP_ONETASK;
+#endif
     if (task <= 2) {
       // ---------------------------------------------------------------------------------------------- gait reward
       if (!do_rew) continue;
@@ -652,12 +694,12 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
       if (do_pv || do_w) {
         // position / linear velocity / angular velocity slots: raw values first, then one pass per Philox quad
         if (do_pv) {
-          const Vec3 p = rot_inv(q, sub3(ld3(sm + L.opos + e * kS3), ld3(sm + L.pos + e * kS3)));
-          const Vec3 v = rot_inv(q, sub3(ld3(sm + L.olin + e * kS3), ld3(sm + L.linw + e * kS3)));
+          const Vec3 p = {s_of[0 * kEnvs + e], s_of[1 * kEnvs + e], s_of[2 * kEnvs + e]};
+          const Vec3 v = {s_of[3 * kEnvs + e], s_of[4 * kEnvs + e], s_of[5 * kEnvs + e]};
           out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = v.x; out[4] = v.y; out[5] = v.z;
         }
         if (do_w) {
-          const Vec3 w = rot_inv(q, sub3(ld3(sm + L.oang + e * kS3), ld3(sm + L.angw + e * kS3)));
+          const Vec3 w = {s_of[6 * kEnvs + e], s_of[7 * kEnvs + e], s_of[8 * kEnvs + e]};
           out[10] = w.x; out[11] = w.y; out[12] = w.z;
         }
 #pragma unroll 1
@@ -685,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
         }
       }
       if (do_q) {
-        const Quat qr = quat_mul(quat_inv(q), ld4(sm + L.oquat + e * kS4));
+        const Quat qr = {s_of[12 * kEnvs + e], s_of[13 * kEnvs + e], s_of[14 * kEnvs + e], s_of[15 * kEnvs + e]};
         float st[4] = {qr.w, qr.x, qr.y, qr.z};
         float cst[4] = {A.os_non_contact[6], A.os_non_contact[7], A.os_non_contact[8], A.os_non_contact[9]};
         if (noise) {  // additive slots, then euler-angle noise composed onto the quaternion
@@ -736,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
     if (!do_rew) continue;
     if (task >= 5 && !live) continue;
     if (task >= 11 && !has_obj) continue;
-    const float* force_env = sm + L.force + e * L.sF;
+    const float* fmx = sm + L.fmax + e;  // [body][kEnvs]
     switch (task) {
       case 3:
       case 4: {  // terminations (terminations.py:10-23 + [IL] terms): task 3 takes the even terms, task 4 the odd ones; is_alive
@@ -752,7 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
               case LT_TK_ROOT_HEIGHT: m = sm[L.pos + e * kS3 + 2] < tt.p[0]; break;
               case LT_TK_ILLEGAL_CONTACT:
 #pragma unroll 1
-                for (int k = 0; k < tt.num_ids; ++k) m = m || body_force_max(force_env, H, S, tt.body_ids[k]) > tt.p[0];
+                for (int k = 0; k < tt.num_ids; ++k) m = m || fmx[tt.body_ids[k] * kEnvs] > tt.p[0];
                 break;
               case LT_TK_OBJECT_BELOW_ROBOT: m = sm[L.opos + e * kS3 + 2] < sm[L.pos + e * kS3 + 2]; break;
               case LT_TK_BAD_ROLL: m = fabsf(asinf(sm[L.ograv + e * kS3 + 1])) > tt.p[0]; break;
@@ -801,7 +843,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
           const float sp = sqrtf(fvel[3 * k] * fvel[3 * k] + fvel[3 * k + 1] * fvel[3 * k + 1]);
-          slip += (body_force_max(force_env, H, S, A.feet_sensor_ids[k]) > slip_thr ? 1.f : 0.f) * sp;
+          slip += (fmx[A.feet_sensor_ids[k] * kEnvs] > slip_thr ? 1.f : 0.f) * sp;
           drag += (fpos[3 * k + 2] <= drag_h && sp > drag_v) ? 1.f : 0.f;
         }
         put(LT_RK_FOOT_SLIP, slip);
@@ -854,7 +896,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
         float c = 0.f;
         if (s_slot[LT_RK_THIGH_CALF_COLLISION] >= 0) {
 #pragma unroll 1
-          for (int k = 0; k < A.num_thigh_calf; ++k) c += body_force_max(force_env, H, S, A.thigh_calf_sensor_ids[k]) > thr ? 1.f : 0.f;
+          for (int k = 0; k < A.num_thigh_calf; ++k) c += fmx[A.thigh_calf_sensor_ids[k] * kEnvs] > thr ? 1.f : 0.f;
         }
         put(LT_RK_THIGH_CALF_COLLISION, c);
         break;
@@ -865,7 +907,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
         const float moving = cmd_norm > 0.f ? 1.f : 0.f;
         const Quat q = ld4(sm + L.quat + e * kS4);
         const Vec3 rel_pos_w = sub3(ld3(sm + L.opos + e * kS3), ld3(sm + L.pos + e * kS3));
-        const Vec3 rel_vel = rot_inv(q, sub3(ld3(sm + L.olin + e * kS3), ld3(sm + L.linw + e * kS3)));
+        const Vec3 rel_vel = {s_of[3 * kEnvs + e], s_of[4 * kEnvs + e], s_of[5 * kEnvs + e]};
         {
           float v = sqrtf(rel_pos_w.x * rel_pos_w.x + rel_pos_w.y * rel_pos_w.y);
           if (par(LT_RK_OBJ_XY_POS, 0) != 0.f) v *= moving;
@@ -875,7 +917,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
         put(LT_RK_OBJ_LOSE_CONTACT, (sm[L.oc_last + e] > 0.f && sm[L.oc_air + e] > 0.f) ? 1.f : 0.f);
         put(LT_RK_OBJ_Z_VEL, rel_vel.z * rel_vel.z);
         if (s_slot[LT_RK_OBJ_DANGER] >= 0) {
-          const Vec3 rel_pos = rot_inv(q, rel_pos_w);
+          const Vec3 rel_pos = {s_of[0 * kEnvs + e], s_of[1 * kEnvs + e], s_of[2 * kEnvs + e]};
           bool bad = fabsf(rel_pos.x) > par(LT_RK_OBJ_DANGER, 0);
           bad = bad || fabsf(rel_pos.y) > par(LT_RK_OBJ_DANGER, 1);
           bad = bad || rel_pos.z < par(LT_RK_OBJ_DANGER, 2);
@@ -888,8 +930,8 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
       }
       case 12: {  // object orientation / angular velocity terms (rewards.py:505-543)
         const Quat q = ld4(sm + L.quat + e * kS4);
-        const Vec3 rel_ang = rot_inv(q, sub3(ld3(sm + L.oang + e * kS3), ld3(sm + L.angw + e * kS3)));
-        const Vec3 g_obj = rot_inv(q, rot(ld4(sm + L.oquat + e * kS4), ld3(sm + L.ograv + e * kS3)));
+        const Vec3 rel_ang = {s_of[6 * kEnvs + e], s_of[7 * kEnvs + e], s_of[8 * kEnvs + e]};
+        const Vec3 g_obj = {s_of[9 * kEnvs + e], s_of[10 * kEnvs + e], s_of[11 * kEnvs + e]};
         put(LT_RK_OBJ_RP_ANGLE, g_obj.x * g_obj.x + g_obj.y * g_obj.y);
         put(LT_RK_OBJ_RP_VEL, fabsf(rel_ang.x) + fabsf(rel_ang.y));
         put(LT_RK_OBJ_ROLL_ANGLE, g_obj.y * g_obj.y);
@@ -1181,6 +1223,8 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   L.gait_out = take(kGaitStride);
   L.esum = take(T); L.raw = take(LT_RK_COUNT);  // [T][kEnvs], [kinds][kEnvs]
   L.gtmp = take(4);
+  L.fmax = take(do_rew ? S : 0);  // [S][kEnvs]
+  L.oframe = take(has_obj ? 16 : 0);  // [16][kEnvs]: object position / velocity / angular velocity / gravity / quaternion in the robot frame
   L.newobs = take(2 * L.sNew);
   L.hist_stride = ((kEnvs * L.D + 3) & ~3) + 4;  // +4: the shifted read of the last element may touch one slot past the block
   L.hist = off; off += do_obs ? 2 * L.hist_stride : 0;

@@ -249,6 +249,8 @@ class PPO:
         else:
             torch.autograd.backward([mu, value], [bufs.grad_mu, bufs.grad_value.view_as(value)])
             opt.grads[off:off + n].add_(bufs.grad_sigma)
+        if adaptive and world > 1:  # the local KL mean travels in the tail of the gradient all-reduce
+            ac.flat_grads_ext[-4:-3].copy_(bufs.out[4:5])
 
     def reduce_and_step(self):
         """[NCCL: flat gradient all-reduce + KL all-reduce + learning-rate decision] then fused clip + Adam (K7)."""
@@ -256,11 +258,10 @@ class PPO:
         _, world = D.world_info()
         grad_scale = 1.0
         if world > 1:
-            grad_scale = D.average_gradients_(opt.grads)  # one flat all-reduce; the 1/W is applied inside K7
-            if self.desired_kl is not None and self.schedule == "adaptive":  # every rank must take the same decision
-                kl = self._loss_bufs.out[4:5]
-                D.allreduce_sum_(kl)
-                ops.adaptive_lr(kl, 1.0 / world, self.desired_kl, opt.lr_t)
+            # ONE all-reduce per mini-batch: flat gradients + the KL statistic in the tail; the 1/W is applied inside K7
+            grad_scale = D.average_gradients_(self.actor_critic.flat_grads_ext)
+            if self.desired_kl is not None and self.schedule == "adaptive":  # every rank takes the same decision
+                ops.adaptive_lr(self.actor_critic.flat_grads_ext[-4:-3], 1.0 / world, self.desired_kl, opt.lr_t)
         opt.step(max_grad_norm=self.max_grad_norm, grad_scale=grad_scale)
 
     def update_epilogue(self):

@@ -89,7 +89,10 @@ class ActorCritic(nn.Module):
             return self.flat_params, self.flat_grads
         total = sum((p.numel() + 3) // 4 * 4 for p in params)  # every tensor starts 16-byte aligned
         flat = torch.zeros(total, device=dev, dtype=torch.float32)
-        grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        # four spare floats after the gradients: statistics that must be summed over ranks (the KL mean) ride along with the
+        # gradient all-reduce instead of paying for a collective of their own
+        self.flat_grads_ext = torch.zeros(total + 4, device=dev, dtype=torch.float32)
+        grads = self.flat_grads_ext[:total]
         off, self._offsets, self._slices = 0, [], {}
         names = [k for k, _ in self.named_parameters()]
         for name, p in zip(names, params):

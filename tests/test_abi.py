@@ -76,3 +76,55 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_mdp_lookup_tables_are_built_on_the_host(lt_lib):
+    """lt_mdp_build_tables: observation column map ([term][history][dim] rows), per-value term info, reward kind -> slot and
+    the per-kind parameter rows -- host arithmetic only, checked against a direct restatement."""
+    import ctypes as C
+    import struct
+
+    from locotouch_b200 import _C
+    from locotouch_b200.mdp import task_spec as TS
+
+    RK_COUNT = TS.RK_OBJ_DANGER + 1  # LT_RK_COUNT
+    a = _C.LtMdpArgs()
+    a.J = 12
+    dims, H = [3, 12, 3], 4
+    a.num_obs_terms, a.history_length = len(dims), H
+    for i, (kind, d) in enumerate(zip((0, 3, 2), dims)):  # LT_OK_COMMAND, LT_OK_JOINT_POS_REL, LT_OK_PROJECTED_GRAVITY
+        a.obs_terms[i].kind, a.obs_terms[i].dim, a.obs_terms[i].scale = kind, d, 1.0
+    kinds = [(TS.RK_ALIVE, 1.0, ()), (TS.RK_TRACK_LIN_VEL_XY, 2.0, (0.25,)), (TS.RK_FOOT_SLIP, 0.0, (0.5,)), (TS.RK_BASE_HEIGHT, -1.0, (0.42,))]
+    a.num_reward_terms = len(kinds)
+    for i, (k, w, p) in enumerate(kinds):
+        a.reward_terms[i].kind, a.reward_terms[i].weight = k, w
+        for j, v in enumerate(p):
+            a.reward_terms[i].p[j] = v
+    n = lt_lib.lt_mdp_tables_len(C.byref(a))
+    dps, D = sum(dims), sum(dims) * H
+    assert n == (((D + 3) // 4 * 4) + dps + RK_COUNT * 7 + 3) // 4 * 4
+    out = (C.c_int32 * n)()
+    assert lt_lib.lt_mdp_build_tables(C.byref(a), out, n) == 0
+    assert lt_lib.lt_mdp_build_tables(C.byref(a), out, n - 1) == 1  # too small
+    out = list(out)
+    col = jb = 0
+    for t, d in enumerate(dims):
+        for h in range(H):
+            for i in range(d):
+                k = col + h * d + i
+                m = out[k] & 0xFFFFFFFF
+                assert m & 0xFFFF == jb + i
+                assert m >> 16 == (0xFFFF if h == H - 1 else k + d)
+        for i in range(d):
+            assert out[(D + 3) // 4 * 4 + jb + i] == t | (i << 8)
+        col += d * H
+        jb += d
+    slot0 = (D + 3) // 4 * 4 + dps
+    slots = out[slot0:slot0 + RK_COUNT]
+    assert slots[TS.RK_ALIVE] == 0 and slots[TS.RK_TRACK_LIN_VEL_XY] == 1 and slots[TS.RK_BASE_HEIGHT] == 3
+    assert slots[TS.RK_FOOT_SLIP] == -1 and slots[TS.RK_GAIT] == -1  # zero weight / absent
+    par = out[slot0 + RK_COUNT:]
+    as_float = lambda v: struct.unpack("f", struct.pack("i", v))[0]  # noqa: E731
+    assert as_float(par[TS.RK_TRACK_LIN_VEL_XY * 6]) == 0.25
+    assert abs(as_float(par[TS.RK_BASE_HEIGHT * 6]) - 0.42) < 1e-7
+    assert as_float(par[TS.RK_FOOT_SLIP * 6]) == 0.0
