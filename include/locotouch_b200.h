@@ -376,6 +376,23 @@ int64_t lt_masked_mse_workspace_bytes(int64_t rows);
 int lt_masked_mse(const float* student, const float* teacher, const uint8_t* masks, int64_t rows, int A,
                   float* grad_student, float* out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * K10  trajectory split / pad / unpad for recurrent mini-batches
+ * replaces  loco_rl/loco_rl/utils/utils.py:37-83 (split_and_pad_trajectories, unpad_trajectories) as used by
+ *           loco_rl/loco_rl/storage/rollout_storage.py:246-318 (recurrent_mini_batch_generator).
+ * Trajectories are numbered env by env in time order; the last step always ends one.  traj_base[n] = exclusive scan over
+ * envs of (1 + number of dones before the last step); M = total number of trajectories (the caller sizes the outputs).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* (env, first step, length) of every trajectory, from dones [T, N] (uint8). */
+int lt_trajectory_index(const uint8_t* dones, const int64_t* traj_base, int32_t* traj_env, int32_t* traj_start,
+                        int32_t* traj_len, int T, int N, void* stream);
+/* x [T, N, D] -> out [T, M, D] (zero padded) and masks [T, M] (may be NULL). */
+int lt_split_pad_trajectories(const float* x, const int32_t* traj_env, const int32_t* traj_start, const int32_t* traj_len,
+                              float* out, uint8_t* masks, int T, int N, int D, int M, void* stream);
+/* padded [T, M, D] -> out [T, N, D] (every row written exactly once). */
+int lt_unpad_trajectories(const float* padded, const int32_t* traj_env, const int32_t* traj_start, const int32_t* traj_len,
+                          float* out, int T, int N, int D, int M, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

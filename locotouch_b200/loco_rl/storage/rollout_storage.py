@@ -110,9 +110,23 @@ class RolloutStorage:
         self.step += 1
 
     def _save_hidden_states(self, hidden_states):
+        """reference rollout_storage.py:112-146: per-step copies of the actor / critic RNN states ([layers, N, hidden]; an LSTM
+        passes a tuple); the critic entry may be None."""
         if hidden_states is None or hidden_states == (None, None):
             return
-        raise NotImplementedError("recurrent policies are outside the LocoTouch hot path (SURVEY.md section 8f, rank 1)")
+        hid_a = hidden_states[0] if isinstance(hidden_states[0], tuple) else (hidden_states[0],)
+        hid_c = None
+        if hidden_states[1] is not None:
+            hid_c = hidden_states[1] if isinstance(hidden_states[1], tuple) else (hidden_states[1],)
+        T = self.observations.shape[0]
+        if self.saved_hidden_states_a is None:
+            self.saved_hidden_states_a = [torch.zeros(T, *h.shape, device=self.device) for h in hid_a]
+            if hid_c is not None:
+                self.saved_hidden_states_c = [torch.zeros(T, *h.shape, device=self.device) for h in hid_c]
+        for i, h in enumerate(hid_a):
+            self.saved_hidden_states_a[i][self.step].copy_(h)
+            if hid_c is not None:
+                self.saved_hidden_states_c[i][self.step].copy_(hid_c[i])
 
     def clear(self):
         self.step = 0
@@ -168,4 +182,38 @@ class RolloutStorage:
                     rnd[sl] if rnd is not None else None)
 
     def recurrent_mini_batch_generator(self, num_mini_batches, num_epochs=8):
-        raise NotImplementedError("recurrent mini-batches are outside the LocoTouch hot path (SURVEY.md section 8f, rank 1)")
+        """reference rollout_storage.py:246-318.  Mini-batches are env ranges; observations travel as zero-padded trajectories
+        (split at the dones) with their masks and the RNN states at each trajectory's first step.  The trajectory index is
+        built once on the device (K10) and its per-env offsets are read back once, instead of the per-mini-batch
+        ``torch.sum(last_was_done[:, start:stop])`` host reads and boolean-mask gathers of the reference."""
+        index = ops.TrajectoryIndex(self.dones)
+        padded_obs, masks = index.split_and_pad(self.observations)
+        if self.privileged_observations is not None:
+            padded_cobs, _ = index.split_and_pad(self.privileged_observations, want_masks=False)
+        else:
+            padded_cobs = padded_obs
+        padded_rnd = index.split_and_pad(self.rnd_state, want_masks=False)[0] if self.rnd_state_shape is not None else None
+        start_steps, envs = index.start.long(), index.env.long()
+
+        def first_step_states(saved):  # [T, layers, N, hidden] -> [layers, M, hidden] at every trajectory's first step
+            if saved is None:
+                return None
+            return [h[start_steps, :, envs].transpose(1, 0).contiguous() for h in saved]
+
+        hid_a_all = first_step_states(self.saved_hidden_states_a)
+        hid_c_all = first_step_states(self.saved_hidden_states_c)
+        mini_batch_size = self.num_envs // num_mini_batches
+        for _ in range(num_epochs):
+            for i in range(num_mini_batches):
+                start, stop = i * mini_batch_size, (i + 1) * mini_batch_size
+                tr = slice(index.base[start], index.base[stop])
+                hid_a = [h[:, tr].contiguous() for h in hid_a_all] if hid_a_all is not None else None
+                hid_c = [h[:, tr].contiguous() for h in hid_c_all] if hid_c_all is not None else None
+                if hid_a is not None and len(hid_a) == 1:  # remove the tuple for GRU
+                    hid_a = hid_a[0]
+                if hid_c is not None and len(hid_c) == 1:
+                    hid_c = hid_c[0]
+                yield (padded_obs[:, tr], padded_cobs[:, tr], self.actions[:, start:stop], self.values[:, start:stop],
+                       self.advantages[:, start:stop], self.returns[:, start:stop], self.actions_log_prob[:, start:stop],
+                       self.mu[:, start:stop], self.sigma[:, start:stop], (hid_a, hid_c), masks[:, tr],
+                       padded_rnd[:, tr] if padded_rnd is not None else None)

@@ -10,3 +10,20 @@ def resolve_nn_activation(act_name: str) -> torch.nn.Module:
     if act_name not in table:
         raise ValueError(f"Invalid activation function '{act_name}'.")
     return table[act_name]()
+
+
+def split_and_pad_trajectories(tensor, dones):
+    """Drop-in for reference loco_rl/loco_rl/utils/utils.py:37-73: cuts ``tensor`` [T, N, ...] at the done flags (the last step
+    always ends a trajectory), lists the trajectories env by env in time order and pads them with zeros to T steps.
+    Returns (padded [T, M, D], masks [T, M] bool).  Two launches (index + output-driven copy) instead of clone / nonzero /
+    tolist / split into M views / pad_sequence."""
+    from ... import ops
+
+    return ops.TrajectoryIndex(dones).split_and_pad(tensor)
+
+
+def unpad_trajectories(trajectories, masks):
+    """Inverse of split_and_pad_trajectories (reference utils.py:76-83): [T, M, D] + masks [T, M] -> [T, N, D]."""
+    from ... import ops
+
+    return ops.TrajectoryIndex.from_masks(masks).unpad(trajectories)

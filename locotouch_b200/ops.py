@@ -293,3 +293,67 @@ def masked_mse(student, teacher, masks, grad=None, out=None, want_grad=True):
                               rows, A, ptr(grad, torch.float32), ptr(out, torch.float32), ptr(ws), nbytes, current_stream()), "lt_masked_mse")
     count_launches(2 if grad is not None else 1)
     return out, grad
+
+
+# ------------------------------------------------------------------------------------------- K10 trajectory split / pad
+class TrajectoryIndex:
+    """(env, first step, length) of every trajectory of a rollout cut at its dones (reference utils.py:55-61), on the device.
+    ``base`` is also read back once (N + 1 host ints): a caller slicing trajectories per env range needs the counts."""
+
+    def __init__(self, dones: torch.Tensor):
+        d = dones.view(dones.shape[0], dones.shape[1])
+        if d.dtype != torch.uint8:
+            d = d.to(torch.uint8)
+        d = d.contiguous()
+        T, N = d.shape
+        counts = 1 + (d[:-1] != 0).sum(dim=0, dtype=torch.int64)  # the last step always ends a trajectory
+        ends = torch.cumsum(counts, dim=0)
+        self.base_dev = (ends - counts).contiguous()
+        self.base = [0] + ends.tolist()  # the one device -> host read (the reference does trajectory_lengths.tolist())
+        self.T, self.N, self.M = T, N, self.base[-1]
+        dev = d.device
+        self.env = torch.empty(self.M, dtype=torch.int32, device=dev)
+        self.start = torch.empty(self.M, dtype=torch.int32, device=dev)
+        self.length = torch.empty(self.M, dtype=torch.int32, device=dev)
+        check(lib().lt_trajectory_index(ptr(d, torch.uint8, "dones"), ptr(self.base_dev, torch.int64), ptr(self.env, torch.int32),
+                                        ptr(self.start, torch.int32), ptr(self.length, torch.int32), T, N, current_stream()), "lt_trajectory_index")
+        count_launches(1)
+
+    def split_and_pad(self, x: torch.Tensor, want_masks: bool = True):
+        """x [T, N, D] -> (padded [T, M, D], masks [T, M] bool)."""
+        T, N = self.T, self.N
+        xc = x.reshape(T, N, -1).contiguous()
+        D = xc.shape[-1]
+        out = torch.empty(T, self.M, D, device=x.device, dtype=torch.float32)
+        masks = torch.empty(T, self.M, device=x.device, dtype=torch.uint8) if want_masks else None
+        check(lib().lt_split_pad_trajectories(ptr(xc, torch.float32, "x"), ptr(self.env), ptr(self.start), ptr(self.length), ptr(out),
+                                              ptr(masks), T, N, D, self.M, current_stream()), "lt_split_pad_trajectories")
+        count_launches(1)
+        return out, (masks.view(torch.bool) if masks is not None else None)
+
+    def unpad(self, padded: torch.Tensor):
+        """padded [T, M, D] -> [T, N, D]."""
+        T, N = self.T, self.N
+        pc = padded.contiguous()
+        D = pc.shape[-1]
+        out = torch.empty(T, N, D, device=padded.device, dtype=torch.float32)
+        check(lib().lt_unpad_trajectories(ptr(pc, torch.float32, "padded"), ptr(self.env), ptr(self.start), ptr(self.length), ptr(out), T, N, D,
+                                          self.M, current_stream()), "lt_unpad_trajectories")
+        count_launches(1)
+        return out
+
+    @classmethod
+    def from_masks(cls, masks: torch.Tensor):
+        """Rebuilds the index from trajectory masks [T, M] alone (what ``unpad_trajectories(trajectories, masks)`` receives):
+        lengths are column sums; trajectories tile the env-major flattened rollout, so start offsets are their exclusive scan."""
+        self = cls.__new__(cls)
+        T, M = masks.shape
+        length = masks.sum(dim=0, dtype=torch.int64)
+        flat_start = torch.cumsum(length, dim=0) - length
+        self.T, self.M = T, M
+        self.N = int(length.sum().item()) // T
+        self.env = (flat_start // T).to(torch.int32).contiguous()
+        self.start = (flat_start % T).to(torch.int32).contiguous()
+        self.length = length.to(torch.int32).contiguous()
+        self.base = None
+        return self

@@ -348,6 +348,50 @@ def golden_student():
     print(f"student_c4: {init.numel()} params, loss {float(loss):.6f}")
 
 
+RECURRENT_SMALL = dict(T=24, N=48, D=10, A=3, L=2, Hd=6, seed=11, num_mini_batches=4)
+
+
+def recurrent_inputs(c=RECURRENT_SMALL):
+    g = torch.Generator().manual_seed(c["seed"])
+    T, N = c["T"], c["N"]
+    dones = (torch.rand(T, N, 1, generator=g) < 0.08)
+    dones[:, 0] = True   # an env that is done at every step
+    dones[:, 1] = False  # one that never is (the forced cut at the last step makes a single trajectory)
+    dones[-1, 2] = True  # done exactly at the last step
+    dones[0, 3] = True   # done at the first step
+    return dict(obs=torch.randn(T, N, c["D"], generator=g), critic_obs=torch.randn(T, N, c["D"] + 2, generator=g), dones=dones,
+                hid_a=torch.randn(T, c["L"], N, c["Hd"], generator=g), hid_c=torch.randn(T, c["L"], N, c["Hd"], generator=g),
+                actions=torch.randn(T, N, c["A"], generator=g))
+
+
+def golden_recurrent():
+    """utils.split_and_pad_trajectories / unpad_trajectories and RolloutStorage.recurrent_mini_batch_generator of the reference."""
+    ref_loader.load_reference_loco_rl()
+    from loco_rl.storage import RolloutStorage
+    from loco_rl.utils import split_and_pad_trajectories, unpad_trajectories
+
+    c = RECURRENT_SMALL
+    r = recurrent_inputs(c)
+    padded, masks = split_and_pad_trajectories(r["obs"], r["dones"])
+    back = unpad_trajectories(padded, masks)
+    assert torch.equal(back, r["obs"])
+    st = RolloutStorage(c["N"], c["T"], [c["D"]], [c["D"] + 2], [c["A"]])
+    for t in range(c["T"]):
+        tr = RolloutStorage.Transition()
+        tr.observations, tr.critic_observations, tr.actions = r["obs"][t], r["critic_obs"][t], r["actions"][t]
+        tr.rewards, tr.dones, tr.values = torch.zeros(c["N"]), r["dones"][t, :, 0], torch.zeros(c["N"], 1)
+        tr.actions_log_prob, tr.action_mean, tr.action_sigma = torch.zeros(c["N"]), r["actions"][t], r["actions"][t].abs()
+        tr.hidden_states = (r["hid_a"][t], r["hid_c"][t])
+        st.add_transitions(tr)
+    out = dict(padded=padded.numpy(), masks=masks.numpy())
+    for i, b in enumerate(st.recurrent_mini_batch_generator(c["num_mini_batches"], num_epochs=1)):
+        obs_b, cobs_b, act_b, _, _, _, _, _, _, (hid_a, hid_c), masks_b, _ = b
+        out[f"mb{i}_obs"], out[f"mb{i}_cobs"], out[f"mb{i}_actions"] = obs_b.numpy(), cobs_b.numpy(), act_b.numpy()
+        out[f"mb{i}_hid_a"], out[f"mb{i}_hid_c"], out[f"mb{i}_masks"] = hid_a.numpy(), hid_c.numpy(), masks_b.numpy()
+    np.savez_compressed(os.path.join(OUT, "recurrent_c1.npz"), **out)
+    print(f"recurrent_c1: {padded.shape[1]} trajectories from {c['N']} envs x {c['T']} steps")
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "the reference is not mounted"
     torch.set_num_threads(1)
@@ -356,6 +400,7 @@ if __name__ == "__main__":
     golden_ppo()
     golden_tactile()
     golden_student()
+    golden_recurrent()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -184,6 +184,20 @@ def bench_k9(b: int, reps: int):
     return out
 
 
+def bench_split_pad(n: int, reps: int, T: int = 24, D: int = 348):
+    """K10 at the teacher observation size: reads the valid rows once, writes [T, M, D] (zero padding included)."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(T, n, D, generator=g).cuda()
+    dones = (torch.rand(T, n, 1, generator=g) < 0.02).cuda()
+    index = ops.TrajectoryIndex(dones)
+    per = T * n * D * 4 + T * index.M * D * 4
+
+    def run(i):
+        index.split_and_pad(x, want_masks=True)
+
+    return {f"split_and_pad [24x{n}x{D}] (M={index.M})": (time_graph(run, 2, max(10, reps // 10)), per)}
+
+
 def bench_gather(n_rows: int, count: int, reps: int, obs_dim: int = 270):
     dims = (obs_dim, obs_dim, 12, 1, 1, 1, 1, 12, 12)
     per = sum(dims) * 4 * 2 * count
@@ -223,6 +237,8 @@ def main():
         res.update(bench_adam(607641 // 4 * 4, args.reps))
     if want("k9"):
         res.update(bench_k9(n * 24 // 4, args.reps))
+    if want("splitpad"):
+        res.update(bench_split_pad(n, args.reps))
     if want("gather"):
         res.update(bench_gather(n * 24, n * 24 // 4, max(20, args.reps // 10)))
     rows = []
