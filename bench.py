@@ -49,15 +49,17 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler process is started ahead of the
+    region (nvidia-smi needs ~100 ms to come up) and polls every 20 ms; only rows read between mark_start() and mark_end()
+    are summarised."""
 
     def __init__(self, index: int = 0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def __enter__(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -67,19 +69,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *exc):
+        if self.t1 is None:
+            self.t1 = time.perf_counter()
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        t0 = self.t0 if self.t0 is not None else 0.0
+        rows = [r for t, r in self.rows if t0 <= t <= self.t1 + 0.03]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
@@ -285,16 +297,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        engine.replay()
-    barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        for _ in range(args.warmup):
+            engine.replay()
+        barrier()
+        clocks.mark_start()
         start.record()
         for _ in range(args.steps):
             engine.replay()
         end.record()
         barrier()
+        clocks.mark_end()
     ms = torch.tensor([start.elapsed_time(end)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
