@@ -393,6 +393,25 @@ int lt_split_pad_trajectories(const float* x, const int32_t* traj_env, const int
 int lt_unpad_trajectories(const float* padded, const int32_t* traj_env, const int32_t* traj_start, const int32_t* traj_len,
                           float* out, int T, int N, int D, int M, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * K11  device-side DAgger replay-buffer bookkeeping
+ * replaces  locotouch/distill/replay_buffer.py:52-80 (the per-step done handling of collect_data) and the packing of
+ *           finished trajectories (:75-80) into the store that lt_pad_trajectories reads (:82-112).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* One env step of the collection.  reward_sums += reward; for every done env (in env-index order): append (reward_sums,
+ * length) to ep_reward / ep_length and zero the sum; while state[0] < limit also append one (env, first step, length)
+ * trajectory record, set start_idx[env] = step_now and add the length to state[0] (the reference's budget test + break).
+ * state (device int64[4]): [0] recorded steps, [1] trajectory records written, [2] episodes logged.  always_restart: set
+ * start_idx of every done env even when it is not recorded (evaluation).  The output arrays must have room for N more
+ * entries.  N <= 65536. */
+int lt_dagger_step(const uint8_t* dones, const float* reward, float* reward_sums, int32_t* start_idx, int N, int step_now,
+                   int64_t limit, int always_restart, int64_t* state, int32_t* traj_env, int32_t* traj_start,
+                   int32_t* traj_len, float* ep_reward, int32_t* ep_length, void* stream);
+/* Copies M trajectories out of a step-major buffer x [S, N, D] (trajectory j = rows (traj_start[j] + p, traj_env[j]),
+ * p < length) back to back into flat [total_rows, D]; traj_offset[j] = first flat row of trajectory j (ascending). */
+int lt_pack_trajectories(const float* x, const int32_t* traj_env, const int32_t* traj_start, const int64_t* traj_offset,
+                         int M, int64_t total_rows, int N, int D, float* flat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,6 +161,8 @@ _SIGNATURES = {
     "lt_trajectory_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lt_split_pad_trajectories": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]),
     "lt_unpad_trajectories": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
+    "lt_dagger_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int64, C.c_int] + [C.c_void_p] * 7),
+    "lt_pack_trajectories": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "lt_mdp_tables_len": (C.c_int, [C.POINTER(LtMdpArgs)]),
     "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),
     "lt_mdp_reset": (C.c_int, [C.POINTER(LtGaitState), f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

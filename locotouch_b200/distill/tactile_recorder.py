@@ -31,6 +31,15 @@ class TactileRecorder:
         # exclusive high, exactly like the reference (tactile_recorder.py:22): delay in [min_delay, max_delay - 1]
         self.delay_steps[env_idx] = torch.randint(low=self.min_delay, high=self.max_delay, size=(env_idx.shape), device=self.device)
 
+    def reset_where(self, mask: torch.Tensor):
+        """``reset(mask.nonzero())`` without the host synchronisation of ``nonzero``: one delay is drawn per env and kept only
+        where ``mask`` is set (same distribution; the reference draws one per reset env)."""
+        m = mask.view(-1).bool()
+        self.tactile_buffer.masked_fill_(m.view(-1, *([1] * (self.tactile_buffer.dim() - 1))), 0.0)
+        self.first_signal_recorded.logical_or_(m)
+        draw = torch.randint(low=self.min_delay, high=self.max_delay, size=(self.env_num,), device=self.device)
+        self.delay_steps.copy_(torch.where(m, draw, self.delay_steps))
+
     def record_new_tactile_signals(self, tactile_signals: torch.Tensor):
         ops.tactile_delay(self.tactile_buffer.view(self.env_num, self.max_delay, self._dim), self.first_signal_recorded, self.delay_steps,
                           tactile_signals.contiguous().view(self.env_num, self._dim), self._out.view(self.env_num, self._dim))

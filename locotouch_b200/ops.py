@@ -357,3 +357,26 @@ class TrajectoryIndex:
         self.length = length.to(torch.int32).contiguous()
         self.base = None
         return self
+
+
+# ------------------------------------------------------------------------------------------- K11 DAgger replay buffer
+def dagger_step(dones, reward, reward_sums, start_idx, step_now: int, limit: int, state, traj_env, traj_start, traj_len, ep_reward, ep_length,
+                always_restart: bool = False):
+    """Per-step done handling of ReplayBuffer.collect_data (reference replay_buffer.py:57-73) on the device."""
+    d = dones.view(torch.uint8) if dones.dtype == torch.bool else dones
+    N = reward_sums.numel()
+    check(lib().lt_dagger_step(ptr(d, torch.uint8, "dones"), ptr(reward, torch.float32, "reward"), ptr(reward_sums, torch.float32), ptr(start_idx, torch.int32),
+                               N, int(step_now), int(limit), int(always_restart), ptr(state, torch.int64), ptr(traj_env, torch.int32),
+                               ptr(traj_start, torch.int32), ptr(traj_len, torch.int32), ptr(ep_reward, torch.float32), ptr(ep_length, torch.int32),
+                               current_stream()), "lt_dagger_step")
+    count_launches(1)
+
+
+def pack_trajectories(x, traj_env, traj_start, traj_offset, total_rows: int, flat):
+    """Copies the recorded trajectories out of the step-major collection buffer x [S, N, D] into flat [total_rows, D]."""
+    S, N, D = x.shape
+    M = traj_env.numel()
+    check(lib().lt_pack_trajectories(ptr(x, torch.float32, "x"), ptr(traj_env, torch.int32), ptr(traj_start, torch.int32), ptr(traj_offset, torch.int64),
+                                     M, int(total_rows), N, D, ptr(flat, torch.float32, "flat"), current_stream()), "lt_pack_trajectories")
+    count_launches(1)
+    return flat

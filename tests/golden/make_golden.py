@@ -392,6 +392,58 @@ def golden_recurrent():
     print(f"recurrent_c1: {padded.shape[1]} trajectories from {c['N']} envs x {c['T']} steps")
 
 
+DAGGER_SMALL = dict(N=24, steps=200, P=22, tactile=16, first=150, second=120, batch=7, np_seed=3)
+
+
+class _DummyStudent:
+    """Stands in for the student during data collection: ignores its inputs, counts reset calls."""
+
+    def __init__(self, num_envs, device="cpu"):
+        self.num_envs, self.device, self.resets = num_envs, device, 0
+
+    def __call__(self, proprioception, tactile):
+        return torch.zeros(self.num_envs, 12, device=self.device)
+
+    def reset(self, dones):
+        self.resets += 1
+
+
+def golden_dagger():
+    """ReplayBuffer.collect_data (teacher roll-out, then a student roll-out appended to it), to_recurrent_generator and
+    evaluate of the reference, driven by the deterministic tape env of tests/helpers.py."""
+    _, recorder_mod, _ = ref_loader.load_reference_distill()
+    import sys as _sys
+    rb_mod = _sys.modules["locotouch.distill.replay_buffer"]
+    rb_mod.tqdm = lambda *a, **k: type("P", (), {"update": lambda self, n: None})()  # silence the progress bar
+    c = DAGGER_SMALL
+    env = H.TapeEnv(c["N"], c["steps"], obs_dim=c["P"] + 8, tactile_dim=c["tactile"])
+    rec = recorder_mod.TactileRecorder("cpu", c["N"], c["tactile"], 1, 2)
+    rb = rb_mod.ReplayBuffer(env, rec, c["P"])
+    teacher = lambda x: torch.zeros(c["N"], 12)  # noqa: E731
+    r1, l1 = rb.collect_data(teacher, None, c["first"])
+    out = dict(rewards1=np.array(r1), lengths1=np.array(l1), steps1=np.array(rb.num_steps), trajs1=np.array(rb.num_trajs), t1=np.array(env.t))
+    r2, l2 = rb.collect_data(teacher, _DummyStudent(c["N"]), c["second"])
+    out.update(rewards2=np.array(r2), lengths2=np.array(l2), steps2=np.array(rb.num_steps), trajs2=np.array(rb.num_trajs), t2=np.array(env.t))
+    out["traj_lengths"] = np.array([p.shape[0] for p in rb._proprioceptions])
+    out["flat_prop"] = torch.cat(rb._proprioceptions).numpy()
+    out["flat_teacher"] = torch.cat(rb._teacher_encoder_obses).numpy()
+    out["flat_tactile"] = torch.cat(rb._tactile_signals).numpy()
+    np.random.seed(c["np_seed"])
+    batches = list(rb.to_recurrent_generator(c["batch"]))
+    out["num_batches"] = np.array(len(batches))
+    for i in (0, len(batches) - 1):
+        b = batches[i]
+        out[f"b{i}_prop"], out[f"b{i}_teacher"] = b["proprioceptions"].numpy(), b["teacher_encoder_obses"].numpy()
+        out[f"b{i}_tactile"], out[f"b{i}_masks"] = b["tactile_signals"].numpy(), b["masks"].numpy()
+    # evaluation on a fresh RSL-style tape
+    env2 = H.TapeEnv(c["N"], c["steps"], seed=5, obs_dim=c["P"] + 8, tactile_dim=c["tactile"], rsl_style=True)
+    rb2 = rb_mod.ReplayBuffer(env2, rec, c["P"])
+    er, el = rb2.evaluate(_DummyStudent(c["N"]), 40)
+    out["eval_rewards"], out["eval_lengths"] = np.array(er), np.array(el)
+    np.savez_compressed(os.path.join(OUT, "dagger_c4.npz"), **out)
+    print(f"dagger_c4: {rb.num_trajs} trajectories / {rb.num_steps} steps, {len(batches)} batches; eval {len(er)} episodes")
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "the reference is not mounted"
     torch.set_num_threads(1)
@@ -401,6 +453,7 @@ if __name__ == "__main__":
     golden_tactile()
     golden_student()
     golden_recurrent()
+    golden_dagger()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

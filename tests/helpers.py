@@ -92,3 +92,42 @@ def make_rollout(T=24, N=64, obs_dim=270, A=12, seed=0):
     r["dones"][:, 1] = False
     r["dones"][-1, 1] = True
     return r
+
+
+class TapeEnv:
+    """Deterministic stand-in for the IsaacLab env of ReplayBuffer tests: replays pre-generated observations, rewards and
+    dones whatever the actions are (the reference's ReplayBuffer and the drop-in consume the same tape).  ``rsl_style``:
+    the tuple API ``evaluate`` uses (get_observations() -> (obs, extras); step -> (obs, reward, dones, extras))."""
+
+    def __init__(self, num_envs=24, steps=200, device="cpu", seed=0, p_done=0.04, obs_dim=30, tactile_dim=16, rsl_style=False):
+        g = torch.Generator().manual_seed(seed)
+        self.num_envs, self.device, self.rsl_style = num_envs, device, rsl_style
+        self.policy = torch.randn(steps + 1, num_envs, obs_dim, generator=g).to(device)
+        self.tactile = (torch.rand(steps + 1, num_envs, tactile_dim, generator=g) < 0.2).float().to(device)
+        self.rewards = (torch.randn(steps, num_envs, generator=g) * 0.1).to(device)
+        dones = torch.rand(steps, num_envs, generator=g) < p_done
+        dones[:, 0] = True    # an env that finishes every step (length-1 trajectories)
+        if num_envs > 1:
+            dones[:, 1] = False   # one that never finishes (never recorded)
+        self.dones = dones.to(device)
+        self.t = 0
+        self.resets = 0
+
+    def _obs(self):
+        if self.rsl_style:
+            return self.policy[self.t], {"observations": {"tactile": self.tactile[self.t]}}
+        return {"policy": self.policy[self.t], "tactile": self.tactile[self.t]}
+
+    def get_observations(self):
+        return self._obs()
+
+    def reset(self):
+        self.resets += 1
+
+    def step(self, action):
+        r, d = self.rewards[self.t], self.dones[self.t]
+        self.t += 1
+        if self.rsl_style:
+            obs, extras = self._obs()
+            return obs, r, d, extras
+        return self._obs(), r, d, {}

@@ -88,7 +88,7 @@ def test_object_state_term_and_binary_tactile_class(cuda, lt_lib):
                   contact_addition_prob=0.005, add_continuous_artifact=0.0)
     term = O.BinaryTactileSignals(SimpleNamespace(params=params), denv)
     thr = term.contact_threshold_envs_sensors
-    assert float(thr.min()) >= 0.04 and float(thr.max()) <= 0.06
+    assert float(thr.min()) >= 0.04 - 1e-6 and float(thr.max()) <= 0.06 + 1e-6  # 0.05 + U(-0.01, 0.01) in fp32
     g = torch.Generator().manual_seed(1)
     ud, ua = torch.rand(128, 221, generator=g), torch.rand(128, 221, generator=g)
     sig = term(denv, u_drop=ud.to(cuda), u_add=ua.to(cuda))
