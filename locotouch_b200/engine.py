@@ -304,7 +304,10 @@ class HotPathEngine:
                 with torch.cuda.graph(g):
                     alg.minibatch_grads(i)
                 g_mb.append(g)
-            self._graphs = dict(split=True, roll=g_roll, begin=g_begin, mb=g_mb)
+            g_tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_tail):
+                alg.step_after_reduce()
+            self._graphs = dict(split=True, roll=g_roll, begin=g_begin, mb=g_mb, tail=g_tail)
         alg.storage.clear()
         torch.cuda.synchronize()
         return self
@@ -340,7 +343,8 @@ class HotPathEngine:
             for _epoch in range(alg.num_learning_epochs):
                 for i in range(alg.num_mini_batches):
                     g["mb"][i].replay()
-                    alg.reduce_and_step()
+                    alg.allreduce_grads()
+                    g["tail"].replay()
             self.finish_iteration()
         alg.storage.clear()
 

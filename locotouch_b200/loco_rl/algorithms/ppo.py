@@ -253,16 +253,24 @@ class PPO:
             ac.flat_grads_ext[-4:-3].copy_(bufs.out[4:5])
 
     def reduce_and_step(self):
-        """[NCCL: flat gradient all-reduce + KL all-reduce + learning-rate decision] then fused clip + Adam (K7)."""
+        """[NCCL: ONE all-reduce of the flat gradients with the KL statistic in its tail] then the learning-rate decision and
+        the fused clip + Adam (K7)."""
+        self.allreduce_grads()
+        self.step_after_reduce()
+
+    def allreduce_grads(self):
+        """The only collective of a mini-batch step (kept outside CUDA-graph capture)."""
+        _, world = D.world_info()
+        if world > 1:
+            D.average_gradients_(self.actor_critic.flat_grads_ext)
+
+    def step_after_reduce(self):
+        """Learning-rate decision from the reduced KL statistic + clip + Adam; collective-free, capturable."""
         opt = self.optimizer
         _, world = D.world_info()
-        grad_scale = 1.0
-        if world > 1:
-            # ONE all-reduce per mini-batch: flat gradients + the KL statistic in the tail; the 1/W is applied inside K7
-            grad_scale = D.average_gradients_(self.actor_critic.flat_grads_ext)
-            if self.desired_kl is not None and self.schedule == "adaptive":  # every rank takes the same decision (SURVEY.md 8e)
-                ops.adaptive_lr(self.actor_critic.flat_grads_ext[-4:-3], 1.0 / world, self.desired_kl, opt.lr_t)
-        opt.step(max_grad_norm=self.max_grad_norm, grad_scale=grad_scale)
+        if world > 1 and self.desired_kl is not None and self.schedule == "adaptive":  # every rank takes the same decision (SURVEY.md 8e)
+            ops.adaptive_lr(self.actor_critic.flat_grads_ext[-4:-3], 1.0 / world, self.desired_kl, opt.lr_t)
+        opt.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world)
 
     def update_epilogue(self):
         """The only device->host read of an update: the three logged means (reference ppo.py:361-363 reads them with
