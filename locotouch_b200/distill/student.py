@@ -95,7 +95,10 @@ class Student(nn.Module):
         return self.student_backbone(torch.cat((proprioception, tactile_embedding), dim=-1))
 
     def forward(self, proprioception, tactile_signal, hidden_states=None):
-        return self.backbone_forward(proprioception, self.encoder_forward(tactile_signal, hidden_states))
+        with warnings.catch_warnings():
+            # once the parameters live in the flat buffer of the fused AdamW kernel, cuDNN compacts the GRU weights per call
+            warnings.filterwarnings("ignore", message="RNN module weights are not part of single contiguous chunk")
+            return self.backbone_forward(proprioception, self.encoder_forward(tactile_signal, hidden_states))
 
     # -------------------------------------------------------------------------------------------------------- training
     def train_on_batch(self, batch):
@@ -104,9 +107,7 @@ class Student(nn.Module):
         f = self._flatten()
         f["grads"].zero_()
         prop, teach_obs, tac, masks = batch["proprioceptions"], batch["teacher_encoder_obses"], batch["tactile_signals"], batch["masks"]
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore", UserWarning)  # 'RNN module weights are not part of single contiguous chunk'
-            student_actions = self.forward(prop, tac)
+        student_actions = self.forward(prop, tac)
         with torch.no_grad():
             teacher_actions = self.teacher_policy_inference(torch.cat((prop, teach_obs), dim=-1))
         loss = masked_mse_loss(student_actions, teacher_actions, masks)

@@ -96,3 +96,39 @@ def test_replay_buffer_matches_oracle_on_other_sizes(cuda, lt_lib, N, steps, bud
     b = rb._prepare_padded_sequence(idx)
     assert int(b["masks"].sum()) == rb.num_steps
     H.assert_equal(b["proprioceptions"].transpose(0, 1)[b["masks"].transpose(0, 1)], rb._flat[0], "masked rows == packed store")
+
+
+@pytest.mark.gpu
+def test_distillation_iteration_on_the_synthetic_transport_env(cuda, lt_lib):
+    """collect_data -> to_recurrent_generator -> Student.train_on_batch on the hot-path env stand-in: shapes, bookkeeping
+    invariants and a finite, decreasing behaviour-cloning loss."""
+    from locotouch_b200.distill import DistillationRandCylinderCNNRNNMonCfg, ReplayBuffer, Student, TactileRecorder
+    from locotouch_b200.sim.transport_env import SyntheticTransportEnv
+
+    N = 64
+    env = SyntheticTransportEnv(N, cuda, seed=1, max_episode_length=40)
+    obs = env.get_observations()
+    assert obs["policy"].shape == (N, 348) and obs["tactile"].shape == (N, 442)
+    assert set(obs["tactile"].unique().tolist()) <= {0.0, 1.0}
+    torch.manual_seed(0)
+    teacher = torch.nn.Linear(348, 12).to(cuda)
+    cfg = DistillationRandCylinderCNNRNNMonCfg(device=str(cuda))
+    student = Student(cfg, 270, 442, 12, teacher_policy_inference=teacher)
+    rb = ReplayBuffer(env, TactileRecorder(cuda, N, 442, 1, 2), 270)
+    rewards, lengths = rb.collect_data(teacher, None, 1500)
+    assert rb.num_steps >= 1500 and rb.num_trajs > 0 and len(rewards) == len(lengths) >= rb.num_trajs
+    assert max(lengths) <= 40 and rb.num_steps == sum(rb._lengths)
+    student.train()
+    losses = []
+    for _ in range(6):
+        for b in rb.to_recurrent_generator(16):
+            L, B = b["masks"].shape
+            assert b["proprioceptions"].shape == (L, B, 270) and b["teacher_encoder_obses"].shape == (L, B, 78)
+            assert b["tactile_signals"].shape == (L, B, 442)
+            losses.append(float(student.train_on_batch(b).reshape(-1)[0]))
+    assert all(np.isfinite(losses)) and np.mean(losses[-3:]) < np.mean(losses[:3])
+    # a second, student-driven collection appends to the buffer (DAgger)
+    before = rb.num_trajs
+    student.eval()
+    rb.collect_data(teacher, student, 500)
+    assert rb.num_trajs > before
