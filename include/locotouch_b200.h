@@ -32,7 +32,8 @@ const char* lt_error_string(int status);
 /* Text of the last CUDA error seen by this thread inside the library ("" if none). */
 const char* lt_last_cuda_error(void);
 /* sizeof() of the argument structs as compiled, so that a foreign-language binding can verify its own layout:
- * which = 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams; -1 otherwise. */
+ * which = 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams, 6 LtTaxelForceArgs;
+ * -1 otherwise. */
 int64_t lt_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -201,6 +202,29 @@ typedef struct {
   float* delayed_signal;      /* [N, 2T] */
 } LtTaxelArgs;
 int lt_taxel_synth(const LtTaxelArgs* args, void* stream);
+/* Force-valued tactile encodings (reference locotouch/mdp/observations.py:166-237; classes NormalizedTactileSignals,
+ * DiscreteTactileSignals, CotinuousTactileSignals, ProcessedTactileSignals :311-429).  Same inputs as lt_taxel_synth.
+ * u[0..6]: optional explicit [N, T] uniforms standing for the reference's rand_like draws (drop, drop force, add, add force,
+ * force noise, too-small replacement, level noise); u[0] == NULL -> Philox (seed, offset [+ *offset_base]).
+ * The derived floats are computed by the caller in double and rounded once, like the Python scalars of the reference:
+ * force_noise_range = n_max - n_min, level_bin = 1 / total_levels, level_noise_range = level_n_max - level_n_min.
+ * Outputs (each optional): element (n, t) at ptr[n * out_stride + t], so the channels of one [N, C, T] tensor can be passed as
+ * ptr + c * T with out_stride = C * T.  contact is written as 0.0 / 1.0. */
+typedef struct {
+  int N, T;
+  const float* body_quat_w; int quat_num_bodies, quat_body_offset;
+  const float* net_forces_w;  /* [N, T, 3] */
+  const float* thresholds;    /* [N, T] */
+  const float* u[7];
+  uint64_t seed, offset; const int64_t* offset_base;
+  float p_drop, p_add;
+  int add_force_noise; float force_noise_min, force_noise_range;
+  float maximal_force;
+  float level_bin; int add_level_noise; float level_noise_min, level_noise_range;
+  int out_stride;
+  float* contact; float* normal_forces; float* normalized; float* minmax; float* discretized;
+} LtTaxelForceArgs;
+int lt_taxel_forces(const LtTaxelForceArgs* args, void* stream);
 /* Generic fp32 delay line: ring [N, max_delay, D]; shift in `signal`, first-frame fill, out[n] = ring[n, delay[n]]. */
 int lt_tactile_delay(float* ring, uint8_t* first, const int64_t* delay_steps, const float* signal, float* out,
                      int N, int max_delay, int D, void* stream);

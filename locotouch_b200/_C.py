@@ -97,6 +97,18 @@ class LtGaitState(C.Structure):
     ]
 
 
+class LtTaxelForceArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("T", C.c_int), ("body_quat_w", C.c_void_p), ("quat_num_bodies", C.c_int), ("quat_body_offset", C.c_int),
+        ("net_forces_w", C.c_void_p), ("thresholds", C.c_void_p), ("u", C.c_void_p * 7),
+        ("seed", C.c_uint64), ("offset", C.c_uint64), ("offset_base", C.c_void_p),
+        ("p_drop", C.c_float), ("p_add", C.c_float), ("add_force_noise", C.c_int), ("force_noise_min", C.c_float), ("force_noise_range", C.c_float),
+        ("maximal_force", C.c_float), ("level_bin", C.c_float), ("add_level_noise", C.c_int), ("level_noise_min", C.c_float),
+        ("level_noise_range", C.c_float), ("out_stride", C.c_int),
+        ("contact", C.c_void_p), ("normal_forces", C.c_void_p), ("normalized", C.c_void_p), ("minmax", C.c_void_p), ("discretized", C.c_void_p),
+    ]
+
+
 class LtMdpArgs(C.Structure):
     _fields_ = [
         ("N", C.c_int), ("phases", C.c_int), ("step_dt", C.c_float), ("max_episode_length", C.c_int64),
@@ -163,6 +175,7 @@ _SIGNATURES = {
     "lt_unpad_trajectories": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
     "lt_dagger_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int64, C.c_int] + [C.c_void_p] * 7),
     "lt_pack_trajectories": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "lt_taxel_forces": (C.c_int, [C.POINTER(LtTaxelForceArgs), C.c_void_p]),
     "lt_mdp_tables_len": (C.c_int, [C.POINTER(LtMdpArgs)]),
     "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),
     "lt_mdp_reset": (C.c_int, [C.POINTER(LtGaitState), f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
@@ -200,7 +213,7 @@ def lib() -> C.CDLL:
         fn.argtypes = argtypes
     if handle.lt_abi_version() != 1:
         raise LocoTouchLibraryError("ABI version mismatch between _C.py and liblocotouch_b200.so")
-    for which, struct in enumerate((LtGatherArgs, LtPpoLossArgs, LtTaxelArgs, LtMdpArgs, LtGaitState, LtGaitParams)):
+    for which, struct in enumerate((LtGatherArgs, LtPpoLossArgs, LtTaxelArgs, LtMdpArgs, LtGaitState, LtGaitParams, LtTaxelForceArgs)):
         if handle.lt_struct_size(which) != C.sizeof(struct):
             raise LocoTouchLibraryError(
                 f"struct layout mismatch for {struct.__name__}: C {handle.lt_struct_size(which)} vs ctypes {C.sizeof(struct)}")

@@ -49,6 +49,7 @@ extern "C" int64_t lt_struct_size(int which) {
     case 3: return (int64_t)sizeof(LtMdpArgs);
     case 4: return (int64_t)sizeof(LtGaitState);
     case 5: return (int64_t)sizeof(LtGaitParams);
+    case 6: return (int64_t)sizeof(LtTaxelForceArgs);
     default: return -1;
   }
 }

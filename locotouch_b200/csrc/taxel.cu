@@ -166,6 +166,93 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) taxel_kernel(const LtTaxe
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Force-valued encodings (reference observations.py:166-237, classes :311-429): one warp per env, up to kMaxRounds x 32 taxels
+// held in registers so that the per-env min / max of the normalised forces (a warp reduction) and the second pass over the
+// taxels need no re-read.  Expression order follows the torch code (file built with -fmad=false).
+constexpr int kMaxRounds = 8;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) taxel_force_kernel(const LtTaxelForceArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (n >= a.N) return;  // warp-uniform
+  const int T = a.T, rounds = (T + 31) >> 5;
+  const float4* quat = reinterpret_cast<const float4*>(a.body_quat_w) + (size_t)n * a.quat_num_bodies + a.quat_body_offset;
+  const float* force = a.net_forces_w + (size_t)n * T * 3;
+  const size_t row = (size_t)n * T;
+  const uint64_t rng_offset = a.offset + (a.offset_base ? (uint64_t)*a.offset_base : 0ull);
+  float norm[kMaxRounds], fn_keep[kMaxRounds];
+  bool con[kMaxRounds];
+  float vmin = 3.0e38f, vmax = -3.0e38f;
+#pragma unroll
+  for (int r = 0; r < kMaxRounds; ++r) {
+    norm[r] = 0.f; fn_keep[r] = 0.f; con[r] = false;
+    const int t = 32 * r + lane;
+    if (r < rounds && t < T) {
+      const float4 q = __ldcs(quat + t);
+      const float thr = __ldcs(a.thresholds + row + t);
+      float fn = -rotate_inverse_z(q, __ldcs(force + 3 * t), __ldcs(force + 3 * t + 1), __ldcs(force + 3 * t + 2));  // :156-158
+      // the seven uniforms of this taxel: explicit tensors (parity) or two Philox draws keyed by (env, taxel)
+      float u[7];
+      if (a.u[0]) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) u[k] = a.u[k] ? __ldcs(a.u[k] + row + t) : 1.0f;
+      } else {
+        const uint4 r0 = lt::Philox::gen(a.seed, rng_offset, (uint32_t)n, (uint32_t)(2 * t));
+        const uint4 r1 = lt::Philox::gen(a.seed, rng_offset, (uint32_t)n, (uint32_t)(2 * t + 1));
+        u[0] = lt::Philox::u01(r0.x); u[1] = lt::Philox::u01(r0.y); u[2] = lt::Philox::u01(r0.z); u[3] = lt::Philox::u01(r0.w);
+        u[4] = lt::Philox::u01(r1.x); u[5] = lt::Philox::u01(r1.y); u[6] = lt::Philox::u01(r1.z);
+      }
+      bool contact = fn > thr;  // :159 (strict)
+      if (a.p_drop > 0.f && contact && u[0] < a.p_drop) {  // :170-176 dropped contact: force in [0, threshold)
+        fn = u[1] * thr;
+        contact = false;
+      }
+      if (a.p_add > 0.f && !contact && u[2] < a.p_add) {  // :180-185 added contact: force in [threshold, 1.2 threshold)
+        fn = thr * (1.0f + 0.2f * u[3]);
+        contact = true;
+      }
+      if (a.add_force_noise) {  // :188-193
+        if (contact) fn = fn * (1.0f + (u[4] * a.force_noise_range + a.force_noise_min));
+        fn = fmaxf(fn, 0.0f);
+        if (contact && fn < thr) fn = thr * (1.0f + 0.2f * u[5]);
+      }
+      const float nf = fminf(fmaxf(fn / a.maximal_force, 0.0f), 1.0f);  // :203
+      const float valid = contact ? nf : 0.0f;                          // :208
+      vmin = fminf(vmin, valid);
+      vmax = fmaxf(vmax, valid);
+      norm[r] = nf; fn_keep[r] = u[6]; con[r] = contact;  // fn_keep carries the level-noise uniform to the second pass
+      if (a.normal_forces) a.normal_forces[(size_t)n * a.out_stride + t] = fn;
+      if (a.contact) a.contact[(size_t)n * a.out_stride + t] = contact ? 1.0f : 0.0f;
+      if (a.normalized) a.normalized[(size_t)n * a.out_stride + t] = nf;
+    }
+  }
+  if (!a.minmax && !a.discretized) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fminf(vmin, __shfl_xor_sync(LT_FULL_MASK, vmin, o));
+    vmax = fmaxf(vmax, __shfl_xor_sync(LT_FULL_MASK, vmax, o));
+  }
+  const float range = (vmax - vmin) > 0.0f ? vmax - vmin : 1.0f;  // :215-217
+#pragma unroll
+  for (int r = 0; r < kMaxRounds; ++r) {
+    const int t = 32 * r + lane;
+    if (r < rounds && t < T) {
+      const float valid = con[r] ? norm[r] : 0.0f;
+      const float mm = fminf(fmaxf((valid - vmin) / range, 0.0f), 1.0f);  // :220-221
+      if (a.minmax) a.minmax[(size_t)n * a.out_stride + t] = mm;
+      if (a.discretized) {
+        float d = rintf(mm / a.level_bin);  // torch.round: half to even (:229)
+        if (a.add_level_noise) d = d + (fn_keep[r] * a.level_noise_range + a.level_noise_min);
+        d = d * a.level_bin;
+        d = fminf(fmaxf(d, 0.0f), 1.0f);
+        a.discretized[(size_t)n * a.out_stride + t] = con[r] ? d : 0.0f;  // :235
+      }
+    }
+  }
+}
+
 // Generic fp32 delay line, one warp per env (the `first` flag is read and cleared by the same warp).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 tactile_delay_kernel(float* __restrict__ ring, uint8_t* __restrict__ first, const int64_t* __restrict__ delay_steps,
@@ -199,6 +286,18 @@ extern "C" int lt_taxel_synth(const LtTaxelArgs* a, void* stream) {
     taxel_kernel<7><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(*a);  // 17 x 13 = 221 taxels
   else
     taxel_kernel<0><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(*a);
+  return lt::check_launch();
+}
+
+extern "C" int lt_taxel_forces(const LtTaxelForceArgs* a, void* stream) {
+  if (!a || a->N <= 0 || a->T <= 0 || a->T > 32 * kMaxRounds) return LT_ERR_INVALID_ARG;
+  if (!a->body_quat_w || !a->net_forces_w || !a->thresholds || a->out_stride < a->T) return LT_ERR_INVALID_ARG;
+  if (((uintptr_t)a->body_quat_w & 15) != 0) return LT_ERR_INVALID_ARG;
+  if (a->quat_body_offset < 0 || a->quat_body_offset + a->T > a->quat_num_bodies) return LT_ERR_INVALID_ARG;
+  if (!(a->maximal_force > 0.f) || !(a->level_bin > 0.f)) return LT_ERR_INVALID_ARG;
+  if (!a->contact && !a->normal_forces && !a->normalized && !a->minmax && !a->discretized) return LT_ERR_INVALID_ARG;
+  const int grid = (int)lt::ceil_div(a->N, kWarpsPerBlock);
+  taxel_force_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(*a);
   return lt::check_launch();
 }
 

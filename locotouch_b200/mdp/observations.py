@@ -99,3 +99,61 @@ class BinaryTactileSignals:
         self._calls += 1
         self.processed_contact_taxels = self._signal[:, :t].view(n, rows, cols) > 0.5
         return self._signal.clone()
+
+
+class _ForceTactileSignals(BinaryTactileSignals):
+    """Shared part of the force-valued encodings (reference observations.py:166-237): one ``lt_taxel_forces`` launch per call writes
+    the channels the subclass lists straight into the [N, C, T] observation; parameters are read from ``cfg.params`` at
+    construction like the reference's ``TactileSignals.__init__`` (observations.py:96-152)."""
+
+    channels: tuple = ()
+
+    def __init__(self, cfg, env):
+        super().__init__(cfg, env)
+        p = cfg.params
+        self.add_force_noise = bool(p.get("add_force_noise"))
+        self.force_n_prop_min = float(p.get("force_n_prop_min") or 0.0)
+        self.force_n_prop_max = float(p.get("force_n_prop_max") or 0.0)
+        self.maximal_force = float(p.get("maximal_force"))
+        self.total_levels = int(p.get("total_levels"))
+        self.add_level_noise = bool(p.get("add_level_noise"))
+        self.level_n_min = float(p.get("level_n_min") or 0.0)
+        self.level_n_max = float(p.get("level_n_max") or 0.0)
+        n, rows, cols = self.tactile_signals_shape
+        self._out = torch.zeros(n, len(self.channels), rows * cols, device=env.device)
+
+    def __call__(self, env, u=None, **params) -> torch.Tensor:
+        n, rows, cols = self.tactile_signals_shape
+        t = rows * cols
+        forces = self.contact_sensor.data.net_forces_w
+        ids = self.sensor_cfg.body_ids
+        if not isinstance(ids, slice):
+            forces = forces[:, ids].contiguous()
+        ops.taxel_forces(self.asset.data.body_quat_w, forces, self.contact_threshold_envs_sensors.view(n, t), self._out, self.channels,
+                         quat_body_offset=self._offset, u=u, p_drop=self.contact_dropout_prob, p_add=self.contact_addition_prob,
+                         add_force_noise=self.add_force_noise, force_n_prop_min=self.force_n_prop_min, force_n_prop_max=self.force_n_prop_max,
+                         maximal_force=self.maximal_force, total_levels=self.total_levels, add_level_noise=self.add_level_noise,
+                         level_n_min=self.level_n_min, level_n_max=self.level_n_max, seed=self.seed, offset=self._calls)
+        self._calls += 1
+        self.processed_contact_taxels = self._out[:, 0].view(n, rows, cols) > 0.5
+        return self._out.view(n, -1).clone()
+
+
+class NormalizedTactileSignals(_ForceTactileSignals):
+    """[contact, per-env min-max normalised force] (reference observations.py:311-337)."""
+    channels = ("contact", "minmax")
+
+
+class DiscreteTactileSignals(_ForceTactileSignals):
+    """[contact, discretised signal] (reference observations.py:340-366)."""
+    channels = ("contact", "discretized")
+
+
+class CotinuousTactileSignals(_ForceTactileSignals):
+    """[contact, force / maximal_force clamped to [0, 1]] (reference observations.py:369-396; the reference's spelling)."""
+    channels = ("contact", "normalized")
+
+
+class ProcessedTactileSignals(_ForceTactileSignals):
+    """[contact, normalised, min-max normalised, discretised] (reference observations.py:399-429)."""
+    channels = ("contact", "normalized", "minmax", "discretized")

@@ -380,3 +380,46 @@ def pack_trajectories(x, traj_env, traj_start, traj_offset, total_rows: int, fla
                                      M, int(total_rows), N, D, ptr(flat, torch.float32, "flat"), current_stream()), "lt_pack_trajectories")
     count_launches(1)
     return flat
+
+
+def taxel_forces(body_quat_w, net_forces_w, thresholds, out, channels, *, quat_body_offset=0, u=None, p_drop=0.0, p_add=0.0,
+                 add_force_noise=False, force_n_prop_min=0.0, force_n_prop_max=0.0, maximal_force=1.0, total_levels=5, add_level_noise=False,
+                 level_n_min=0.0, level_n_max=0.0, seed=0, offset=0, offset_base=None, normal_forces=None):
+    """Force-valued tactile encodings (reference observations.py:166-237) into ``out`` [N, C, T]: ``channels`` lists what each of
+    the C channels receives ("contact", "normalized", "minmax", "discretized").  ``u``: optional dict of explicit [N, T] uniforms
+    (drop, drop_force, add, add_force, noise, small, level)."""
+    N, T = net_forces_w.shape[0], net_forces_w.shape[1]
+    a = _C.LtTaxelForceArgs()
+    a.N, a.T = N, T
+    a.body_quat_w = ptr(body_quat_w, torch.float32, "body_quat_w")
+    a.quat_num_bodies, a.quat_body_offset = body_quat_w.shape[1], quat_body_offset
+    a.net_forces_w = ptr(net_forces_w, torch.float32, "net_forces_w")
+    a.thresholds = ptr(thresholds, torch.float32, "thresholds")
+    if u is not None:
+        for k, name in enumerate(("drop", "drop_force", "add", "add_force", "noise", "small", "level")):
+            a.u[k] = ptr(u[name], torch.float32, "u_" + name) if u.get(name) is not None else None
+    a.seed, a.offset = seed, offset
+    a.offset_base = ptr(offset_base, torch.int64, "offset_base")
+    a.p_drop, a.p_add = p_drop, p_add
+    a.add_force_noise = int(add_force_noise)
+    a.force_noise_min, a.force_noise_range = force_n_prop_min, force_n_prop_max - force_n_prop_min  # double arithmetic, rounded once
+    a.maximal_force = maximal_force
+    a.level_bin = 1.0 / total_levels
+    a.add_level_noise = int(add_level_noise)
+    a.level_noise_min, a.level_noise_range = level_n_min, level_n_max - level_n_min
+    C_ = len(channels)
+    if out.shape != (N, C_, T) or not out.is_contiguous():
+        raise _C.LocoTouchLibraryError(f"out must be a contiguous [N, {C_}, T] tensor")
+    a.out_stride = C_ * T
+    base = ptr(out, torch.float32, "out")
+    for c, name in enumerate(channels):
+        if name not in ("contact", "normalized", "minmax", "discretized"):
+            raise _C.LocoTouchLibraryError(f"unknown channel {name}")
+        setattr(a, name, base + 4 * c * T)
+    if normal_forces is not None:
+        if C_ * T != T and normal_forces.stride(0) != C_ * T:
+            raise _C.LocoTouchLibraryError("normal_forces must have the row stride of `out` (pass a [N, T] slice of a [N, C, T] tensor)")
+        a.normal_forces = ptr(normal_forces, torch.float32, "normal_forces") if normal_forces.is_contiguous() else normal_forces.data_ptr()
+    check(lib().lt_taxel_forces(C.byref(a), current_stream()), "lt_taxel_forces")
+    count_launches(1)
+    return out

@@ -71,3 +71,47 @@ class TactileDelayOracle:
 
     def get(self):
         return self.buf[torch.arange(self.buf.shape[0]), self.delay]
+
+
+def force_signals(body_quat_w, net_forces_w, thresholds, u, p_drop=0.0, p_add=0.0, add_force_noise=False, force_n_prop_min=0.0,
+                  force_n_prop_max=0.0, maximal_force=1.0, total_levels=5, add_level_noise=False, level_n_min=0.0, level_n_max=0.0):
+    """Force-valued tactile encodings: reference observations.py:166-199 (get_normal_forces: dropout / addition with synthetic
+    forces, proportional force noise), :201-205 (normalised forces), :207-224 (per-env min-max normalisation), :226-237
+    (discretisation with level noise).  ``u`` = dict of explicit [N, T] uniforms standing for the reference's ``rand_like`` draws:
+    drop, drop_force, add, add_force, noise, small, level (the reference draws the masked ones only for the selected taxels, in
+    row-major order -- element (n, t) of the full tensor is the draw that taxel would get).  Returns every intermediate the
+    reference keeps (processed_* attributes) plus the masks that selected the draws."""
+    fn = normal_forces(body_quat_w, net_forces_w)
+    contact = fn > thresholds
+    out = dict(original_contact=contact.clone(), original_normal_forces=fn.clone())
+    drop = torch.zeros_like(contact)
+    if p_drop > 0.0:
+        drop = contact & (u["drop"] < p_drop)
+        fn = torch.where(drop, u["drop_force"] * thresholds, fn)
+        contact = contact & ~drop
+    add = torch.zeros_like(contact)
+    if p_add > 0.0:
+        add = ~contact & (u["add"] < p_add)
+        fn = torch.where(add, thresholds * (1.0 + 0.2 * u["add_force"]), fn)
+        contact = contact | add
+    small = torch.zeros_like(contact)
+    if add_force_noise:
+        fn = torch.where(contact, fn * (1.0 + (u["noise"] * (force_n_prop_max - force_n_prop_min) + force_n_prop_min)), fn)
+        fn = torch.clamp(fn, min=0.0)
+        small = contact & (fn < thresholds)
+        fn = torch.where(small, thresholds * (1.0 + 0.2 * u["small"]), fn)
+    normalized = torch.clamp(fn / maximal_force, 0.0, 1.0)
+    valid = torch.where(contact, normalized, torch.zeros_like(normalized))
+    mn = valid.min(dim=-1, keepdim=True)[0]
+    mx = valid.max(dim=-1, keepdim=True)[0]
+    rng = torch.where((mx - mn) > 0.0, mx - mn, torch.ones_like(mx))
+    minmax = torch.clamp((valid - mn) / rng, 0.0, 1.0)
+    bin_ = 1.0 / total_levels
+    disc = torch.round(minmax / bin_)
+    if add_level_noise:
+        disc = disc + (u["level"] * (level_n_max - level_n_min) + level_n_min)
+    disc = torch.clamp(disc * bin_, 0.0, 1.0)
+    disc = torch.where(contact, disc, torch.zeros_like(disc))
+    out.update(contact=contact, normal_forces=fn, normalized=normalized, minmax=minmax, discretized=disc, drop_mask=drop, add_mask=add,
+               noise_mask=contact.clone(), small_mask=small)
+    return out

@@ -297,6 +297,70 @@ def golden_tactile():
     np.savez_compressed(os.path.join(OUT, "tactile_c4.npz"), **out)
 
 
+TACTILE_FORCE = dict(N=96, seed=23, steps=3)
+
+
+def tactile_force_uniforms(step: int, n: int):
+    g = torch.Generator().manual_seed(9000 + step)
+    return {k: torch.rand(n, 221, generator=g) for k in ("drop", "drop_force", "add", "add_force", "noise", "small", "level")}
+
+
+TACTILE_FORCE_PARAMS = dict(tactile_signal_shape=(17, 13), contact_threshold=0.05, add_threshold_noise=True, threshold_n_min=-0.01,
+                            threshold_n_max=0.01, contact_dropout_prob=0.15, contact_addition_prob=0.05, add_continuous_artifact=0.0,
+                            artifact_taxel_num_min=0, artifact_taxel_num_max=3, add_force_noise=True, force_n_prop_min=-0.6,
+                            force_n_prop_max=0.1, maximal_force=1.5, total_levels=5, add_level_noise=True, level_n_min=-1, level_n_max=1)
+
+
+def golden_tactile_forces():
+    """Processed / Normalized / Discrete / Continuous tactile signal classes of the reference (observations.py:311-429) with
+    every ``rand_like`` draw fed from explicit uniforms; the masked draws are cut out of full-size tensors with the masks the
+    oracle derives (a wrong oracle mask would make the shapes disagree and the patched draw assert)."""
+    from oracle import tactile as OT
+    from types import SimpleNamespace
+
+    _, ob, _, _ = ref_loader.load_reference_mdp()
+    c = TACTILE_FORCE
+    env = synth.make_env(c["N"], seed=c["seed"], with_object=True, with_tactile=True, tactile_jitter=0.2)
+    params = dict(asset_cfg=SceneEntityCfg("robot", body_names="sensor_.*").resolve(env.scene),
+                  sensor_cfg=SceneEntityCfg("tactile_contact_sensor", body_names="sensor_.*").resolve(env.scene), **TACTILE_FORCE_PARAMS)
+    g = torch.Generator().manual_seed(555)
+    u_thr = torch.rand(c["N"], 17, 13, generator=g)
+    terms = {}
+    for name in ("ProcessedTactileSignals", "NormalizedTactileSignals", "DiscreteTactileSignals", "CotinuousTactileSignals"):
+        with patched_rand([u_thr.clone()]):
+            terms[name] = getattr(ob, name)(SimpleNamespace(params=params), env)
+    thr = terms["ProcessedTactileSignals"].contact_threshold_envs_sensors.reshape(c["N"], 221)
+    out = dict(thresholds=thr.numpy().copy())
+    sensor_ids = params["sensor_cfg"].body_ids
+    for step in range(c["steps"]):
+        u = tactile_force_uniforms(step, c["N"])
+        quat = env.scene["robot"].data.body_quat_w[:, params["asset_cfg"].body_ids]
+        force = env.scene.sensors["tactile_contact_sensor"].data.net_forces_w[:, sensor_ids]
+        o = OT.force_signals(quat, force, thr, u, p_drop=0.15, p_add=0.05, add_force_noise=True, force_n_prop_min=-0.6, force_n_prop_max=0.1,
+                             maximal_force=1.5, total_levels=5, add_level_noise=True, level_n_min=-1, level_n_max=1)
+        sh = lambda t: t.reshape(c["N"], 17, 13)  # noqa: E731
+
+        def queue():
+            return [sh(u["drop"]).clone(), u["drop_force"][o["drop_mask"]].clone(), sh(u["add"]).clone(), u["add_force"][o["add_mask"]].clone(),
+                    u["noise"][o["noise_mask"]].clone(), u["small"][o["small_mask"]].clone(), sh(u["level"]).clone()]
+
+        with patched_rand(queue()):
+            sig = terms["ProcessedTactileSignals"](env, **params)
+        out[f"processed_{step}"] = sig.numpy().copy()
+        if step == 0:
+            print("drop / add / small counts:", int(o["drop_mask"].sum()), int(o["add_mask"].sum()), int(o["small_mask"].sum()),
+                  " contact fraction", float(o["contact"].float().mean()))
+            for name, key in (("NormalizedTactileSignals", "normalized_0"), ("DiscreteTactileSignals", "discrete_0"), ("CotinuousTactileSignals", "continuous_0")):
+                q = queue()
+                if name != "DiscreteTactileSignals":
+                    q = q[:6]  # no discretisation -> no level-noise draw
+                with patched_rand(q):
+                    out[key] = terms[name](env, **params).numpy().copy()
+        synth.advance(env, tactile_jitter=0.2)
+    np.savez_compressed(os.path.join(OUT, "tactile_force_c4.npz"), **out)
+    print("tactile_force_c4:", {k: v.shape for k, v in out.items() if k.endswith("_0")})
+
+
 STUDENT_SMALL = dict(rnn_hidden=32, enc_hidden=[32, 16], pol_hidden=[32, 16], cnn_channels=(4, 4, 4), L=11, B=4, lengths=[11, 3, 7, 1], seed=31)
 
 
@@ -454,6 +518,7 @@ if __name__ == "__main__":
     golden_student()
     golden_recurrent()
     golden_dagger()
+    golden_tactile_forces()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -117,7 +117,16 @@ def bench_taxel(n: int, reps: int):
         ops.taxel_synth(q, f, thr, quat_body_offset=17, seed=1, offset=i, signal=None, packed=packed, want_signal=False, delay_ring=ring,
                         delay_first=first, delay_steps=delay, delayed_signal=dsig)
 
-    return {"taxel_synth": (time_graph(plain, copies, reps), per_env * n),
+    fsets = [torch.empty(n, 4, 221, device="cuda") for _ in range(copies)]
+
+    def forces(i):
+        q, f, thr, *_ = sets[i]
+        ops.taxel_forces(q, f, thr, fsets[i], ("contact", "normalized", "minmax", "discretized"), quat_body_offset=17, p_drop=0.005, p_add=0.005,
+                         add_force_noise=True, force_n_prop_min=-0.1, force_n_prop_max=0.1, maximal_force=3.0, total_levels=5,
+                         add_level_noise=True, level_n_min=-1, level_n_max=1, seed=1, offset=i)
+
+    extra = {"taxel_forces (4 channels)": (time_graph(forces, copies, reps), (221 * 32 + 4 * 221 * 4) * n)}
+    return {**extra, "taxel_synth": (time_graph(plain, copies, reps), per_env * n),
             "taxel_synth+delay": (time_graph(delayed, copies, reps), (per_env + 28 * 3) * n)}
 
 
