@@ -436,6 +436,17 @@ int lt_dagger_step(const uint8_t* dones, const float* reward, float* reward_sums
 int lt_pack_trajectories(const float* x, const int32_t* traj_env, const int32_t* traj_start, const int64_t* traj_offset,
                          int M, int64_t total_rows, int N, int D, float* flat, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * K12  fused linear layer: out[M, N] = act(x[M, K] . w[N, K]^T + bias[N]), act = ELU (alpha 1) or identity
+ * replaces  nn.Linear (+ nn.ELU) of loco_rl/loco_rl/modules/actor_critic.py:33-56 and models/mlp.py:4-25 (cuBLAS GEMM +
+ *           an elementwise ELU launch) with one tcgen05 TF32 GEMM whose epilogue adds the bias and applies the activation.
+ * K and N must be multiples of 4 and all pointers 16-byte aligned; LT_ERR_UNSUPPORTED otherwise (or when the library was
+ * built without the CUTLASS headers) -- the caller then uses its cuBLAS path.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int64_t lt_linear_bias_act_workspace_bytes(int M, int N, int K);
+int lt_linear_bias_act(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, int apply_elu,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ LT_MAX_REWARD_TERMS = 32
 LT_MAX_TERMINATION_TERMS = 8
 LT_MAX_OBS_TERMS = 8
 LT_MAX_CONTACT_IDS = 8
+LT_ERR_UNSUPPORTED = 4  # enum LtStatus
 LT_PHASE_REWARDS = 1
 LT_PHASE_OBS = 2
 
@@ -176,6 +177,8 @@ _SIGNATURES = {
     "lt_dagger_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int64, C.c_int] + [C.c_void_p] * 7),
     "lt_pack_trajectories": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "lt_taxel_forces": (C.c_int, [C.POINTER(LtTaxelForceArgs), C.c_void_p]),
+    "lt_linear_bias_act_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "lt_linear_bias_act": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_mdp_tables_len": (C.c_int, [C.POINTER(LtMdpArgs)]),
     "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),
     "lt_mdp_reset": (C.c_int, [C.POINTER(LtGaitState), f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

@@ -21,6 +21,24 @@ LIB_PATH = os.path.join(PKG, "liblocotouch_b200.so")
 # (torch evaluates a*b+c as two rounded ops).
 PER_FILE_FLAGS = {"mdp_step.cu": ["-fmad=false"], "taxel.cu": ["-fmad=false"], "gae.cu": ["-fmad=false"]}
 
+def cutlass_include_dirs() -> list[str]:
+    """CUTLASS / CuTe header trees for the tcgen05 GEMM with the fused bias + ELU epilogue (gemm_fused.cu).  The image vendors
+    CUTLASS 4.x under flashinfer's data directory; LT_CUTLASS_DIR overrides.  Empty list: the file is built as a stub that
+    reports LT_ERR_UNSUPPORTED and the callers keep the cuBLAS + elementwise path."""
+    roots = [os.environ.get("LT_CUTLASS_DIR")]
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("flashinfer")
+        if spec is not None and spec.origin:
+            roots.append(os.path.join(os.path.dirname(spec.origin), "data", "cutlass"))
+    except Exception:
+        pass
+    for r in roots:
+        if r and os.path.exists(os.path.join(r, "include", "cutlass", "cutlass.h")):
+            return [os.path.join(r, "include"), os.path.join(r, "tools", "util", "include")]
+    return []
+
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -61,6 +79,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not force and os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))):
             continue
         extra = [f"-D{k}={v}" for k, v in os.environ.items() if k.startswith("LT_MDP_")]  # tuning knobs (see mdp_step.cu)
+        if os.path.basename(src) == "gemm_fused.cu":
+            dirs = cutlass_include_dirs()
+            extra += ["--expt-extended-lambda", "-DLT_HAVE_CUTLASS=1"] + [x for d in dirs for x in ("-I", d)] if dirs else ["-DLT_HAVE_CUTLASS=0"]
         cmd = [nvcc, *NVCC_FLAGS, *PER_FILE_FLAGS.get(os.path.basename(src), []), *extra, "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

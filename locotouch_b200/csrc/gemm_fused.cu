@@ -1,0 +1,137 @@
+// K12: fused linear layer of the actor-critic / student MLPs: out = act(x W^T + bias), one tcgen05 (UTCHMMA, kind::tf32) GEMM with
+// TMA-fed operands, the accumulator in TMEM and the bias add + ELU applied in the epilogue before the single store of the
+// activation.  Replaces, per nn.Linear + nn.ELU pair of reference loco_rl/loco_rl/modules/actor_critic.py:33-56 (and
+// models/mlp.py:4-25), the cuBLAS GEMM + separate elementwise ELU pass (which re-reads and re-writes the [B, n] activation:
+// 100 MB of the 150 MB a 24576 x 512 layer moves).  Built from the CUTLASS 4.x sm100 collective builders + epilogue fusion
+// (CuTe/CUTLASS templates inside our own translation unit, instantiated for these layer shapes); TF32 like the reference's
+// training configuration (locotouch/scripts/train.py:66-69).
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#if LT_HAVE_CUTLASS
+
+#include "cutlass/cutlass.h"
+#include "cutlass/epilogue/collective/collective_builder.hpp"
+#include "cutlass/epilogue/fusion/operations.hpp"
+#include "cutlass/epilogue/thread/activation.h"
+#include "cutlass/gemm/collective/collective_builder.hpp"
+#include "cutlass/gemm/device/gemm_universal_adapter.h"
+#include "cutlass/gemm/kernel/gemm_universal.hpp"
+#include "cutlass/util/packed_stride.hpp"
+
+#include "lt_common.cuh"
+
+namespace {
+
+using namespace cute;
+
+// torch.nn.functional.elu (alpha = 1): x > 0 ? x : exp(x) - 1   (ATen evaluates exp(x) - 1, not expm1)
+template <typename T>
+struct Elu {
+  static const bool kIsHeavy = true;
+  CUTLASS_HOST_DEVICE T operator()(T const& x) const { return x > T(0) ? x : T(expf(float(x)) - 1.0f); }
+};
+template <typename T, int N>
+struct Elu<cutlass::Array<T, N>> {
+  static const bool kIsHeavy = true;
+  CUTLASS_HOST_DEVICE cutlass::Array<T, N> operator()(cutlass::Array<T, N> const& v) const {
+    cutlass::Array<T, N> y;
+    Elu<T> op;
+    CUTLASS_PRAGMA_UNROLL
+    for (int i = 0; i < N; ++i) y[i] = op(v[i]);
+    return y;
+  }
+};
+
+template <template <class> class Act, class TileShape, class ClusterShape_ = Shape<_1, _1, _1>>
+struct FusedLinear {
+  using ElementA = float;
+  using ElementB = float;
+  using ElementD = float;
+  using ElementC = void;
+  using ElementAcc = float;
+  using ElementCompute = float;
+  using LayoutA = cutlass::layout::RowMajor;     // x [M, K]
+  using LayoutB = cutlass::layout::ColumnMajor;  // W [N, K] row-major == [K, N] column-major
+  using LayoutD = cutlass::layout::RowMajor;     // out [M, N]
+  static constexpr int kAlign = 4;               // 16 bytes
+  using ClusterShape = ClusterShape_;
+  using FusionOp = cutlass::epilogue::fusion::LinCombPerColBiasEltAct<Act, ElementD, ElementCompute, float, ElementC, ElementCompute>;
+  using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, TileShape, ClusterShape, cutlass::epilogue::collective::EpilogueTileAuto,
+      ElementAcc, ElementCompute, ElementC, LayoutD, kAlign, ElementD, LayoutD, kAlign, cutlass::epilogue::collective::EpilogueScheduleAuto,
+      FusionOp>::CollectiveOp;
+  using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutA, kAlign, ElementB, LayoutB, kAlign, ElementAcc, TileShape,
+      ClusterShape, cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
+      cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
+  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, void>;
+  using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
+
+  static int run(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
+    using StrideA = typename Gemm::GemmKernel::StrideA;
+    using StrideB = typename Gemm::GemmKernel::StrideB;
+    using StrideD = typename Gemm::GemmKernel::StrideD;
+    StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, make_shape(M, K, 1));
+    StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, make_shape(N, K, 1));
+    StrideD sd = cutlass::make_cute_packed_stride(StrideD{}, make_shape(M, N, 1));
+    typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K, 1}, {x, sa, w, sb}, {{}, nullptr, sd, out, sd}};
+    args.epilogue.thread.alpha = 1.0f;
+    args.epilogue.thread.beta = 0.0f;
+    args.epilogue.thread.bias_ptr = bias;
+    Gemm gemm;
+    if (Gemm::get_workspace_size(args) > workspace_bytes) return LT_ERR_WORKSPACE;
+    if (gemm.can_implement(args) != cutlass::Status::kSuccess) return LT_ERR_UNSUPPORTED;
+    if (gemm.initialize(args, workspace, stream) != cutlass::Status::kSuccess) return LT_ERR_CUDA;
+    if (gemm.run(stream) != cutlass::Status::kSuccess) return LT_ERR_CUDA;
+    return LT_OK;
+  }
+};
+
+template <typename T>
+using Identity = cutlass::epilogue::thread::Identity<T>;
+
+}  // namespace
+
+#endif  // LT_HAVE_CUTLASS
+
+#if !LT_HAVE_CUTLASS
+#include "lt_common.cuh"
+extern "C" int lt_linear_bias_act(const float*, const float*, const float*, float*, int, int, int, int, void*, int64_t, void*) {
+  return LT_ERR_UNSUPPORTED;  // built without the CUTLASS headers: callers keep the cuBLAS + elementwise path
+}
+extern "C" int64_t lt_linear_bias_act_workspace_bytes(int, int, int) { return 0; }
+#else
+extern "C" int64_t lt_linear_bias_act_workspace_bytes(int M, int N, int K) {
+  (void)M; (void)N; (void)K;
+  return 1 << 20;  // the non-stream-K schedules used here need none; one MiB covers the adapter's bookkeeping
+}
+
+extern "C" int lt_linear_bias_act(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, int apply_elu, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  if (!x || !w || !bias || !out || M <= 0 || N <= 0 || K <= 0) return LT_ERR_INVALID_ARG;
+  if ((K & 3) || (N & 3) || (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out | (uintptr_t)bias) & 15)) return LT_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t wsb = (size_t)workspace_bytes;
+  // tile choice: LT_LINEAR_TILE (0: 128x128, 1: 256x128 on an SM pair, 2: 128x256, 3: 256x256 on an SM pair) overrides the shape heuristic (tuning knob)
+  static const int forced = [] { const char* e = getenv("LT_LINEAR_TILE"); return e ? atoi(e) : -1; }();
+  // measured (B200, in-graph): 24576x348x512 33.6 us with 256x256 tiles on an SM pair (cuBLAS GEMM + ELU pass: 40.7), 24576x512x256
+  // 19.7 us with 256x128 (25.0), 24576x256x128 12.8 us with 128x128 (13.2)
+  int tile = forced >= 0 ? forced : ((N >= 512 && M >= 8192) ? 3 : (N >= 256 ? 1 : 0));
+  using T0 = Shape<_128, _128, _32>;
+  using T1 = Shape<_256, _128, _32>;
+  using T2 = Shape<_128, _256, _32>;
+  using T3 = Shape<_256, _256, _32>;
+  using C1 = Shape<_1, _1, _1>;
+  using C2 = Shape<_2, _1, _1>;
+  if (apply_elu) {
+    if (tile == 1) return FusedLinear<Elu, T1, C2>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
+    if (tile == 2) return FusedLinear<Elu, T2, C1>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
+    if (tile == 3) return FusedLinear<Elu, T3, C2>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
+    return FusedLinear<Elu, T0, C1>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
+  }
+  if (tile == 1 || tile == 3) return FusedLinear<Identity, T1, C2>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
+  return FusedLinear<Identity, T0, C1>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
+}
+#endif  // LT_HAVE_CUTLASS

@@ -151,12 +151,20 @@ class ActorCritic(nn.Module):
         self._saved = []
         outs = []
 
+        fused = torch.backends.cuda.matmul.allow_tf32  # K12 computes in TF32, like cuBLAS does under the reference's train.py:66-69
+
         def chain(linears, hs, x):
             acts, h = [x], x
             for i, lin in enumerate(linears):
-                h = torch.addmm(lin.bias, h, lin.weight.t(), out=hs[i])
-                if i < len(linears) - 1:
-                    F.elu_(h)
+                hidden = i < len(linears) - 1
+                out = None
+                if fused and lin.out_features >= 64:  # one tcgen05 GEMM with bias + ELU in the epilogue (K12)
+                    out = ops.linear_bias_act(h, lin.weight, lin.bias, out=hs[i], elu=hidden)
+                if out is None:  # fp32 mode, narrow output layers, unaligned K: cuBLAS GEMM with fused bias, ELU in place
+                    out = torch.addmm(lin.bias, h, lin.weight.t(), out=hs[i])
+                    if hidden:
+                        F.elu_(out)
+                h = out
                 acts.append(h)
             return acts
 

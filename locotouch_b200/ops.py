@@ -423,3 +423,27 @@ def taxel_forces(body_quat_w, net_forces_w, thresholds, out, channels, *, quat_b
     check(lib().lt_taxel_forces(C.byref(a), current_stream()), "lt_taxel_forces")
     count_launches(1)
     return out
+
+
+# ------------------------------------------------------------------------------------------------- K12 fused linear layer
+def linear_bias_act(x, weight, bias, out=None, elu: bool = True):
+    """out = elu(x @ weight.T + bias) (or without the activation) in ONE tcgen05 TF32 GEMM with a fused epilogue.  Returns None
+    when the shape / alignment is not supported (K, N multiples of 4, 16-byte aligned pointers) so that the caller can keep
+    its cuBLAS path."""
+    M, K = x.shape
+    N = weight.shape[0]
+    if (K & 3) or (N & 3) or not (x.is_contiguous() and weight.is_contiguous() and bias.is_contiguous()):
+        return None
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    if (x.data_ptr() | weight.data_ptr() | bias.data_ptr() | out.data_ptr()) & 15:
+        return None
+    nbytes = lib().lt_linear_bias_act_workspace_bytes(M, N, K)
+    ws = _workspace("linear", max(nbytes, 256), x.device)
+    rc = lib().lt_linear_bias_act(ptr(x, torch.float32, "x"), ptr(weight, torch.float32, "weight"), ptr(bias, torch.float32, "bias"),
+                                  ptr(out, torch.float32, "out"), M, N, K, int(elu), ptr(ws), ws.numel(), current_stream())
+    if rc == _C.LT_ERR_UNSUPPORTED:
+        return None
+    check(rc, "lt_linear_bias_act")
+    count_launches(1)
+    return out

@@ -1,0 +1,43 @@
+"""K12: fused linear layer (tcgen05 TF32 GEMM + bias + ELU epilogue) against torch on the layer shapes of the actor-critic."""
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,K,N,elu", [(24576, 348, 512, True), (24576, 512, 256, True), (4096, 256, 128, True), (24576, 128, 12, False),
+                                       (1000, 348, 512, True), (37, 64, 8, True), (129, 36, 132, False)])
+def test_fused_linear_matches_torch(cuda, lt_lib, M, K, N, elu):
+    from locotouch_b200 import ops
+
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g).to(cuda)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    out = ops.linear_bias_act(x, w, b, elu=elu)
+    assert out is not None, "shape should be supported"
+    ref64 = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    if elu:
+        ref64 = torch.nn.functional.elu(ref64)
+    # TF32 operands (10-bit mantissa): |error| <~ 2^-11 * sqrt(K) * |x||w| per output, fp32 accumulation
+    err = (out.double() - ref64).abs().max().item()
+    assert err < 4e-3, f"max abs error {err}"
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        ref_tf32 = torch.nn.functional.linear(x, w, b)
+        if elu:
+            ref_tf32 = torch.nn.functional.elu(ref_tf32)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    H.assert_close(out, ref_tf32, "fused linear vs cuBLAS TF32 + ELU", rtol=2e-3, atol=2e-3)
+
+
+def test_unsupported_shapes_are_reported_not_faked(cuda, lt_lib):
+    from locotouch_b200 import ops
+
+    x, b = torch.randn(64, 270, device=cuda), torch.randn(16, device=cuda)
+    assert ops.linear_bias_act(x, torch.randn(16, 270, device=cuda), b) is None  # K = 270 is not a multiple of 4
+    assert ops.linear_bias_act(torch.randn(64, 128, device=cuda), torch.randn(1, 128, device=cuda), torch.randn(1, device=cuda)) is None  # N = 1
