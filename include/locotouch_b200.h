@@ -446,6 +446,12 @@ int lt_pack_trajectories(const float* x, const int32_t* traj_env, const int32_t*
 int64_t lt_linear_bias_act_workspace_bytes(int M, int N, int K);
 int lt_linear_bias_act(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, int apply_elu,
                        void* workspace, int64_t workspace_bytes, void* stream);
+/* Backward companion: grad_in[M, Kin] = (grad_out[M, Nout] . w[Nout, Kin]) * elu'(act_in[M, Kin]), act_in = the stored
+ * post-ELU activation that fed the layer (elu' = act_in > 0 ? 1 : act_in + 1) -- the dgrad GEMM of a layer with the ELU
+ * backward of the layer below in its epilogue (replaces a cuBLAS GEMM + the elu_backward pass of autograd).  Same shape /
+ * alignment rules and workspace as lt_linear_bias_act. */
+int lt_dgrad_act_bwd(const float* grad_out, const float* w, const float* act_in, float* grad_in, int M, int Nout, int Kin,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

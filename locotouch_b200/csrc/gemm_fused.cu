@@ -89,6 +89,64 @@ struct FusedLinear {
   }
 };
 
+// d/dz elu(z) through the stored activation h = elu(z): h > 0 ? 1 : h + 1 (alpha = 1), applied to the incoming gradient
+template <typename T>
+struct dElu {
+  static const bool kIsHeavy = false;
+  CUTLASS_HOST_DEVICE T operator()(T const& g, T const& h) const { return h > T(0) ? g : g * (h + T(1)); }
+};
+template <typename T, int N>
+struct dElu<cutlass::Array<T, N>> {
+  static const bool kIsHeavy = false;
+  CUTLASS_HOST_DEVICE cutlass::Array<T, N> operator()(cutlass::Array<T, N> const& g, cutlass::Array<T, N> const& h) const {
+    cutlass::Array<T, N> y;
+    dElu<T> op;
+    CUTLASS_PRAGMA_UNROLL
+    for (int i = 0; i < N; ++i) y[i] = op(g[i], h[i]);
+    return y;
+  }
+};
+
+// dgrad with the ELU backward of the layer below in the epilogue: out[M, Kin] = (g[M, Nout] . W[Nout, Kin]) * elu'(h[M, Kin])
+template <class TileShape, class ClusterShape>
+struct FusedDgrad {
+  using LayoutA = cutlass::layout::RowMajor;  // g [M, Nout]
+  using LayoutB = cutlass::layout::RowMajor;  // W [Nout, Kin] == B [K' = Nout, N' = Kin] row-major (MN-major operand)
+  using LayoutD = cutlass::layout::RowMajor;  // out [M, Kin], same layout as the auxiliary h
+  static constexpr int kAlign = 4;
+  using FusionOp = cutlass::epilogue::fusion::LinCombDeEltAct<LayoutD, dElu, float, float, float, void, float, kAlign>;
+  using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, TileShape, ClusterShape, cutlass::epilogue::collective::EpilogueTileAuto, float, float,
+      void, LayoutD, kAlign, float, LayoutD, kAlign, cutlass::epilogue::collective::EpilogueScheduleAuto, FusionOp>::CollectiveOp;
+  using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, float, LayoutA, kAlign, float, LayoutB, kAlign, float, TileShape, ClusterShape,
+      cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
+      cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
+  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, void>;
+  using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
+
+  static int run(const float* g, const float* w, const float* h, float* out, int M, int Nout, int Kin, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
+    using StrideA = typename Gemm::GemmKernel::StrideA;
+    using StrideB = typename Gemm::GemmKernel::StrideB;
+    using StrideD = typename Gemm::GemmKernel::StrideD;
+    StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, make_shape(M, Nout, 1));
+    StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, make_shape(Kin, Nout, 1));
+    StrideD sd = cutlass::make_cute_packed_stride(StrideD{}, make_shape(M, Kin, 1));
+    typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, Kin, Nout, 1}, {g, sa, w, sb}, {{}, nullptr, sd, out, sd}};
+    args.epilogue.thread.alpha = 1.0f;
+    args.epilogue.thread.beta = 0.0f;
+    args.epilogue.thread.aux_ptr = h;
+    args.epilogue.thread.dAux = sd;
+    Gemm gemm;
+    if (Gemm::get_workspace_size(args) > workspace_bytes) return LT_ERR_WORKSPACE;
+    if (gemm.can_implement(args) != cutlass::Status::kSuccess) return LT_ERR_UNSUPPORTED;
+    if (gemm.initialize(args, workspace, stream) != cutlass::Status::kSuccess) return LT_ERR_CUDA;
+    if (gemm.run(stream) != cutlass::Status::kSuccess) return LT_ERR_CUDA;
+    return LT_OK;
+  }
+};
+
 template <typename T>
 using Identity = cutlass::epilogue::thread::Identity<T>;
 
@@ -102,6 +160,7 @@ extern "C" int lt_linear_bias_act(const float*, const float*, const float*, floa
   return LT_ERR_UNSUPPORTED;  // built without the CUTLASS headers: callers keep the cuBLAS + elementwise path
 }
 extern "C" int64_t lt_linear_bias_act_workspace_bytes(int, int, int) { return 0; }
+extern "C" int lt_dgrad_act_bwd(const float*, const float*, const float*, float*, int, int, int, void*, int64_t, void*) { return LT_ERR_UNSUPPORTED; }
 #else
 extern "C" int64_t lt_linear_bias_act_workspace_bytes(int M, int N, int K) {
   (void)M; (void)N; (void)K;
@@ -133,5 +192,18 @@ extern "C" int lt_linear_bias_act(const float* x, const float* w, const float* b
   }
   if (tile == 1 || tile == 3) return FusedLinear<Identity, T1, C2>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
   return FusedLinear<Identity, T0, C1>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
+}
+
+extern "C" int lt_dgrad_act_bwd(const float* grad_out, const float* w, const float* act_in, float* grad_in, int M, int Nout, int Kin, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  if (!grad_out || !w || !act_in || !grad_in || M <= 0 || Nout <= 0 || Kin <= 0) return LT_ERR_INVALID_ARG;
+  if ((Kin & 3) || (Nout & 3) || (((uintptr_t)grad_out | (uintptr_t)w | (uintptr_t)act_in | (uintptr_t)grad_in) & 15)) return LT_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t wsb = (size_t)workspace_bytes;
+  static const int forced = [] { const char* e = getenv("LT_DGRAD_TILE"); return e ? atoi(e) : -1; }();
+  const int tile = forced >= 0 ? forced : (Kin >= 256 && M >= 8192 ? 1 : 0);
+  if (tile == 1) return FusedDgrad<Shape<_256, _128, _32>, Shape<_2, _1, _1>>::run(grad_out, w, act_in, grad_in, M, Nout, Kin, workspace, wsb, st);
+  if (tile == 3) return FusedDgrad<Shape<_256, _256, _32>, Shape<_2, _1, _1>>::run(grad_out, w, act_in, grad_in, M, Nout, Kin, workspace, wsb, st);
+  return FusedDgrad<Shape<_128, _128, _32>, Shape<_1, _1, _1>>::run(grad_out, w, act_in, grad_in, M, Nout, Kin, workspace, wsb, st);
 }
 #endif  // LT_HAVE_CUTLASS

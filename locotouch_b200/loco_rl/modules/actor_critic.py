@@ -187,17 +187,28 @@ class ActorCritic(nn.Module):
         """Writes dLoss/dW and dLoss/db of every layer straight into the flat gradient buffer: per layer one fused
         ELU-backward + bias-gradient pass (K9), one wgrad GEMM (out = the gradient view) and one dgrad GEMM."""
 
+        fused = torch.backends.cuda.matmul.allow_tf32
+
         def chain(linears, acts, gs, g, wstream):
             # dgrad feeds the next layer; the weight gradients only have to be complete before the optimizer step, so they
-            # trail on their own stream
+            # trail on their own stream.  acts[i] is the input of layer i = the post-ELU output of layer i - 1.
             last = len(linears) - 1
+            ops.bias_act_bwd(g, None, linears[last].bias.grad)  # output layer: no activation, bias gradient = column sums
             for i in range(last, -1, -1):
                 lin = linears[i]
-                ops.bias_act_bwd(g, acts[i + 1] if i < last else None, lin.bias.grad)  # in place on g
                 with wstream.forked():
                     self._wgrad(g, acts[i], lin.weight.grad, lin._wgrad_part)
                 if i > 0:
-                    g = torch.mm(g, lin.weight, out=gs[i])
+                    below = linears[i - 1]
+                    out = None
+                    if fused and lin.out_features >= 64:  # K12: dgrad GEMM with the ELU backward of the layer below in its epilogue
+                        out = ops.dgrad_act_bwd(g, lin.weight, acts[i], out=gs[i])
+                    if out is None:
+                        out = torch.mm(g, lin.weight, out=gs[i])
+                        ops.bias_act_bwd(out, acts[i], below.bias.grad)  # K9: ELU backward in place + bias gradient
+                    else:
+                        ops.bias_act_bwd(out, None, below.bias.grad)     # K9, reduction only
+                    g = out
 
         side, w_actor, w_critic = self.side_streams(grad_mu.device)
         for k, ((linears, acts, gs), g) in enumerate(zip(self._saved, (grad_mu, grad_value))):

@@ -447,3 +447,25 @@ def linear_bias_act(x, weight, bias, out=None, elu: bool = True):
     check(rc, "lt_linear_bias_act")
     count_launches(1)
     return out
+
+
+def dgrad_act_bwd(grad_out, weight, act_in, out=None):
+    """out = (grad_out @ weight) * elu'(act_in): the dgrad GEMM with the ELU backward of the layer below in its epilogue (K12).
+    Returns None when the shape / alignment is not supported."""
+    M, Nout = grad_out.shape
+    Kin = weight.shape[1]
+    if (Kin & 3) or (Nout & 3) or not (grad_out.is_contiguous() and weight.is_contiguous() and act_in.is_contiguous()):
+        return None
+    if out is None:
+        out = torch.empty(M, Kin, device=grad_out.device, dtype=torch.float32)
+    if (grad_out.data_ptr() | weight.data_ptr() | act_in.data_ptr() | out.data_ptr()) & 15:
+        return None
+    nbytes = lib().lt_linear_bias_act_workspace_bytes(M, Kin, Nout)
+    ws = _workspace("linear", max(nbytes, 256), grad_out.device)
+    rc = lib().lt_dgrad_act_bwd(ptr(grad_out, torch.float32, "grad_out"), ptr(weight, torch.float32, "weight"), ptr(act_in, torch.float32, "act_in"),
+                                ptr(out, torch.float32, "out"), M, Nout, Kin, ptr(ws), ws.numel(), current_stream())
+    if rc == _C.LT_ERR_UNSUPPORTED:
+        return None
+    check(rc, "lt_dgrad_act_bwd")
+    count_launches(1)
+    return out

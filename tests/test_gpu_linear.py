@@ -41,3 +41,18 @@ def test_unsupported_shapes_are_reported_not_faked(cuda, lt_lib):
     x, b = torch.randn(64, 270, device=cuda), torch.randn(16, device=cuda)
     assert ops.linear_bias_act(x, torch.randn(16, 270, device=cuda), b) is None  # K = 270 is not a multiple of 4
     assert ops.linear_bias_act(torch.randn(64, 128, device=cuda), torch.randn(1, 128, device=cuda), torch.randn(1, device=cuda)) is None  # N = 1
+
+
+@pytest.mark.parametrize("M,Nout,Kin", [(24576, 512, 348), (24576, 256, 512), (4096, 128, 256), (1000, 64, 128), (37, 8, 64)])
+def test_fused_dgrad_elu_backward_matches_torch(cuda, lt_lib, M, Nout, Kin):
+    from locotouch_b200 import ops
+
+    g = torch.Generator().manual_seed(M + Nout + Kin)
+    go = torch.randn(M, Nout, generator=g).to(cuda)
+    w = (torch.randn(Nout, Kin, generator=g) / Nout ** 0.5).to(cuda)
+    h = torch.nn.functional.elu(torch.randn(M, Kin, generator=g)).to(cuda)
+    out = ops.dgrad_act_bwd(go, w, h)
+    assert out is not None
+    ref = (go.double() @ w.double()) * torch.where(h > 0, torch.ones_like(h), h + 1.0).double()
+    err = (out.double() - ref).abs().max().item()
+    assert err < 6e-3, f"max abs error {err}"
