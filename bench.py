@@ -209,6 +209,7 @@ def kernel_rooflines(engine, reps: int = 96):
     graph on the timing stream, cycling through the engine's state sets (6 x ~33 MB > L2), CUDA events around the replay."""
     from locotouch_b200 import ops
     from locotouch_b200.sim import synth
+    from locotouch_b200.streams import graph_capture
 
     st = engine.alg.storage
     stream = torch.cuda.current_stream()
@@ -219,7 +220,7 @@ def kernel_rooflines(engine, reps: int = 96):
             launch(k)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with graph_capture(g):
             for r in range(reps):
                 launch(r % engine.K)
         for _ in range(3):

@@ -26,7 +26,7 @@ from .mdp import task_spec as TS
 from .mdp.fused import FusedMdp
 from .sim import synth
 from .sim.scene import ActionTermState
-from .streams import SideStream
+from .streams import SideStream, graph_capture
 
 # reference locotouch/config/locotouch/agents/rsl_rl_ppo_cfg.py:6-30
 PPO_CFG = dict(num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0, entropy_coef=0.01,
@@ -283,29 +283,29 @@ class HotPathEngine:
         for bank in range(self.banks):
             alg.storage.clear()  # host-side slot counter: every bank records the same T slots
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with graph_capture(g):
                 self.rollout_steps(bank=bank)
                 if not split:
                     self.rollout_finish()
             g_roll.append(g)
         if not split:
             g_upd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_upd):
+            with graph_capture(g_upd):
                 alg.update_body(self.perm)
                 self.finish_iteration()
             self._graphs = dict(split=False, roll=g_roll, update=g_upd)
         else:
             g_begin = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_begin):
+            with graph_capture(g_begin):
                 alg.update_begin(self.perm)
             g_mb = []
             for i in range(alg.num_mini_batches):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with graph_capture(g):
                     alg.minibatch_grads(i)
                 g_mb.append(g)
             g_tail = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_tail):
+            with graph_capture(g_tail):
                 alg.step_after_reduce()
             self._graphs = dict(split=True, roll=g_roll, begin=g_begin, mb=g_mb, tail=g_tail)
         alg.storage.clear()

@@ -6,9 +6,29 @@ and, because event record / wait are capturable, as parallel branches of a CUDA 
 from __future__ import annotations
 
 import contextlib
+import gc
 import os
 
 import torch
+
+
+@contextlib.contextmanager
+def graph_capture(graph: "torch.cuda.CUDAGraph", **kwargs):
+    """``torch.cuda.graph`` with Python's cyclic garbage collector held off for the duration of the capture.
+
+    Destroying an old ``CUDAGraph`` (cudaGraphExecDestroy, release of its memory pool) is not permitted while a stream of the
+    thread is capturing and INVALIDATES the capture in progress; an unreachable engine of an earlier run that the cyclic collector
+    happens to free in the middle of a capture does exactly that (torch >= 2.9 no longer collects on entry).  So: collect once
+    before the capture starts, then keep the automatic collector off until it ends."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph, **kwargs):
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 class SideStream:

@@ -114,6 +114,11 @@ def install_isaaclab_stub():
     _module("isaaclab.envs", ManagerBasedRLEnv=dummy, ManagerBasedEnv=dummy)
     _module("isaaclab.envs.mdp")
     _module("isaaclab.envs.mdp.actions", JointPositionAction=JointPositionAction, JointPositionActionCfg=_Cfg)
+    from oracle import il_commands
+
+    _module("isaaclab.managers", CurriculumTermCfg=_Cfg, CommandTerm=il_commands.CommandTerm, CommandTermCfg=il_commands.CommandTermCfg)
+    _module("isaaclab.envs.mdp.commands", UniformVelocityCommand=il_commands.UniformVelocityCommand,
+            UniformVelocityCommandCfg=il_commands.UniformVelocityCommandCfg)
     _INSTALLED = True
 
 
@@ -138,6 +143,17 @@ def load_reference_mdp():
     observations = _load_file("locotouch.mdp.observations", "locotouch/mdp/observations.py")
     terminations = _load_file("locotouch.mdp.terminations", "locotouch/mdp/terminations.py")
     return rewards, observations, terminations, actions
+
+
+def load_reference_commands():
+    """Returns ``(commands, curriculums)`` modules of reference ``locotouch/mdp`` (command terms over the [IL] base classes
+    restated in ``oracle/il_commands.py``; the velocity curriculum term)."""
+    install_isaaclab_stub()
+    _module("locotouch")
+    _module("locotouch.mdp")
+    commands = _load_file("locotouch.mdp.commands", "locotouch/mdp/commands.py")
+    curriculums = _load_file("locotouch.mdp.curriculums", "locotouch/mdp/curriculums.py")
+    return commands, curriculums
 
 
 def load_reference_loco_rl():

@@ -22,6 +22,7 @@ from locotouch_b200 import ops  # noqa: E402
 from locotouch_b200.mdp import task_spec as TS  # noqa: E402
 from locotouch_b200.mdp.fused import FusedMdp  # noqa: E402
 from locotouch_b200.sim import synth  # noqa: E402
+from locotouch_b200.streams import graph_capture  # noqa: E402
 
 L2_BYTES = 126e6
 
@@ -41,7 +42,7 @@ def time_graph(launch, copies: int, reps: int, warmup: int = 3):
             launch(i)
         stream.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
+        with graph_capture(graph, stream=stream):
             for r in range(reps):
                 launch(r % copies)
         for _ in range(warmup):
@@ -221,6 +222,23 @@ def bench_gather(n_rows: int, count: int, reps: int, obs_dim: int = 270):
     return {"gather_rows (9 tensors)": (time_graph(run, copies, reps), per)}
 
 
+def bench_copy(sizes_mb, reps: int):
+    """Launch-size calibration: a plain device-to-device copy (cudaMemcpyAsync through torch) that moves the same number of bytes
+    (half read, half written) as a kernel's algorithmic traffic, timed the same way.  What fraction of the 4 GB copy peak a launch
+    of this size can reach at all (launch latency + ramp) -- the ceiling the small-launch fractions above should be read against."""
+    out = {}
+    for mb in sizes_mb:
+        half = int(mb * 1e6 / 2) // 16 * 16
+        copies = min(copies_for(2 * half), 64)
+        sets = [(torch.empty(half, dtype=torch.uint8, device="cuda"), torch.empty(half, dtype=torch.uint8, device="cuda")) for _ in range(copies)]
+
+        def run(i, sets=sets):
+            sets[i][1].copy_(sets[i][0])
+
+        out[f"d2d copy calibration [{mb:g} MB]"] = (time_graph(run, copies, reps), 2 * half)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=4096)
@@ -250,13 +268,15 @@ def main():
         res.update(bench_split_pad(n, args.reps))
     if want("gather"):
         res.update(bench_gather(n * 24, n * 24 // 4, max(20, args.reps // 10)))
+    if want("copy"):
+        res.update(bench_copy([2.47 * n / 4096, 6.49 * n / 4096, 22.85 * n / 4096, 28.34 * n / 4096, 36.21 * n / 4096], args.reps))
     rows = []
     print(f"envs={n}  peak={peak} GB/s ({kind})")
-    print(f"{'kernel':38s} {'us/launch':>10s} {'alg MB':>9s} {'GB/s':>9s} {'frac':>6s}")
+    print(f"{'kernel':42s} {'us/launch':>10s} {'alg MB':>9s} {'GB/s':>9s} {'frac':>6s}")
     for k, (us, nbytes) in res.items():
         gbs = nbytes / us / 1e3
         rows.append(dict(kernel=k, us=us, bytes=nbytes, gbs=gbs, frac=gbs / peak))
-        print(f"{k:38s} {us:10.2f} {nbytes / 1e6:9.2f} {gbs:9.1f} {gbs / peak:6.3f}")
+        print(f"{k:42s} {us:10.2f} {nbytes / 1e6:9.2f} {gbs:9.1f} {gbs / peak:6.3f}")
     if args.json:
         json.dump(dict(envs=n, peak_gbs=peak, peak_kind=kind, rows=rows), open(args.json, "w"), indent=1)
 

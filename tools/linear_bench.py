@@ -7,6 +7,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from locotouch_b200 import ops  # noqa: E402
+from locotouch_b200.streams import graph_capture  # noqa: E402
 
 torch.backends.cuda.matmul.allow_tf32 = True
 
@@ -19,7 +20,7 @@ def timed(fn, reps=40):
             fn()
         s.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=s):
+        with graph_capture(g, stream=s):
             for _ in range(reps):
                 fn()
         g.replay()

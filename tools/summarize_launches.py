@@ -40,7 +40,11 @@ for k, us in rows:
     a[1] += us
 total = sum(a[1] for a in agg.values())
 mine = ("mdp_step", "taxel", "gae_scan", "adv_normalize", "ppo_loss", "clip_adam", "grad_sqnorm", "act_sample", "store_scalars", "gather_rows",
-        "process_actions", "counter_add", "bias_act_bwd", "copy4", "copy1", "any_nonzero", "adaptive_lr", "masked_mse", "pad_traj", "tactile_delay")
+        "process_actions", "counter_add", "bias_act_bwd", "copy4", "copy1", "any_nonzero", "adaptive_lr", "masked_mse", "pad_traj", "tactile_delay",
+        "command_step", "vel_curriculum",
+        # K12 (gemm_fused.cu): our translation unit built from the CUTLASS sm100 collective builders; cuBLAS's own kernels are
+        # named cutlass3x_* / cutlass::Kernel2<cutlass_80_*> and are NOT ours
+        "cutlass::device_kernel<")
 print(f"launches: {len(rows)}   summed kernel time: {total / 1e3:.3f} ms (ncu: serialised, cold cache)\n")
 print("| kernel | launches | total us | share | avg us | ours |")
 print("|---|---:|---:|---:|---:|:-:|")
@@ -48,4 +52,5 @@ for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     ours = "x" if any(m in k for m in mine) else ""
     print(f"| `{k}` | {n} | {us:.1f} | {100 * us / total:.1f}% | {us / n:.2f} | {ours} |")
 own = sum(us for k, (n, us) in agg.items() if any(m in k for m in mine))
-print(f"\nhand-written kernels: {100 * own / total:.1f}% of the summed kernel time; cuBLAS / ATen (GEMMs, ELU, copies): {100 - 100 * own / total:.1f}%")
+print(f"\nkernels of this library (hand-written + K12 fused tcgen05 GEMMs): {100 * own / total:.1f}% of the summed kernel time; "
+      f"cuBLAS / ATen (wgrad GEMMs, small layers, ELU, reductions, copies): {100 - 100 * own / total:.1f}%")
