@@ -32,8 +32,8 @@ const char* lt_error_string(int status);
 /* Text of the last CUDA error seen by this thread inside the library ("" if none). */
 const char* lt_last_cuda_error(void);
 /* sizeof() of the argument structs as compiled, so that a foreign-language binding can verify its own layout:
- * which = 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams, 6 LtTaxelForceArgs;
- * -1 otherwise. */
+ * which = 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams, 6 LtTaxelForceArgs,
+ * 7 LtCommandRanges, 8 LtCommandArgs, 9 LtVelCurriculumArgs; -1 otherwise. */
 int64_t lt_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -452,6 +452,97 @@ int lt_linear_bias_act(const float* x, const float* w, const float* bias, float*
  * alignment rules and workspace as lt_linear_bias_act. */
 int lt_dgrad_act_bwd(const float* grad_out, const float* w, const float* act_in, float* grad_in, int M, int Nout, int Kin,
                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K13  velocity command term + reward-driven velocity curriculum, device resident
+ * replaces  locotouch/mdp/commands.py:379-576  UniformVelocityCommandGaitLoggingMultiSampling (reset / compute / set_ranges,
+ *           over IsaacLab's CommandTerm + UniformVelocityCommand) and
+ *           locotouch/mdp/curriculums.py:184-274  ModifyVelCommandsRangeBasedonReward.__call__
+ * The reference runs both as per-reset host logic (nonzero, multinomial, boolean-index writes, torch.all / torch.mean read on
+ * the host, ranges as Python tuples).  Here the ranges live in one device block that both entry points share, env ids are a
+ * device mask and no host read is needed between a reset and the next command.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Scalar state of the command term (cfg.ranges, cfg.previous_ranges, *_equal_ranges, initial_zero_command_steps,
+ * cfg.rel_standing_envs) and of the curriculum term (forward bins, success counters).  Doubles: the reference keeps these as
+ * Python floats and decides *_equal_ranges by tuple equality.  Index 0 lin_vel_x, 1 lin_vel_y, 2 ang_vel_z; [lo, hi]. */
+typedef struct LtCommandRanges {
+  double ranges[3][2];
+  double previous[3][2];
+  int32_t equal[3];
+  int32_t initial_zero_command_steps;
+  double rel_standing_envs;
+  int32_t final_initial_zero_command_steps;
+  int32_t reserved;
+  double final_rel_standing_envs;
+  int32_t lin_forward_bins, ang_forward_bins, success_repeat_times_lin, success_repeat_times_ang;
+} LtCommandRanges;
+
+#define LT_CMD_RESET 1   /* [IL] CommandTerm.reset(env_ids), env ids given as reset_mask */
+#define LT_CMD_COMPUTE 2 /* [IL] CommandTerm.compute(dt) */
+/* rows of the [LT_CMD_NUM_METRICS, N] metrics block (= the reference's metrics dict of [N] tensors) */
+enum LtCommandMetric {
+  LT_CMD_M_ERROR_VEL_XY = 0, LT_CMD_M_ERROR_VEL_YAW, LT_CMD_M_FOOT_AIR_TIME_VAR, LT_CMD_M_FOOT_STEP_FREQ, LT_CMD_M_PAIR1_STEP_FREQ,
+  LT_CMD_M_PAIR2_STEP_FREQ, LT_CMD_M_STEP_AIR_TIME, LT_CMD_M_PAIR1_AIR_TIME, LT_CMD_M_PAIR2_AIR_TIME, LT_CMD_M_LIN_VEL_X,
+  LT_CMD_M_LIN_VEL_Y, LT_CMD_M_ANG_VEL_Z, LT_CMD_M_ZERO_STEPS, LT_CMD_M_REL_STANDING, LT_CMD_NUM_METRICS
+};
+
+typedef struct LtCommandArgs {
+  int32_t N;
+  int32_t phases;                  /* LT_CMD_RESET | LT_CMD_COMPUTE (reset runs first) */
+  float dt;                        /* env.step_dt */
+  float resampling_time_lo, resampling_time_hi; /* cfg.resampling_time_range */
+  float bin_c0, bin_c1;            /* normalised cumulative [p, 1 - p] of sampling_probs (commands.py:448), fp32 */
+  int32_t binary_maximal_command;
+  const LtCommandRanges* ranges;   /* device */
+  /* term state, read-write */
+  float* vel_command_b;            /* [N,3] the command tensor lt_mdp_step reads */
+  float* vel_command_b_buffer;     /* [N,3] */
+  float* time_left;                /* [N] */
+  int64_t* command_counter;        /* [N] */
+  uint8_t* is_standing_env;        /* [N] */
+  float* metrics;                  /* [LT_CMD_NUM_METRICS, N] */
+  float* metric_scalars;           /* [LT_CMD_NUM_METRICS] launch-wide values of rows 3..13 (written by COMPUTE) */
+  /* inputs */
+  const uint8_t* reset_mask;       /* [N], RESET */
+  double* reset_extras;            /* [LT_CMD_NUM_METRICS + 1], RESET: += sum of every metric row over the reset envs, last =
+                                      their count (the caller zeroes it; mean = sum / count is what the reference logs) */
+  const int64_t* episode_length_buf;
+  const float* root_lin_vel_b;     /* [N,3], COMPUTE */
+  const float* root_ang_vel_b;     /* [N,3], COMPUTE */
+  const float* last_air_time;      /* [N, num_sensor_bodies], COMPUTE */
+  int32_t num_sensor_bodies;
+  int32_t feet_ids[4];             /* sensor_cfg.body_ids */
+  const float* gait_valid_last_air_time; /* [N,4] state of the gait reward term (rewards.py:99) or NULL; 16-byte aligned */
+  /* randomness: explicit uniforms [N,8] (slot 0 time_left, 1-3 x / y / yaw value, 4-6 bin, 7 standing) for ONE phase, or NULL:
+   * Philox4x32-10 keyed by (seed, offset + *offset_base), counter (env, phase) */
+  const float* u;
+  uint64_t seed, offset;
+  const int64_t* offset_base;
+  void* workspace;                 /* COMPUTE: lt_command_workspace_bytes(N), zero-initialised once */
+  int64_t workspace_bytes;
+} LtCommandArgs;
+
+int64_t lt_command_workspace_bytes(int N);
+int lt_command_step(const LtCommandArgs* args, void* stream);
+
+typedef struct LtVelCurriculumArgs {
+  int32_t N;
+  int32_t repeat_times_lin, repeat_times_ang, max_distance_bins;
+  LtCommandRanges* ranges;            /* device, read-write */
+  const uint8_t* reset_mask;          /* [N] env_ids of the call */
+  const int64_t* episode_length_buf;  /* [N] */
+  const float* episode_sums_lin;      /* [N] RewardManager._episode_sums[reward_name_lin] */
+  const float* episode_sums_ang;      /* [N] */
+  uint8_t* env_reseted_lin; float* episode_length_buf_lin; float* episode_reward_sum_lin; /* term state [N] */
+  uint8_t* env_reseted_ang; float* episode_length_buf_ang; float* episode_reward_sum_ang;
+  double command_maximum_ranges[3];
+  double expansion[3];                /* (maximum - initial upper bound) / curriculum_bins, curriculums.py:191-193 */
+  double reset_envs_episode_length;   /* cfg value * max_episode_length_s (:194) */
+  double reward_threshold_lin, reward_threshold_ang; /* :199-200 */
+} LtVelCurriculumArgs;
+
+/* One block; N <= 1 << 20. */
+int lt_vel_curriculum(const LtVelCurriculumArgs* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -146,6 +146,45 @@ class LtMdpArgs(C.Structure):
     ]
 
 
+class LtCommandRanges(C.Structure):
+    _fields_ = [
+        ("ranges", (C.c_double * 2) * 3), ("previous", (C.c_double * 2) * 3), ("equal", C.c_int32 * 3), ("initial_zero_command_steps", C.c_int32),
+        ("rel_standing_envs", C.c_double), ("final_initial_zero_command_steps", C.c_int32), ("reserved", C.c_int32),
+        ("final_rel_standing_envs", C.c_double), ("lin_forward_bins", C.c_int32), ("ang_forward_bins", C.c_int32),
+        ("success_repeat_times_lin", C.c_int32), ("success_repeat_times_ang", C.c_int32),
+    ]
+
+
+LT_CMD_RESET, LT_CMD_COMPUTE = 1, 2
+LT_CMD_METRICS = ("error_vel_xy", "error_vel_yaw", "foot_air_time_variance", "foot_step_frequency", "pair_1_step_frequency",
+                  "pair_2_step_frequency", "step_air_time", "pair_1_air_time", "pair_2_air_time", "lin_vel_x", "lin_vel_y", "ang_vel_z",
+                  "initial_zero_command_steps", "rel_standing_envs")  # enum LtCommandMetric
+
+
+class LtCommandArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("phases", C.c_int32), ("dt", C.c_float), ("resampling_time_lo", C.c_float), ("resampling_time_hi", C.c_float),
+        ("bin_c0", C.c_float), ("bin_c1", C.c_float), ("binary_maximal_command", C.c_int32),
+        ("ranges", C.c_void_p), ("vel_command_b", C.c_void_p), ("vel_command_b_buffer", C.c_void_p), ("time_left", C.c_void_p),
+        ("command_counter", C.c_void_p), ("is_standing_env", C.c_void_p), ("metrics", C.c_void_p), ("metric_scalars", C.c_void_p),
+        ("reset_mask", C.c_void_p), ("reset_extras", C.c_void_p), ("episode_length_buf", C.c_void_p), ("root_lin_vel_b", C.c_void_p),
+        ("root_ang_vel_b", C.c_void_p), ("last_air_time", C.c_void_p), ("num_sensor_bodies", C.c_int32), ("feet_ids", C.c_int32 * 4),
+        ("gait_valid_last_air_time", C.c_void_p), ("u", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("offset_base", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
+class LtVelCurriculumArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("repeat_times_lin", C.c_int32), ("repeat_times_ang", C.c_int32), ("max_distance_bins", C.c_int32),
+        ("ranges", C.c_void_p), ("reset_mask", C.c_void_p), ("episode_length_buf", C.c_void_p), ("episode_sums_lin", C.c_void_p),
+        ("episode_sums_ang", C.c_void_p), ("env_reseted_lin", C.c_void_p), ("episode_length_buf_lin", C.c_void_p),
+        ("episode_reward_sum_lin", C.c_void_p), ("env_reseted_ang", C.c_void_p), ("episode_length_buf_ang", C.c_void_p),
+        ("episode_reward_sum_ang", C.c_void_p), ("command_maximum_ranges", C.c_double * 3), ("expansion", C.c_double * 3),
+        ("reset_envs_episode_length", C.c_double), ("reward_threshold_lin", C.c_double), ("reward_threshold_ang", C.c_double),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/locotouch_b200.h declares
 _SIGNATURES = {
     "lt_abi_version": (C.c_int, []),
@@ -185,6 +224,9 @@ _SIGNATURES = {
     "lt_mdp_reset": (C.c_int, [C.POINTER(LtGaitState), f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "lt_pad_trajectories": (C.c_int, [f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, C.c_void_p, C.c_void_p]),
     "lt_masked_mse_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "lt_command_workspace_bytes": (C.c_int64, [C.c_int]),
+    "lt_command_step": (C.c_int, [C.POINTER(LtCommandArgs), C.c_void_p]),
+    "lt_vel_curriculum": (C.c_int, [C.POINTER(LtVelCurriculumArgs), C.c_void_p]),
     "lt_masked_mse": (C.c_int, [f32p, f32p, C.c_void_p, C.c_int64, C.c_int, f32p, f32p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
@@ -217,7 +259,8 @@ def lib() -> C.CDLL:
         fn.argtypes = argtypes
     if handle.lt_abi_version() != 1:
         raise LocoTouchLibraryError("ABI version mismatch between _C.py and liblocotouch_b200.so")
-    for which, struct in enumerate((LtGatherArgs, LtPpoLossArgs, LtTaxelArgs, LtMdpArgs, LtGaitState, LtGaitParams, LtTaxelForceArgs)):
+    for which, struct in enumerate((LtGatherArgs, LtPpoLossArgs, LtTaxelArgs, LtMdpArgs, LtGaitState, LtGaitParams, LtTaxelForceArgs,
+                                    LtCommandRanges, LtCommandArgs, LtVelCurriculumArgs)):
         if handle.lt_struct_size(which) != C.sizeof(struct):
             raise LocoTouchLibraryError(
                 f"struct layout mismatch for {struct.__name__}: C {handle.lt_struct_size(which)} vs ctypes {C.sizeof(struct)}")

@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(PKG, "liblocotouch_b200.so")
 
 # Kernels whose masks must be bit-exact against the torch expression order are built without FMA contraction
 # (torch evaluates a*b+c as two rounded ops).
-PER_FILE_FLAGS = {"mdp_step.cu": ["-fmad=false"], "taxel.cu": ["-fmad=false"], "gae.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"mdp_step.cu": ["-fmad=false"], "taxel.cu": ["-fmad=false"], "gae.cu": ["-fmad=false"],
+                  "commands.cu": ["-fmad=false"]}
 
 def cutlass_include_dirs() -> list[str]:
     """CUTLASS / CuTe header trees for the tcgen05 GEMM with the fused bias + ELU epilogue (gemm_fused.cu).  The image vendors

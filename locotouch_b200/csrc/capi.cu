@@ -50,6 +50,9 @@ extern "C" int64_t lt_struct_size(int which) {
     case 4: return (int64_t)sizeof(LtGaitState);
     case 5: return (int64_t)sizeof(LtGaitParams);
     case 6: return (int64_t)sizeof(LtTaxelForceArgs);
+    case 7: return (int64_t)sizeof(LtCommandRanges);
+    case 8: return (int64_t)sizeof(LtCommandArgs);
+    case 9: return (int64_t)sizeof(LtVelCurriculumArgs);
     default: return -1;
   }
 }

@@ -14,7 +14,7 @@ Randomness goes through a small ``rng`` object so that the SAME statements serve
                     (tests/golden/commands_c3.npz, tests/test_commands.py).
   * ``ExplicitRng`` takes per-env uniforms ``u[N, 8]`` (slot 0 time_left, 1-3 x / y / yaw value, 4-6 x / y / yaw bin,
                     7 standing) -- the parity mode of the CUDA kernel (lt_command_step), which cannot share torch's CPU
-                    stream.  Value arithmetic is torch's: ``u * (hi - lo) + lo`` in fp32 with fp32-rounded bounds
+                    stream.  Value arithmetic is torch's: ``fma(u, hi - lo, lo)`` in fp32 with fp32-rounded bounds
                     (checked against ``Tensor.uniform_`` in tests/test_commands.py).
 """
 from __future__ import annotations
@@ -43,8 +43,10 @@ class ExplicitRng:
         self.u = u
 
     def uniform(self, env_ids, lo, hi, slot):
+        # torch's CPU uniform_ transform is ONE fused multiply-add in fp32: fma(u, hi32 - lo32, lo32).  Emulated through double
+        # (the product of two 24-bit significands is exact there)
         lo32, hi32 = torch.tensor(lo, dtype=torch.float32), torch.tensor(hi, dtype=torch.float32)
-        return self.u[env_ids, slot] * (hi32 - lo32) + lo32
+        return (self.u[env_ids, slot].double() * (hi32 - lo32).double() + lo32.double()).float()
 
     def multinomial(self, probs, env_ids, slot):
         c = torch.cumsum(probs, 0) / probs.sum()  # fp32, like the normalised distribution torch.multinomial searches
@@ -65,7 +67,8 @@ class CommandOracle:
 
     def __init__(self, env, *, ranges, resampling_time_range=(8.0, 8.0), rel_standing_envs=0.1, final_rel_standing_envs=0.0,
                  new_command_probs=0.15, initial_zero_command_steps=0, final_initial_zero_command_steps=0,
-                 binary_maximal_command=False, feet_sensor_ids=(13, 14, 15, 16), gait_valid_last_air_time=None, rng=None):
+                 binary_maximal_command=False, feet_sensor_ids=(13, 14, 15, 16), gait_valid_last_air_time=None, rng=None,
+                 cast_maximal_to_fp32=False):
         n = env.num_envs
         self.env, self.rng = env, rng or TorchRng()
         self.ranges = {k: tuple(v) for k, v in ranges.items()}  # lin_vel_x / lin_vel_y / ang_vel_z
@@ -78,6 +81,9 @@ class CommandOracle:
         self.initial_zero_command_steps = initial_zero_command_steps  # :451
         self.final_initial_zero_command_steps = final_initial_zero_command_steps
         self.binary_maximal_command = binary_maximal_command
+        # reference quirk: after the curriculum has run, cfg.ranges hold np.float64 (np.clip) and commands.py:520-521 builds a float64
+        # tensor that index_put_ rejects.  False reproduces that (RuntimeError); True rounds to fp32, which is what the CUDA path does.
+        self.cast_maximal_to_fp32 = cast_maximal_to_fp32
         self.maximal_command_sampling = torch.tensor([[i, j, k] for i in (-1, 1) for j in (-1, 1) for k in (-1, 1)], dtype=torch.float32)  # :453-463
         self.feet = list(feet_sensor_ids)
         self.gait_vla = gait_valid_last_air_time  # callable -> [N, 4] tensor (rewards.py:99), or None
@@ -144,6 +150,8 @@ class CommandOracle:
         if self.binary_maximal_command:
             idx = rng.randint(self.maximal_command_sampling.shape[0], env_ids, SLOT_X)
             maximal = torch.tensor([self.ranges["lin_vel_x"][1], self.ranges["lin_vel_y"][1], self.ranges["ang_vel_z"][1]])
+            if self.cast_maximal_to_fp32:
+                maximal = maximal.float()
             self.vel_command_b[env_ids] = self.maximal_command_sampling[idx] * maximal
         else:
             dims = (("lin_vel_x", 0, SLOT_X, SLOT_BIN_X), ("lin_vel_y", 1, SLOT_Y, SLOT_BIN_Y), ("ang_vel_z", 2, SLOT_Z, SLOT_BIN_Z))

@@ -12,6 +12,8 @@ Fixtures (all < 1 MB):
                                         ``locotouch/mdp`` callables driven through the IsaacLab stub namespace.
   ppo_c1.npz                            RolloutStorage.compute_returns outputs and one full PPO.update() (losses,
                                         learning-rate, parameters after the update) from the reference ``loco_rl``.
+  commands_c3.npz                       velocity command term (multi-sampling bins, zero-command steps, gait logging metrics) and the
+                                        reward-driven velocity curriculum over 70 steps of a reset tape, torch global RNG seeded.
   tactile_c4.npz                        BinaryTactileSignals bitmaps (explicit dropout / addition uniforms) and
                                         TactileRecorder outputs across resets.
 """
@@ -508,6 +510,60 @@ def golden_dagger():
     print(f"dagger_c4: {rb.num_trajs} trajectories / {rb.num_steps} steps, {len(batches)} batches; eval {len(er)} episodes")
 
 
+def reference_command_view(cmd, cur):
+    def view():
+        r, p = cmd.cfg.ranges, cmd.cfg.previous_ranges
+        return dict(cmd=cmd.vel_command_b, buffer=cmd.vel_command_b_buffer, time_left=cmd.time_left, standing=cmd.is_standing_env,
+                    counter=cmd.command_counter, metrics=cmd.metrics, ranges=[*r.lin_vel_x, *r.lin_vel_y, *r.ang_vel_z],
+                    previous=[*p.lin_vel_x, *p.lin_vel_y, *p.ang_vel_z],
+                    equal=[cmd.lin_vel_x_equal_ranges, cmd.lin_vel_y_equal_ranges, cmd.ang_vel_z_equal_ranges], izcs=cmd.initial_zero_command_steps,
+                    rel_standing=cmd.cfg.rel_standing_envs,
+                    curriculum=[cur.lin_forward_bins, cur.ang_forward_bins, cur.success_repeat_times_lin, cur.success_repeat_times_ang,
+                                int(cur.env_reseted_lin.sum()), int(cur.env_reseted_ang.sum()), float(cur.episode_length_buf_lin.sum()),
+                                float(cur.episode_length_buf_ang.sum())])
+    return view
+
+
+def golden_commands():
+    """UniformVelocityCommandGaitLoggingMultiSampling + ModifyVelCommandsRangeBasedonReward (reference commands.py:427-576,
+    curriculums.py:184-274, UNMODIFIED, over the restated [IL] base classes of oracle/il_commands.py) driven by
+    tests/scenarios.CommandScenario under torch.manual_seed; the oracle reproduces the run call for call (TorchRng)."""
+    from types import SimpleNamespace
+
+    from tests import scenarios as S
+
+    commands, curriculums = ref_loader.load_reference_commands()
+    out = {}
+    for tag, binary in (("", False), ("bin_", True)):
+        torch.manual_seed(S.CMD_SCENARIO["seed"])
+        sc = S.CommandScenario(binary_maximal_command=binary)
+        c = S.CMD_CFG
+        Cfg = commands.UniformVelocityCommandGaitLoggingMultiSamplingCfg
+        cfg = Cfg(asset_name="robot", resampling_time_range=c["resampling_time_range"], rel_heading_envs=0.0, heading_command=False,
+                  ranges=Cfg.Ranges(**c["ranges"]), new_command_probs=c["new_command_probs"], rel_standing_envs=c["rel_standing_envs"],
+                  final_rel_standing_envs=c["final_rel_standing_envs"], initial_zero_command_steps=c["initial_zero_command_steps"],
+                  final_initial_zero_command_steps=c["final_initial_zero_command_steps"], binary_maximal_command=binary,
+                  sensor_cfg=SceneEntityCfg("robot_contact_senosr", body_names=".*foot"))
+        cmd = commands.UniformVelocityCommandGaitLoggingMultiSampling(cfg, sc.env)
+        assert list(cmd.sensor_cfg.body_ids) == S.FEET_SENSOR_IDS
+        sc.env.command_manager._terms["base_velocity"] = cmd
+        params = dict(command_name="base_velocity", reward_name_lin="track_lin_vel_xy", reward_name_ang="track_ang_vel_z", **S.CUR_CFG)
+        cur = curriculums.ModifyVelCommandsRangeBasedonReward(SimpleNamespace(params=params), sc.env)
+        rec = S.CommandRecorder(reference_command_view(cmd, cur))
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):  # set_ranges prints banners
+            # binary_maximal_command: the curriculum stays out -- once it has run, cfg.ranges hold np.float64 values (np.clip,
+            # curriculums.py:239) and commands.py:520-521 builds a float64 tensor that index_put_ rejects (latent reference bug)
+            sc.run(cmd, (lambda env, ids: None) if binary else (lambda env, ids: cur(env, ids, **params)), rec)
+        st = rec.stacked()
+        for k, v in st.items():
+            out[tag + k] = v.numpy()
+        if not binary:
+            assert st["scalars"][-1, 12:15].tolist() == [1.0, 1.0, 1.0] and st["scalars"][-1, 15] == c["final_initial_zero_command_steps"], "scenario must reach the final ranges"
+    out["checksum"] = np.float64(env_checksum(S.CommandScenario().env))
+    np.savez_compressed(os.path.join(OUT, "commands_c3.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "the reference is not mounted"
     torch.set_num_threads(1)
@@ -519,6 +575,7 @@ if __name__ == "__main__":
     golden_recurrent()
     golden_dagger()
     golden_tactile_forces()
+    golden_commands()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
