@@ -13,6 +13,8 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "liblocotouch_b200.so")
+if os.environ.get("LT_LIB_VARIANT"):  # tuning builds of the same library (python -m locotouch_b200.csrc.build with LT_LIB_VARIANT set)
+    LIB_PATH = LIB_PATH[:-3] + f".{os.environ['LT_LIB_VARIANT']}.so"
 
 LT_GATHER_MAX = 12
 LT_MAX_REWARD_TERMS = 32

@@ -65,8 +65,16 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    variant = os.environ.get("LT_LIB_VARIANT")  # tuning builds: liblocotouch_b200.<variant>.so with LT_MDP_* knobs, next to the product
+    if variant:
+        return _build(True, verbose, variant)
     if not force and not needs_build():
         return LIB_PATH
+    return _build(force, verbose, None)
+
+
+def _build(force: bool, verbose: bool, variant: str | None) -> str:
+    lib_path = LIB_PATH if not variant else LIB_PATH[:-3] + f".{variant}.so"
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
@@ -75,11 +83,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in sources():
-        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
+        knobbed = variant and os.path.basename(src) == "mdp_step.cu"  # the only file the LT_MDP_* knobs touch
+        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + (f".{variant}.o" if knobbed else ".o"))
         objs.append(obj)
-        if not force and os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))):
+        if (not force or (variant and not knobbed)) and os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))):
             continue
-        extra = [f"-D{k}={v}" for k, v in os.environ.items() if k.startswith("LT_MDP_")]  # tuning knobs (see mdp_step.cu)
+        extra = [f"-D{k}={v}" for k, v in os.environ.items() if k.startswith("LT_MDP_")] if (knobbed or not variant) else []  # tuning knobs
         if os.path.basename(src) == "gemm_fused.cu":
             dirs = cutlass_include_dirs()
             extra += ["--expt-extended-lambda", "-DLT_HAVE_CUTLASS=1"] + [x for d in dirs for x in ("-I", d)] if dirs else ["-DLT_HAVE_CUTLASS=0"]
@@ -98,11 +107,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-cudart", "static"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path, *objs, "-cudart", "static"]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

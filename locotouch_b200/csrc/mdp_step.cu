@@ -282,6 +282,10 @@ __device__ __forceinline__ float body_force_max(const float* force_env, int H, i
   return m;
 }
 
+// Measured and rejected (round 1, tools/mdp_timeline.py): touching every 64-byte line of the 3.4 KB parameter block up front, or
+// copying the block into shared memory, changes nothing (15.08 vs 15.06 us) or costs 1 us -- parameter reads are not what the
+// chains wait for; writing the old 5/6 of every observation row from the task queue (ahead of stage 2b) only moves the same
+// latency-bound copy loop earlier (14.3 vs 13.9 us).  What did pay: see the reward sum in stage 2a.
 __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A, const Layout L, const StageTable ST) {
   extern __shared__ __align__(16) float sm[];
   __shared__ unsigned char s_done[kEnvs], s_fill[kEnvs], s_tflag[kEnvs];
@@ -970,13 +974,15 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
   PROF_STAMP(6);
 
   // ---------------------------------------------------------------------------- stage 2a: reward accumulation + outputs
+  // The last warp owns the per-env reward (a sequential fp32 sum over the terms, the longest chain of this stage) and nothing
+  // else; the other warps share the per-term outputs.
   const int a_warps = kWarps, b_first = 0;
   if (do_rew && warp < a_warps) {
     const float dt = A.step_dt;
-    const int a_threads = a_warps * 32;
+    const int a_threads = (a_warps - 1) * 32;
     // [IL] RewardManager.compute: value = f * weight * dt ; episode_sums += value ; step_reward = value / dt
 #pragma unroll 1
-    for (int i = tid; i < T * kEnvs; i += a_threads) {
+    for (int i = tid; i < T * kEnvs && warp < a_warps - 1; i += a_threads) {
       const int t = i >> 5, ee = i & 31, nn = e0 + ee;
       if (ee >= nvalid) continue;
       const LtRewardTerm& rt = A.reward_terms[t];
@@ -996,12 +1002,29 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
       }
     }
     if (warp == a_warps - 1 && live) {  // reward_buf: sequential fp32 sum in term order
+      // Branch-free body: kind / weight / raw value are loaded unconditionally (a skipped term reads a stale slot and is
+      // replaced by 0 with a select), so the loads of a whole unrolled group are in flight together and only the additions,
+      // which must keep the term order, form a chain.  With a branch per term every term was its own serial
+      // constant-load -> branch -> constant-load -> shared-load -> multiply chain (~200 cycles each, 2.3 us in total).
       float reward = 0.f;
-#pragma unroll 8
-      for (int t = 0; t < T; ++t) {  // the products are independent (loads overlap); the additions keep the term order
-        const LtRewardTerm& rt = A.reward_terms[t];
-        const float value = rt.weight != 0.f ? (s_raw[rt.kind * kEnvs + e] * rt.weight) * dt : 0.f;
-        reward = reward + value;
+      int t = 0;
+#pragma unroll 1
+      for (; t + 8 <= T; t += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float w = A.reward_terms[t + k].weight;
+          const float raw = s_raw[A.reward_terms[t + k].kind * kEnvs + e];
+          v[k] = w != 0.f ? (raw * w) * dt : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) reward = reward + v[k];
+      }
+#pragma unroll 1
+      for (; t < T; ++t) {
+        const float w = A.reward_terms[t].weight;
+        const float raw = s_raw[A.reward_terms[t].kind * kEnvs + e];
+        reward = reward + (w != 0.f ? (raw * w) * dt : 0.f);
       }
       A.reward[n] = reward;
       if (A.auto_reset && s_done[e] && A.episode_log_sums) atomicAdd(A.episode_log_sums + T, 1.0f);
@@ -1010,7 +1033,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
     {
       const LtGaitState& G = A.gait_state;
 #pragma unroll 1
-      for (int i = tid; i < nvalid * kGaitFloats; i += a_threads) {
+      for (int i = tid; i < nvalid * kGaitFloats && warp < a_warps - 1; i += a_threads) {
         const int ee = i / kGaitFloats, k = i - ee * kGaitFloats, nn = e0 + ee;
         const float v = (A.auto_reset && s_done[ee]) ? 0.f : sm[L.gait_out + ee * kGaitStride + k];
         if (k < 4) G.last_step_current_air_time[nn * 4 + k] = v;
