@@ -37,20 +37,38 @@ HIDDEN = (512, 256, 128)
 ACTION_CLIP, ACTION_RAW_SCALE = 100.0, 0.25
 
 
-# State tensors the hot path never reads (not uploaded), and [N, num_bodies, 3] tensors of which it reads the four feet rows only
-# (uploaded as compact [N, 4, 3] tensors and scattered into place on the device).  Everything else is uploaded whole.
+# What travels host -> device per env step.  Not uploaded at all: state tensors the hot path never reads.  Uploaded ONCE (at
+# construction): the articulation constants (IsaacLab keeps them as persistent buffers, PhysX never rewrites them).  Uploaded as
+# compact row subsets and scattered into place on the device: [N, num_bodies, .] tensors of which the path reads a few rows -- the
+# four feet of body_pos_w / body_lin_vel_w, the 221 taxel bodies of body_quat_w.  Everything else is uploaded whole.
 UNREAD = ("robot_contact_senosr.last_contact_time", "robot_contact_senosr.net_forces_w", "object_contact_sensor.last_air_time")
+STATIC = ("robot.default_joint_pos", "robot.default_joint_vel", "robot.soft_joint_pos_limits")
 FEET_ROWS_ONLY = ("robot.body_pos_w", "robot.body_lin_vel_w")
 FEET = ("a_FR_foot", "b_FL_foot", "c_RR_foot", "d_RL_foot")
+
+
+def row_subsets(env) -> dict[str, torch.Tensor]:
+    """name -> int64 row (body) indices the hot path reads of that [N, num_bodies, .] tensor."""
+    feet = torch.tensor(env.scene["robot"].find_bodies(list(FEET))[0], dtype=torch.int64)
+    rows = {name: feet for name in FEET_ROWS_ONLY}
+    quat = getattr(env.scene["robot"].data, "body_quat_w", None)
+    if quat is None:
+        return rows
+    nb = quat.shape[1]
+    if nb > synth.NUM_ROBOT_BODIES:  # taxel bodies follow the robot bodies (reference observations.py:154-159 reads only those)
+        rows["robot.body_quat_w"] = torch.arange(synth.NUM_ROBOT_BODIES, nb, dtype=torch.int64)
+    else:
+        rows["robot.body_quat_w"] = torch.zeros(0, dtype=torch.int64)  # no tactile sensor: nothing reads body_quat_w
+    return rows
 
 
 def pack_host(env, pin: bool = False):
     """Lays every state tensor of a SynthEnv out in ONE contiguous host buffer (256-byte aligned slices) so that a single
     H2D copy of the first ``upload_bytes`` refreshes everything the hot path reads.  Returns (layout, compact, upload_bytes,
-    flat_host_buffer); ``compact`` = [(full_name, offset, nbytes, shape)] of the feet-row tensors."""
+    flat_host_buffer); ``compact`` = [(full_name, offset, nbytes, dtype, shape)] of the row-subset tensors."""
     tensors = env.named_tensors()
     skip = {k for k in tensors if k.startswith("action.") or k in ("terminated", "time_outs")}
-    feet = torch.tensor(env.scene["robot"].find_bodies(list(FEET))[0], dtype=torch.int64)
+    subsets = {k: v for k, v in row_subsets(env).items() if k in tensors}
     layout, compact, off = [], [], 0
 
     def place(name, t, into):
@@ -59,15 +77,15 @@ def pack_host(env, pin: bool = False):
         into.append((name, off, nbytes, t.dtype, tuple(t.shape)))
         off += (nbytes + 255) // 256 * 256
 
-    for name, t in tensors.items():  # uploaded whole
-        if name not in skip and name not in UNREAD and name not in FEET_ROWS_ONLY:
+    for name, t in tensors.items():  # uploaded whole, every step
+        if name not in skip and name not in UNREAD and name not in STATIC and name not in subsets:
             place(name, t, layout)
-    rows = {name: tensors[name][:, feet].contiguous() for name in FEET_ROWS_ONLY if name in tensors}
+    rows = {name: tensors[name][:, idx].contiguous() for name, idx in subsets.items() if idx.numel()}
     for name, t in rows.items():
         place(name, t, compact)
     upload_bytes = off
-    for name, t in tensors.items():  # device-resident only
-        if name in UNREAD or name in FEET_ROWS_ONLY:
+    for name, t in tensors.items():  # device-resident: copied once with the rest of the buffer at construction
+        if name in UNREAD or name in STATIC or name in subsets:
             place(name, t, layout)
     host = torch.empty(off, dtype=torch.uint8, pin_memory=pin)
     for name, o, nbytes, dtype, shape in layout:
@@ -79,12 +97,13 @@ def pack_host(env, pin: bool = False):
 
 def device_set(env, layout, compact, host, device):
     """A device copy of the packed state set: (device_env whose tensors are views of the flat buffer, flat_device_buffer,
-    [(full tensor, compact feet rows)] to scatter after an upload)."""
+    [(full tensor, row indices, compact rows)] to scatter after an upload)."""
     flat = host.to(device)
     denv = env.to(device)
     views = {name: flat[o:o + nbytes].view(dtype).view(shape) for name, o, nbytes, dtype, shape in layout}
     denv.load_named_tensors(views)
-    scatter = [(views[name], flat[o:o + nbytes].view(dtype).view(shape)) for name, o, nbytes, dtype, shape in compact]
+    subsets = row_subsets(env)
+    scatter = [(views[name], subsets[name].to(device), flat[o:o + nbytes].view(dtype).view(shape)) for name, o, nbytes, dtype, shape in compact]
     return denv, flat, scatter
 
 
@@ -176,10 +195,10 @@ class HotPathEngine:
 
     def upload_state(self, k: int):
         """H2D refresh of device state set k from (pinned) host memory: what an env living on the host would have to do."""
-        n = self.upload_bytes  # the tensors the path reads; of body_pos_w / body_lin_vel_w only the feet rows travel
+        n = self.upload_bytes  # the per-step tensors the path reads; row subsets travel compact (see pack_host)
         self.dev_flat[k][:n].copy_(self.host_flat[k % self.K][:n], non_blocking=True)
-        for full, rows in self.scatter[k]:
-            full.index_copy_(1, self.feet_idx, rows)
+        for full, idx, rows in self.scatter[k]:
+            full.index_copy_(1, idx, rows)
 
     def prefetch_bank(self, bank: int):
         """Enqueues, on the copy stream, the H2D upload of the T state sets of ``bank``; it starts once the rollout that last

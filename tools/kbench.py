@@ -222,6 +222,54 @@ def bench_gather(n_rows: int, count: int, reps: int, obs_dim: int = 270):
     return {"gather_rows (9 tensors)": (time_graph(run, copies, reps), per)}
 
 
+def bench_command(n: int, reps: int):
+    """K13: [IL] CommandTerm.reset (all envs marked) + compute per env step, and the single-block curriculum decision."""
+    from types import SimpleNamespace
+
+    from locotouch_b200.mdp.commands import UniformVelocityCommandGaitLoggingMultiSampling
+    from locotouch_b200.mdp.curriculums import ModifyVelCommandsRangeBasedonReward
+    from locotouch_b200.sim.scene import SceneEntityCfg
+
+    env = synth.make_env(n, seed=0).to("cuda")
+    env.episode_length_buf[:] = 400
+    vla = torch.rand(n, 4, device="cuda")
+    sums = {"track_lin_vel_xy": torch.rand(n, device="cuda") * 20, "track_ang_vel_z": torch.rand(n, device="cuda") * 10}
+    env.reward_manager._episode_sums = sums
+    env.reward_manager.set_term_cfg("track_lin_vel_xy", SimpleNamespace(weight=1.0, params={"sigma": 0.25}))
+    env.reward_manager.set_term_cfg("track_ang_vel_z", SimpleNamespace(weight=0.5, params={"sigma": 0.25}))
+    env.reward_manager.set_term_cfg("gait", SimpleNamespace(func=SimpleNamespace(valid_last_air_time=vla)))
+    cfg = SimpleNamespace(asset_name="robot", resampling_time_range=(8.0, 8.0), heading_command=False, ranges=SimpleNamespace(
+        lin_vel_x=(-0.2, 0.2), lin_vel_y=(-0.1, 0.1), ang_vel_z=(-0.3, 0.3)), new_command_probs=0.15, rel_standing_envs=0.1,
+        final_rel_standing_envs=0.05, initial_zero_command_steps=0, final_initial_zero_command_steps=50, binary_maximal_command=False,
+        sensor_cfg=SceneEntityCfg("robot_contact_senosr", body_names=".*foot"))
+    term = UniformVelocityCommandGaitLoggingMultiSampling(cfg, env)
+    env.command_manager._terms["base_velocity"] = term
+    params = dict(command_name="base_velocity", command_maximum_ranges=[0.5, 0.25, 0.785], curriculum_bins=[20, 20, 20], reset_envs_episode_length=0.98,
+                  reward_name_lin="track_lin_vel_xy", reward_name_ang="track_ang_vel_z", error_threshold_lin=0.08, error_threshold_ang=0.1,
+                  repeat_times_lin=1, repeat_times_ang=1, max_distance_bins=4)
+    cur = ModifyVelCommandsRangeBasedonReward(SimpleNamespace(params=params), env)
+    mask = torch.rand(n, device="cuda") < 0.02
+    term._set_mask(mask)
+    a_reset, a_comp = term._args(1, 0.0, None), term._args(2, 0.02, None)
+    import ctypes as C
+
+    from locotouch_b200 import _C
+
+    def reset(i):
+        _C.check(_C.lib().lt_command_step(C.byref(a_reset), _C.current_stream()))
+
+    def compute(i):
+        _C.check(_C.lib().lt_command_step(C.byref(a_comp), _C.current_stream()))
+
+    def curriculum(i):
+        cur(env, mask)
+
+    per_reset = n * (14 * 4 * 0.02 + 1 + 8 + 12 + 12)  # mask, episode length, command rows (+ the metric rows of the 2 % reset envs)
+    per_comp = n * (12 + 24 + 16 + 16 + 4 + 8 + 12 + 1 + 3 * 4 + 4 + 12 + 11 * 4)
+    return {"command reset (2 % of envs)": (time_graph(reset, 1, reps), per_reset), "command compute (2 launches)": (time_graph(compute, 1, reps), per_comp),
+            "velocity curriculum (1 block)": (time_graph(curriculum, 1, reps), n * (1 + 2 * (1 + 4 + 4)))}
+
+
 def bench_copy(sizes_mb, reps: int):
     """Launch-size calibration: a plain device-to-device copy (cudaMemcpyAsync through torch) that moves the same number of bytes
     (half read, half written) as a kernel's algorithmic traffic, timed the same way.  What fraction of the 4 GB copy peak a launch
@@ -268,6 +316,8 @@ def main():
         res.update(bench_split_pad(n, args.reps))
     if want("gather"):
         res.update(bench_gather(n * 24, n * 24 // 4, max(20, args.reps // 10)))
+    if want("command"):
+        res.update(bench_command(n, args.reps))
     if want("copy"):
         res.update(bench_copy([2.47 * n / 4096, 6.49 * n / 4096, 22.85 * n / 4096, 28.34 * n / 4096, 36.21 * n / 4096], args.reps))
     rows = []
