@@ -94,17 +94,23 @@ __global__ void __launch_bounds__(kThreads) command_step_kernel(const LtCommandA
   if (phase == LT_CMD_RESET) {
     // ---- [IL] CommandTerm.reset: mean of every metric row over the reset envs (sums + count here), rows cleared for them
     const bool rs = live && A.reset_mask[n];
-    for (int m = 0; m < LT_CMD_NUM_METRICS; ++m) {
-      double v = 0.0;
-      if (rs) {
-        v = A.metrics[(size_t)m * N + n];
-        A.metrics[(size_t)m * N + n] = 0.f;
+    // only warps that hold a reset env reduce (a few per cent of the envs reset in a typical step): warp sums, one atomic per
+    // row and warp
+    if (__ballot_sync(LT_FULL_MASK, rs)) {
+      const int lane = tid & 31;
+#pragma unroll 1
+      for (int m = 0; m < LT_CMD_NUM_METRICS; ++m) {
+        double v = 0.0;
+        if (rs) {
+          v = A.metrics[(size_t)m * N + n];
+          A.metrics[(size_t)m * N + n] = 0.f;
+        }
+        v = lt::warp_sum(v);
+        if (lane == 0 && v != 0.0) atomicAdd(&A.reset_extras[m], v);
       }
-      v = lt::block_sum(v, s_red);
-      if (tid == 0 && v != 0.0) atomicAdd(&A.reset_extras[m], v);
+      const double c = lt::warp_sum(rs ? 1.0 : 0.0);
+      if (lane == 0) atomicAdd(&A.reset_extras[LT_CMD_NUM_METRICS], c);
     }
-    double c = lt::block_sum(rs ? 1.0 : 0.0, s_red);
-    if (tid == 0 && c != 0.0) atomicAdd(&A.reset_extras[LT_CMD_NUM_METRICS], c);
     if (!live) return;
     float cmd[3] = {A.vel_command_b[3 * n], A.vel_command_b[3 * n + 1], A.vel_command_b[3 * n + 2]};
     if (rs) {
@@ -257,15 +263,20 @@ __global__ void __launch_bounds__(kCurThreads) vel_curriculum_kernel(const LtVel
     const float* sums = branch ? A.episode_sums_ang : A.episode_sums_lin;
     double len_sum = 0.0, rew_sum = 0.0;
     int all = 1;
-    for (int n = tid; n < N; n += kCurThreads) {
-      if (A.reset_mask[n]) {
+#pragma unroll 4
+    for (int n = tid; n < N; n += kCurThreads) {  // every load is unconditional and independent: one memory round trip per batch
+      const bool rs = A.reset_mask[n] != 0;
+      const bool was = reseted[n] != 0;
+      const float len_old = len_buf[n], sum_old = sum_buf[n];
+      const float len_new = (float)A.episode_length_buf[n], sum_new = sums[n];
+      if (rs) {
         reseted[n] = 1;
-        len_buf[n] = (float)A.episode_length_buf[n];
-        sum_buf[n] = sums[n];
+        len_buf[n] = len_new;
+        sum_buf[n] = sum_new;
       }
-      all &= reseted[n] ? 1 : 0;
-      len_sum += len_buf[n];
-      rew_sum += sum_buf[n];
+      all &= (rs || was) ? 1 : 0;
+      len_sum += rs ? len_new : len_old;
+      rew_sum += rs ? sum_new : sum_old;
     }
     all = __syncthreads_and(all);
     len_sum = lt::block_sum(len_sum, s_red);
