@@ -189,8 +189,9 @@ def run_reference(args, rank: int):
 # ------------------------------------------------------------------------------------------------------ kernel roofline
 def ncu_traffic_bytes(kernel_substr: str):
     """DRAM bytes per launch (read + write) of the committed `ncu --set full` capture, or None."""
-    path = os.path.join(ROOT, "profiles", "r1_k1_k2_ncu_full_summary.json")
-    if not os.path.exists(path):
+    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
+                 if os.path.exists(q)), None)  # newest capture first
+    if path is None:
         return None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     vals = []
@@ -383,7 +384,7 @@ def main():
                          "alg_bytes_per_launch": nbytes})
         top = max(rows, key=lambda r: r["us_per_launch"])
         line["roofline"] = {"bound": "hbm", "achieved": top["achieved"], "peak": hbm, "unit": "GB/s", "frac": top["frac"], "traffic": ncu_traffic_bytes("mdp_step_kernel"),
-                            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1_k1_k2_ncu_full_summary.json (one ncu --set full capture; "
+                            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1*_k1_k2_ncu_full_summary.json (one ncu --set full capture; "
                                             "the kernel's 12.6 MB of writes are still in L2 when it ends, ncu counts 0 written)",
                             "kernel": top["kernel"], "us_per_launch": top["us_per_launch"], "peak_kind": kind,
                             "how": "96 launches in one CUDA graph cycling 6 state sets (> L2), CUDA events on the launch stream"}

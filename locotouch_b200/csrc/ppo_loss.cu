@@ -203,10 +203,21 @@ __global__ void __launch_bounds__(kThreads) ppo_loss_kernel(const Params p) {
   const int groups = (kFoldGroups * K <= (kThreads / 32) * (3 + kMaxA)) ? kFoldGroups : (kThreads / 32) * (3 + kMaxA) / K;
   for (int idx = threadIdx.x; idx < groups * K; idx += kThreads) {
     const int g = idx / K, k = idx - g * K;
-    float v = 0.f;
-#pragma unroll 8
-    for (int i = g; i < (int)gridDim.x; i += groups) v += __ldcg(p.ws->partial + (size_t)i * K + k);
-    s_fold[idx] = v;
+    // eight loads per trip with no bounds test between them (a test per load makes every load wait for the previous add);
+    // fixed association order, so the result does not depend on timing
+    const float* col = p.ws->partial + k;
+    const int G = (int)gridDim.x;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int i = g;
+    for (; i + 7 * groups < G; i += 8 * groups) {
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = __ldcg(col + (size_t)(i + u * groups) * K);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += x[u];
+    }
+    for (; i < G; i += groups) a[0] += __ldcg(col + (size_t)i * K);
+    s_fold[idx] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += kThreads) {

@@ -1,6 +1,7 @@
 """One launch of each streaming kernel at BASELINE size (for one `ncu --set full` capture: DRAM bytes per launch).
 
-    ncu --set full --clock-control none -k regex:"mdp_step_kernel|taxel_kernel" -c 6 -o out python tools/prof_traffic.py
+    ncu --set full --clock-control none --import-source on -k regex:"mdp_step_kernel|taxel_kernel|ppo_loss_kernel" -c 9 -o out \
+        python tools/prof_traffic.py        # then tools/ncu_summary.py
 """
 import os
 import sys
@@ -27,5 +28,12 @@ f = (torch.randn(n, 221, 3, generator=g) * 0.1).cuda()
 thr = (0.05 + (torch.rand(n, 221, generator=g) - 0.5) * 0.02).cuda()
 for i in range(3):
     ops.taxel_synth(q, f, thr, quat_body_offset=17, seed=1, offset=i)
+b, A = n * 24 // 4, 12  # launches 6-8: the fused PPO loss on one mini-batch
+rn = lambda *s: torch.randn(*s, device="cuda")  # noqa: E731
+args = dict(mu=rn(b, A), sigma=0.5 + torch.rand(A, device="cuda"), value=rn(b), actions=rn(b, A), old_logp=rn(b), old_mu=rn(b, A),
+            old_sigma=0.5 + torch.rand(b, A, device="cuda"), advantages=rn(b), returns=rn(b), old_values=rn(b))
+lr = torch.tensor([1e-3], device="cuda")
+for _ in range(3):
+    ops.ppo_loss(**args, entropy_coef=0.01, desired_kl=0.01, lr=lr)
 torch.cuda.synchronize()
 print("ok")
