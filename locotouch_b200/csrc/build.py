@@ -83,12 +83,13 @@ def _build(force: bool, verbose: bool, variant: str | None) -> str:
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in sources():
-        knobbed = variant and os.path.basename(src) == "mdp_step.cu"  # the only file the LT_MDP_* knobs touch
+        knob_files = os.environ.get("LT_VARIANT_FILES", "mdp_step.cu").split(",")  # files the LT_MDP_* / LT_TAXEL_* knobs touch
+        knobbed = variant and os.path.basename(src) in knob_files
         obj = os.path.join(build_dir, os.path.basename(src)[:-3] + (f".{variant}.o" if knobbed else ".o"))
         objs.append(obj)
         if (not force or (variant and not knobbed)) and os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))):
             continue
-        extra = [f"-D{k}={v}" for k, v in os.environ.items() if k.startswith("LT_MDP_")] if (knobbed or not variant) else []  # tuning knobs
+        extra = [f"-D{k}={v}" for k, v in os.environ.items() if k.startswith(("LT_MDP_", "LT_TAXEL_"))] if (knobbed or not variant) else []  # tuning knobs
         if os.path.basename(src) == "gemm_fused.cu":
             dirs = cutlass_include_dirs()
             extra += ["--expt-extended-lambda", "-DLT_HAVE_CUTLASS=1"] + [x for d in dirs for x in ("-I", d)] if dirs else ["-DLT_HAVE_CUTLASS=0"]

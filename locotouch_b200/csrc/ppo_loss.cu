@@ -34,6 +34,9 @@ struct Params {
   PpoWs* ws;
 };
 
+// kChunks = float4 chunks per lane (A <= 16 * kChunks): the row registers are sized for the actual action dimension -- with the
+// arrays dimensioned for A = 64 the kernel needed 120 registers and two blocks per SM, i.e. two waves for 384 blocks.
+template <int kChunks>
 __global__ void __launch_bounds__(kThreads) ppo_loss_kernel(const Params p) {
   __shared__ float s_sigma[kMaxA], s_inv_var[kMaxA], s_log_sigma[kMaxA];
   __shared__ float s_red[kThreads / 32][3 + kMaxA];
@@ -51,20 +54,20 @@ __global__ void __launch_bounds__(kThreads) ppo_loss_kernel(const Params p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 3;
   const float inv_b = 1.0f / (float)p.B;
   float acc_surr = 0.f, acc_vloss = 0.f, acc_kl = 0.f;
-  float acc_dsig[kMaxChunks][4];
+  float acc_dsig[kChunks][4];
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) acc_dsig[c][0] = acc_dsig[c][1] = acc_dsig[c][2] = acc_dsig[c][3] = 0.f;
+  for (int c = 0; c < kChunks; ++c) acc_dsig[c][0] = acc_dsig[c][1] = acc_dsig[c][2] = acc_dsig[c][3] = 0.f;
 
   const int groups_per_block = kThreads / 4;
   // block-uniform trip count: every lane of a warp takes part in the lane-group shuffles below
   for (int base = blockIdx.x * groups_per_block; base < p.B; base += gridDim.x * groups_per_block) {
     const int b = base + (threadIdx.x >> 2);
     const bool valid = b < p.B;
-    // ---- load: up to kMaxChunks float4 of each [A] row + 5 scalars (same address in the 4 lanes: one transaction)
-    float4 mu[kMaxChunks], ac[kMaxChunks], omu[kMaxChunks], osg[kMaxChunks];
+    // ---- load: up to kChunks float4 of each [A] row + 5 scalars (same address in the 4 lanes: one transaction)
+    float4 mu[kChunks], ac[kChunks], omu[kChunks], osg[kChunks];
     const size_t row = (size_t)b * A;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < kChunks; ++c) {
       const int ch = sub + 4 * c;
       mu[c] = ac[c] = omu[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       osg[c] = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(kThreads) ppo_loss_kernel(const Params p) {
     // ---- per-sample log-prob and KL (partial over this lane's elements)
     float logp = 0.f, kl = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < kChunks; ++c) {
       const int ch = sub + 4 * c;
       if (ch < chunks) {
         const float m[4] = {mu[c].x, mu[c].y, mu[c].z, mu[c].w}, a[4] = {ac[c].x, ac[c].y, ac[c].z, ac[c].w};
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) ppo_loss_kernel(const Params p) {
 
     // ---- gradients w.r.t. mu (stored) and sigma (accumulated)
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < kChunks; ++c) {
       const int ch = sub + 4 * c;
       if (valid && ch < chunks) {
         const float m[4] = {mu[c].x, mu[c].y, mu[c].z, mu[c].w}, a[4] = {ac[c].x, ac[c].y, ac[c].z, ac[c].w};
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kThreads) ppo_loss_kernel(const Params p) {
   acc_vloss = lt::warp_sum(acc_vloss);
   acc_kl = lt::warp_sum(acc_kl);
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c)
+  for (int c = 0; c < kChunks; ++c)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float v = acc_dsig[c][e];
@@ -304,7 +307,14 @@ extern "C" int lt_ppo_loss(const LtPpoLossArgs* a, void* stream) {
   p.desired_kl = a->desired_kl; p.grad_scale = a->grad_scale;
   p.grad_mu = a->grad_mu; p.grad_value = a->grad_value; p.grad_sigma = a->grad_sigma; p.out = a->out;
   p.lr_inout = a->lr_inout; p.loss_accum = a->loss_accum; p.ws = (PpoWs*)a->workspace;
-  ppo_loss_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(p);
+  const int per_lane = (a->A / 4 + 3) / 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (per_lane) {
+    case 1: ppo_loss_kernel<1><<<grid, kThreads, 0, st>>>(p); break;
+    case 2: ppo_loss_kernel<2><<<grid, kThreads, 0, st>>>(p); break;
+    case 3: ppo_loss_kernel<3><<<grid, kThreads, 0, st>>>(p); break;
+    default: ppo_loss_kernel<4><<<grid, kThreads, 0, st>>>(p); break;
+  }
   return lt::check_launch();
 }
 
