@@ -239,6 +239,33 @@ class ActorCritic(nn.Module):
         else:
             torch.mm(g.t(), x, out=out)
 
+    def _infer(self, net, x, tag: str):
+        """Inference forward of one MLP (rollout ``act`` / ``evaluate``): K12 per hidden layer -- one tcgen05 GEMM with bias + ELU in
+        its epilogue instead of a cuBLAS GEMM and an ELU launch -- into persistent hidden buffers (graph-capture safe; actor and
+        critic, which run on parallel streams, own separate buffers).  Falls back to the torch modules whenever autograd is
+        recording, TF32 is off (fp32 parity mode), the stack is not Linear/ELU or a layer shape is not supported."""
+        if (torch.is_grad_enabled() or not torch.backends.cuda.matmul.allow_tf32 or not x.is_cuda or x.dtype != torch.float32
+                or x.dim() != 2 or not self._elu_stack(net)):
+            return net(x)
+        linears = [m for m in net if isinstance(m, nn.Linear)]
+        key = (tag, x.shape[0], str(x.device))
+        cache = self.__dict__.setdefault("_infer_bufs", {})
+        if key not in cache:
+            cache[key] = [torch.empty(x.shape[0], lin.out_features, device=x.device) for lin in linears[:-1]]
+        hs = cache[key]
+        h = x.contiguous()
+        for i, lin in enumerate(linears):
+            hidden = i < len(linears) - 1
+            out = None
+            if hidden and lin.out_features >= 64:
+                out = ops.linear_bias_act(h, lin.weight, lin.bias, out=hs[i], elu=True)
+            if out is None:
+                out = torch.addmm(lin.bias, h, lin.weight.t(), out=hs[i] if hidden else None)
+                if hidden:
+                    F.elu_(out)
+            h = out
+        return h
+
     # ---------------------------------------------------------------------------------------------- reference interface
     @staticmethod
     def init_weights(sequential, scales):
@@ -274,7 +301,7 @@ class ActorCritic(nn.Module):
 
     def act(self, observations, out=None, **kwargs):
         """Samples actions.  ``out`` = dict(actions, logp, mu, sigma) of pre-allocated rows (e.g. a RolloutStorage slot)."""
-        mean = self.actor(observations)
+        mean = self._infer(self.actor, observations, "actor")
         std = self._std_vector()
         if mean.requires_grad:  # training-time call (PPO.update in the reference): distribution only
             self.distribution = _GaussianView(mean, std.expand_as(mean))
@@ -303,10 +330,10 @@ class ActorCritic(nn.Module):
         return self.distribution.log_prob(actions).sum(dim=-1)
 
     def act_inference(self, observations):
-        return self.actor(observations)
+        return self._infer(self.actor, observations, "actor")
 
     def evaluate(self, critic_observations, **kwargs):
-        return self.critic(critic_observations)
+        return self._infer(self.critic, critic_observations, "critic")
 
     def reset_init_std(self):
         if self.noise_std_type == "scalar":

@@ -56,3 +56,31 @@ def test_fused_dgrad_elu_backward_matches_torch(cuda, lt_lib, M, Nout, Kin):
     ref = (go.double() @ w.double()) * torch.where(h > 0, torch.ones_like(h), h + 1.0).double()
     err = (out.double() - ref).abs().max().item()
     assert err < 6e-3, f"max abs error {err}"
+
+
+def test_inference_forward_uses_fused_layers_and_matches_the_modules(cuda, lt_lib):
+    """ActorCritic.act_inference / evaluate in TF32 mode (rollout path): K12 per hidden layer, same numbers as the torch modules
+    at TF32 tolerance; with autograd recording or TF32 off the torch modules run (bit-identical to calling them)."""
+    from locotouch_b200 import _C
+    from locotouch_b200.loco_rl import ActorCritic
+
+    torch.manual_seed(0)
+    ac = ActorCritic(348, 348, 12, [512, 256, 128], [512, 256, 128], "elu", 1.0).to(cuda)
+    obs = torch.randn(4096, 348, device=cuda)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        with torch.no_grad():
+            n0 = _C.launch_count
+            mu, v = ac.act_inference(obs), ac.evaluate(obs)
+            assert _C.launch_count - n0 == 6, "three fused hidden layers per network"
+            H.assert_close(mu, ac.actor(obs), "actor: fused inference vs modules (TF32)", rtol=5e-3, atol=5e-3)
+            H.assert_close(v, ac.critic(obs), "critic: fused inference vs modules (TF32)", rtol=5e-3, atol=5e-3)
+        n0 = _C.launch_count
+        assert ac.act_inference(obs).requires_grad and _C.launch_count == n0  # autograd recording: torch modules
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.no_grad():
+            H.assert_equal(ac.act_inference(obs), ac.actor(obs), "fp32 mode: the modules themselves")
+            assert _C.launch_count == n0
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
