@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
       for (int i = tid; i < L.tables_len; i += kThreads) s_map[i] = A.tables[i];
     }
   }
+  PROF_STAMP(16);
   // gathers with arbitrary body ids / non-float types: ONE pass, every thread issues a few independent copies
   if (do_rew) {
     if (tid >= 384 && tid < 384 + nvalid * 4) {  // feet rows of the contact timers
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
     else if (A.any_flag_ws) any_nz = A.any_flag_ws[st & 1] == st;
     s_any_nz = any_nz;
   }
+  PROF_STAMP(17);
   __pipeline_commit();
   if (do_obs && !bulk_hist) {  // observation history blocks, per-element path
     const int total = nvalid * D;
@@ -400,6 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
     s_fill[i] = (i < nvalid && do_obs && A.obs_fill) ? A.obs_fill[e0 + i] : 0;
     s_done[i] = 0;
   }
+  PROF_STAMP(18);
   if (!A.tables) {
     // Observation layout tables built in the kernel (callers that do not pass lt_mdp_build_tables() output):
     //   s_map[k]  for column k of the flattened [term][history][dim] row: low 16 bits = index j of the per-step value that
@@ -487,6 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
       s_of[12 * kEnvs + e] = qr.w; s_of[13 * kEnvs + e] = qr.x; s_of[14 * kEnvs + e] = qr.y; s_of[15 * kEnvs + e] = qr.z;
     }
   }
+  PROF_STAMP(21);
   if (do_rew || has_obj) __syncthreads();
 
   // ------------------------------------------------------------------------------------------------ stage 1: tasks
@@ -1001,6 +1005,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
         A.episode_sums[(size_t)t * A.N + nn] = rst ? 0.f : total;
       }
     }
+    PROF_STAMP(19);
     if (warp == a_warps - 1 && live) {  // reward_buf: sequential fp32 sum in term order
       // Branch-free body: kind / weight / raw value are loaded unconditionally (a skipped term reads a stale slot and is
       // replaced by 0 with a select), so the loads of a whole unrolled group are in flight together and only the additions,
@@ -1029,6 +1034,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
       A.reward[n] = reward;
       if (A.auto_reset && s_done[e] && A.episode_log_sums) atomicAdd(A.episode_log_sums + T, 1.0f);
     }
+    PROF_STAMP(20);
     // gait state write back; zeroed when the env is being reset (the manager's reset(env_ids) follows, rewards.py:107-114)
     {
       const LtGaitState& G = A.gait_state;

@@ -70,8 +70,8 @@ for rep in range(3):
 assert fn(0) == 0
 mhz = 1965.0
 mean = acc / cnt / mhz
-names = {0: "entry", 1: "issued", 2: "landed", 3: "sync1", 8: "round0", 10: "round1", 13: "pass0_end", 12: "pass1", 4: "tasks_done", 5: "hist_landed", 6: "sync2", 7: "2a_done", 15: "end"}
-order = [0, 1, 2, 3, 8, 10, 13, 12, 4, 5, 6, 7, 15]
+names = {16: "bulk_iss", 17: "gathers", 18: "nonfloat", 21: "pre_done", 19: "2a_loop", 20: "2a_sum", 0: "entry", 1: "issued", 2: "landed", 3: "sync1", 8: "round0", 10: "round1", 13: "pass0_end", 12: "pass1", 4: "tasks_done", 5: "hist_landed", 6: "sync2", 7: "2a_done", 15: "end"}
+order = [0, 16, 17, 18, 1, 2, 3, 21, 8, 10, 4, 5, 6, 19, 20, 7, 15]
 print(f"task={task} envs={n} phases={phases}; microseconds since block start (mean over {blocks} blocks, {cnt} launches)")
 print("warp " + " ".join(f"{names[s]:>11s}" for s in order))
 for w in range(WARPS):
