@@ -363,7 +363,8 @@ def main():
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core GEMMs, as the reference)",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "steps_per_env": T_STEPS, "parallelism": f"env-sharded dp{world}, NCCL all-reduce of flat PPO gradients" if world > 1 else "single GPU",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "steps_per_env": T_STEPS, "parallelism": (f"env-sharded dp{world}, " + ("gradients summed by peer loads over NVLink inside the optimizer kernel (K14)" if engine.peer_gradients
+                                                                   else "NCCL all-reduce of flat PPO gradients")) if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (48 state sets ~2.7 GB + 290 MB rollout storage per rank)", "timing": "CUDA events on the launch stream around K graph replays, max over ranks"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "how": "HotPathEngine.replay(upload=True): the drop-in classes' calls replayed from CUDA graphs; the T state sets of iteration i+1 are "

@@ -454,6 +454,24 @@ int lt_dgrad_act_bwd(const float* grad_out, const float* w, const float* act_in,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * K14  gradient all-reduce folded into the optimizer step (env-sharded data parallelism)
+ * replaces  the NCCL all-reduce of the flat PPO gradient + nn.utils.clip_grad_norm_ + Adam.step per mini-batch
+ *           (loco_rl/loco_rl/algorithms/ppo.py:350-353 run under one process per GPU)
+ * peer_grads[r] = device-visible address of rank r's flat gradient buffer [n + tail] (NVLink peer mapping / symmetric memory;
+ * entry `rank` is the caller's own buffer).  The caller separates the ranks' writes from these reads with a cross-GPU barrier
+ * (and the reads from the next writes with another).  grad_sum [n + tail] (local) receives sum_r peer_grads[r] added in rank
+ * order -- bit-identical on every rank --; the norm, clip and Adam update then run on grad_sum * grad_scale exactly as in
+ * lt_clip_adam (same workspace).  `tail` extra floats behind the gradients are summed but not part of the norm; with
+ * desired_kl > 0 the first of them is the per-rank KL mean and *lr is adapted from sum * kl_scale (ppo.py:275-281) before the step.
+ * n must be a multiple of 4; world <= LT_MAX_PEERS.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define LT_MAX_PEERS 16
+int lt_peer_sum_clip_adam(float* params, const float* const* peer_grads, int world, float* grad_sum, int tail, float* exp_avg,
+                          float* exp_avg_sq, int64_t n, float* lr, float* step_inout, float max_grad_norm, double beta1,
+                          double beta2, float eps, float weight_decay, float grad_scale, float desired_kl, float kl_scale,
+                          float* grad_norm_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * K13  velocity command term + reward-driven velocity curriculum, device resident
  * replaces  locotouch/mdp/commands.py:379-576  UniformVelocityCommandGaitLoggingMultiSampling (reset / compute / set_ranges,
  *           over IsaacLab's CommandTerm + UniformVelocityCommand) and

@@ -159,6 +159,9 @@ class HotPathEngine:
         cfg.update(ppo_cfg or {})
         self.alg = PPO(ac, device=str(self.device), **cfg)
         self.alg.init_storage(num_envs, num_steps, [D], [D], [synth.NUM_JOINTS])
+        # several ranks on one NVLink domain: gradients are exchanged by peer loads inside the optimizer kernel (K14) when the
+        # symmetric-memory mapping can be set up; otherwise the NCCL all-reduce stays
+        self.peer_gradients = self.alg.enable_peer_gradients() if self.world > 1 else False
         ac.seed = seed * 7919 + self.rank
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int64)  # device-resident env-step index
         # ---- fused MDP: one instance, re-bound to the state set of each step
@@ -362,8 +365,9 @@ class HotPathEngine:
             for _epoch in range(alg.num_learning_epochs):
                 for i in range(alg.num_mini_batches):
                     g["mb"][i].replay()
-                    alg.allreduce_grads()
+                    alg.allreduce_grads()  # NCCL all-reduce, or (K14) the barrier in front of the peer reads of the tail graph
                     g["tail"].replay()
+                    alg.after_step_barrier()
             self.finish_iteration()
         alg.storage.clear()
 

@@ -43,6 +43,16 @@ class _FusedAdam:
         self.param_groups = [dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, params=list(range(len(list(actor_critic.parameters())))))]
         self._host_lr = lr
 
+    def use_gradient_buffer(self, buf: torch.Tensor):
+        self.grads = self.ac.rebind_gradients(buf)
+
+    def step_peer_sum(self, peer_ptrs, grad_sum, tail: int, max_grad_norm=None, grad_scale: float = 1.0, desired_kl=None, kl_scale=1.0):
+        """K14: sum of the ranks' gradient buffers (peer loads, rank order) + learning-rate decision + clip + Adam."""
+        g = self.param_groups[0]
+        ops.peer_sum_clip_adam(self.flat, peer_ptrs, grad_sum, tail, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t,
+                               max_grad_norm=max_grad_norm, betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"],
+                               grad_scale=grad_scale, desired_kl=desired_kl, kl_scale=kl_scale, grad_norm_out=self.grad_norm)
+
     def sync_lr_to_device(self):
         lr = self.param_groups[0]["lr"]
         if lr != self._host_lr:  # someone (runner, user) wrote param_groups[...]["lr"]
@@ -252,25 +262,75 @@ class PPO:
         if adaptive and world > 1:  # the local KL mean travels in the tail of the gradient all-reduce
             ac.flat_grads_ext[-4:-3].copy_(bufs.out[4:5])
 
+    # ---------------------------------------------------------------------------------- K14: peer-memory gradient exchange
+    def enable_peer_gradients(self, group=None) -> bool:
+        """Puts the flat gradient buffer into NVLink-mapped symmetric memory (``torch.distributed._symmetric_memory``) so that
+        every rank can read every other rank's gradients directly: the per-mini-batch NCCL all-reduce becomes a cross-GPU barrier
+        + ONE kernel that sums the W buffers in rank order while it computes the clip norm (K14).  Returns False (and leaves the
+        NCCL path in place) when there is one process, when symmetric memory cannot be set up, or when LT_PEER_GRADS=0.
+        Call before capturing CUDA graphs."""
+        import os
+
+        self._peer = None
+        _, world = D.world_info()
+        mode = os.environ.get("LT_PEER_GRADS", "auto")
+        if world == 1 or mode == "0" or (mode == "auto" and world > 4):
+            return False  # one-shot exchange reads W buffers per rank: beyond 4 ranks the NCCL ring / NVLS path is not slower
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            ac = self.actor_critic
+            ac.flatten_parameters()
+            group = group if group is not None else dist.group.WORLD
+            buf = symm.empty(ac.flat_grads_ext.numel(), dtype=torch.float32, device=ac.flat_grads_ext.device)
+            hdl = symm.rendezvous(buf, group)
+            self.optimizer.use_gradient_buffer(buf)
+            self._peer = dict(handle=hdl, ptrs=[int(x) for x in hdl.buffer_ptrs], sum=torch.zeros_like(buf), buf=buf)
+        except Exception as exc:  # noqa: BLE001 -- any failure leaves the NCCL path untouched
+            self._peer = None
+            self._peer_error = repr(exc)
+            return False
+        return True
+
+    @property
+    def peer_gradients(self) -> bool:
+        return getattr(self, "_peer", None) is not None
+
     def reduce_and_step(self):
         """[NCCL: ONE all-reduce of the flat gradients with the KL statistic in its tail] then the learning-rate decision and
         the fused clip + Adam (K7)."""
         self.allreduce_grads()
         self.step_after_reduce()
+        self.after_step_barrier()
 
     def allreduce_grads(self):
         """The only collective of a mini-batch step (kept outside CUDA-graph capture)."""
         _, world = D.world_info()
-        if world > 1:
+        if self.peer_gradients:
+            self._peer["handle"].barrier(channel=0)  # every rank's backward has written its gradient buffer
+        elif world > 1:
             D.average_gradients_(self.actor_critic.flat_grads_ext)
 
     def step_after_reduce(self):
         """Learning-rate decision from the reduced KL statistic + clip + Adam; collective-free, capturable."""
         opt = self.optimizer
         _, world = D.world_info()
-        if world > 1 and self.desired_kl is not None and self.schedule == "adaptive":  # every rank takes the same decision (SURVEY.md 8e)
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        if self.peer_gradients:
+            pr = self._peer
+            # the summed KL statistic sits behind the summed gradients: the first kernel takes the learning-rate decision
+            # (every rank the same one), the second applies it
+            opt.step_peer_sum(pr["ptrs"], pr["sum"], 4, max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world,
+                              desired_kl=self.desired_kl if adaptive else None, kl_scale=1.0 / world)
+            return
+        if world > 1 and adaptive:  # every rank takes the same decision (SURVEY.md 8e)
             ops.adaptive_lr(self.actor_critic.flat_grads_ext[-4:-3], 1.0 / world, self.desired_kl, opt.lr_t)
         opt.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world)
+
+    def after_step_barrier(self):
+        """K14: nobody may overwrite its gradient buffer (next backward) before every rank has read it."""
+        if self.peer_gradients:
+            self._peer["handle"].barrier(channel=1)
 
     def update_epilogue(self):
         """The only device->host read of an update: the three logged means (reference ppo.py:361-363 reads them with

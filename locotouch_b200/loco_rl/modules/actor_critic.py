@@ -106,6 +106,22 @@ class ActorCritic(nn.Module):
         self.flat_params, self.flat_grads = flat, grads
         return flat, grads
 
+    def rebind_gradients(self, buf: torch.Tensor):
+        """Moves the flat gradient storage (and every ``p.grad`` view) into ``buf`` [total + 4] -- e.g. a buffer in NVLink-mapped
+        symmetric memory that the other ranks read directly (K14).  Call before capturing CUDA graphs."""
+        self.flatten_parameters()
+        if buf.numel() != self.flat_grads_ext.numel() or buf.dtype != torch.float32 or buf.device != self.flat_grads_ext.device:
+            raise ValueError("gradient buffer must be float32 [total + 4] on the parameters' device")
+        buf.copy_(self.flat_grads_ext)
+        self.flat_grads_ext = buf
+        total = self.flat_params.numel()
+        grads = buf[:total]
+        for name, p in self.named_parameters():
+            off, n = self._slices[name]
+            p.grad = grads[off:off + n].view(p.shape)
+        self.flat_grads = grads
+        return grads
+
     def _apply(self, fn, *a, **k):  # .to(device) invalidates the views
         out = super()._apply(fn, *a, **k)
         self.flat_params = None

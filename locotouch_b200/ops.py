@@ -200,6 +200,25 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0
     count_launches(2)
 
 
+def peer_sum_clip_adam(params, peer_ptrs, grad_sum, tail, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0, betas=(0.9, 0.999), eps=1e-8,
+                       weight_decay=0.0, grad_scale=1.0, desired_kl=None, kl_scale=1.0, grad_norm_out=None):
+    """K14: grad_sum = sum over ranks of the flat gradient buffers at ``peer_ptrs`` (raw device-visible addresses, rank order), then
+    (``desired_kl``: adaptive learning-rate decision from the summed KL statistic in the tail) clip_grad_norm_ + Adam on
+    grad_sum * grad_scale.  The caller has put a cross-GPU barrier between the ranks' gradient writes and
+    this call."""
+    n = params.numel()
+    nbytes = lib().lt_clip_adam_workspace_bytes(n)
+    ws = _workspace("adam", nbytes, params.device)
+    arr = (C.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
+    check(lib().lt_peer_sum_clip_adam(ptr(params, torch.float32, "params"), arr, len(peer_ptrs), ptr(grad_sum, torch.float32, "grad_sum"), int(tail),
+                                      ptr(exp_avg, torch.float32), ptr(exp_avg_sq, torch.float32), n, ptr(lr, torch.float32, "lr"),
+                                      ptr(step, torch.float32, "step"), float(max_grad_norm if max_grad_norm is not None else 0.0), betas[0], betas[1],
+                                      eps, weight_decay, grad_scale, float(desired_kl) if desired_kl else 0.0, float(kl_scale),
+                                      ptr(grad_norm_out, torch.float32), ptr(ws), nbytes, current_stream()),
+          "lt_peer_sum_clip_adam")
+    count_launches(2)
+
+
 # ------------------------------------------------------------------------------------------------- K9 MLP backward helper
 def bias_act_bwd(grad_out, act_out, bias_grad, grad_pre=None, alpha: float = 1.0):
     """grad_pre = grad_out * elu'(act_out) (in place when ``grad_pre`` is None) and bias_grad = grad_pre.sum(0), one pass."""

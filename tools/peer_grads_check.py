@@ -1,0 +1,84 @@
+"""K14 check on N GPUs of one node: gradients summed by peer loads inside the optimizer kernel == NCCL all-reduce + clip + Adam.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 tools/peer_grads_check.py
+
+Every rank builds two identical PPO learners, fills both gradient buffers with the same rank-dependent values (and a rank-dependent
+KL statistic in the tail), then runs learner A through NCCL (`allreduce_grads` + `step_after_reduce`) and learner B through K14
+(barrier + `lt_peer_sum_clip_adam` + barrier) for a few steps.  Checks: parameters, Adam state and learning rate agree between A and
+B (bit-exact for 2 ranks: a + b is commutative; 1e-6 beyond, where NCCL's association order differs), and B's parameters are
+bit-identical on every rank.  Prints the per-step device time of both exchanges."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from locotouch_b200.loco_rl import PPO, ActorCritic  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+
+
+def learner():
+    torch.manual_seed(0)
+    ac = ActorCritic(348, 348, 12, [512, 256, 128], [512, 256, 128], "elu", 1.0)
+    return PPO(ac, device=str(dev), num_learning_epochs=1, num_mini_batches=1, desired_kl=0.01, schedule="adaptive", learning_rate=1e-3, max_grad_norm=1.0)
+
+
+os.environ["LT_PEER_GRADS"] = "0"
+a = learner()
+assert not a.enable_peer_gradients()
+os.environ["LT_PEER_GRADS"] = "1"
+b = learner()
+ok = b.enable_peer_gradients()
+if not ok:
+    print(f"[rank {rank}] symmetric memory unavailable: {getattr(b, '_peer_error', '?')}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(3)
+n = a.actor_critic.flat_grads_ext.numel()
+for step in range(4):
+    g = torch.Generator(device="cpu").manual_seed(100 * step + rank)
+    vals = (torch.randn(n, generator=g) * (0.05 if step else 5.0)).to(dev)  # step 0: the clip is active
+    vals[-4] = 0.03 if step < 2 else 0.001  # KL statistic: first "too large" (lr / 1.5), then "too small" (lr * 1.5)
+    vals[-3:] = 0
+    for alg in (a, b):
+        alg.actor_critic.flat_grads_ext.copy_(vals)
+        alg.reduce_and_step()
+    torch.cuda.synchronize()
+    pa, pb = a.optimizer.flat, b.optimizer.flat
+    tol = 0.0 if world == 2 else 1e-6
+    for name, x, y in (("params", pa, pb), ("exp_avg", a.optimizer.exp_avg, b.optimizer.exp_avg), ("exp_avg_sq", a.optimizer.exp_avg_sq, b.optimizer.exp_avg_sq),
+                       ("lr", a.optimizer.lr_t, b.optimizer.lr_t), ("grad_norm", a.optimizer.grad_norm, b.optimizer.grad_norm)):
+        err = (x - y).abs().max().item()
+        assert err <= tol * max(1.0, y.abs().max().item()), f"step {step} {name}: NCCL vs peer-sum differ by {err}"
+    lo, hi = pb.clone(), pb.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "replicas diverged"
+    if rank == 0:
+        print(f"step {step}: lr {float(b.optimizer.lr_t):.6g} grad_norm {float(b.optimizer.grad_norm):.6g} -- NCCL and peer-sum agree, replicas identical", flush=True)
+
+
+def timed(alg, reps=50):
+    for _ in range(5):
+        alg.reduce_and_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        alg.reduce_and_step()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
+ta, tb = timed(a), timed(b)
+if rank == 0:
+    print(f"world={world}: NCCL all-reduce + clip + Adam {ta:.1f} us per step; barrier + peer-sum + clip + Adam + barrier {tb:.1f} us per step", flush=True)
+dist.barrier()
+dist.destroy_process_group()
