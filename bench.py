@@ -283,7 +283,19 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="nccl", device_id=device)
+        # NCCL prints its version banner on stdout when the communicator comes up: send it to stderr so that the JSON line is the
+        # only thing rank 0 writes to stdout
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend="nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from locotouch_b200 import _C
     from locotouch_b200.engine import HotPathEngine
 

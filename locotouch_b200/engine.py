@@ -17,6 +17,8 @@ PhysX stepping replaced by pre-generated synthetic state sets (BASELINE.json nor
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -290,6 +292,10 @@ class HotPathEngine:
         Several processes (``split``): NCCL collectives stay OUTSIDE the graphs -- graphs are the T env steps, the gather,
         and one forward/loss/backward graph per mini-batch slice; GAE, the all-reduces and clip+Adam run eagerly between."""
         alg = self.alg
+        # With the peer-memory gradient exchange (K14) the update holds no NCCL call -- cross-GPU barrier and peer-sum kernel are
+        # plain launches -- so several processes capture it as ONE graph like a single process does; only the advantage-statistics
+        # all-reduce of the rollout's tail stays eager.
+        whole_update = self.world > 1 and self.peer_gradients and split is None and os.environ.get("LT_PEER_GRAPH", "1") != "0"
         split = (self.world > 1) if split is None else split
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
@@ -310,12 +316,12 @@ class HotPathEngine:
                 if not split:
                     self.rollout_finish()
             g_roll.append(g)
-        if not split:
+        if not split or whole_update:
             g_upd = torch.cuda.CUDAGraph()
             with graph_capture(g_upd):
                 alg.update_body(self.perm)
                 self.finish_iteration()
-            self._graphs = dict(split=False, roll=g_roll, update=g_upd)
+            self._graphs = dict(split=False, roll=g_roll, update=g_upd, finish_eager=split)
         else:
             g_begin = torch.cuda.CUDAGraph()
             with graph_capture(g_begin):
@@ -356,6 +362,8 @@ class HotPathEngine:
             ev.record()
             self._rollout_done[bank] = ev
         if not g["split"]:
+            if g.get("finish_eager"):
+                self.rollout_finish()
             self.draw_permutation()
             g["update"].replay()
         else:
