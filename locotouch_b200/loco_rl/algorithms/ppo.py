@@ -27,6 +27,9 @@ from ..modules import ActorCritic
 from ..storage import RolloutStorage
 
 
+_C_MAX_PEERS = 16  # LT_MAX_PEERS of the C ABI
+
+
 class _FusedAdam:
     """``optimizer``-shaped facade over the fused clip + Adam kernel: keeps ``param_groups[0]['lr']`` and
     ``state_dict`` / ``load_state_dict`` in torch.optim.Adam's format so runner checkpoints stay interchangeable."""
@@ -274,8 +277,8 @@ class PPO:
         self._peer = None
         _, world = D.world_info()
         mode = os.environ.get("LT_PEER_GRADS", "auto")
-        if world == 1 or mode == "0" or (mode == "auto" and world > 4):
-            return False  # one-shot exchange reads W buffers per rank: beyond 4 ranks the NCCL ring / NVLS path is not slower
+        if world == 1 or mode == "0" or world > _C_MAX_PEERS:
+            return False
         try:
             import torch.distributed._symmetric_memory as symm
 
