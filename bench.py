@@ -71,6 +71,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
+    def wait_ready(self, timeout: float = 4.0):
+        """Blocks until nvidia-smi has delivered its first row (it needs 0.1-1 s to come up on a fresh box)."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
     def mark_start(self):
         self.t0 = time.perf_counter()
 
@@ -88,6 +94,8 @@ class ClockSampler:
     def summary(self):
         t0 = self.t0 if self.t0 is not None else 0.0
         rows = [r for t, r in self.rows if t0 <= t <= self.t1 + 0.03]
+        if not rows:  # a region shorter than the polling period: the rows nearest to it (the GPU is under the same load right around it)
+            rows = [r for t, r in self.rows if t0 - 0.1 <= t <= self.t1 + 0.1]
         sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -314,6 +322,9 @@ def main():
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         for _ in range(args.warmup):
+            engine.replay()
+        clocks.wait_ready()
+        for _ in range(2):  # keep the GPU under load while the sampler's first rows arrive
             engine.replay()
         barrier()
         clocks.mark_start()
