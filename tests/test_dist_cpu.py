@@ -99,3 +99,33 @@ def test_peer_gradient_exchange_is_off_without_a_process_group_and_validates_its
     assert lib.lt_peer_sum_clip_adam(None, ptrs, 2, None, 4, None, None, 16, None, None, 1.0, 0.9, 0.999, 1e-8, 0.0, 0.5, 0.01, 0.5, None, None, 0, None) == 1
     src = open(__import__("os").path.join(__import__("os").path.dirname(_C.__file__), "loco_rl", "algorithms", "ppo.py")).read()
     assert "def enable_peer_gradients" in src and "world == 1" in src
+
+
+def test_state_upload_layout_carries_only_what_the_path_reads():
+    """engine.pack_host: one contiguous host buffer; the per-step upload prefix holds every per-step tensor the path reads whole, the
+    feet rows of body_pos_w / body_lin_vel_w and the taxel-body rows of body_quat_w compact; articulation constants and unread
+    tensors sit behind the prefix (uploaded once)."""
+    import torch
+
+    from locotouch_b200.engine import STATIC, UNREAD, pack_host, row_subsets
+    from locotouch_b200.sim import synth
+
+    env = synth.make_env(16, seed=3, with_object=True, with_tactile=True)
+    layout, compact, upload_bytes, host = pack_host(env)
+    tensors = env.named_tensors()
+    subsets = row_subsets(env)
+    assert list(subsets["robot.body_quat_w"]) == list(range(17, 238)) and len(subsets["robot.body_pos_w"]) == 4
+    for name, off, nbytes, dtype, shape in layout:
+        got = host[off:off + nbytes].view(dtype).view(shape)
+        assert torch.equal(got, tensors[name]), name
+        behind = name in UNREAD or name in STATIC or name in subsets
+        assert (off >= upload_bytes) == behind, f"{name}: wrong side of the upload prefix"
+    for name, off, nbytes, dtype, shape in compact:
+        assert off + nbytes <= upload_bytes
+        assert torch.equal(host[off:off + nbytes].view(dtype).view(shape), tensors[name][:, subsets[name]]), name
+    per_env = upload_bytes / 16
+    assert 7000 < per_env < 8200, per_env  # 7 476 B of payload + 256-byte slice alignment at 16 envs
+    # no tactile sensor: body_quat_w is not read at all, nothing of it travels
+    env2 = synth.make_env(16, seed=3)
+    _, compact2, ub2, _ = pack_host(env2)
+    assert [c[0] for c in compact2] == ["robot.body_pos_w", "robot.body_lin_vel_w"]
