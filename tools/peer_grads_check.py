@@ -77,6 +77,33 @@ def timed(alg, reps=50):
     return e0.elapsed_time(e1) * 1e3 / reps
 
 
+# ---- the same exchange replayed from the captured update graph (barriers and peer loads are graph nodes): after a few iterations the
+# replicas must still be bit-identical -- a barrier that let a rank read a buffer early or late would break that at once
+from locotouch_b200.engine import HotPathEngine  # noqa: E402
+
+eng = HotPathEngine(num_envs=512, task="teacher", tactile=True, device=dev, seed=3, num_state_sets=3, hidden=(128, 64))
+assert eng.peer_gradients, "engine did not enable the peer exchange"
+eng.capture()
+assert not eng._graphs["split"] and eng._graphs.get("finish_eager"), "whole-update graph expected"
+p0 = eng.alg.optimizer.flat.clone()
+for _ in range(4):
+    eng.replay()
+torch.cuda.synchronize()
+pe = eng.alg.optimizer.flat
+assert not torch.equal(pe, p0), "parameters did not move"
+assert bool(torch.isfinite(pe).all())
+lo, hi = pe.clone(), pe.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+assert torch.equal(lo, hi), "replicas diverged under graph replay"
+lr = eng.alg.optimizer.lr_t.clone()
+lr_lo, lr_hi = lr.clone(), lr.clone()
+dist.all_reduce(lr_lo, op=dist.ReduceOp.MIN)
+dist.all_reduce(lr_hi, op=dist.ReduceOp.MAX)
+assert torch.equal(lr_lo, lr_hi)
+if rank == 0:
+    print(f"graph replay: 4 iterations x 20 mini-batch exchanges, replicas bit-identical (lr {float(lr):.6g})", flush=True)
+
 ta, tb = timed(a), timed(b)
 if rank == 0:
     print(f"world={world}: NCCL all-reduce + clip + Adam {ta:.1f} us per step; barrier + peer-sum + clip + Adam + barrier {tb:.1f} us per step", flush=True)
