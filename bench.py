@@ -392,7 +392,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "how": "HotPathEngine.replay(upload=True): the drop-in classes' calls replayed from CUDA graphs; the T state sets of iteration i+1 are "
                        "copied pinned-host -> device on a copy stream while iteration i computes (two device banks); metrics read back every iteration",
-                "h2d_gbs_alone": h2d_gbs, "eager_per_rank": {"value": eager_value, "unit": "env-steps/s",
+                "h2d_gbs_alone": h2d_gbs, "host_affinity": engine.host_affinity, "eager_per_rank": {"value": eager_value, "unit": "env-steps/s",
                                                          "how": "eager PPO/RolloutStorage/FusedMdp calls, one state-set upload per env step on the compute stream"}},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks.summary(),

@@ -109,6 +109,36 @@ def device_set(env, layout, compact, host, device):
     return denv, flat, scatter
 
 
+def bind_host_thread_to_gpu(device: torch.device) -> str:
+    """Pins the calling thread to the CPUs NVML names as local to ``device`` (same socket / PCIe root), so that the pinned host
+    buffers allocated next land on the GPU's NUMA node and the upload threads of several ranks do not all sit on node 0.  Best effort:
+    returns what happened; any failure (no NVML, restricted cpuset, ...) leaves the affinity untouched."""
+    if os.environ.get("LT_NUMA_BIND", "1") == "0":
+        return "off (LT_NUMA_BIND=0)"
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device)
+        handle = None
+        uuid = getattr(props, "uuid", None)
+        if uuid is not None:
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:  # noqa: BLE001
+                handle = None
+        if handle is None:  # no uuid in this torch build: NVML index == CUDA index unless CUDA_VISIBLE_DEVICES reorders
+            if os.environ.get("CUDA_VISIBLE_DEVICES"):
+                return "unchanged (cannot map the CUDA index to NVML under CUDA_VISIBLE_DEVICES)"
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device.index or 0)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = len(os.sched_getaffinity(0))
+        return f"gpu-local cpus ({after} of {before})"
+    except Exception as exc:  # noqa: BLE001
+        return f"unchanged ({type(exc).__name__})"
+
+
 class HotPathEngine:
     def __init__(self, num_envs: int = 4096, task: str = "teacher", tactile: bool = True, device="cuda:0", seed: int = 0,
                  num_state_sets: int = 6, num_steps: int = NUM_STEPS_PER_ENV, hidden=HIDDEN, ppo_cfg: dict | None = None,
@@ -122,6 +152,8 @@ class HotPathEngine:
         if tf32:  # reference locotouch/scripts/train.py:66-69
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
+        # several ranks uploading from pinned host memory: keep every rank's thread and buffers on its GPU's NUMA node
+        self.host_affinity = bind_host_thread_to_gpu(self.device) if (pin_host and self.world > 1 and self.device.type == "cuda") else "unchanged"
         # ---- synthetic state sets (stand-in for PhysX), one packed buffer each
         self.envs, self.dev_flat, self.host_flat = [], [], []
         base = synth.make_env(num_envs, seed=seed * 1000 + self.rank, with_object=self.spec.with_object, with_tactile=tactile,
