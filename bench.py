@@ -8,11 +8,13 @@
 One "step" = one PPO iteration at 4096 envs per GPU: 24 x [actor-critic act, action pre-processing, fused MDP step of
 the RandCylinderTransportTeacher task (23 active rewards incl. the gait term, 6 terminations, 2 x 348-D observations),
 binary taxel synthesis + delay line, transition store] + GAE + 5 epochs x 4 mini-batches of PPO update.  Synthetic state
-tensors stand in for PhysX (6 pre-generated state sets per rank, ~200 MB, cycled through).
+tensors stand in for PhysX (6 distinct pinned host sets per rank, 48 device-resident sets ~2.7 GB, cycled: larger than L2).
 value = (N_gpus * 4096 * 24) / seconds per step, device-timed (CUDA events, max over ranks), inputs resident in HBM,
-the whole step replayed from CUDA graphs.  e2e = the same metric through the public drop-in classes (eager calls) with
-every env step's state set copied host->device from pinned memory and the iteration's metrics read back.
-Prints ONE JSON line (rank 0).
+the whole step replayed from CUDA graphs.  e2e = the same iteration through HotPathEngine.replay(upload=True): every env
+step's state set is copied host -> device from pinned memory inside the timed region (double-buffered on a copy stream) and the
+iteration's metrics are read back; the eager per-step-upload variant is reported next to it.  Several GPUs: envs are sharded, the
+flat PPO gradient is exchanged by peer loads inside the optimizer kernel (K14; NCCL all-reduce as fallback).
+Prints ONE JSON line (rank 0) on stdout.
 """
 from __future__ import annotations
 
