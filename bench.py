@@ -106,92 +106,106 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_sample(envs: int = ENVS_PER_GPU, env_steps: int = 2, minibatches: int = 2, threads: int | None = None):
-    """Times the reference algorithm (oracle port, torch CPU fp32) on the host cores over a bounded sample of one step and
-    extrapolates to the full iteration: T x env-step + GAE + 20 x mini-batch.  Returns (env_steps_per_s, detail dict)."""
-    from oracle import ppo as OP
-    from oracle import tactile as OT
-    from oracle.mdp import MdpOracle
-    from locotouch_b200.mdp import task_spec as TS
-    from locotouch_b200.sim import synth
+def bench_config(envs: int = ENVS_PER_GPU):
+    """The workload description BOTH arms print (identical dicts: the driver compares them)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": envs, "steps_per_env": T_STEPS, "ppo": "5 epochs x 4 mini-batches, adaptive lr, clip 0.2, MLP [512,256,128] x 2",
+            "inputs": "synthetic Go1 + cylinder state sets (seeded), larger than L2 in aggregate"}
 
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    spec = TS.teacher_spec()
-    env = synth.make_env(envs, seed=0, with_object=True, with_tactile=True)
-    oracle = MdpOracle(env, spec)
-    D, A = spec.obs_dim, 12
-    g = torch.Generator().manual_seed(0)
-    shapes = OP.actor_critic_shapes(D, D, A, [512, 256, 128], [512, 256, 128])
-    n_params = sum(int(torch.tensor(s).prod()) for _, s in shapes)
-    flat = torch.randn(n_params, generator=g) * 0.05
-    flat[:A] = 1.0
-    params = OP.unflatten(flat, shapes)
-    aw, ab, cw, cb = OP._split(params)
-    thr = 0.05 + (torch.rand(envs, 221, generator=g) * 0.02 - 0.01)
-    delay = OT.TactileDelayOracle(envs, 442, 1, 2)
-    obs = torch.zeros(envs, D)
-    # ---- env-step sample
-    t_env = []
-    for i in range(env_steps + 1):
-        t0 = time.perf_counter()
+
+class CpuReference:
+    """The reference algorithm for the whole step (oracle port of the reference's torch code, torch CPU fp32, all host threads):
+    one call of ``iteration()`` = 24 x [actor-critic act, MDP terms + observations, binary taxels + delay line, time-out bootstrap,
+    store] + GAE + PPO update of 5 epochs x 4 mini-batches -- a WHOLE iteration, nothing extrapolated."""
+
+    def __init__(self, envs: int = ENVS_PER_GPU, threads: int | None = None):
+        from oracle import ppo as OP
+        from oracle import tactile as OT
+        from oracle.mdp import MdpOracle
+        from locotouch_b200.mdp import task_spec as TS
+        from locotouch_b200.sim import synth
+
+        self.OP, self.OT = OP, OT
+        self.threads = threads or os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.envs = envs
+        self.spec = TS.teacher_spec()
+        self.env = synth.make_env(envs, seed=0, with_object=True, with_tactile=True)
+        self.oracle = MdpOracle(self.env, self.spec)
+        D, A = self.spec.obs_dim, 12
+        self.D, self.A = D, A
+        self.g = torch.Generator().manual_seed(0)
+        self.shapes = OP.actor_critic_shapes(D, D, A, [512, 256, 128], [512, 256, 128])
+        n_params = sum(int(torch.tensor(s).prod()) for _, s in self.shapes)
+        self.flat = torch.randn(n_params, generator=self.g) * 0.05
+        self.flat[:A] = 1.0
+        self.thr = 0.05 + (torch.rand(envs, 221, generator=self.g) * 0.02 - 0.01)
+        self.delay = OT.TactileDelayOracle(envs, 442, 1, 2)
+        self.obs = torch.zeros(envs, D)
+        self.cobs = torch.zeros(envs, D)
+        self.lr = 1e-3
+
+    def iteration(self):
+        OP, OT, g, env, spec, N, A, D = self.OP, self.OT, self.g, self.env, self.spec, self.envs, self.A, self.D
+        params = OP.unflatten(self.flat, self.shapes)
+        aw, ab, cw, cb = OP._split(params)
+        T = T_STEPS
+        st = dict(obs=torch.empty(T, N, D), critic_obs=torch.empty(T, N, D), actions=torch.empty(T, N, A), values=torch.empty(T, N, 1),
+                  logp=torch.empty(T, N, 1), mu=torch.empty(T, N, A), sigma=torch.empty(T, N, A), rewards=torch.empty(T, N, 1), dones=torch.empty(T, N, 1, dtype=torch.uint8))
         with torch.no_grad():
-            mu = OP.mlp_forward(obs, aw, ab)
-            actions, logp = OP.act_sample(mu, params["std"], torch.randn(envs, A, generator=g))
-            values = OP.mlp_forward(obs, cw, cb)
-            out = oracle.step(env)
-            obs, cobs = oracle.observe(env, u_noise=torch.rand(envs, spec.obs_dim_per_step, generator=g), u_obj_euler=torch.rand(envs, 3, generator=g))
-            tac = OT.binary_taxels(env.scene["robot"].data.body_quat_w[:, 17:], env.scene.sensors["tactile_contact_sensor"].data.net_forces_w, thr,
-                                   torch.rand(envs, 221, generator=g), torch.rand(envs, 221, generator=g))
-            delay.record(tac["signal"])
-            delay.get()
-            OP.bootstrap_rewards(out["reward"], values, out["time_outs"], 0.99)
-        if i > 0:
-            t_env.append(time.perf_counter() - t0)
-    # ---- GAE
-    r = torch.randn(T_STEPS, envs, 1, generator=g) * 0.02
-    v = torch.randn(T_STEPS, envs, 1, generator=g)
-    d = (torch.rand(T_STEPS, envs, 1, generator=g) < 0.02).byte()
-    t0 = time.perf_counter()
-    OP.gae_returns(r, v, d, torch.randn(envs, 1, generator=g), 0.99, 0.95, True)
-    t_gae = time.perf_counter() - t0
-    # ---- mini-batch sample
-    B = envs * T_STEPS // 4
-    st = dict(obs=torch.randn(B, D, generator=g), critic_obs=torch.randn(B, D, generator=g), actions=torch.randn(B, A, generator=g),
-              values=torch.randn(B, 1, generator=g), returns=torch.randn(B, 1, generator=g), logp=torch.randn(B, 1, generator=g) - 12,
-              advantages=torch.randn(B, 1, generator=g), mu=torch.randn(B, A, generator=g), sigma=torch.ones(B, A))
-    t0 = time.perf_counter()
-    OP.ppo_update(flat, shapes, st, torch.arange(B), num_learning_epochs=minibatches, num_mini_batches=1, clip_param=0.2, value_loss_coef=1.0,
-                  entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0, desired_kl=0.01)
-    t_mb = (time.perf_counter() - t0) / minibatches
-    t_env_mean = sum(t_env) / len(t_env)
-    iteration = T_STEPS * t_env_mean + t_gae + 20 * t_mb
-    detail = dict(env_step_s=t_env_mean, gae_s=t_gae, minibatch_s=t_mb, iteration_s=iteration,
-                  sample=f"{env_steps} env steps (act+MDP+taxels+store) + 1 GAE + {minibatches} of 20 PPO mini-batches at {envs} envs, extrapolated to 24 steps + 20 mini-batches")
-    return envs * T_STEPS / iteration, detail
+            for t in range(T):
+                mu = OP.mlp_forward(self.obs, aw, ab)
+                actions, logp = OP.act_sample(mu, params["std"], torch.randn(N, A, generator=g))
+                values = OP.mlp_forward(self.cobs, cw, cb)
+                st["obs"][t], st["critic_obs"][t], st["actions"][t], st["values"][t] = self.obs, self.cobs, actions, values
+                st["logp"][t, :, 0], st["mu"][t], st["sigma"][t] = logp, mu, params["std"].expand_as(mu)
+                out = self.oracle.step(env)
+                self.obs, self.cobs = self.oracle.observe(env, u_noise=torch.rand(N, spec.obs_dim_per_step, generator=g), u_obj_euler=torch.rand(N, 3, generator=g))
+                tac = OT.binary_taxels(env.scene["robot"].data.body_quat_w[:, 17:], env.scene.sensors["tactile_contact_sensor"].data.net_forces_w, self.thr,
+                                       torch.rand(N, 221, generator=g), torch.rand(N, 221, generator=g))
+                self.delay.record(tac["signal"])
+                self.delay.get()
+                st["rewards"][t, :, 0] = OP.bootstrap_rewards(out["reward"], values, out["time_outs"], 0.99)
+                st["dones"][t, :, 0] = out["done"].to(torch.uint8)
+            last_values = OP.mlp_forward(self.cobs, cw, cb)
+            returns, adv = OP.gae_returns(st["rewards"], st["values"], st["dones"], last_values, 0.99, 0.95, True)
+        flat_st = {k: st[k].flatten(0, 1) for k in ("obs", "critic_obs", "actions", "values", "logp", "mu", "sigma")}
+        flat_st["returns"], flat_st["advantages"] = returns.flatten(0, 1), adv.flatten(0, 1)
+        perm = torch.randperm(T * N, generator=g)
+        _, _, _, lrs, flat = OP.ppo_update(self.flat, self.shapes, flat_st, perm, num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, value_loss_coef=1.0,
+                                           entropy_coef=0.01, learning_rate=self.lr, max_grad_norm=1.0, desired_kl=0.01)
+        self.flat, self.lr = flat, lrs[-1]
+
+
+def time_cpu_reference(steps: int, warmup: int, envs: int = ENVS_PER_GPU):
+    """(env-steps/s, seconds per iteration list, cores) over ``steps`` whole iterations after ``warmup`` untimed ones."""
+    ref = CpuReference(envs)
+    for _ in range(warmup):
+        ref.iteration()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ref.iteration()
+        times.append(time.perf_counter() - t0)
+    per = statistics.median(times)
+    return envs * T_STEPS / per, times, ref.threads
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        cpu_reference_sample(env_steps=1, minibatches=1, threads=cores)
-    vals, details = [], None
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        v, details = cpu_reference_sample(threads=cores)
-        vals.append(v)
+    value, times, cores = time_cpu_reference(args.steps, args.warmup, args.envs_per_gpu)
     wall = time.perf_counter() - t0
-    value = statistics.median(vals)
+    sample = f"{args.steps} whole PPO iterations ({T_STEPS} env steps + GAE + 20 mini-batches at {args.envs_per_gpu} envs) after {args.warmup} warm-up, median"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * ENVS_PER_GPU * T_STEPS / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "inputs": "host memory (torch CPU tensors)"},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": details["sample"],
-                         "detail": {k: details[k] for k in ("env_step_s", "gae_s", "minibatch_s", "iteration_s")}},
+        "ms_per_step": 1e3 * args.envs_per_gpu * T_STEPS / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": bench_config(args.envs_per_gpu),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample, "iteration_s": times},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "sample_wall_s": wall,
+        "note": "the reference is torch-CPU Python that needs IsaacLab to import as a package; its algorithm for this path is timed through the oracle port "
+                "(oracle/*.py, pinned to the unmodified reference by tests/golden); one rank's workload whatever --gpus says (the reference is single-process)",
     }
     print(json.dumps(line), flush=True)
 
@@ -264,6 +278,101 @@ def kernel_rooflines(engine, reps: int = 96):
     return out
 
 
+def gemm_rows(engine, peak_tflops: float):
+    """The tensor-core side of one PPO mini-batch (BASELINE.md "Tensor-core side"): forward + explicit backward of both MLPs at the
+    mini-batch size through ActorCritic.train_forward / train_backward, timed as one CUDA graph; FLOPs = 6 x B x (weights of both
+    MLPs) (forward 2, dgrad 2, wgrad 2 per multiply-accumulate; the first layer has no dgrad)."""
+    from locotouch_b200.streams import graph_capture
+
+    ac = engine.alg.actor_critic
+    B = engine.N * T_STEPS // 4
+    D = engine.spec.obs_dim
+    dev = engine.device
+    obs = [torch.randn(B, D, device=dev) for _ in range(3)]
+    gmu, gv = torch.randn(B, ac.num_actions, device=dev) * 1e-4, torch.randn(B, 1, device=dev) * 1e-4
+    saved = engine.alg.optimizer.flat.clone()
+
+    def run(i):
+        ac.train_forward(obs[i % 3], obs[(i + 1) % 3])
+        ac.train_backward(gmu, gv)
+
+    for i in range(3):
+        run(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    reps = 12
+    with graph_capture(g):
+        for i in range(reps):
+            run(i)
+    g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e30
+    for _ in range(3):
+        e0.record()
+        g.replay()
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+    engine.alg.optimizer.flat.copy_(saved)
+    import torch.nn as nn
+
+    macs, first = 0, 0
+    for net in (ac.actor, ac.critic):
+        lin = [m for m in net if isinstance(m, nn.Linear)]
+        macs += sum(m.in_features * m.out_features for m in lin)
+        first += lin[0].in_features * lin[0].out_features
+    flops = 2.0 * B * (3 * macs - first)
+    tfs = flops / best / 1e6
+    tf32_peak = peak_tflops / 2.0  # TF32 dense = half the bf16 rate on B200 (2.25 vs 1.1 PFLOP/s nominal); measured bf16 peak / 2
+    return [{"kernel": "actor-critic MLPs fwd + bwd (one mini-batch, TF32 tcgen05 GEMMs + fused epilogues)", "bound": "tensor", "achieved": tfs, "peak": tf32_peak,
+             "unit": "TFLOP/s", "frac": tfs / tf32_peak, "us_per_launch": best, "flops_per_launch": flops,
+             "peak_note": "measured sustained bf16 cuBLAS peak / 2 (TF32 runs at half the bf16 rate)"}]
+
+
+def replica_check(engine, world: int):
+    """All ranks must hold bit-identical parameters, Adam moments and learning rate (they take the same summed gradient in the same
+    order): all-reduced min == max of an integer checksum of the fp32 bit patterns."""
+    import torch.distributed as dist
+
+    opt = engine.alg.optimizer
+    sums = torch.stack([opt.flat.view(torch.int32).to(torch.int64).sum(), opt.exp_avg_sq.view(torch.int32).to(torch.int64).sum(),
+                        opt.lr_t.view(torch.int32).to(torch.int64).sum()])
+    if world == 1:
+        return {"identical": True, "world": 1}
+    lo, hi = sums.clone(), sums.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = (lo == hi).tolist()
+    return {"identical": all(same), "params": same[0], "adam_state": same[1], "learning_rate": same[2], "world": world}
+
+
+def diagnose_replicas(args, device, rank, world):
+    """Eager PPO iterations with the trace the adaptive schedule saw: per mini-batch (local KL, learning rate after the decision,
+    gradient norm).  --same-data: every rank holds rank 0's envs and random streams and normalises advantages per rank, so the summed
+    gradient / W and the mean KL are EXACTLY the single-GPU values (x + x is exact, x / 2 is exact): the W-rank trace must equal the
+    W = 1 trace bit for bit.  Without it: the ordinary env-sharded job (different envs per rank, global advantage statistics)."""
+    from locotouch_b200.engine import HotPathEngine
+
+    eng = HotPathEngine(num_envs=args.envs_per_gpu, task="teacher", tactile=True, device=device, seed=0, num_state_sets=6,
+                        data_rank=0 if args.same_data else None)
+    if args.same_data:
+        eng.alg.global_advantage_normalization = False
+    eng.alg.trace = []
+    out = []
+    for it in range(args.diag_iters):
+        torch.manual_seed(1234 + it)  # the same permutation on every rank and every world size
+        eng.iteration()
+        r = eng.read_results()
+        out.append({"iteration": it, "lr_end": r["learning_rate"], "surrogate": r["surrogate_loss"], "value_loss": r["value_loss"], "entropy": r["entropy"],
+                    "kl_local": [t[0] for t in eng.alg.trace], "lr_after": [t[1] for t in eng.alg.trace], "grad_norm": [t[2] for t in eng.alg.trace]})
+        eng.alg.trace = []
+    chk = replica_check(eng, world)
+    csum = int(eng.alg.optimizer.flat.view(torch.int32).to(torch.int64).sum())
+    if rank == 0:
+        print(json.dumps({"diagnose_replicas": True, "world": world, "same_data": args.same_data, "peer_gradients": bool(eng.peer_gradients),
+                          "replica_check": chk, "param_checksum": csum, "iterations": out}), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -275,6 +384,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-lite", action="store_true", help="for ncu launch lists: skip e2e / roofline / cpu legs")
+    ap.add_argument("--diagnose-replicas", action="store_true",
+                    help="eager iterations with the per-mini-batch KL / learning-rate trace; with --same-data every rank gets rank 0's data "
+                         "and a W-rank run must reproduce the single-GPU trace")
+    ap.add_argument("--same-data", action="store_true")
+    ap.add_argument("--diag-iters", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if (args.impl == "ours" and not args.profile_lite) else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -310,6 +424,12 @@ def main():
     from locotouch_b200.engine import HotPathEngine
 
     N = args.envs_per_gpu
+    if args.diagnose_replicas:
+        diagnose_replicas(args, device, rank, world)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     engine = HotPathEngine(num_envs=N, task="teacher", tactile=True, device=device, seed=0, num_state_sets=6, pin_host=True, prefetch=True)
     launches_before = _C.launch_count
     engine.capture()
@@ -342,6 +462,7 @@ def main():
     ms_per_step = float(ms.item()) / args.steps
     value = world * N * T_STEPS / (ms_per_step * 1e-3)
     metrics = engine.read_results()
+    replicas = replica_check(engine, world)
 
     if args.profile_lite:
         if rank == 0:
@@ -388,9 +509,11 @@ def main():
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core GEMMs, as the reference)",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "steps_per_env": T_STEPS, "parallelism": (f"env-sharded dp{world}, " + ("gradients summed by peer loads over NVLink inside the optimizer kernel (K14)" if engine.peer_gradients
+        "config": bench_config(N),
+        "setup": {"parallelism": (f"env-sharded dp{world}, " + ("gradients summed by peer loads over NVLink inside the optimizer kernel (K14)" if engine.peer_gradients
                                                                    else "NCCL all-reduce of flat PPO gradients")) if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2 (48 state sets ~2.7 GB + 290 MB rollout storage per rank)", "timing": "CUDA events on the launch stream around K graph replays, max over ranks"},
+                  "l2": "inputs larger than L2 (48 state sets ~2.7 GB + 290 MB rollout storage per rank)", "timing": "CUDA events on the launch stream around K graph replays, max over ranks",
+                  "gemm_kernels": _C.gemm_backend()},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "how": "HotPathEngine.replay(upload=True): the drop-in classes' calls replayed from CUDA graphs; the T state sets of iteration i+1 are "
                        "copied pinned-host -> device on a copy stream while iteration i computes (two device banks); metrics read back every iteration",
@@ -399,6 +522,7 @@ def main():
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks.summary(),
         "iteration_metrics": metrics,
+        "replica_check": replicas["identical"], "replica_detail": replicas,
     }
     if rank == 0:
         hbm, tf, kind = peaks()
@@ -414,11 +538,29 @@ def main():
                                             "the kernel's 12.6 MB of writes are still in L2 when it ends, ncu counts 0 written)",
                             "kernel": top["kernel"], "us_per_launch": top["us_per_launch"], "peak_kind": kind,
                             "how": "96 launches in one CUDA graph cycling 6 state sets (> L2), CUDA events on the launch stream"}
+        try:  # the small kernels of the update + GAE, timed the same way (tools/kbench.py: graph of launches over > L2 of inputs)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import kbench as KB
+
+            extra = {}
+            extra.update(KB.bench_gae(N, 100))
+            extra.update(KB.bench_ppo_loss(N * T_STEPS // 4, 100))
+            extra.update(KB.bench_adam(engine.alg.optimizer.flat.numel(), 100))
+            extra.update(KB.bench_k9(N * T_STEPS // 4, 80))
+            extra.update(KB.bench_gather(N * T_STEPS, N * T_STEPS // 4, 20, obs_dim=engine.spec.obs_dim))
+            for name, (us, nbytes) in extra.items():
+                gbs = nbytes / us / 1e3
+                rows.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "us_per_launch": us,
+                             "alg_bytes_per_launch": nbytes})
+            rows.extend(gemm_rows(engine, tf))
+        except Exception as exc:  # noqa: BLE001 -- the table is diagnostics; the headline numbers above do not depend on it
+            line["kernels_error"] = repr(exc)
         line["kernels"] = rows
         if world == 1 and not args.no_cpu_baseline:
-            v, detail = cpu_reference_sample()
-            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": detail["sample"],
-                                    "detail": {k: detail[k] for k in ("env_step_s", "gae_s", "minibatch_s", "iteration_s")}}
+            v, times, cores = time_cpu_reference(steps=2, warmup=1, envs=N)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"2 whole PPO iterations ({T_STEPS} env steps + GAE + 20 mini-batches at {N} envs) after 1 warm-up, median; nothing extrapolated",
+                                    "iteration_s": times}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -443,6 +443,7 @@ int lt_pack_trajectories(const float* x, const int32_t* traj_env, const int32_t*
  * K and N must be multiples of 4 and all pointers 16-byte aligned; LT_ERR_UNSUPPORTED otherwise (or when the library was
  * built without the CUTLASS headers) -- the caller then uses its cuBLAS path.
  * ------------------------------------------------------------------------------------------------------------------ */
+const char* lt_gemm_backend(void); /* "stub" when the library was built without the tcgen05 GEMMs (callers then raise / fall back to cuBLAS) */
 int64_t lt_linear_bias_act_workspace_bytes(int M, int N, int K);
 int lt_linear_bias_act(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, int apply_elu,
                        void* workspace, int64_t workspace_bytes, void* stream);

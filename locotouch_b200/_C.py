@@ -227,6 +227,7 @@ _SIGNATURES = {
     "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),
     "lt_mdp_reset": (C.c_int, [C.POINTER(LtGaitState), f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "lt_pad_trajectories": (C.c_int, [f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, C.c_void_p, C.c_void_p]),
+    "lt_gemm_backend": (C.c_char_p, []),
     "lt_masked_mse_workspace_bytes": (C.c_int64, [C.c_int64]),
     "lt_command_workspace_bytes": (C.c_int64, [C.c_int]),
     "lt_command_step": (C.c_int, [C.POINTER(LtCommandArgs), C.c_void_p]),
@@ -290,7 +291,17 @@ def ptr(t: torch.Tensor | None, dtype: torch.dtype | None = None, name: str = "t
         raise LocoTouchLibraryError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
         raise LocoTouchLibraryError(f"{name} must be {dtype} (got {t.dtype})")
+    if t.device.index != torch.cuda.current_device():
+        # every launch goes to the CURRENT device's current stream (and sizes its grid from that device): a tensor of another GPU
+        # would be dereferenced on the wrong device
+        raise LocoTouchLibraryError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                                    "call torch.cuda.set_device(...) / use `with torch.cuda.device(...)` around locotouch_b200 calls")
     return t.data_ptr()
+
+
+def gemm_backend() -> str:
+    """Which implementation of the fused GEMMs (K12 ...) this build of the library carries; "stub" = built without them."""
+    return lib().lt_gemm_backend().decode()
 
 
 def current_stream() -> int:

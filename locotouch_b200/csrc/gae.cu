@@ -6,6 +6,14 @@
 // 3*T loads of a thread are issued before the scan starts (they do not depend on it), and the reverse recurrence is
 // then evaluated in registers in the reference's operation order (no FMA contraction) so that returns are bit-exact.
 // Algorithmic traffic: 9 B read + 8 B written per (t, env) + 4 B/env  (SURVEY.md 8d).
+//
+// lt_gae with normalisation at T = 24 is ONE launch (gae_fused_kernel): blocks of one warp (4096 envs = 128 blocks, one per SM
+// instead of 32 blocks of 128 threads on a 148-SM part), the 24 advantages of an env stay in registers across a grid-wide
+// arrive / spin barrier on a device counter, every block folds the block partials of sum / sum of squares in the same fixed order
+// (so all blocks normalise with bit-identical mean / std) and writes its normalised advantages: the advantages are written once
+// instead of written, re-read and re-written by a second launch.  The grid is bounded (<= 8 blocks per SM) so that all blocks are
+// co-resident; larger env counts and other T take the two-launch path (scan + normalise), which is also what an env-sharded job
+// uses (the statistics are summed over ranks between the two).
 #include "lt_common.cuh"
 
 namespace {
@@ -103,6 +111,97 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
   }
 }
 
+// ------------------------------------------------------------------------------------------------- one-launch variant
+constexpr int kFusedThreads = 32;
+
+struct GaeFusedWs {
+  unsigned int arrive, depart;
+  unsigned int pad[2];
+  double partial[1];  // [2 * blocks]
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int TT>
+__global__ void __launch_bounds__(kFusedThreads)
+gae_fused_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
+                 const float* __restrict__ last_values, float* __restrict__ returns, float* __restrict__ advantages,
+                 int N, float gamma, float lam, GaeFusedWs* ws, double* __restrict__ stats) {
+  const int n = blockIdx.x * kFusedThreads + threadIdx.x;
+  const bool valid = n < N;
+  float a[TT];
+  double s = 0.0, ss = 0.0;
+  {
+    float r[TT], v[TT + 1], d[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      r[t] = valid ? __ldcs(rewards + (size_t)t * N + n) : 0.f;
+      v[t] = valid ? __ldcs(values + (size_t)t * N + n) : 0.f;
+      d[t] = valid ? (float)__ldcs(dones + (size_t)t * N + n) : 0.f;
+    }
+    v[TT] = valid ? __ldcs(last_values + n) : 0.f;
+    float adv = 0.0f;
+#pragma unroll
+    for (int t = TT - 1; t >= 0; --t) {
+      float ret;
+      gae_step(r[t], v[t], d[t], v[t + 1], gamma, lam, adv, ret, a[t]);
+      if (valid) {
+        __stcs(returns + (size_t)t * N + n, ret);
+        s += (double)a[t];
+        ss += (double)a[t] * (double)a[t];
+      }
+    }
+  }
+  // same association as the two-launch path for one warp: lane partial (t descending), then the shuffle tree
+  s = lt::warp_sum(s);
+  ss = lt::warp_sum(ss);
+  if (threadIdx.x == 0) {
+    ws->partial[2 * blockIdx.x] = s;
+    ws->partial[2 * blockIdx.x + 1] = ss;
+    __threadfence();
+    atomicAdd(&ws->arrive, 1u);
+    while (ld_acquire_u32(&ws->arrive) < gridDim.x) {
+    }
+  }
+  __syncwarp();
+  // every block folds all partials in the same order -> identical statistics everywhere
+  double fa = 0.0, fb = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kFusedThreads) {
+    fa += __ldcg(&ws->partial[2 * i]);
+    fb += __ldcg(&ws->partial[2 * i + 1]);
+  }
+  fa = lt::warp_sum(fa);
+  fb = lt::warp_sum(fb);
+  const double cnt = (double)TT * (double)N;
+  const double mean = fa / cnt;
+  double var = (fb - fa * mean) / (cnt - 1.0);  // unbiased, rollout_storage.py:174 (.std())
+  var = var > 0.0 ? var : 0.0;
+  const float mean_f = (float)mean;
+  const float denom = __fadd_rn((float)sqrt(var), 1e-8f);
+  if (valid) {
+#pragma unroll
+    for (int t = 0; t < TT; ++t) __stcs(advantages + (size_t)t * N + n, __fdiv_rn(__fsub_rn(a[t], mean_f), denom));
+  }
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      stats[0] = fa;
+      stats[1] = fb;
+      stats[2] = cnt;
+      stats[3] = 0.0;
+    }
+    // the last block to leave re-arms the barrier: everybody has passed the spin by then
+    if (atomicAdd(&ws->depart, 1u) == gridDim.x - 1) {
+      ws->arrive = 0;
+      ws->depart = 0;
+      __threadfence();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 adv_normalize_kernel(float* __restrict__ adv, int64_t count, const double* __restrict__ stats) {
   const double s = stats[0], ss = stats[1], cnt = stats[2];
@@ -130,7 +229,7 @@ adv_normalize_kernel(float* __restrict__ adv, int64_t count, const double* __res
 
 extern "C" int64_t lt_gae_workspace_bytes(int T, int N) {
   (void)T;
-  const int64_t blocks = lt::ceil_div(N > 0 ? N : 1, kThreads);
+  const int64_t blocks = lt::ceil_div(N > 0 ? N : 1, kFusedThreads);  // the one-launch variant has the most blocks
   return 16 + 2 * blocks * (int64_t)sizeof(double) + 4 * (int64_t)sizeof(double);
 }
 
@@ -166,6 +265,14 @@ extern "C" int lt_gae(const float* rewards, const float* values, const uint8_t* 
   // stats live at the tail of the workspace
   double* stats = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + workspace_bytes - 4 * sizeof(double));
   if ((reinterpret_cast<uintptr_t>(stats) & 7) != 0) return LT_ERR_INVALID_ARG;
+  if (!rewards || !values || !dones || !last_values || !returns || !advantages || T <= 0 || N <= 0) return LT_ERR_INVALID_ARG;
+  const int64_t fused_blocks = lt::ceil_div(N, kFusedThreads);
+  if (normalize && T == 24 && (int64_t)T * N > 1 && fused_blocks <= 8LL * lt::sm_count() &&
+      workspace_bytes >= 16 + 2 * fused_blocks * (int64_t)sizeof(double) + 4 * (int64_t)sizeof(double)) {
+    gae_fused_kernel<24><<<(int)fused_blocks, kFusedThreads, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, returns, advantages, N, gamma,
+                                                                                          lam, (GaeFusedWs*)workspace, stats);
+    return lt::check_launch();
+  }
   int rc = lt_gae_scan(rewards, values, dones, last_values, returns, advantages, T, N, gamma, lam, stats, workspace,
                        workspace_bytes - 4 * (int64_t)sizeof(double), stream);
   if (rc != LT_OK || !normalize) return rc;

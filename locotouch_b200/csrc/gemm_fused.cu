@@ -154,6 +154,15 @@ using Identity = cutlass::epilogue::thread::Identity<T>;
 
 #endif  // LT_HAVE_CUTLASS
 
+// Which GEMM implementation this build carries: bench.py prints it, __graft_entry__.build() refuses a stub build.
+extern "C" const char* lt_gemm_backend(void) {
+#if LT_HAVE_CUTLASS
+  return "tcgen05 (CuTe/CUTLASS sm100 collectives, kind::tf32)";
+#else
+  return "stub";
+#endif
+}
+
 #if !LT_HAVE_CUTLASS
 #include "lt_common.cuh"
 extern "C" int lt_linear_bias_act(const float*, const float*, const float*, float*, int, int, int, int, void*, int64_t, void*) {

@@ -49,6 +49,17 @@ FEET_ROWS_ONLY = ("robot.body_pos_w", "robot.body_lin_vel_w")
 FEET = ("a_FR_foot", "b_FL_foot", "c_RR_foot", "d_RL_foot")
 
 
+def stream_seed(seed: int, rank: int, consumer: int) -> int:
+    """Philox key of one random-number consumer (0 = exploration noise, 1 = observation noise, 2 = taxel dropout / addition) of one
+    rank: pairwise distinct for every (seed, rank, consumer), so no two consumers ever draw from the same counter blocks
+    (splitmix64 finaliser over the packed triple; 63 bits so that it stays a non-negative int64 across the C ABI)."""
+    x = ((seed & 0xFFFFFFFF) << 24) ^ ((rank & 0xFFFF) << 8) ^ (consumer & 0xFF)
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return (x ^ (x >> 31)) & 0x7FFFFFFFFFFFFFFF
+
+
 def row_subsets(env) -> dict[str, torch.Tensor]:
     """name -> int64 row (body) indices the hot path reads of that [N, num_bodies, .] tensor."""
     feet = torch.tensor(env.scene["robot"].find_bodies(list(FEET))[0], dtype=torch.int64)
@@ -142,13 +153,18 @@ def bind_host_thread_to_gpu(device: torch.device) -> str:
 class HotPathEngine:
     def __init__(self, num_envs: int = 4096, task: str = "teacher", tactile: bool = True, device="cuda:0", seed: int = 0,
                  num_state_sets: int = 6, num_steps: int = NUM_STEPS_PER_ENV, hidden=HIDDEN, ppo_cfg: dict | None = None,
-                 pin_host: bool = False, tf32: bool = True, prefetch: bool = False):
+                 pin_host: bool = False, tf32: bool = True, prefetch: bool = False, data_rank: int | None = None):
         self.device = torch.device(device)
+        if self.device.type == "cuda":  # every kernel launch goes to the current device's stream (see _C.ptr)
+            torch.cuda.set_device(self.device)
         self.N, self.T, self.K = num_envs, num_steps, num_state_sets
         self.spec = TS.SPECS[task]()
         self.tactile = tactile
         self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        # which shard's synthetic data / random streams this rank uses: its own; diagnostics give every rank shard 0 so that a
+        # W-rank run must reproduce the single-GPU run (bench.py --diagnose-replicas)
+        drank = self.rank if data_rank is None else data_rank
         if tf32:  # reference locotouch/scripts/train.py:66-69
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
@@ -156,7 +172,7 @@ class HotPathEngine:
         self.host_affinity = bind_host_thread_to_gpu(self.device) if (pin_host and self.world > 1 and self.device.type == "cuda") else "unchanged"
         # ---- synthetic state sets (stand-in for PhysX), one packed buffer each
         self.envs, self.dev_flat, self.host_flat = [], [], []
-        base = synth.make_env(num_envs, seed=seed * 1000 + self.rank, with_object=self.spec.with_object, with_tactile=tactile,
+        base = synth.make_env(num_envs, seed=seed * 1000 + drank, with_object=self.spec.with_object, with_tactile=tactile,
                               max_episode_length=self.spec.max_episode_length)
         self.action_term = ActionTermState(num_envs, synth.NUM_JOINTS, self.device)
         # ``prefetch``: two banks of T device-resident sets, so that the H2D upload of the NEXT iteration's T state sets runs on
@@ -196,10 +212,11 @@ class HotPathEngine:
         # several ranks on one NVLink domain: gradients are exchanged by peer loads inside the optimizer kernel (K14) when the
         # symmetric-memory mapping can be set up; otherwise the NCCL all-reduce stays
         self.peer_gradients = self.alg.enable_peer_gradients() if self.world > 1 else False
-        ac.seed = seed * 7919 + self.rank
+        ac.seed = stream_seed(seed, drank, 0)
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int64)  # device-resident env-step index
         # ---- fused MDP: one instance, re-bound to the state set of each step
-        self.mdp = FusedMdp(self.envs[0], self.spec, seed=seed * 104729 + self.rank)
+        self.mdp = FusedMdp(self.envs[0], self.spec, seed=stream_seed(seed, drank, 1))
+        self.taxel_seed = stream_seed(seed, drank, 2)
         self.mdp_args = []  # per state set: a frozen copy of the argument block (pointers never change afterwards)
         # ---- tactile
         if tactile:
@@ -261,7 +278,7 @@ class HotPathEngine:
             with self._taxel_stream.forked():
                 env = self.envs[k]
                 ops.taxel_synth(env.scene["robot"].data.body_quat_w, env.scene.sensors["tactile_contact_sensor"].data.net_forces_w,
-                                self.taxel_thr, quat_body_offset=synth.NUM_ROBOT_BODIES, p_drop=0.005, p_add=0.005, seed=self.mdp.seed + 1,
+                                self.taxel_thr, quat_body_offset=synth.NUM_ROBOT_BODIES, p_drop=0.005, p_add=0.005, seed=self.taxel_seed,
                                 offset=t, offset_base=self.step_counter, signal=None, want_signal=False, packed=self.taxel_packed,
                                 delay_ring=self.taxel_ring, delay_first=self.taxel_first, delay_steps=self.taxel_delay,
                                 delayed_signal=self.tactile_obs)

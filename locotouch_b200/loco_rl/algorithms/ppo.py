@@ -30,6 +30,13 @@ from ..storage import RolloutStorage
 _C_MAX_PEERS = 16  # LT_MAX_PEERS of the C ABI
 
 
+class _NoBarrier:
+    """Barrier of same-process replicas driven in lock step on one stream: stream order already is the barrier."""
+
+    def barrier(self, channel: int = 0):
+        pass
+
+
 class _FusedAdam:
     """``optimizer``-shaped facade over the fused clip + Adam kernel: keeps ``param_groups[0]['lr']`` and
     ``state_dict`` / ``load_state_dict`` in torch.optim.Adam's format so runner checkpoints stay interchangeable."""
@@ -45,13 +52,39 @@ class _FusedAdam:
         self.grad_norm = torch.zeros(1, device=dev)
         self.param_groups = [dict(lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, params=list(range(len(list(actor_critic.parameters())))))]
         self._host_lr = lr
+        self._peer_buf = None
+
+    def _check_group(self):
+        g = self.param_groups[0]
+        if g.get("weight_decay", 0):  # torch.optim.Adam's weight decay is the L2 form (grad += wd * p); the kernel's is AdamW's
+            raise NotImplementedError("PPO's optimizer is torch.optim.Adam: weight_decay != 0 (L2 form) is not implemented by the fused kernel")
+        return g
 
     def use_gradient_buffer(self, buf: torch.Tensor):
         self.grads = self.ac.rebind_gradients(buf)
+        self._peer_buf = buf
+
+    def refresh(self):
+        """Re-attaches the optimizer to the actor-critic's flat buffers when they were re-created (``module.to(...)`` to another
+        device / dtype after construction re-homes the parameters): the Adam moments follow the parameters, and a gradient buffer
+        installed with ``use_gradient_buffer`` (K14 symmetric memory) is bound again.  No-op in the common case."""
+        flat, grads = self.ac.flatten_parameters()
+        if flat is self.flat:
+            return False
+        if flat.numel() != self.flat.numel():
+            raise RuntimeError("the actor-critic's parameter count changed after the optimizer was built")
+        dev = flat.device
+        self.exp_avg, self.exp_avg_sq = self.exp_avg.to(dev), self.exp_avg_sq.to(dev)
+        self.step_t, self.lr_t, self.grad_norm = self.step_t.to(dev), self.lr_t.to(dev), self.grad_norm.to(dev)
+        self.flat, self.grads = flat, grads
+        buf = getattr(self, "_peer_buf", None)
+        if buf is not None and buf.device == dev:
+            self.grads = self.ac.rebind_gradients(buf)
+        return True
 
     def step_peer_sum(self, peer_ptrs, grad_sum, tail: int, max_grad_norm=None, grad_scale: float = 1.0, desired_kl=None, kl_scale=1.0):
         """K14: sum of the ranks' gradient buffers (peer loads, rank order) + learning-rate decision + clip + Adam."""
-        g = self.param_groups[0]
+        g = self._check_group()
         ops.peer_sum_clip_adam(self.flat, peer_ptrs, grad_sum, tail, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t,
                                max_grad_norm=max_grad_norm, betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"],
                                grad_scale=grad_scale, desired_kl=desired_kl, kl_scale=kl_scale, grad_norm_out=self.grad_norm)
@@ -66,7 +99,7 @@ class _FusedAdam:
         self.grads.zero_()
 
     def step(self, max_grad_norm=None, grad_scale: float = 1.0):
-        g = self.param_groups[0]
+        g = self._check_group()
         ops.clip_adam(self.flat, self.grads, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t, max_grad_norm=max_grad_norm,
                       betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], grad_scale=grad_scale, grad_norm_out=self.grad_norm)
 
@@ -123,7 +156,13 @@ class PPO:
         self.symmetry = None
         self.actor_critic = actor_critic
         self.actor_critic.to(self.device)
+        A = getattr(actor_critic, "num_actions", None)
+        if A is not None and (A % 4 != 0 or A > 64):  # lt_act_sample / lt_ppo_loss move [A] rows as float4 chunks, up to 16 of them
+            raise ValueError(f"locotouch_b200 PPO needs num_actions to be a multiple of 4 and <= 64 (got {A})")
         self.optimizer = _FusedAdam(self.actor_critic, learning_rate)
+        self.trace = None  # list -> reduce_and_step appends (local KL, lr, grad norm) per mini-batch (eager diagnostics)
+        self._world_override = None  # (rank, world) of same-process replicas attached with attach_local_peers()
+        self._peer = None
         self.storage: RolloutStorage = None  # type: ignore
         self.transition = RolloutStorage.Transition()
         self.clip_param = clip_param
@@ -178,19 +217,34 @@ class PPO:
         t.clear()
         self.actor_critic.reset(dones)
 
+    def _world_info(self):
+        """(rank, world) of the env-sharded job this learner is part of: the process group's, or the one declared by
+        ``attach_local_peers`` for replicas that live in ONE process."""
+        return self._world_override if self._world_override is not None else D.world_info()
+
     def compute_returns(self, last_critic_obs):
+        if self.compute_returns_scan(last_critic_obs):
+            D.reduce_adv_stats_(self._adv_stats)
+            self.compute_returns_normalize()
+
+    def compute_returns_scan(self, last_critic_obs) -> bool:
+        """GAE scan.  Returns True when the advantage statistics still have to be summed over the shards (env-sharded job with
+        global normalisation): the caller reduces ``self._adv_stats`` = (sum, sum of squares, count) and then calls
+        ``compute_returns_normalize``; otherwise everything, normalisation included, is done (K4, one launch)."""
         with torch.no_grad():
             last_values = self.actor_critic.evaluate(last_critic_obs).detach()
         st = self.storage
         normalize = not self.normalize_advantage_per_mini_batch
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        _, world = self._world_info()
         if world == 1 or not normalize or not self.global_advantage_normalization:
             st.compute_returns(last_values, self.gamma, self.lam, normalize_advantage=normalize)
-            return
+            return False
         # env-sharded ranks: sum / sum of squares / count are all-reduced between the scan and the normalisation
         ops.gae_scan(st.rewards, st.values, st.dones, last_values.contiguous().view(-1), self.gamma, self.lam, st.returns, st.advantages, self._adv_stats)
-        D.reduce_adv_stats_(self._adv_stats)
-        ops.adv_normalize(st.advantages, self._adv_stats)
+        return True
+
+    def compute_returns_normalize(self):
+        ops.adv_normalize(self.storage.advantages, self._adv_stats)
 
     # ---------------------------------------------------------------------------------------------------------- update
     def update(self, indices=None):
@@ -220,7 +274,7 @@ class PPO:
             raise NotImplementedError("per-mini-batch advantage normalisation is not used by the LocoTouch cfgs")
         if ac.noise_std_type != "scalar":
             raise NotImplementedError("noise_std_type='log' is not used by the LocoTouch cfgs")
-        ac.flatten_parameters()
+        self.optimizer.refresh()  # no-op unless the module was moved after construction
         self._loss_accum.zero_()
         batch_size = st.num_envs * st.num_transitions_per_env
         self._mb_size = batch_size // self.num_mini_batches
@@ -242,7 +296,7 @@ class PPO:
             self._loss_bufs = ops.PpoLossBuffers(B, A, self.device)
         bufs = self._loss_bufs
         adaptive = self.desired_kl is not None and self.schedule == "adaptive"
-        _, world = D.world_info()
+        _, world = self._world_info()
         local_lr = adaptive and world == 1  # one process: the learning-rate decision is taken inside the loss kernel
         explicit = ac.supports_explicit_backward
         if explicit:
@@ -275,7 +329,7 @@ class PPO:
         import os
 
         self._peer = None
-        _, world = D.world_info()
+        _, world = self._world_info()
         mode = os.environ.get("LT_PEER_GRADS", "auto")
         if world == 1 or mode == "0" or world > _C_MAX_PEERS:
             return False
@@ -295,6 +349,38 @@ class PPO:
             return False
         return True
 
+    @staticmethod
+    def attach_local_peers(learners: "list[PPO]") -> None:
+        """Makes ``learners`` -- replicas of one policy that live in THIS process, one per env shard, on one device or on
+        peer-accessible devices -- an env-sharded job of world size ``len(learners)``: every learner's flat gradient buffer is an
+        ordinary device allocation whose address all the others pass to ``lt_peer_sum_clip_adam`` (K14 takes raw pointers; symmetric
+        memory is only how SEPARATE processes obtain them).  The caller runs the learners in lock step on one stream -- all
+        ``minibatch_grads(i)`` before any ``step_after_reduce()`` -- which is what the cross-GPU barriers enforce between processes.
+        Advantage statistics: ``compute_returns_scan`` on every learner, ``sum_local_adv_stats(learners)``, then
+        ``compute_returns_normalize``."""
+        W = len(learners)
+        if not 1 <= W <= _C_MAX_PEERS:
+            raise ValueError(f"1..{_C_MAX_PEERS} learners")
+        bufs = []
+        for alg in learners:
+            ac = alg.actor_critic
+            ac.flatten_parameters()
+            buf = torch.zeros(ac.flat_grads_ext.numel(), dtype=torch.float32, device=ac.flat_grads_ext.device)
+            alg.optimizer.use_gradient_buffer(buf)
+            bufs.append(buf)
+        for r, alg in enumerate(learners):
+            alg._world_override = (r, W)
+            alg._peer = dict(handle=_NoBarrier(), ptrs=[b.data_ptr() for b in bufs], sum=torch.zeros_like(bufs[r]), buf=bufs[r]) if W > 1 else None
+
+    @staticmethod
+    def sum_local_adv_stats(learners: "list[PPO]") -> None:
+        """The 3-double exchange of ``compute_returns`` for same-process replicas (rank order, like the all-reduce of equal shards)."""
+        total = learners[0]._adv_stats.clone()
+        for alg in learners[1:]:
+            total += alg._adv_stats.to(total.device)
+        for alg in learners:
+            alg._adv_stats.copy_(total)
+
     @property
     def peer_gradients(self) -> bool:
         return getattr(self, "_peer", None) is not None
@@ -305,10 +391,12 @@ class PPO:
         self.allreduce_grads()
         self.step_after_reduce()
         self.after_step_barrier()
+        if self.trace is not None:  # diagnostics only (host reads): local KL of this mini-batch, learning rate after the decision
+            self.trace.append((float(self._loss_bufs.out[4]), float(self.optimizer.lr_t), float(self.optimizer.grad_norm)))
 
     def allreduce_grads(self):
         """The only collective of a mini-batch step (kept outside CUDA-graph capture)."""
-        _, world = D.world_info()
+        _, world = self._world_info()
         if self.peer_gradients:
             self._peer["handle"].barrier(channel=0)  # every rank's backward has written its gradient buffer
         elif world > 1:
@@ -317,7 +405,7 @@ class PPO:
     def step_after_reduce(self):
         """Learning-rate decision from the reduced KL statistic + clip + Adam; collective-free, capturable."""
         opt = self.optimizer
-        _, world = D.world_info()
+        _, world = self._world_info()
         adaptive = self.desired_kl is not None and self.schedule == "adaptive"
         if self.peer_gradients:
             pr = self._peer

@@ -122,9 +122,22 @@ class ActorCritic(nn.Module):
         self.flat_grads = grads
         return grads
 
-    def _apply(self, fn, *a, **k):  # .to(device) invalidates the views
+    def _apply(self, fn, *a, **k):
+        """``.to()`` / ``.cuda()`` / ``.float()``: the flat buffers are dropped only when the parameters really moved (another
+        device or dtype re-creates every tensor); a no-op conversion keeps them -- the optimizer and a peer-mapped gradient buffer
+        hold references to them (``_FusedAdam.refresh`` re-attaches after a real move)."""
         out = super()._apply(fn, *a, **k)
-        self.flat_params = None
+        if self.flat_params is not None:
+            params = list(self.parameters())
+            still_views = (len(params) == len(self._offsets) and params[0].device == self.flat_params.device
+                           and all(p.dtype == torch.float32 and p.data.data_ptr() == self._offsets[i][0] for i, p in enumerate(params)))
+            if not still_views:
+                self.flat_params = None
+            else:  # torch may have replaced p.grad by a converted copy: point it at the flat gradient buffer again
+                for (name, p) in self.named_parameters():
+                    off, n = self._slices[name]
+                    if p.grad is None or p.grad.data_ptr() != self.flat_grads[off:off + n].data_ptr():
+                        p.grad = self.flat_grads[off:off + n].view(p.shape)
         return out
 
     # ------------------------------------------------------------------------------ explicit training forward / backward

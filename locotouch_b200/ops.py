@@ -42,7 +42,8 @@ def gae(rewards, values, dones, last_values, gamma: float, lam: float, normalize
     check(lib().lt_gae(ptr(rewards, torch.float32, "rewards"), ptr(values, torch.float32, "values"), ptr(dones, torch.uint8, "dones"),
                        ptr(last_values, torch.float32, "last_values"), ptr(returns, torch.float32), ptr(advantages, torch.float32),
                        T, N, gamma, lam, int(normalize_advantage), ptr(ws), nbytes, current_stream()), "lt_gae")
-    count_launches(2 if normalize_advantage else 1)
+    fused = normalize_advantage and T == 24 and (N + 31) // 32 <= 8 * torch.cuda.get_device_properties(rewards.device).multi_processor_count
+    count_launches(2 if (normalize_advantage and not fused) else 1)
     return returns, advantages
 
 
@@ -187,6 +188,13 @@ def adaptive_lr(kl_sum, kl_scale: float, desired_kl: float, lr):
 
 
 # ------------------------------------------------------------------------------------------------------- K7 clip + Adam
+def _adam_launches(n: int, device) -> int:
+    """1 when the parameter count fits the co-resident grid of the one-launch kernel (optim.cu: 4 blocks x 256 threads x 4 float4
+    per SM, at most 1024 blocks), else the norm pass + update pass."""
+    blocks = -(-max(n // 4, 1) // (256 * 4))
+    return 1 if blocks <= min(1024, 4 * torch.cuda.get_device_properties(device).multi_processor_count) else 2
+
+
 def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
               grad_scale=1.0, grad_norm_out=None):
     """clip_grad_norm_ + Adam/AdamW step over flat fp32 buffers (reference ppo.py:350-353).  ``lr``/``step`` are device scalars."""
@@ -197,7 +205,7 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0
                              ptr(exp_avg_sq, torch.float32), n, ptr(lr, torch.float32, "lr"), ptr(step, torch.float32, "step"),
                              float(max_grad_norm if max_grad_norm is not None else 0.0), betas[0], betas[1], eps, weight_decay,
                              grad_scale, ptr(grad_norm_out, torch.float32), ptr(ws), nbytes, current_stream()), "lt_clip_adam")
-    count_launches(2)
+    count_launches(_adam_launches(n, params.device))
 
 
 def peer_sum_clip_adam(params, peer_ptrs, grad_sum, tail, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0, betas=(0.9, 0.999), eps=1e-8,
@@ -216,7 +224,7 @@ def peer_sum_clip_adam(params, peer_ptrs, grad_sum, tail, exp_avg, exp_avg_sq, l
                                       eps, weight_decay, grad_scale, float(desired_kl) if desired_kl else 0.0, float(kl_scale),
                                       ptr(grad_norm_out, torch.float32), ptr(ws), nbytes, current_stream()),
           "lt_peer_sum_clip_adam")
-    count_launches(2)
+    count_launches(_adam_launches(n, params.device))
 
 
 # ------------------------------------------------------------------------------------------------- K9 MLP backward helper

@@ -87,9 +87,8 @@ def test_env_sharding_world_size_2(tmp_path):
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
 
 
-def test_peer_gradient_exchange_is_off_without_a_process_group_and_validates_its_arguments():
-    """K14 needs several ranks on one NVLink domain: with one process `enable_peer_gradients` declines (the NCCL / single-GPU path
-    stays); the C entry point rejects bad arguments before any CUDA call."""
+def test_peer_gradient_exchange_validates_its_arguments():
+    """The C entry point of K14 rejects bad arguments before any CUDA call."""
     import ctypes as C
 
     from locotouch_b200 import _C
@@ -97,8 +96,20 @@ def test_peer_gradient_exchange_is_off_without_a_process_group_and_validates_its
     lib = _C.lib()
     ptrs = (C.c_void_p * 2)(None, None)
     assert lib.lt_peer_sum_clip_adam(None, ptrs, 2, None, 4, None, None, 16, None, None, 1.0, 0.9, 0.999, 1e-8, 0.0, 0.5, 0.01, 0.5, None, None, 0, None) == 1
-    src = open(__import__("os").path.join(__import__("os").path.dirname(_C.__file__), "loco_rl", "algorithms", "ppo.py")).read()
-    assert "def enable_peer_gradients" in src and "world == 1" in src
+
+
+def test_random_streams_of_one_rank_and_of_neighbouring_ranks_never_share_a_philox_key():
+    """engine.stream_seed: exploration noise, observation noise and taxel dropout of every (seed, rank) draw from distinct keys."""
+    from locotouch_b200.engine import stream_seed
+
+    keys = {}
+    for seed in range(0, 40):
+        for rank in range(0, 16):
+            for consumer in range(3):
+                k = stream_seed(seed, rank, consumer)
+                assert 0 <= k < 2**63
+                assert k not in keys, (seed, rank, consumer, keys[k])
+                keys[k] = (seed, rank, consumer)
 
 
 def test_state_upload_layout_carries_only_what_the_path_reads():
