@@ -1,0 +1,312 @@
+// K15: weight gradient of one Linear layer of the actor-critic / student MLPs,
+//     dW[n, k] (+)= sum_b g[b, n] * x[b, k]          (B = 24576 rows of a PPO mini-batch, n x k <= 512 x 512)
+// as ONE hand-written tcgen05 kernel with in-kernel split-K: replaces, per nn.Linear of reference
+// loco_rl/loco_rl/modules/actor_critic.py:33-56 (autograd's `grad_output.t().mm(input)` in algorithms/ppo.py:350), the 8-way torch.bmm
+// split + torch.sum (cuBLAS tf32gemm / an sm_80 s1688gemm / splitKreduce / ATen reduce_kernel launches) of round 1.
+//
+// GEMM view: M = n (columns of g), N = k (columns of x), K = B (the batch).  Both operands are consumed exactly as they lie in HBM:
+// g [B, n] and x [B, k] are row-major, i.e. "MN-major" operands for the tensor core -- tcgen05.mma kind::tf32 takes MN-major A and B
+// from shared memory (wgmma could not for 32-bit types), so no transpose pass exists anywhere.
+//
+// One CTA = one 128 x BN output tile x one slice of the batch (blockIdx.z): warp 0 streams [32 x 128] / [32 x BN] boxes of g and x
+// into a STAGES-deep shared-memory ring with TMA (128B swizzle, mbarrier expect-tx), warp 1 issues 4 tcgen05.mma (K = 8 each) per
+// stage into a 128 x BN fp32 accumulator in TMEM and releases the stage with tcgen05.commit, warps 2-5 read the accumulator back
+// (tcgen05.ld 32x32b) when the slice is done and add it into the flat gradient buffer with 16-byte vector reductions
+// (red.global.add.v4.f32) -- the split-K partials never exist in memory.  Grid = tiles x splits sized to one CTA per SM.
+// Layouts / descriptors come from CuTe (UMMA::Layout_MN_SW128_32B_Atom -- the one shared-memory layout tcgen05 accepts for MN-major 32-bit operands --, make_tma_atom, make_umma_desc through the MMA atom); the
+// kernel, its pipeline, the split-K schedule and the epilogue are ours.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lt_common.cuh"
+
+#if LT_HAVE_CUTLASS
+
+#include <cute/tensor.hpp>
+#include <cute/arch/tmem_allocator_sm100.hpp>
+#include <cute/atom/mma_atom.hpp>
+#include <cute/atom/copy_traits_sm90_tma.hpp>
+#include <cutlass/arch/barrier.h>
+
+namespace lt_wgrad {
+
+using namespace cute;
+using TF = cute::tfloat32_t;
+
+constexpr int kBM = 128;   // rows of the output tile = one UMMA M
+constexpr int kBK = 32;    // batch rows per pipeline stage = one 128-byte swizzle atom of fp32 ... x 4 UMMA K steps
+constexpr int kThreads = 192;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  using Mma = decltype(make_tiled_mma(SM100_MMA_TF32_SS<TF, TF, float, kBM, BN, UMMA::Major::MN, UMMA::Major::MN>{}));
+  using ShapeA = decltype(partition_shape_A(Mma{}, make_shape(Int<kBM>{}, Int<kBK>{})));
+  using ShapeB = decltype(partition_shape_B(Mma{}, make_shape(Int<BN>{}, Int<kBK>{})));
+  // ((MMA_MN, MMA_K), MNs, Ks, stage); K-blocks of one stage are laid out first, like the CUTLASS collectives do for MN-major operands
+  using SmemA = decltype(UMMA::tile_to_mma_shape(UMMA::Layout_MN_SW128_32B_Atom<TF>{}, append(ShapeA{}, Int<kStages>{}), Step<_2, _1, _3>{}));
+  using SmemB = decltype(UMMA::tile_to_mma_shape(UMMA::Layout_MN_SW128_32B_Atom<TF>{}, append(ShapeB{}, Int<kStages>{}), Step<_2, _1, _3>{}));
+  struct Storage {
+    alignas(1024) cute::ArrayEngine<TF, cute::cosize_v<SmemA>> a;
+    alignas(1024) cute::ArrayEngine<TF, cute::cosize_v<SmemB>> b;
+    alignas(16) uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t acc_full;
+    uint32_t tmem_base;
+  };
+  static constexpr int kStageBytes = (kBM + BN) * kBK * 4;
+  static constexpr int kSmemBytes = (int)sizeof(Storage) + 1024;  // + slack for the manual 1024-byte alignment
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, class TmaA, class TmaB, class TensorA, class TensorB>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_splitk_kernel(TensorA mA, TensorB mB, float* __restrict__ dw, int n_out, int k_in, int k_tiles, int k_tiles_per_split,
+                    CUTE_GRID_CONSTANT TmaA const tma_a, CUTE_GRID_CONSTANT TmaB const tma_b) {
+  using C = Cfg<BN>;
+  constexpr int S = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  typename C::Storage& ss = *reinterpret_cast<typename C::Storage*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int kt0 = blockIdx.z * k_tiles_per_split;
+  const int nkt = min(k_tiles, kt0 + k_tiles_per_split) - kt0;
+  if (nkt <= 0) return;  // uniform per CTA (only when splits * per_split overshoots)
+
+  typename C::Mma tiled_mma;
+  auto tiler = make_shape(Int<kBM>{}, Int<BN>{}, Int<kBK>{});
+  auto coord = make_coord(blockIdx.x, blockIdx.y, _);
+  Tensor gA = local_tile(mA, tiler, coord, Step<_1, X, _1>{});  // (BM, BK, k_tiles)
+  Tensor gB = local_tile(mB, tiler, coord, Step<X, _1, _1>{});  // (BN, BK, k_tiles)
+  Tensor sA = make_tensor(make_smem_ptr(ss.a.begin()), typename C::SmemA{});
+  Tensor sB = make_tensor(make_smem_ptr(ss.b.begin()), typename C::SmemB{});
+  ThrMMA cta_mma = tiled_mma.get_slice(0);
+  Tensor tCgA = cta_mma.partition_A(gA);
+  Tensor tCgB = cta_mma.partition_B(gB);
+  Tensor tCrA = cta_mma.make_fragment_A(sA);  // shared-memory matrix descriptors, (1, MNs, Ks, stage)
+  Tensor tCrB = cta_mma.make_fragment_B(sB);
+  Tensor tCtAcc = tiled_mma.make_fragment_C(partition_shape_C(tiled_mma, make_shape(Int<kBM>{}, Int<BN>{})));
+
+  auto [tAgA, tAsA] = tma_partition(tma_a, Int<0>{}, Layout<_1>{}, group_modes<0, 3>(sA), group_modes<0, 3>(tCgA));
+  auto [tBgB, tBsB] = tma_partition(tma_b, Int<0>{}, Layout<_1>{}, group_modes<0, 3>(sB), group_modes<0, 3>(tCgB));
+
+  if (warp == 0 && cute::elect_one_sync()) {
+    cute::prefetch_tma_descriptor(tma_a.get_tma_descriptor());
+    cute::prefetch_tma_descriptor(tma_b.get_tma_descriptor());
+    for (int s = 0; s < S; ++s) {
+      cute::initialize_barrier(ss.full[s], 1);
+      cute::initialize_barrier(ss.empty[s], 1);
+    }
+    cute::initialize_barrier(ss.acc_full, 1);
+    cutlass::arch::fence_barrier_init();
+  }
+  cute::TMEM::Allocator1Sm tmem;
+  if (warp == 1) {
+    tmem.allocate(BN, &ss.tmem_base);
+    tmem.release_allocation_lock();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = ss.tmem_base;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (cute::elect_one_sync()) {
+      for (int i = 0; i < nkt; ++i) {
+        const int s = i % S;
+        if (i >= S) cute::wait_barrier(ss.empty[s], ((i / S) - 1) & 1);
+        cute::set_barrier_transaction_bytes(ss.full[s], C::kStageBytes);
+        copy(tma_a.with(ss.full[s]), tAgA(_, kt0 + i), tAsA(_, s));
+        copy(tma_b.with(ss.full[s]), tBgB(_, kt0 + i), tBsB(_, s));
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (the atom elects one lane itself)
+    tCtAcc.data() = tmem_base;
+    tiled_mma.accumulate_ = UMMA::ScaleOut::Zero;
+    for (int i = 0; i < nkt; ++i) {
+      const int s = i % S;
+      cute::wait_barrier(ss.full[s], (i / S) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      CUTE_UNROLL
+      for (int kb = 0; kb < size<2>(tCrA); ++kb) {
+        gemm(tiled_mma, tCrA(_, _, kb, s), tCrB(_, _, kb, s), tCtAcc);
+        tiled_mma.accumulate_ = UMMA::ScaleOut::One;
+      }
+      cutlass::arch::umma_arrive(&ss.empty[s]);  // tcgen05.commit: the stage is free once these MMAs have read it
+    }
+    cutlass::arch::umma_arrive(&ss.acc_full);
+  } else {
+    // ---------------------------------------------------------------- epilogue: TMEM -> registers -> red.add into dW
+    cute::wait_barrier(ss.acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int row = blockIdx.x * kBM + q * 32 + (threadIdx.x & 31);
+    const int col0 = blockIdx.y * BN;
+    float* out = dw + (size_t)row * k_in + col0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (col0 + c >= k_in) break;               // warp-uniform
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < n_out) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (col0 + c + j < k_in)  // k_in % 4 == 0: a float4 is inside or outside as a whole
+            red_add_v4(out + c + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) tmem.free(tmem_base, BN);
+}
+
+template <int BN>
+int launch(const float* g, const float* x, float* dw, int B, int n_out, int k_in, int sms, cudaStream_t st) {
+  using C = Cfg<BN>;
+  // (MN, K) views with the MN mode contiguous: exactly the row-major [B, n] / [B, k] tensors
+  Tensor mA = make_tensor(make_gmem_ptr(reinterpret_cast<TF const*>(g)), make_layout(make_shape(n_out, B), make_stride(Int<1>{}, n_out)));
+  Tensor mB = make_tensor(make_gmem_ptr(reinterpret_cast<TF const*>(x)), make_layout(make_shape(k_in, B), make_stride(Int<1>{}, k_in)));
+  typename C::SmemA sa;
+  typename C::SmemB sb;
+  auto tma_a = make_tma_atom(SM90_TMA_LOAD{}, mA, sa(_, _, _, Int<0>{}), make_shape(Int<kBM>{}, Int<kBK>{}));
+  auto tma_b = make_tma_atom(SM90_TMA_LOAD{}, mB, sb(_, _, _, Int<0>{}), make_shape(Int<BN>{}, Int<kBK>{}));
+  Tensor cA = tma_a.get_tma_tensor(shape(mA));
+  Tensor cB = tma_b.get_tma_tensor(shape(mB));
+  const int tiles_m = (n_out + kBM - 1) / kBM, tiles_n = (k_in + BN - 1) / BN;
+  const int k_tiles = (B + kBK - 1) / kBK;
+  int splits = sms / (tiles_m * tiles_n);
+  if (splits < 1) splits = 1;
+  if (splits > k_tiles) splits = k_tiles;
+  const int per = (k_tiles + splits - 1) / splits;
+  splits = (k_tiles + per - 1) / per;
+  auto* kern = &wgrad_splitk_kernel<BN, decltype(tma_a), decltype(tma_b), decltype(cA), decltype(cB)>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) != cudaSuccess) return LT_ERR_CUDA;
+    attr_set = true;
+  }
+  dim3 grid(tiles_m, tiles_n, splits);
+  kern<<<grid, kThreads, C::kSmemBytes, st>>>(cA, cB, dw, n_out, k_in, k_tiles, per, tma_a, tma_b);
+  return lt::check_launch();
+}
+
+// narrow output layers (the action-mean head n = 12, the value head n = 1): CUDA cores, ONE pass over x with 16-byte loads.
+// A thread owns four consecutive columns of x and every (blockDim / quads)-th row of the block's row range; the g row it needs
+// (<= 16 floats) is a warp-broadcast load.  Row groups are folded through shared memory, one vector reduction per block and quad.
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+wgrad_narrow_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ dw, int B, int n_out, int k_in, int rows_per_block) {
+  __shared__ float4 fold[256];
+  const int quads = k_in >> 2;                       // k_in % 4 == 0, quads <= 256 (checked by the caller)
+  const int groups = blockDim.x / quads;             // rows in flight per block
+  const int cq = threadIdx.x % quads, rg = threadIdx.x / quads;
+  const bool live = rg < groups;
+  const int b0 = blockIdx.x * rows_per_block;
+  const int b1 = min(B, b0 + rows_per_block);
+  float4 acc[NMAX];
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+#pragma unroll 4
+    for (int r = b0 + rg; r < b1; r += groups) {
+      const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + (size_t)r * k_in) + cq);
+      const float* gr = g + (size_t)r * n_out;
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j)
+        if (j < n_out) {
+          const float gv = __ldg(gr + j);
+          acc[j].x = fmaf(gv, xv.x, acc[j].x);
+          acc[j].y = fmaf(gv, xv.y, acc[j].y);
+          acc[j].z = fmaf(gv, xv.z, acc[j].z);
+          acc[j].w = fmaf(gv, xv.w, acc[j].w);
+        }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    if (j >= n_out) break;  // uniform
+    __syncthreads();
+    fold[threadIdx.x] = acc[j];
+    __syncthreads();
+    if (rg == 0) {
+      float4 s = fold[cq];
+      for (int q = 1; q < groups; ++q) {
+        const float4 v = fold[q * quads + cq];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      red_add_v4(dw + (size_t)j * k_in + 4 * cq, s.x, s.y, s.z, s.w);
+    }
+  }
+}
+
+// any other narrow shape (k_in % 4 != 0 or k_in > 1024): one thread per column, scalar loads
+__global__ void __launch_bounds__(256)
+wgrad_narrow_scalar_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ dw, int B, int n_out, int k_in, int rows_per_block) {
+  const int b0 = blockIdx.x * rows_per_block;
+  const int b1 = min(B, b0 + rows_per_block);
+  for (int kc = threadIdx.x; kc < k_in; kc += blockDim.x) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+    for (int r = b0; r < b1; ++r) {
+      const float xv = __ldg(x + (size_t)r * k_in + kc);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < n_out) acc[j] = fmaf(__ldg(g + (size_t)r * n_out + j), xv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < n_out) atomicAdd(dw + (size_t)j * k_in + kc, acc[j]);
+  }
+}
+
+}  // namespace lt_wgrad
+
+using lt_wgrad::launch;
+using lt_wgrad::wgrad_narrow_kernel;
+using lt_wgrad::wgrad_narrow_scalar_kernel;
+
+// dw[n_out, k_in] (+)= g[B, n_out]^T x[B, k_in].  zero_first != 0: dw is cleared on the stream first (a memset node under capture);
+// otherwise the caller has cleared it (PPO clears the whole flat gradient buffer once per mini-batch).
+extern "C" int lt_wgrad_splitk(const float* grad_out, const float* act_in, float* dw, int B, int n_out, int k_in, int zero_first, void* stream) {
+  if (!grad_out || !act_in || !dw || B <= 0 || n_out <= 0 || k_in <= 0) return LT_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zero_first && cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)n_out * k_in, st) != cudaSuccess) return LT_ERR_CUDA;
+  if (n_out <= 16) {
+    const int blocks = 2 * lt::sm_count();
+    const int rows = (B + blocks - 1) / blocks;
+    const int grid = (B + rows - 1) / rows;
+    if ((k_in & 3) == 0 && k_in <= 1024 && (((uintptr_t)act_in | (uintptr_t)dw) & 15) == 0)
+      wgrad_narrow_kernel<16><<<grid, 256, 0, st>>>(grad_out, act_in, dw, B, n_out, k_in, rows);
+    else
+      wgrad_narrow_scalar_kernel<<<grid, 256, 0, st>>>(grad_out, act_in, dw, B, n_out, k_in, rows);
+    return lt::check_launch();
+  }
+  if ((n_out & 3) || (k_in & 3) || (((uintptr_t)grad_out | (uintptr_t)act_in | (uintptr_t)dw) & 15)) return LT_ERR_UNSUPPORTED;  // TMA: 16-byte rows
+  const int sms = lt::sm_count();
+  if (k_in > 128) return launch<256>(grad_out, act_in, dw, B, n_out, k_in, sms, st);
+  if (k_in > 64) return launch<128>(grad_out, act_in, dw, B, n_out, k_in, sms, st);
+  return launch<64>(grad_out, act_in, dw, B, n_out, k_in, sms, st);
+}
+
+#else  // !LT_HAVE_CUTLASS
+
+extern "C" int lt_wgrad_splitk(const float*, const float*, float*, int, int, int, int, void*) { return LT_ERR_UNSUPPORTED; }
+
+#endif

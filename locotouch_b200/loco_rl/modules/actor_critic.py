@@ -258,10 +258,13 @@ class ActorCritic(nn.Module):
         return batch % S == 0 and batch // S >= 512 and out_features >= 64
 
     def _wgrad(self, g, x, out, part=None):
-        """out[n,k] = g[B,n]^T x[B,k].  For the tall-skinny shapes of a PPO mini-batch (B = 24576, n*k <= 512*348) cuBLAS'
-        own split-K choice leaves most SMs idle; an explicit 8-way split through one batched GEMM + a sum is ~2x faster."""
+        """out[n,k] = g[B,n]^T x[B,k].  TF32 mode: K15 (``lt_wgrad_splitk``), a hand-written tcgen05 kernel that accumulates the
+        batch slices straight into the flat gradient view.  fp32 parity mode / unsupported shapes: cuBLAS (for the tall-skinny
+        shapes of a PPO mini-batch an explicit 8-way split through one batched GEMM + a sum)."""
         B = g.shape[0]
         S = self._WGRAD_SPLIT
+        if torch.backends.cuda.matmul.allow_tf32 and ops.wgrad(g, x, out) is not None:  # K15: one tcgen05 kernel, in-kernel split-K
+            return
         if self._wgrad_split_ok(B, g.shape[1]):
             part = torch.bmm(g.view(S, B // S, -1).transpose(1, 2), x.view(S, B // S, -1), out=part)
             torch.sum(part, dim=0, out=out)

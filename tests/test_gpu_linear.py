@@ -84,3 +84,41 @@ def test_inference_forward_uses_fused_layers_and_matches_the_modules(cuda, lt_li
             assert _C.launch_count == n0
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("B,n,k", [(24576, 512, 348), (24576, 256, 512), (24576, 128, 256), (24576, 12, 128), (24576, 1, 128),
+                                   (1000, 132, 100), (37, 8, 64), (4096, 64, 36), (8192, 512, 512), (333, 20, 12)])
+def test_wgrad_splitk_matches_torch(cuda, lt_lib, B, n, k):
+    """K15: dW = g^T x with in-kernel split-K (tcgen05 kind::tf32 on row-major = MN-major operands, TMEM accumulator, vector
+    reductions into dW) against the fp64 product; TF32 operand rounding bounds the error by ~2^-11 sqrt(B) |g||x|."""
+    from locotouch_b200 import ops
+
+    gen = torch.Generator().manual_seed(B + n + k)
+    g = (torch.randn(B, n, generator=gen) / B ** 0.5).to(cuda)
+    x = torch.randn(B, k, generator=gen).to(cuda)
+    out = torch.full((n, k), 7.0, device=cuda)  # zero_first must clear it
+    res = ops.wgrad(g, x, out)
+    assert res is not None, "shape should be supported"
+    ref = g.double().t() @ x.double()
+    err = (out.double() - ref).abs().max().item()
+    assert err < 4e-3, f"max abs error {err}"
+    # accumulate mode: a second call without clearing doubles the result
+    ops.wgrad(g, x, out, zero_first=False)
+    err2 = (out.double() - 2 * ref).abs().max().item()
+    assert err2 < 8e-3, f"accumulate: max abs error {err2}"
+    # structure check that a transposed / shifted operand would fail: compare against cuBLAS TF32 as well
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        ref_tf32 = g.t() @ x
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    ops.wgrad(g, x, out)
+    H.assert_close(out, ref_tf32, "wgrad vs cuBLAS TF32", rtol=2e-3, atol=2e-3)
+
+
+def test_wgrad_unsupported_shapes_are_reported(cuda, lt_lib):
+    from locotouch_b200 import ops
+
+    assert ops.wgrad(torch.randn(64, 32, device=cuda), torch.randn(64, 270, device=cuda), torch.zeros(32, 270, device=cuda)) is None  # k % 4
+    assert ops.wgrad(torch.randn(64, 34, device=cuda), torch.randn(64, 128, device=cuda), torch.zeros(34, 128, device=cuda)) is None  # n % 4
