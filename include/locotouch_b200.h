@@ -455,16 +455,19 @@ int lt_dgrad_act_bwd(const float* grad_out, const float* w, const float* act_in,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * K15  weight gradient of a Linear layer with in-kernel split-K
- * replaces  autograd's `grad_output.t().mm(input)` per nn.Linear of loco_rl/loco_rl/modules/actor_critic.py:33-56 under
- *           loss.backward() (loco_rl/loco_rl/algorithms/ppo.py:350), i.e. a cuBLAS split-K GEMM + its reduction kernel
- * dw[n_out, k_in] (+)= grad_out[B, n_out]^T . act_in[B, k_in]: a hand-written tcgen05 (kind::tf32) kernel; both operands are read
- * as they lie (row-major = MN-major, TMA), every CTA accumulates one 128 x BN tile over a slice of the batch in TMEM and adds it
- * into dw with red.global.add.v4.f32 (no partial buffers, no second pass).  zero_first != 0 clears dw on the stream first;
- * with 0 the caller has cleared it (or wants accumulation).  n_out <= 16 (the action-mean / value heads) runs on CUDA cores.
+ * K15  weight + bias gradient of a Linear layer with in-kernel split-K
+ * replaces  autograd's `grad_output.t().mm(input)` and `grad_output.sum(0)` per nn.Linear of
+ *           loco_rl/loco_rl/modules/actor_critic.py:33-56 under loss.backward() (loco_rl/loco_rl/algorithms/ppo.py:350), i.e. a
+ *           cuBLAS split-K GEMM + its reduction kernel + a column-sum kernel
+ * dw[n_out, k_in] (+)= grad_out[B, n_out]^T . act_in[B, k_in], dbias[n_out] (+)= column sums of grad_out (dbias may be NULL):
+ * a hand-written tcgen05 (kind::tf32) kernel; both operands are read as they lie (row-major = MN-major, TMA), every CTA
+ * accumulates a 128-row slab of dw over its full width (<= 512 columns: the whole TMEM) for a slice of the batch and adds it into
+ * dw with red.global.add.v4.f32 (no partial buffers, no second pass); the bias gradient is summed from the grad_out tiles while
+ * they sit in shared memory.  zero_first != 0 clears dw (and dbias) on the stream first; with 0 the caller has cleared them (or
+ * wants accumulation).  n_out <= 16 (the action-mean / value heads) runs on CUDA cores.
  * Wider layers need n_out % 4 == 0, k_in % 4 == 0 and 16-byte aligned pointers (LT_ERR_UNSUPPORTED otherwise or in a stub build).
  * Summation order over the batch slices is not fixed (fp32 atomics): results are reproducible to rounding, not bit for bit. */
-int lt_wgrad_splitk(const float* grad_out, const float* act_in, float* dw, int B, int n_out, int k_in, int zero_first, void* stream);
+int lt_wgrad_splitk(const float* grad_out, const float* act_in, float* dw, float* dbias, int B, int n_out, int k_in, int zero_first, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * K14  gradient all-reduce folded into the optimizer step (env-sharded data parallelism)

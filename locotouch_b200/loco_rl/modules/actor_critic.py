@@ -7,7 +7,8 @@ so reference checkpoints load unchanged.  Differences are below the interface:
   gradient all-reduce is a single NCCL call and clip + Adam is a single fused kernel (K7);
 * ``act`` / ``get_actions_log_prob`` run the fused act epilogue (K3) instead of ``torch.distributions.Normal``: no
   distribution object, no expanded-std tensor, outputs can be written straight into a RolloutStorage slot.
-The MLP GEMMs stay cuBLAS (TF32 allowed exactly like reference locotouch/scripts/train.py:66-69).
+In TF32 mode (allowed exactly like reference locotouch/scripts/train.py:66-69) the MLP GEMMs are this library's tcgen05 kernels
+(K12 forward / dgrad with fused epilogues, K15 weight + bias gradients); fp32 parity mode keeps cuBLAS.
 """
 from __future__ import annotations
 
@@ -217,26 +218,31 @@ class ActorCritic(nn.Module):
         ELU-backward + bias-gradient pass (K9), one wgrad GEMM (out = the gradient view) and one dgrad GEMM."""
 
         fused = torch.backends.cuda.matmul.allow_tf32
+        if fused:
+            # K15 ADDS the batch slices into the gradient views (vector reductions): clear the flat buffer once, ahead of both
+            # chains, instead of one memset node per layer
+            self.flat_grads.zero_()
 
         def chain(linears, acts, gs, g, wstream):
             # dgrad feeds the next layer; the weight gradients only have to be complete before the optimizer step, so they
             # trail on their own stream.  acts[i] is the input of layer i = the post-ELU output of layer i - 1.
+            # TF32 mode: K15 produces dW and db of a layer from ONE read of g (the bias gradient is summed from the tiles in
+            # shared memory), so no separate reduction pass (K9) runs; fp32 parity mode keeps K9 + cuBLAS.
             last = len(linears) - 1
-            ops.bias_act_bwd(g, None, linears[last].bias.grad)  # output layer: no activation, bias gradient = column sums
+            have_bias = False  # bias gradient of the layer that produced g already written (by the K9 pass of the unfused path)
             for i in range(last, -1, -1):
                 lin = linears[i]
-                with wstream.forked():
-                    self._wgrad(g, acts[i], lin.weight.grad, lin._wgrad_part)
+                if not self._wgrad_launch(g, acts[i], lin, wstream, with_bias=not have_bias) and not have_bias:
+                    ops.bias_act_bwd(g, None, lin.bias.grad)            # K9, reduction only (bias gradient = column sums)
+                have_bias = False
                 if i > 0:
-                    below = linears[i - 1]
                     out = None
                     if fused and lin.out_features >= 64:  # K12: dgrad GEMM with the ELU backward of the layer below in its epilogue
                         out = ops.dgrad_act_bwd(g, lin.weight, acts[i], out=gs[i])
                     if out is None:
                         out = torch.mm(g, lin.weight, out=gs[i])
-                        ops.bias_act_bwd(out, acts[i], below.bias.grad)  # K9: ELU backward in place + bias gradient
-                    else:
-                        ops.bias_act_bwd(out, None, below.bias.grad)     # K9, reduction only
+                        ops.bias_act_bwd(out, acts[i], linears[i - 1].bias.grad)  # K9: ELU backward in place + bias gradient
+                        have_bias = True
                     g = out
 
         side, w_actor, w_critic = self.side_streams(grad_mu.device)
@@ -257,14 +263,20 @@ class ActorCritic(nn.Module):
         S = self._WGRAD_SPLIT
         return batch % S == 0 and batch // S >= 512 and out_features >= 64
 
+    def _wgrad_launch(self, g, x, lin, wstream, with_bias: bool = True) -> bool:
+        """Weight gradient of ``lin`` on the trailing stream.  Returns True when the same kernel also produced the bias gradient
+        (K15, TF32 mode, ``with_bias``)."""
+        with wstream.forked():
+            if torch.backends.cuda.matmul.allow_tf32 and ops.wgrad(g, x, lin.weight.grad, lin.bias.grad if with_bias else None, zero_first=False) is not None:
+                return with_bias  # K15: one tcgen05 kernel, in-kernel split-K, dW and db
+            self._wgrad(g, x, lin.weight.grad, lin._wgrad_part)
+        return False
+
     def _wgrad(self, g, x, out, part=None):
-        """out[n,k] = g[B,n]^T x[B,k].  TF32 mode: K15 (``lt_wgrad_splitk``), a hand-written tcgen05 kernel that accumulates the
-        batch slices straight into the flat gradient view.  fp32 parity mode / unsupported shapes: cuBLAS (for the tall-skinny
-        shapes of a PPO mini-batch an explicit 8-way split through one batched GEMM + a sum)."""
+        """out[n,k] = g[B,n]^T x[B,k] through cuBLAS (fp32 parity mode / shapes K15 does not take): for the tall-skinny shapes of a
+        PPO mini-batch an explicit 8-way split through one batched GEMM + a sum (cuBLAS' own split-K choice leaves most SMs idle)."""
         B = g.shape[0]
         S = self._WGRAD_SPLIT
-        if torch.backends.cuda.matmul.allow_tf32 and ops.wgrad(g, x, out) is not None:  # K15: one tcgen05 kernel, in-kernel split-K
-            return
         if self._wgrad_split_ok(B, g.shape[1]):
             part = torch.bmm(g.view(S, B // S, -1).transpose(1, 2), x.view(S, B // S, -1), out=part)
             torch.sum(part, dim=0, out=out)

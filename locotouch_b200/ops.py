@@ -499,20 +499,21 @@ def dgrad_act_bwd(grad_out, weight, act_in, out=None):
 
 
 # ------------------------------------------------------------------------------------------- K15 split-K weight gradient
-def wgrad(grad_out, act_in, out, zero_first: bool = True):
-    """out[n, k] (+)= grad_out[B, n]^T @ act_in[B, k] in ONE tcgen05 TF32 kernel with in-kernel split-K (fp32 vector reductions
-    straight into ``out``, e.g. a view of the flat gradient buffer).  ``zero_first=False``: the caller cleared ``out`` (or wants
-    accumulation).  Returns None when the shape / alignment is not supported so that the caller can keep its cuBLAS path."""
+def wgrad(grad_out, act_in, out, bias_out=None, zero_first: bool = True):
+    """out[n, k] (+)= grad_out[B, n]^T @ act_in[B, k] and, with ``bias_out`` [n], bias_out (+)= grad_out.sum(0), in ONE tcgen05 TF32
+    kernel with in-kernel split-K (fp32 vector reductions straight into ``out``, e.g. a view of the flat gradient buffer; the bias
+    gradient is summed from the tiles that pass through shared memory).  ``zero_first=False``: the caller cleared the outputs (or
+    wants accumulation).  Returns None when the shape / alignment is not supported so that the caller can keep its cuBLAS path."""
     B, n = grad_out.shape
     k = act_in.shape[1]
-    if act_in.shape[0] != B or tuple(out.shape) != (n, k):
+    if act_in.shape[0] != B or tuple(out.shape) != (n, k) or (bias_out is not None and bias_out.numel() != n):
         raise _C.LocoTouchLibraryError("wgrad: shape mismatch")
-    if not (grad_out.is_contiguous() and act_in.is_contiguous() and out.is_contiguous()):
+    if not (grad_out.is_contiguous() and act_in.is_contiguous() and out.is_contiguous()) or (bias_out is not None and not bias_out.is_contiguous()):
         return None
     if n > 16 and ((n & 3) or (k & 3) or ((grad_out.data_ptr() | act_in.data_ptr() | out.data_ptr()) & 15)):
         return None
     rc = lib().lt_wgrad_splitk(ptr(grad_out, torch.float32, "grad_out"), ptr(act_in, torch.float32, "act_in"), ptr(out, torch.float32, "out"),
-                               B, n, k, int(zero_first), current_stream())
+                               ptr(bias_out, torch.float32, "bias_out") if bias_out is not None else None, B, n, k, int(zero_first), current_stream())
     if rc == _C.LT_ERR_UNSUPPORTED:
         return None
     check(rc, "lt_wgrad_splitk")

@@ -87,7 +87,7 @@ def test_inference_forward_uses_fused_layers_and_matches_the_modules(cuda, lt_li
 
 
 @pytest.mark.parametrize("B,n,k", [(24576, 512, 348), (24576, 256, 512), (24576, 128, 256), (24576, 12, 128), (24576, 1, 128),
-                                   (1000, 132, 100), (37, 8, 64), (4096, 64, 36), (8192, 512, 512), (333, 20, 12)])
+                                   (1000, 132, 100), (37, 8, 64), (4096, 64, 36), (8192, 512, 512), (333, 20, 12), (2048, 640, 600), (5000, 256, 272), (777, 3, 50)])
 def test_wgrad_splitk_matches_torch(cuda, lt_lib, B, n, k):
     """K15: dW = g^T x with in-kernel split-K (tcgen05 kind::tf32 on row-major = MN-major operands, TMEM accumulator, vector
     reductions into dW) against the fp64 product; TF32 operand rounding bounds the error by ~2^-11 sqrt(B) |g||x|."""
@@ -97,15 +97,21 @@ def test_wgrad_splitk_matches_torch(cuda, lt_lib, B, n, k):
     g = (torch.randn(B, n, generator=gen) / B ** 0.5).to(cuda)
     x = torch.randn(B, k, generator=gen).to(cuda)
     out = torch.full((n, k), 7.0, device=cuda)  # zero_first must clear it
-    res = ops.wgrad(g, x, out)
+    db = torch.full((n,), -3.0, device=cuda)
+    res = ops.wgrad(g, x, out, db)
     assert res is not None, "shape should be supported"
     ref = g.double().t() @ x.double()
+    ref_b = g.double().sum(0)
     err = (out.double() - ref).abs().max().item()
     assert err < 4e-3, f"max abs error {err}"
+    # bias gradient: column sums of g (TF32-rounded operands on the tensor-core path: |g| ~ B^-1/2, B terms, 2^-11 relative each)
+    err_b = (db.double() - ref_b).abs().max().item()
+    assert err_b < 2e-3, f"bias gradient: max abs error {err_b}"
     # accumulate mode: a second call without clearing doubles the result
-    ops.wgrad(g, x, out, zero_first=False)
+    ops.wgrad(g, x, out, db, zero_first=False)
     err2 = (out.double() - 2 * ref).abs().max().item()
     assert err2 < 8e-3, f"accumulate: max abs error {err2}"
+    assert (db.double() - 2 * ref_b).abs().max().item() < 4e-3
     # structure check that a transposed / shifted operand would fail: compare against cuBLAS TF32 as well
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -113,7 +119,7 @@ def test_wgrad_splitk_matches_torch(cuda, lt_lib, B, n, k):
         ref_tf32 = g.t() @ x
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    ops.wgrad(g, x, out)
+    ops.wgrad(g, x, out)  # without the bias output
     H.assert_close(out, ref_tf32, "wgrad vs cuBLAS TF32", rtol=2e-3, atol=2e-3)
 
 
@@ -122,3 +128,47 @@ def test_wgrad_unsupported_shapes_are_reported(cuda, lt_lib):
 
     assert ops.wgrad(torch.randn(64, 32, device=cuda), torch.randn(64, 270, device=cuda), torch.zeros(32, 270, device=cuda)) is None  # k % 4
     assert ops.wgrad(torch.randn(64, 34, device=cuda), torch.randn(64, 128, device=cuda), torch.zeros(34, 128, device=cuda)) is None  # n % 4
+
+
+@pytest.mark.parametrize("B,hidden", [(24576, [512, 256, 128]), (1000, [128, 64])])
+def test_tf32_training_pass_gradients_match_autograd(cuda, lt_lib, B, hidden):
+    """The production (TF32) composition bench.py times -- K12 forward, K12 dgrad + ELU backward, K15 weight + bias gradients
+    accumulated into the flat buffer -- against autograd through the same torch modules in float64 (reference
+    loco_rl/loco_rl/modules/actor_critic.py:33-56 under loss.backward(), algorithms/ppo.py:350).  TF32 operand rounding bounds
+    the error: every gradient tensor must agree to 1 % of its own largest entry."""
+    import copy
+
+    from locotouch_b200 import _C
+    from locotouch_b200.loco_rl.modules.actor_critic import ActorCritic
+
+    torch.manual_seed(B)
+    A, OBS = 12, 348
+    ac = ActorCritic(OBS, OBS, A, actor_hidden_dims=hidden, critic_hidden_dims=hidden, activation="elu").to(cuda)
+    ref = copy.deepcopy(ac).double()
+    ac.flatten_parameters()
+    obs, cobs = torch.randn(B, OBS, device=cuda), torch.randn(B, OBS, device=cuda)
+    g_mu, g_v = torch.randn(B, A, device=cuda) / B, torch.randn(B, 1, device=cuda) / B
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n0 = _C.launch_count
+        mu, v = ac.train_forward(obs, cobs)
+        ac.train_backward(g_mu, g_v)
+        torch.cuda.synchronize()
+        own = _C.launch_count - n0
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    # library launches only: per network 3 fused forward layers, 2 fused dgrad layers and one K15 per Linear (heads included)
+    assert own >= 2 * (len(hidden) + (len(hidden) - 1) + len(hidden) + 1), own
+    mu64, v64 = ref.actor(obs.double()), ref.critic(cobs.double())
+    H.assert_close(mu, mu64.float(), "mu (TF32 forward)", rtol=2e-2, atol=2e-2)
+    torch.autograd.backward([mu64, v64], [g_mu.double(), g_v.double()])
+    got = dict(ac.named_parameters())
+    for name, p in ref.named_parameters():
+        if name in ("std", "log_std"):
+            continue
+        want = p.grad
+        have = got[name].grad.double()
+        scale = want.abs().max().item()
+        err = (have - want).abs().max().item()
+        assert err <= 1e-2 * scale + 1e-9, f"{name}: max abs error {err:.3e} against a largest entry of {scale:.3e}"

@@ -22,6 +22,7 @@ from locotouch_b200 import ops  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=24576)
+    ap.add_argument("--no-zero", action="store_true", help="K15 without its memset nodes (accumulate mode)")
     args = ap.parse_args()
     B = args.batch
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -30,10 +31,11 @@ def main():
         copies = 4
         sets = [(torch.randn(B, n, device="cuda"), torch.randn(B, k, device="cuda"), torch.zeros(n, k, device="cuda"),
                  torch.empty(8, n, k, device="cuda")) for _ in range(copies)]
+        db = torch.zeros(n, device="cuda")
 
         def k15(i):
             g, x, o, _ = sets[i]
-            ops.wgrad(g, x, o)
+            ops.wgrad(g, x, o, db, zero_first=not args.no_zero)
 
         def bmm8(i):
             g, x, o, part = sets[i]

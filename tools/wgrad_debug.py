@@ -19,20 +19,22 @@ from locotouch_b200 import ops  # noqa: E402
 def main():
     dev = torch.device("cuda:0")
     shapes = [(32, 128, 32), (64, 128, 64), (256, 128, 128), (4096, 128, 256), (4096, 256, 256), (4096, 512, 348), (24576, 512, 348), (24576, 256, 512),
-              (24576, 128, 256), (1000, 132, 100), (37, 20, 64), (4096, 64, 36), (8192, 512, 512), (333, 20, 12), (24576, 12, 128), (24576, 1, 128)]
+              (24576, 128, 256), (1000, 132, 100), (37, 20, 64), (4096, 64, 36), (8192, 512, 512), (333, 20, 12), (2048, 640, 600), (5000, 256, 272), (24576, 12, 128), (24576, 1, 128)]
     for B, n, k in shapes:
         gen = torch.Generator().manual_seed(B + n + k)
         g = (torch.randn(B, n, generator=gen) / B ** 0.5).to(dev)
         x = torch.randn(B, k, generator=gen).to(dev)
         out = torch.full((n, k), 7.0, device=dev)
-        res = ops.wgrad(g, x, out)
+        db = torch.full((n,), 5.0, device=dev)
+        res = ops.wgrad(g, x, out, db)
         torch.cuda.synchronize()
         if res is None:
             print(f"B={B} n={n} k={k}: unsupported")
             continue
         ref = g.double().t() @ x.double()
         err = (out.double() - ref).abs()
-        print(f"B={B} n={n} k={k}: max err {err.max().item():.3e}  (ref rms {ref.pow(2).mean().sqrt().item():.3f})")
+        errb = (db.double() - g.double().sum(0)).abs().max().item()
+        print(f"B={B} n={n} k={k}: max err {err.max().item():.3e}  bias err {errb:.3e}  (ref rms {ref.pow(2).mean().sqrt().item():.3f})")
         if err.max().item() > 4e-3:
             bad = err > 4e-3
             for r0 in range(0, n, 32):
