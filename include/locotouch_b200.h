@@ -32,7 +32,7 @@ const char* lt_error_string(int status);
 /* Text of the last CUDA error seen by this thread inside the library ("" if none). */
 const char* lt_last_cuda_error(void);
 /* sizeof() of the argument structs as compiled, so that a foreign-language binding can verify its own layout:
- * which = 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams, 6 LtTaxelForceArgs,
+ * which = 10 LtPpoHeadsArgs, 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams, 6 LtTaxelForceArgs,
  * 7 LtCommandRanges, 8 LtCommandArgs, 9 LtVelCurriculumArgs; -1 otherwise. */
 int64_t lt_struct_size(int which);
 
@@ -139,6 +139,32 @@ typedef struct {
 } LtPpoLossArgs;
 int64_t lt_ppo_loss_workspace_bytes(int B, int A);
 int lt_ppo_loss(const LtPpoLossArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K16  output heads of both MLPs + PPO loss + head dgrad in ONE pass over the mini-batch
+ * replaces  the two head nn.Linear layers of loco_rl/loco_rl/modules/actor_critic.py:33-56 as PPO.update evaluates them
+ *           (algorithms/ppo.py:252-255: `act` / `evaluate` on the mini-batch), the loss block ppo.py:256-302 (= K6) and autograd's
+ *           backward of the heads down to the pre-activation of the last hidden layer (ppo.py:350): mu = h_a W_a^T + b_a,
+ *           V = h_c W_c^T + b_c, the loss and its derivatives, g_h = (dL/dout . W) * elu'(h) for both networks.
+ * `loss` is the K6 argument block with mu / value turned into optional OUTPUTS (may be NULL) and grad_mu [B,A] / grad_value [B]
+ * required outputs (the head weight / bias gradients are K15's, from these two tensors and h).  h_* are the post-ELU activations
+ * [B,H] of the last hidden layers (both of width H, H % 128 == 0, H <= 256; A % 4 == 0, A <= 16; LT_ERR_UNSUPPORTED otherwise),
+ * w_actor [A,H], b_actor [A], w_critic [1,H], b_critic [1]; g_h_* [B,H] are overwritten.  fp32 FMA arithmetic throughout.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  LtPpoLossArgs loss;
+  int H;
+  const float* h_actor;
+  const float* h_critic;
+  const float* w_actor;
+  const float* b_actor;
+  const float* w_critic;
+  const float* b_critic;
+  float* g_h_actor;
+  float* g_h_critic;
+} LtPpoHeadsArgs;
+int64_t lt_ppo_heads_workspace_bytes(int B, int A);
+int lt_ppo_heads_loss(const LtPpoHeadsArgs* args, void* stream);
 /* lr = max(1e-5, lr/1.5) if kl > 2*desired ; lr = min(1e-2, lr*1.5) if 0 < kl < desired/2.  kl = *kl_sum * kl_scale. */
 int lt_adaptive_lr(const float* kl_sum, float kl_scale, float desired_kl, float* lr_inout, void* stream);
 

@@ -52,6 +52,14 @@ class LtPpoLossArgs(C.Structure):
     ]
 
 
+class LtPpoHeadsArgs(C.Structure):
+    _fields_ = [
+        ("loss", LtPpoLossArgs), ("H", C.c_int),
+        ("h_actor", C.c_void_p), ("h_critic", C.c_void_p), ("w_actor", C.c_void_p), ("b_actor", C.c_void_p),
+        ("w_critic", C.c_void_p), ("b_critic", C.c_void_p), ("g_h_actor", C.c_void_p), ("g_h_critic", C.c_void_p),
+    ]
+
+
 class LtTaxelArgs(C.Structure):
     _fields_ = [
         ("N", C.c_int), ("T", C.c_int),
@@ -223,6 +231,8 @@ _SIGNATURES = {
     "lt_linear_bias_act_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "lt_linear_bias_act": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_dgrad_act_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p, C.c_int64, C.c_void_p]),
+    "lt_ppo_heads_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "lt_ppo_heads_loss": (C.c_int, [C.POINTER(LtPpoHeadsArgs), C.c_void_p]),
     "lt_wgrad_splitk": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
     "lt_mdp_tables_len": (C.c_int, [C.POINTER(LtMdpArgs)]),
     "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),
@@ -266,7 +276,7 @@ def lib() -> C.CDLL:
     if handle.lt_abi_version() != 1:
         raise LocoTouchLibraryError("ABI version mismatch between _C.py and liblocotouch_b200.so")
     for which, struct in enumerate((LtGatherArgs, LtPpoLossArgs, LtTaxelArgs, LtMdpArgs, LtGaitState, LtGaitParams, LtTaxelForceArgs,
-                                    LtCommandRanges, LtCommandArgs, LtVelCurriculumArgs)):
+                                    LtCommandRanges, LtCommandArgs, LtVelCurriculumArgs, LtPpoHeadsArgs)):
         if handle.lt_struct_size(which) != C.sizeof(struct):
             raise LocoTouchLibraryError(
                 f"struct layout mismatch for {struct.__name__}: C {handle.lt_struct_size(which)} vs ctypes {C.sizeof(struct)}")

@@ -53,6 +53,7 @@ extern "C" int64_t lt_struct_size(int which) {
     case 7: return (int64_t)sizeof(LtCommandRanges);
     case 8: return (int64_t)sizeof(LtCommandArgs);
     case 9: return (int64_t)sizeof(LtVelCurriculumArgs);
+    case 10: return (int64_t)sizeof(LtPpoHeadsArgs);
     default: return -1;
   }
 }

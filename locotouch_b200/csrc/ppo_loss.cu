@@ -9,30 +9,11 @@
 // partial row per block in the workspace -> the last block to finish folds the rows in index order, writes the means,
 // dL/dsigma and (adaptive schedule) the new learning rate.  No atomics on floating point, no host synchronisation.
 // Algorithmic traffic per sample: 4 x A x 4 B + 20 B read, A x 4 B + 4 B written (A=12: 264 B).
-#include "lt_common.cuh"
+#include "ppo_loss_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kMaxChunks = 4;   // A <= 64
-constexpr int kMaxA = 64;
-constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2 pi))
-
-struct PpoWs {
-  unsigned int counter;
-  unsigned int pad[3];
-  float partial[1];  // [blocks][3 + A]
-};
-
-struct Params {
-  int B, A;
-  const float *mu, *sigma, *value, *actions, *old_logp, *old_mu, *old_sigma, *adv, *returns, *old_values;
-  float clip, clip_lo, clip_hi, vcoef, ecoef;
-  int use_clipped_value;
-  float desired_kl, grad_scale;
-  float *grad_mu, *grad_value, *grad_sigma, *out, *lr_inout, *loss_accum;
-  PpoWs* ws;
-};
+using namespace lt_ppo;
 
 // kChunks = float4 chunks per lane (A <= 16 * kChunks): the row registers are sized for the actual action dimension -- with the
 // arrays dimensioned for A = 64 the kernel needed 120 registers and two blocks per SM, i.e. two waves for 384 blocks.
@@ -40,9 +21,7 @@ template <int kChunks>
 __global__ void __launch_bounds__(kThreads) ppo_loss_kernel(const Params p) {
   __shared__ float s_sigma[kMaxA], s_inv_var[kMaxA], s_log_sigma[kMaxA];
   __shared__ float s_red[kThreads / 32][3 + kMaxA];
-  __shared__ bool is_last;
   const int A = p.A, chunks = A >> 2;
-  const int K = 3 + A;
   for (int j = threadIdx.x; j < A; j += kThreads) {
     const float s = p.sigma[j];
     s_sigma[j] = s;
@@ -180,88 +159,7 @@ __global__ void __launch_bounds__(kThreads) ppo_loss_kernel(const Params p) {
     s_red[warp][1] = acc_vloss;
     s_red[warp][2] = acc_kl;
   }
-  __syncthreads();
-  float* my_partial = p.ws->partial + (size_t)blockIdx.x * K;
-  for (int k = threadIdx.x; k < K; k += kThreads) {
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) v += s_red[w][k];
-    my_partial[k] = v;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&p.ws->counter, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-
-  // ---- finalize (one block): fold block partials in index order
-  __threadfence();
-  // Work item = (row group g of kFoldGroups, column k): a thread adds rows g, g + kFoldGroups, ... of its column -- consecutive
-  // threads read consecutive floats of a partial row, and the loads of an unrolled batch are in flight together.  (One warp
-  // per column with 12 dependent L2 round trips per lane, two columns per warp, was half of this kernel's 13.8 us.)
-  constexpr int kFoldGroups = 16;
-  __shared__ float s_tot[3 + kMaxA];
-  float* s_fold = &s_red[0][0];  // reused: kFoldGroups x K <= (kThreads / 32) x (3 + kMaxA) needs kFoldGroups <= ... see static_assert
-  static_assert(kFoldGroups * 15 <= (kThreads / 32) * (3 + kMaxA), "fold scratch (A = 12) must fit the reduction scratch");
-  const int groups = (kFoldGroups * K <= (kThreads / 32) * (3 + kMaxA)) ? kFoldGroups : (kThreads / 32) * (3 + kMaxA) / K;
-  for (int idx = threadIdx.x; idx < groups * K; idx += kThreads) {
-    const int g = idx / K, k = idx - g * K;
-    // eight loads per trip with no bounds test between them (a test per load makes every load wait for the previous add);
-    // fixed association order, so the result does not depend on timing
-    const float* col = p.ws->partial + k;
-    const int G = (int)gridDim.x;
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int i = g;
-    for (; i + 7 * groups < G; i += 8 * groups) {
-      float x[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = __ldcg(col + (size_t)(i + u * groups) * K);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] += x[u];
-    }
-    for (; i < G; i += groups) a[0] += __ldcg(col + (size_t)i * K);
-    s_fold[idx] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += kThreads) {
-    float v = 0.f;
-    for (int g = 0; g < groups; ++g) v += s_fold[g * K + k];
-    s_tot[k] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < A) {
-    const int j = threadIdx.x;
-    // d(-ecoef * mean(entropy))/dsigma_j = -ecoef / sigma_j
-    p.grad_sigma[j] = s_tot[3 + j] - p.ecoef * p.grad_scale / s_sigma[j];
-  }
-  if (threadIdx.x == 0) {
-    float entropy = 0.f;
-    for (int j = 0; j < A; ++j) entropy += 0.5f + kHalfLog2Pi + s_log_sigma[j];  // Normal.entropy().sum(-1)
-    const float surr = s_tot[0] * inv_b, vloss = s_tot[1] * inv_b, kl = s_tot[2] * inv_b;
-    p.out[0] = surr + p.vcoef * vloss - p.ecoef * entropy;  // ppo.py:302
-    p.out[1] = surr;
-    p.out[2] = vloss;
-    p.out[3] = entropy;
-    p.out[4] = kl;
-    float lr = p.lr_inout ? *p.lr_inout : 0.f;
-    if (p.lr_inout && p.desired_kl > 0.f) {  // ppo.py:275-281
-      if (kl > p.desired_kl * 2.0f)
-        lr = fmaxf(1e-5f, lr / 1.5f);
-      else if (kl < p.desired_kl / 2.0f && kl > 0.0f)
-        lr = fminf(1e-2f, lr * 1.5f);
-      *p.lr_inout = lr;
-    }
-    p.out[5] = lr;
-    p.out[6] = 0.f;
-    p.out[7] = 0.f;
-    if (p.loss_accum) {  // ppo.py:361-363 without the three .item() syncs
-      p.loss_accum[0] += vloss;
-      p.loss_accum[1] += surr;
-      p.loss_accum[2] += entropy;
-      p.loss_accum[3] += 1.0f;
-    }
-    p.ws->counter = 0;  // self-cleaning
-  }
+  fold_and_finalize(p, s_red, s_sigma, s_log_sigma, inv_b);
 }
 
 __global__ void adaptive_lr_kernel(const float* kl_sum, float kl_scale, float desired_kl, float* lr_inout) {

@@ -160,6 +160,9 @@ class PPO:
         if A is not None and (A % 4 != 0 or A > 64):  # lt_act_sample / lt_ppo_loss move [A] rows as float4 chunks, up to 16 of them
             raise ValueError(f"locotouch_b200 PPO needs num_actions to be a multiple of 4 and <= 64 (got {A})")
         self.optimizer = _FusedAdam(self.actor_critic, learning_rate)
+        # K16 (heads + loss + head dgrad in one kernel).  The head arithmetic is fp32 FMA in either GEMM mode, so it is used in the
+        # fp32 parity mode too; set False to keep the separate head GEMMs + K6.
+        self.fused_heads = True
         self.trace = None  # list -> reduce_and_step appends (local KL, lr, grad norm) per mini-batch (eager diagnostics)
         self._world_override = None  # (rank, world) of same-process replicas attached with attach_local_peers()
         self._peer = None
@@ -299,23 +302,34 @@ class PPO:
         _, world = self._world_info()
         local_lr = adaptive and world == 1  # one process: the learning-rate decision is taken inside the loss kernel
         explicit = ac.supports_explicit_backward
-        if explicit:
-            mu, value = ac.train_forward(obs, cobs)
-        else:  # non-ELU activations: autograd through the torch modules
-            mu = ac.actor(obs)
-            value = ac.critic(cobs)
-            opt.zero_grad()
-        ops.ppo_loss(mu.detach(), ac.std.detach(), value.detach().view(-1), actions, logp.view(-1), mu_old, sigma_old, adv.view(-1),
-                     returns.view(-1), values.view(-1), clip_param=self.clip_param, value_loss_coef=self.value_loss_coef,
-                     entropy_coef=self.entropy_coef, use_clipped_value_loss=self.use_clipped_value_loss,
-                     desired_kl=self.desired_kl if local_lr else None, lr=opt.lr_t if local_lr else None, loss_accum=self._loss_accum, buffers=bufs)
         off, n = ac._slices["std"]
-        if explicit:
-            ac.train_backward(bufs.grad_mu, bufs.grad_value.view(-1, 1))
-            opt.grads[off:off + n].copy_(bufs.grad_sigma)  # every gradient slot is overwritten: no zero_grad pass
+        loss_kw = dict(clip_param=self.clip_param, value_loss_coef=self.value_loss_coef, entropy_coef=self.entropy_coef,
+                       use_clipped_value_loss=self.use_clipped_value_loss, desired_kl=self.desired_kl if local_lr else None,
+                       lr=opt.lr_t if local_lr else None, loss_accum=self._loss_accum, buffers=bufs)
+        if explicit and self.fused_heads and ac.supports_fused_heads:
+            # K16: head layers + loss + head dgrad in one kernel between the fused hidden layers (K12) and their backward
+            h_a, h_c = ac.train_forward(obs, cobs, heads=False)
+            g_ha, g_hc = ac.hidden_grad_buffers()
+            head_a, head_c = ac.actor[-1], ac.critic[-1]
+            ops.ppo_heads_loss(h_a, h_c, head_a.weight, head_a.bias, head_c.weight, head_c.bias, ac.std.detach(), actions, logp.view(-1), mu_old,
+                               sigma_old, adv.view(-1), returns.view(-1), values.view(-1), g_ha, g_hc, **loss_kw)
+            ac.train_backward(bufs.grad_mu, bufs.grad_value.view(-1, 1), from_hidden=True)
+            opt.grads[off:off + n].copy_(bufs.grad_sigma)
         else:
-            torch.autograd.backward([mu, value], [bufs.grad_mu, bufs.grad_value.view_as(value)])
-            opt.grads[off:off + n].add_(bufs.grad_sigma)
+            if explicit:
+                mu, value = ac.train_forward(obs, cobs)
+            else:  # non-ELU activations: autograd through the torch modules
+                mu = ac.actor(obs)
+                value = ac.critic(cobs)
+                opt.zero_grad()
+            ops.ppo_loss(mu.detach(), ac.std.detach(), value.detach().view(-1), actions, logp.view(-1), mu_old, sigma_old, adv.view(-1),
+                         returns.view(-1), values.view(-1), **loss_kw)
+            if explicit:
+                ac.train_backward(bufs.grad_mu, bufs.grad_value.view(-1, 1))
+                opt.grads[off:off + n].copy_(bufs.grad_sigma)  # every gradient slot is overwritten: no zero_grad pass
+            else:
+                torch.autograd.backward([mu, value], [bufs.grad_mu, bufs.grad_value.view_as(value)])
+                opt.grads[off:off + n].add_(bufs.grad_sigma)
         if adaptive and world > 1:  # the local KL mean travels in the tail of the gradient all-reduce
             ac.flat_grads_ext[-4:-3].copy_(bufs.out[4:5])
 

@@ -173,10 +173,21 @@ class ActorCritic(nn.Module):
             self._train_bufs, self._train_buf_key = bufs, key
         return self._train_bufs
 
+    @property
+    def supports_fused_heads(self) -> bool:
+        """K16 (heads + PPO loss + head dgrad in one kernel) takes this module: explicit backward, scalar std, supported widths."""
+        if not self.supports_explicit_backward or self.noise_std_type != "scalar":
+            return False
+        la = [m for m in self.actor if isinstance(m, nn.Linear)]
+        lc = [m for m in self.critic if isinstance(m, nn.Linear)]
+        return len(la) >= 2 and len(lc) >= 2 and ops.ppo_heads_supported(self.num_actions, la[-1].in_features, lc[-1].in_features)
+
     @torch.no_grad()
-    def train_forward(self, observations, critic_observations):
-        """Forward of both MLPs keeping the post-activation tensors (cuBLAS GEMM with fused bias, ELU in place); no autograd
-        graph is built -- ``train_backward`` produces the parameter gradients explicitly."""
+    def train_forward(self, observations, critic_observations, heads: bool = True):
+        """Forward of both MLPs keeping the post-activation tensors (K12: tcgen05 GEMM with bias + ELU in its epilogue; fp32 mode:
+        cuBLAS GEMM with fused bias, ELU in place); no autograd graph is built -- ``train_backward`` produces the parameter
+        gradients explicitly.  ``heads=False`` stops at the last hidden layers and returns their activations (h_actor, h_critic):
+        the head layers then belong to K16 (``ops.ppo_heads_loss``)."""
         bufs = self._train_buffers(observations.shape[0], observations.device)
         self._saved = []
         outs = []
@@ -187,6 +198,8 @@ class ActorCritic(nn.Module):
             acts, h = [x], x
             for i, lin in enumerate(linears):
                 hidden = i < len(linears) - 1
+                if not hidden and not heads:
+                    break
                 out = None
                 if fused and lin.out_features >= 64:  # one tcgen05 GEMM with bias + ELU in the epilogue (K12)
                     out = ops.linear_bias_act(h, lin.weight, lin.bias, out=hs[i], elu=hidden)
@@ -212,10 +225,16 @@ class ActorCritic(nn.Module):
         side.join()
         return outs[0], outs[1]
 
+    def hidden_grad_buffers(self):
+        """(g_h_actor, g_h_critic): where the gradient w.r.t. the pre-activation of the last hidden layers goes (K16 output)."""
+        return tuple(gs[-1] for (_, _, gs) in self._saved)
+
     @torch.no_grad()
-    def train_backward(self, grad_mu, grad_value):
-        """Writes dLoss/dW and dLoss/db of every layer straight into the flat gradient buffer: per layer one fused
-        ELU-backward + bias-gradient pass (K9), one wgrad GEMM (out = the gradient view) and one dgrad GEMM."""
+    def train_backward(self, grad_mu, grad_value, from_hidden: bool = False):
+        """Writes dLoss/dW and dLoss/db of every layer straight into the flat gradient buffer.  TF32 mode: per layer one K15 launch
+        (weight + bias gradient) on a trailing stream and one K12 dgrad GEMM with the ELU backward in its epilogue; fp32 mode: K9 +
+        cuBLAS.  ``from_hidden``: the gradients of the last hidden layers already sit in ``hidden_grad_buffers()`` (K16 wrote
+        them), so the head layers only need their weight gradients."""
 
         fused = torch.backends.cuda.matmul.allow_tf32
         if fused:
@@ -235,6 +254,9 @@ class ActorCritic(nn.Module):
                 if not self._wgrad_launch(g, acts[i], lin, wstream, with_bias=not have_bias) and not have_bias:
                     ops.bias_act_bwd(g, None, lin.bias.grad)            # K9, reduction only (bias gradient = column sums)
                 have_bias = False
+                if i == last and from_hidden:                           # K16 already produced the gradient below the head
+                    g = gs[i]
+                    continue
                 if i > 0:
                     out = None
                     if fused and lin.out_features >= 64:  # K12: dgrad GEMM with the ELU backward of the layer below in its epilogue

@@ -18,6 +18,8 @@ _workspaces: dict[tuple, torch.Tensor] = {}
 
 def _workspace(key: str, nbytes: int, device) -> torch.Tensor:
     """Zero-initialised, cached device workspace (the kernels keep their counters self-cleaning)."""
+    if torch.device(device).type != "cuda":
+        raise _C.LocoTouchLibraryError(f"workspace requested on {device}: locotouch_b200 has no CPU path")
     k = (key, str(device), torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0)
     ws = _workspaces.get(k)
     if ws is None or ws.numel() < nbytes:
@@ -144,7 +146,7 @@ class PpoLossBuffers:
         self.grad_value = torch.empty(B, device=device)
         self.grad_sigma = torch.empty(A, device=device)
         self.out = torch.zeros(8, device=device)
-        self.nbytes = lib().lt_ppo_loss_workspace_bytes(B, A)
+        self.nbytes = max(lib().lt_ppo_loss_workspace_bytes(B, A), lib().lt_ppo_heads_workspace_bytes(B, A))
         self.ws = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
 
 
@@ -178,6 +180,58 @@ def ppo_loss(mu, sigma, value, actions, old_logp, old_mu, old_sigma, advantages,
     a.loss_accum = ptr(loss_accum, torch.float32, "loss_accum")
     a.workspace, a.workspace_bytes = ptr(buffers.ws), buffers.nbytes
     check(lib().lt_ppo_loss(C.byref(a), current_stream()), "lt_ppo_loss")
+    count_launches(1)
+    return buffers
+
+
+def _fill_loss_args(a, B, A, sigma, actions, old_logp, old_mu, old_sigma, advantages, returns, old_values, clip_param, value_loss_coef, entropy_coef,
+                    use_clipped_value_loss, desired_kl, lr, loss_accum, grad_scale, buffers):
+    a.B, a.A = B, A
+    a.sigma = ptr(sigma, torch.float32, "sigma")
+    a.actions = ptr(actions, torch.float32, "actions")
+    a.old_logp = ptr(old_logp, torch.float32, "old_logp")
+    a.old_mu = ptr(old_mu, torch.float32, "old_mu")
+    a.old_sigma = ptr(old_sigma, torch.float32, "old_sigma")
+    a.advantages = ptr(advantages, torch.float32, "advantages")
+    a.returns = ptr(returns, torch.float32, "returns")
+    a.old_values = ptr(old_values, torch.float32, "old_values")
+    a.clip_param, a.value_loss_coef, a.entropy_coef = clip_param, value_loss_coef, entropy_coef
+    a.use_clipped_value_loss = int(use_clipped_value_loss)
+    a.desired_kl = float(desired_kl) if (desired_kl is not None and lr is not None) else 0.0
+    a.grad_scale = grad_scale
+    a.grad_mu, a.grad_value, a.grad_sigma = ptr(buffers.grad_mu), ptr(buffers.grad_value), ptr(buffers.grad_sigma)
+    a.out = ptr(buffers.out)
+    a.lr_inout = ptr(lr, torch.float32, "lr")
+    a.loss_accum = ptr(loss_accum, torch.float32, "loss_accum")
+    a.workspace, a.workspace_bytes = ptr(buffers.ws), buffers.nbytes
+
+
+def ppo_heads_supported(A: int, H_actor: int, H_critic: int) -> bool:
+    """Shapes K16 takes: A % 4 == 0, A <= 16, both last hidden layers of one width H with H % 128 == 0 and H <= 256."""
+    return A % 4 == 0 and A <= 16 and H_actor == H_critic and H_actor % 128 == 0 and H_actor <= 256
+
+
+def ppo_heads_loss(h_actor, h_critic, w_actor, b_actor, w_critic, b_critic, sigma, actions, old_logp, old_mu, old_sigma, advantages, returns,
+                   old_values, g_h_actor, g_h_critic, *, clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.0, use_clipped_value_loss=True,
+                   desired_kl=None, lr=None, loss_accum=None, grad_scale=1.0, buffers: PpoLossBuffers, mu_out=None, value_out=None):
+    """K16: head layers of both MLPs + PPO loss (reference ppo.py:252-302) + head dgrad with the ELU backward of the last hidden
+    layer, one pass.  Writes ``g_h_actor`` / ``g_h_critic`` [B,H], ``buffers.grad_mu`` / ``grad_value`` (inputs of the head weight
+    gradients), ``buffers.grad_sigma`` and ``buffers.out``; ``mu_out`` [B,A] / ``value_out`` [B] optionally receive the head outputs."""
+    B, H = h_actor.shape
+    A = w_actor.shape[0]
+    if tuple(h_critic.shape) != (B, H) or tuple(w_actor.shape) != (A, H) or w_critic.numel() != H or tuple(g_h_actor.shape) != (B, H) or tuple(g_h_critic.shape) != (B, H):
+        raise _C.LocoTouchLibraryError("ppo_heads_loss: shape mismatch")
+    h = _C.LtPpoHeadsArgs()
+    _fill_loss_args(h.loss, B, A, sigma, actions, old_logp, old_mu, old_sigma, advantages, returns, old_values, clip_param, value_loss_coef, entropy_coef,
+                    use_clipped_value_loss, desired_kl, lr, loss_accum, grad_scale, buffers)
+    h.loss.mu = ptr(mu_out, torch.float32, "mu_out")
+    h.loss.value = ptr(value_out, torch.float32, "value_out")
+    h.H = H
+    h.h_actor, h.h_critic = ptr(h_actor, torch.float32, "h_actor"), ptr(h_critic, torch.float32, "h_critic")
+    h.w_actor, h.b_actor = ptr(w_actor, torch.float32, "w_actor"), ptr(b_actor, torch.float32, "b_actor")
+    h.w_critic, h.b_critic = ptr(w_critic, torch.float32, "w_critic"), ptr(b_critic, torch.float32, "b_critic")
+    h.g_h_actor, h.g_h_critic = ptr(g_h_actor, torch.float32, "g_h_actor"), ptr(g_h_critic, torch.float32, "g_h_critic")
+    check(lib().lt_ppo_heads_loss(C.byref(h), current_stream()), "lt_ppo_heads_loss")
     count_launches(1)
     return buffers
 
