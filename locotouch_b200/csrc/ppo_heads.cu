@@ -97,13 +97,36 @@ __global__ void __launch_bounds__(kThreads, V == 1 ? 2 : 1) ppo_heads_kernel(con
 
   const int warps_total = gridDim.x * kWarps;
   int b = blockIdx.x * kWarps + warp;                  // warp-uniform
+  // the warp's NEXT row (hidden rows and the rollout scalars) travels while the current one is processed
+  struct RowScalars {
+    float act, omu, osg, old_logp, adv, old_val, ret;
+  };
+  auto load_scalars = [&](int r) {
+    RowScalars q;
+    q.act = 0.f; q.omu = 0.f; q.osg = 1.f;
+    if (own) {
+      const size_t rr = (size_t)r * A + j_own;
+      q.act = __ldcs(p.actions + rr);
+      q.omu = __ldcs(p.old_mu + rr);
+      q.osg = __ldcs(p.old_sigma + rr);
+    }
+    q.old_logp = __ldcs(p.old_logp + r);
+    q.adv = __ldcs(p.adv + r);
+    q.old_val = __ldcs(p.old_values + r);
+    q.ret = __ldcs(p.returns + r);
+    return q;
+  };
   float4 ha[V], hc[V], ha_n[V], hc_n[V];
+  RowScalars sc_n;
+  sc_n.act = sc_n.omu = sc_n.old_logp = sc_n.adv = sc_n.old_val = sc_n.ret = 0.f;
+  sc_n.osg = 1.f;
   if (b < p.B) {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       ha_n[v] = __ldcs(reinterpret_cast<const float4*>(hp.h_actor + (size_t)b * H) + lane * V + v);
       hc_n[v] = __ldcs(reinterpret_cast<const float4*>(hp.h_critic + (size_t)b * H) + lane * V + v);
     }
+    sc_n = load_scalars(b);
   }
   for (; b < p.B; b += warps_total) {
 #pragma unroll
@@ -111,22 +134,18 @@ __global__ void __launch_bounds__(kThreads, V == 1 ? 2 : 1) ppo_heads_kernel(con
       ha[v] = ha_n[v];
       hc[v] = hc_n[v];
     }
+    const RowScalars sc = sc_n;
     const int bn = b + warps_total;
-    if (bn < p.B) {                                    // the warp's next row travels while this one is processed
+    if (bn < p.B) {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         ha_n[v] = __ldcs(reinterpret_cast<const float4*>(hp.h_actor + (size_t)bn * H) + lane * V + v);
         hc_n[v] = __ldcs(reinterpret_cast<const float4*>(hp.h_critic + (size_t)bn * H) + lane * V + v);
       }
+      sc_n = load_scalars(bn);
     }
     const size_t row = (size_t)b * A;
-    float act = 0.f, omu = 0.f, osg = 1.f;
-    if (own) {
-      act = __ldcs(p.actions + row + j_own);
-      omu = __ldcs(p.old_mu + row + j_own);
-      osg = __ldcs(p.old_sigma + row + j_own);
-    }
-    const float old_logp = __ldcs(p.old_logp + b), adv = __ldcs(p.adv + b), old_val = __ldcs(p.old_values + b), ret = __ldcs(p.returns + b);
+    const float act = sc.act, omu = sc.omu, osg = sc.osg, old_logp = sc.old_logp, adv = sc.adv, old_val = sc.old_val, ret = sc.ret;
 
     // ---- heads
     float part[kHeadA];
