@@ -32,7 +32,7 @@ const char* lt_error_string(int status);
 /* Text of the last CUDA error seen by this thread inside the library ("" if none). */
 const char* lt_last_cuda_error(void);
 /* sizeof() of the argument structs as compiled, so that a foreign-language binding can verify its own layout:
- * which = 10 LtPpoHeadsArgs, 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams, 6 LtTaxelForceArgs,
+ * which = 10 LtPpoHeadsArgs, 11 LtStudentCnnArgs, 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams, 6 LtTaxelForceArgs,
  * 7 LtCommandRanges, 8 LtCommandArgs, 9 LtVelCurriculumArgs; -1 otherwise. */
 int64_t lt_struct_size(int which);
 
@@ -494,6 +494,46 @@ int lt_dgrad_act_bwd(const float* grad_out, const float* w, const float* act_in,
  * Wider layers need n_out % 4 == 0, k_in % 4 == 0 and 16-byte aligned pointers (LT_ERR_UNSUPPORTED otherwise or in a stub build).
  * Summation order over the batch slices is not fixed (fp32 atomics): results are reproducible to rounding, not bit for bit. */
 int lt_wgrad_splitk(const float* grad_out, const float* act_in, float* dw, float* dbias, int B, int n_out, int k_in, int zero_first, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K17  tactile pre-encoder of the CNN-RNN student, forward, one kernel per batch of frames
+ * replaces  loco_rl/loco_rl/models/cnn_2d.py:16-131 (CNN2dHead.forward = 3 x [Conv2d, ReLU(, MaxPool2d)] + flatten + MLP head) as
+ *           built by loco_rl/loco_rl/models/model_generation.py:16-20 from locotouch/config/locotouch/agents/distillation_cfg.py:78-85
+ *           and called by locotouch/distill/student.py:88-103 (8 cuDNN / cuBLAS / ATen launches per call in the reference)
+ * Geometry taken: image (2,17,13), channels (24,24,24), kernels (4,3,2), MaxPool2d(2) after conv1 only, ReLU, no padding, head =
+ * one Linear 192 -> embedding_dim <= 64 (LT_ERR_UNSUPPORTED for anything else: the torch modules stay in charge).
+ * Input: `image` [M, 442] fp32 (channel-major like the observation) or `packed` [M, packed_words] uint32 (bit t%32 of word t/32 =
+ * taxel t of the 17 x 13 grid, both channels equal -- the bitmap K2 emits); exactly one of the two may be NULL.
+ * Weights are the nn.Module tensors as they lie: w1 [24,2,4,4], w2 [24,24,3,3], w3 [24,24,2,2], wh [E,192], biases [24]/[E].
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int M;                       /* frames */
+  int in_channels, height, width;
+  int channels[3], kernel_sizes[3], pool[3];
+  int embedding_dim;
+  const float* image;
+  const uint32_t* packed;
+  int packed_words;
+  const float *w1, *b1, *w2, *b2, *w3, *b3, *wh, *bh;
+  float* out;                  /* [M, embedding_dim] */
+} LtStudentCnnArgs;
+int lt_student_cnn_forward(const LtStudentCnnArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K18  ContactSensor bookkeeping: net-force history ring + air / contact-time state machine, one launch per sensor and step
+ * replaces  [IL] isaaclab.sensors.ContactSensor._update_buffers_impl / reset (IsaacLab 2.2.1; configured by the reference in
+ *           locotouch/config/locotouch/locomotion_base_env_cfg.py:35-39,358-359: history_length 3, track_air_time) whose outputs
+ *           the reference terms read (locotouch/mdp/rewards.py:116-156,596-604, observations.py:60-66)
+ * forces [N,Bd,3] = this step's net contact forces; net_forces_w (may alias forces, may be NULL) receives them; history
+ * [N,H,Bd,3] is shifted by one slot and gets them in slot 0 (NULL: no history); the four timers [N,Bd] follow
+ *   is_contact = |F| > force_threshold; last_air = (cur_air > 0 & contact) ? cur_air + dt : last_air; cur_air = contact ? 0 : cur_air + dt;
+ *   last_contact = (cur_contact > 0 & !contact) ? cur_contact + dt : last_contact; cur_contact = contact ? cur_contact + dt : 0
+ * (all four NULL: forces / history only).  dt_per_env [N] overrides the scalar dt when not NULL.  Envs with reset_mask[n] != 0 get
+ * ContactSensor.reset instead: forces, history and timers cleared.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int lt_contact_sensor_update(const float* forces, float* net_forces_w, float* net_forces_w_history, int history_length, int N, int num_bodies,
+                             float* current_air_time, float* last_air_time, float* current_contact_time, float* last_contact_time,
+                             const float* dt_per_env, float dt, float force_threshold, const uint8_t* reset_mask, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * K14  gradient all-reduce folded into the optimizer step (env-sharded data parallelism)

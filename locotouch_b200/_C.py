@@ -60,6 +60,16 @@ class LtPpoHeadsArgs(C.Structure):
     ]
 
 
+class LtStudentCnnArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("in_channels", C.c_int), ("height", C.c_int), ("width", C.c_int),
+        ("channels", C.c_int * 3), ("kernel_sizes", C.c_int * 3), ("pool", C.c_int * 3), ("embedding_dim", C.c_int),
+        ("image", C.c_void_p), ("packed", C.c_void_p), ("packed_words", C.c_int),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("wh", C.c_void_p), ("bh", C.c_void_p), ("out", C.c_void_p),
+    ]
+
+
 class LtTaxelArgs(C.Structure):
     _fields_ = [
         ("N", C.c_int), ("T", C.c_int),
@@ -233,6 +243,8 @@ _SIGNATURES = {
     "lt_dgrad_act_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_ppo_heads_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "lt_ppo_heads_loss": (C.c_int, [C.POINTER(LtPpoHeadsArgs), C.c_void_p]),
+    "lt_student_cnn_forward": (C.c_int, [C.POINTER(LtStudentCnnArgs), C.c_void_p]),
+    "lt_contact_sensor_update": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "lt_wgrad_splitk": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
     "lt_mdp_tables_len": (C.c_int, [C.POINTER(LtMdpArgs)]),
     "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),
@@ -276,7 +288,7 @@ def lib() -> C.CDLL:
     if handle.lt_abi_version() != 1:
         raise LocoTouchLibraryError("ABI version mismatch between _C.py and liblocotouch_b200.so")
     for which, struct in enumerate((LtGatherArgs, LtPpoLossArgs, LtTaxelArgs, LtMdpArgs, LtGaitState, LtGaitParams, LtTaxelForceArgs,
-                                    LtCommandRanges, LtCommandArgs, LtVelCurriculumArgs, LtPpoHeadsArgs)):
+                                    LtCommandRanges, LtCommandArgs, LtVelCurriculumArgs, LtPpoHeadsArgs, LtStudentCnnArgs)):
         if handle.lt_struct_size(which) != C.sizeof(struct):
             raise LocoTouchLibraryError(
                 f"struct layout mismatch for {struct.__name__}: C {handle.lt_struct_size(which)} vs ctypes {C.sizeof(struct)}")

@@ -54,6 +54,7 @@ extern "C" int64_t lt_struct_size(int which) {
     case 8: return (int64_t)sizeof(LtCommandArgs);
     case 9: return (int64_t)sizeof(LtVelCurriculumArgs);
     case 10: return (int64_t)sizeof(LtPpoHeadsArgs);
+    case 11: return (int64_t)sizeof(LtStudentCnnArgs);
     default: return -1;
   }
 }

@@ -136,6 +136,10 @@ class Student(nn.Module):
         self.load_state_dict(torch.load(model_path, map_location=self.device))
 
     def extract_input_and_forward(self, obs):
+        if "tactile_packed" in obs and self.use_pre_encoder and hasattr(self.pre_encoder, "forward_packed") and not torch.is_grad_enabled():
+            # K2's ballot-packed bitmap straight into K17: the 442-float image is never read
+            emb = self.pre_encoder.forward_packed(obs["tactile_packed"])
+            return self.backbone_forward(obs["policy"][:, :self.proprioception_dim], self.student_encoder(emb, None))
         return self.forward(obs["policy"][:, :self.proprioception_dim], obs["tactile"])
 
     def reset(self, dones=None):

@@ -1,12 +1,18 @@
 """Building blocks of the student network with the reference's names, constructor arguments and ``state_dict`` keys
 (reference loco_rl/loco_rl/models/{mlp,cnn_2d,rnn,memory_module,model_cfg,model_generation,activation}.py).
-The layers are cuBLAS / cuDNN through torch (as in the reference); the hand-written parts of the student batch are the
-padded-batch assembly and the masked loss (K8) and the fused AdamW step (K7)."""
+Training runs the layers through torch (cuBLAS / cuDNN, as in the reference) -- autograd needs their intermediates; the
+inference path of the LocoTouch student's tactile pre-encoder (``CNN2dHead`` under ``torch.no_grad()``, i.e. the student acting in
+the DAgger collection / evaluation) is ONE hand-written kernel (K17, ``lt_student_cnn_forward``), optionally fed with the
+ballot-packed taxel bitmap K2 emits.  The other hand-written parts of the student batch are the padded-batch assembly and the
+masked loss (K8) and the fused AdamW step (K7)."""
 from __future__ import annotations
 
 import copy
 
+import torch
 import torch.nn as nn
+
+from ... import ops
 
 
 def get_activation(act_name):
@@ -93,6 +99,8 @@ class CNN2dHead(nn.Module):
                  output_size=None, nonlinearity="relu", use_maxpool=False, normlayer=None):
         super().__init__()
         c, h, w = image_shape
+        self._image_shape = tuple(image_shape)
+        self._fused_ok = None if (nonlinearity in ("relu", "crelu") and normlayer is None and use_maxpool and tuple(strides) == (2, 1, 1)) else False
         self.conv = CNN2d(c, channels, kernel_sizes, strides, paddings, nonlinearity, use_maxpool, normlayer)
         conv_out = self.conv.conv_out_size(h, w)
         if hidden_sizes or output_size:
@@ -102,8 +110,40 @@ class CNN2dHead(nn.Module):
             self.head = lambda x: x
             self._output_size = conv_out
 
+    def _fused_weights(self):
+        """(w1, b1, w2, b2, w3, b3, wh, bh) when K17 takes this instance's geometry, else None."""
+        ok = getattr(self, "_fused_ok", None)
+        if ok is None:
+            convs = [m for m in self.conv.conv if isinstance(m, nn.Conv2d)]
+            head = getattr(self.head, "model", None)
+            ok = (len(convs) == 3 and head is not None and len(head) == 1 and isinstance(head[0], nn.Linear)
+                  and all(isinstance(m, (nn.Conv2d, nn.ReLU, nn.MaxPool2d)) for m in self.conv.conv)
+                  and [type(m).__name__ for m in self.conv.conv] == ["Conv2d", "ReLU", "MaxPool2d", "Conv2d", "ReLU", "Conv2d", "ReLU"]
+                  and self.conv.conv[2].kernel_size in (2, (2, 2)) and self.conv.conv[2].stride in (2, (2, 2))
+                  and all(c.stride == (1, 1) and c.dilation == (1, 1) and c.groups == 1 for c in convs)
+                  and ops.student_cnn_supported(self._image_shape, [c.out_channels for c in convs], [c.kernel_size[0] for c in convs],
+                                                (2, 1, 1), [c.padding[0] for c in convs], head[0].out_features))
+            self._fused_ok = ok
+        if not ok:
+            return None
+        convs = [m for m in self.conv.conv if isinstance(m, nn.Conv2d)]
+        lin = self.head.model[0]
+        return (convs[0].weight, convs[0].bias, convs[1].weight, convs[1].bias, convs[2].weight, convs[2].bias, lin.weight, lin.bias)
+
     def forward(self, x):
+        if not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32:
+            w = self._fused_weights()
+            if w is not None and w[0].is_cuda:
+                return ops.student_cnn_forward(w, image=x.reshape(x.shape[0], -1).contiguous())  # K17: one kernel
         return self.head(self.conv(x).view(x.shape[0], -1))
+
+    def forward_packed(self, packed):
+        """Inference from the ballot-packed taxel bitmap [M, words] (int32; bit t % 32 of word t // 32 = taxel t, both image channels
+        equal) that K2 (``lt_taxel_synth``) emits next to -- or instead of -- the 442-float observation."""
+        w = self._fused_weights()
+        if w is None:
+            raise NotImplementedError("forward_packed needs the LocoTouch student pre-encoder geometry (K17)")
+        return ops.student_cnn_forward(w, packed=packed.contiguous())
 
     @property
     def output_size(self):

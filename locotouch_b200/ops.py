@@ -573,3 +573,60 @@ def wgrad(grad_out, act_in, out, bias_out=None, zero_first: bool = True):
     check(rc, "lt_wgrad_splitk")
     count_launches(1)
     return out
+
+
+# ------------------------------------------------------------------------------------------- K17 student tactile pre-encoder
+def student_cnn_supported(image_shape, channels, kernel_sizes, pool_strides, paddings, embedding_dim, nonlinearity="relu", normlayer=None) -> bool:
+    """The geometry K17 takes (the LocoTouch student pre-encoder, reference loco_rl/models/model_cfg.py:17-25)."""
+    return (tuple(image_shape) == (2, 17, 13) and tuple(channels) == (24, 24, 24) and tuple(kernel_sizes) == (4, 3, 2)
+            and tuple(pool_strides) == (2, 1, 1) and all(int(q) == 0 for q in paddings) and 0 < embedding_dim <= 64
+            and nonlinearity in ("relu", "crelu") and normlayer is None)
+
+
+def student_cnn_forward(weights, *, image=None, packed=None, out=None):
+    """CNN2dHead.forward (reference loco_rl/models/cnn_2d.py:75-131) of the LocoTouch student cfg in one kernel.  ``weights`` =
+    (w1, b1, w2, b2, w3, b3, wh, bh) as the modules hold them; ``image`` [M, 442] fp32 or ``packed`` [M, words] int32 bitmaps."""
+    if (image is None) == (packed is None):
+        raise _C.LocoTouchLibraryError("student_cnn_forward: give exactly one of image / packed")
+    src = image if image is not None else packed
+    M = src.shape[0]
+    w1, b1, w2, b2, w3, b3, wh, bh = weights
+    E = wh.shape[0]
+    if out is None:
+        out = torch.empty(M, E, device=src.device)
+    a = _C.LtStudentCnnArgs()
+    a.M, a.in_channels, a.height, a.width = M, 2, 17, 13
+    a.channels[:] = [w1.shape[0], w2.shape[0], w3.shape[0]]
+    a.kernel_sizes[:] = [w1.shape[-1], w2.shape[-1], w3.shape[-1]]
+    a.pool[:] = [2, 1, 1]
+    a.embedding_dim = E
+    a.image = ptr(image, torch.float32, "image")
+    a.packed = ptr(packed, torch.int32, "packed")
+    a.packed_words = packed.shape[1] if packed is not None else 0
+    for name, t in zip(("w1", "b1", "w2", "b2", "w3", "b3", "wh", "bh"), weights):
+        setattr(a, name, ptr(t.detach(), torch.float32, name))
+    a.out = ptr(out, torch.float32, "out")
+    check(lib().lt_student_cnn_forward(C.byref(a), current_stream()), "lt_student_cnn_forward")
+    count_launches(1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K18 ContactSensor bookkeeping
+def contact_sensor_update(forces, *, net_forces_w=None, history=None, current_air_time=None, last_air_time=None, current_contact_time=None,
+                          last_contact_time=None, dt: float = 0.0, dt_per_env=None, force_threshold: float = 1.0, reset_mask=None):
+    """[IL] ContactSensor._update_buffers_impl (+ reset for the envs in ``reset_mask``) in one launch: history ring shift + insert and
+    the air / contact-time state machine of every body.  All state tensors are updated in place."""
+    N, Bd = forces.shape[0], forces.shape[1]
+    H = history.shape[1] if history is not None else 0
+    if history is not None and tuple(history.shape) != (N, H, Bd, 3):
+        raise _C.LocoTouchLibraryError("contact_sensor_update: history must be [N, H, bodies, 3]")
+    for t in (current_air_time, last_air_time, current_contact_time, last_contact_time):
+        if t is not None and tuple(t.shape) != (N, Bd):
+            raise _C.LocoTouchLibraryError("contact_sensor_update: timers must be [N, bodies]")
+    check(lib().lt_contact_sensor_update(ptr(forces, torch.float32, "forces"), ptr(net_forces_w, torch.float32, "net_forces_w"),
+                                         ptr(history, torch.float32, "history"), H, N, Bd, ptr(current_air_time, torch.float32),
+                                         ptr(last_air_time, torch.float32), ptr(current_contact_time, torch.float32),
+                                         ptr(last_contact_time, torch.float32), ptr(dt_per_env, torch.float32, "dt_per_env"), float(dt),
+                                         float(force_threshold), ptr(reset_mask, torch.uint8, "reset_mask"), current_stream()),
+          "lt_contact_sensor_update")
+    count_launches(1)

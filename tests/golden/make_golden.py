@@ -414,6 +414,41 @@ def golden_student():
     print(f"student_c4: {init.numel()} params, loss {float(loss):.6f}")
 
 
+STUDENT_CNN = dict(M=37, seed=53, E=64)
+
+
+def student_cnn_inputs(c=STUDENT_CNN):
+    """Frames for the full-geometry pre-encoder: binary taxel bitmaps (both channels equal, ~12 % set) and, second half, fp32
+    frames with independent channels (the normalised / continuous encodings)."""
+    g = torch.Generator().manual_seed(c["seed"])
+    M = c["M"]
+    bits = (torch.rand(M, 1, 17 * 13, generator=g) < 0.12).float().expand(M, 2, 17 * 13).reshape(M, 442).contiguous()
+    dense = torch.rand(M, 442, generator=g)
+    return bits, dense
+
+
+def golden_student_cnn():
+    """reference loco_rl/models/cnn_2d.py CNN2dHead at the LocoTouch student geometry (model_cfg.py:17-25), built by the reference's
+    own generate_model from DistillationRandCylinderCNNRNNMonCfg.pre_encoder."""
+    _, _, cfg_mod = ref_loader.load_reference_distill()
+    loco = ref_loader.load_reference_loco_rl()
+    from loco_rl.models.model_generation import generate_model  # the reference package (asserted by the loader)
+
+    assert os.path.realpath(loco.__file__).startswith(os.path.realpath(ref_loader.REFERENCE_ROOT))
+    cfg = cfg_mod.DistillationRandCylinderCNNRNNMonCfg()
+    torch.manual_seed(STUDENT_CNN["seed"])
+    net = generate_model(442, cfg.pre_encoder.embedding_dim, cfg.pre_encoder)
+    names = list(net.state_dict().keys())
+    flat = torch.cat([v.flatten() for v in net.state_dict().values()]).clone()
+    bits, dense = student_cnn_inputs()
+    with torch.no_grad():
+        out_bits = net(bits.reshape(-1, 2, 17, 13))
+        out_dense = net(dense.reshape(-1, 2, 17, 13))
+    np.savez_compressed(os.path.join(OUT, "student_cnn_c4.npz"), names=np.array(names), params=flat.numpy(), out_bits=out_bits.numpy(),
+                        out_dense=out_dense.numpy(), checksum=np.array(float(bits.double().sum() + dense.double().sum())))
+    print(f"student_cnn_c4: {flat.numel()} params, out {tuple(out_bits.shape)}")
+
+
 RECURRENT_SMALL = dict(T=24, N=48, D=10, A=3, L=2, Hd=6, seed=11, num_mini_batches=4)
 
 
@@ -576,6 +611,7 @@ if __name__ == "__main__":
     golden_dagger()
     golden_tactile_forces()
     golden_commands()
+    golden_student_cnn()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
