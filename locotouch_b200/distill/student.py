@@ -57,6 +57,12 @@ class Student(nn.Module):
     # ------------------------------------------------------------------------------------------------ fused AdamW state
     def _flatten(self):
         params = [p for p in self.parameters() if p.requires_grad]
+        # cuDNN takes RNN weights in place only when they sit at the START of their storage in its own layout (ATen's
+        # try_get_weight_buf builds the candidate buffer from storage offset 0); otherwise every call copies them into a fresh
+        # buffer first.  So the GRU's tensors (weight_ih, weight_hh, bias_ih, bias_hh: cuDNN's order for one layer) lead the flat buffer.
+        rnn_first = [p for m in self.modules() if isinstance(m, nn.RNNBase) for p in m._flat_weights if p is not None and p.requires_grad]
+        seen = {id(p) for p in rnn_first}
+        params = rnn_first + [p for p in params if id(p) not in seen]
         dev = params[0].device
         if self._flat is not None and self._flat["params"].device == dev and all(p.data_ptr() == q for p, q in zip(params, self._flat["ptrs"])):
             return self._flat
@@ -70,7 +76,8 @@ class Student(nn.Module):
             p.grad = grads[off:off + n].view(p.shape)
             off += (n + 3) // 4 * 4
         # NOTE: nn.GRU.flatten_parameters() must NOT be called afterwards: it would re-home the recurrent weights into a
-        # cuDNN-owned buffer and detach them from the flat buffer the fused AdamW kernel updates.
+        # cuDNN-owned buffer and detach them from the flat buffer the fused AdamW kernel updates (it is not needed either:
+        # the tensors already lie the way cuDNN wants them).
         self._flat = dict(params=flat, grads=grads, m=torch.zeros_like(flat), v=torch.zeros_like(flat), step=torch.zeros(1, device=dev),
                           lr=torch.full((1,), self._distill_lr, device=dev), ptrs=[p.data_ptr() for p in params])
         return self._flat
@@ -95,10 +102,7 @@ class Student(nn.Module):
         return self.student_backbone(torch.cat((proprioception, tactile_embedding), dim=-1))
 
     def forward(self, proprioception, tactile_signal, hidden_states=None):
-        with warnings.catch_warnings():
-            # once the parameters live in the flat buffer of the fused AdamW kernel, cuDNN compacts the GRU weights per call
-            warnings.filterwarnings("ignore", message="RNN module weights are not part of single contiguous chunk")
-            return self.backbone_forward(proprioception, self.encoder_forward(tactile_signal, hidden_states))
+        return self.backbone_forward(proprioception, self.encoder_forward(tactile_signal, hidden_states))
 
     # -------------------------------------------------------------------------------------------------------- training
     def train_on_batch(self, batch):

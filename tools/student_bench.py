@@ -58,6 +58,51 @@ def main():
     e1.synchronize()
     gpu_ms = e0.elapsed_time(e1) / args.reps
     print(f"GPU  student step [L={args.L}, B={args.B}] ({steps} valid steps): {gpu_ms:8.2f} ms  -> {steps / gpu_ms * 1e3:,.0f} steps/s   loss {float(loss[0] if loss.ndim else loss):.5f}")
+    # ---- does cuDNN take the GRU weights where they lie (inside the flat AdamW buffer) or re-compact them per call?
+    import warnings
+
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        student.student_encoder.memory.rnn(torch.randn(4, 3, student.student_encoder.memory.rnn.input_size, device=dev))
+        torch.cuda.synchronize()
+    compact = [str(w.message)[:60] for w in rec if "contiguous chunk" in str(w.message)]
+    print(f"GRU weights inside the flat buffer: {'re-compacted per call (' + compact[0] + '...)' if compact else 'used in place (no cuDNN weight copy)'}")
+    # ---- inference: the student acting for N envs (one env step of the DAgger collection): K17 + GRU cell + MLPs vs the torch modules
+    student.eval()
+    for n_envs in (405, 4096, 16384):
+        obs = {"policy": torch.randn(n_envs, 270, device=dev), "tactile": (torch.rand(n_envs, 442, device=dev) < 0.1).float()}
+        res = {}
+        for name, ctx in (("fused pre-encoder (K17)", torch.no_grad), ("torch modules (cuDNN)", torch.enable_grad)):
+            student.reset()
+            with ctx():
+                for _ in range(3):
+                    student.extract_input_and_forward(obs)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(20):
+                    out = student.extract_input_and_forward(obs)
+                e1.record()
+                e1.synchronize()
+            res[name] = e0.elapsed_time(e1) / 20 * 1e3
+            del out
+        a, b = res["fused pre-encoder (K17)"], res["torch modules (cuDNN)"]
+        print(f"student act, {n_envs:6d} envs: {a:8.1f} us with K17   {b:8.1f} us through the torch modules   ({n_envs / a:,.1f} M env-steps/s)")
+        with torch.no_grad():
+            e0.record()
+            for _ in range(20):
+                student.pre_encoder(obs["tactile"].reshape(-1, 2, 17, 13))
+            e1.record()
+            e1.synchronize()
+        k17 = e0.elapsed_time(e1) / 20 * 1e3
+        with torch.enable_grad():
+            e0.record()
+            for _ in range(20):
+                student.pre_encoder(obs["tactile"].reshape(-1, 2, 17, 13))
+            e1.record()
+            e1.synchronize()
+        ref = e0.elapsed_time(e1) / 20 * 1e3
+        print(f"   pre-encoder alone: K17 {k17:7.1f} us   torch {ref:7.1f} us   ({2 * 216.0e3 * n_envs / k17 / 1e6:.2f} TFLOP/s fp32 FMA)")
+    student.train()
     # ---- the same architecture / loss in plain torch on the host cores
     torch.set_num_threads(os.cpu_count() or 1)
     cpu = build(torch.device("cpu"))
