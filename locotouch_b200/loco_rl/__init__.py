@@ -3,5 +3,5 @@
 ``loco_rl.models`` building blocks of the student.  Same names, constructor arguments, attributes and error
 behaviour as the reference fork of rsl_rl 2.2.4; the arithmetic runs in the sm_100a kernels of this package."""
 from .algorithms import PPO  # noqa: F401
-from .modules import ActorCritic  # noqa: F401
+from .modules import ActorCritic, ActorCriticPreEncoderRNNEncoder, ActorCriticRecurrent, ActorCriticRNNEncoder  # noqa: F401
 from .storage import RolloutStorage  # noqa: F401

@@ -196,6 +196,9 @@ class PPO:
     def act(self, obs, critic_obs):
         slot = self.storage.slot()
         t = self.transition
+        if self.actor_critic.is_recurrent:  # the states BEFORE this step (reference ppo.py:130-131); cloned: the GRU output is re-used
+            t.hidden_states = tuple(None if h is None else (tuple(x.clone() for x in h) if isinstance(h, tuple) else h.clone())
+                                    for h in self.actor_critic.get_hidden_states())
         with torch.no_grad():
             side = self.actor_critic.side_streams(obs.device)[0]
             with side.forked():  # the critic runs next to the actor (two independent chains of small GEMMs)
@@ -253,7 +256,10 @@ class PPO:
     def update(self, indices=None):
         """reference ppo.py:179-385.  ``indices``: optional explicit permutation (the reference draws it with randperm)."""
         self.optimizer.sync_lr_to_device()
-        self.update_body(indices)
+        if self.actor_critic.is_recurrent:
+            self.update_recurrent()
+        else:
+            self.update_body(indices)
         return self.update_epilogue()
 
     def update_body(self, indices=None):
@@ -272,7 +278,7 @@ class PPO:
         """Draws / takes the permutation (rollout_storage.py:189) and gathers the permuted rollout once (K5)."""
         ac, st = self.actor_critic, self.storage
         if ac.is_recurrent:
-            raise NotImplementedError("recurrent policies are outside the LocoTouch hot path")
+            raise ValueError("recurrent policies update through update_recurrent()")
         if self.normalize_advantage_per_mini_batch:
             raise NotImplementedError("per-mini-batch advantage normalisation is not used by the LocoTouch cfgs")
         if ac.noise_std_type != "scalar":
@@ -332,6 +338,46 @@ class PPO:
                 opt.grads[off:off + n].add_(bufs.grad_sigma)
         if adaptive and world > 1:  # the local KL mean travels in the tail of the gradient all-reduce
             ac.flat_grads_ext[-4:-3].copy_(bufs.out[4:5])
+
+    def update_recurrent(self):
+        """The recurrent branch of reference ppo.py:195-196,251-302,350-353: mini-batches are env ranges whose observations travel as
+        zero-padded trajectories with the RNN states of every trajectory's first step (K10 builds them once per update); the policy
+        is re-evaluated in batch mode through cuDNN's GRU under autograd, the loss and its gradients w.r.t. (mu, V, sigma) are K6,
+        autograd carries them back through the MLPs / GRU into the flat gradient buffer, clip + Adam is K7."""
+        ac, opt, st = self.actor_critic, self.optimizer, self.storage
+        if ac.noise_std_type != "scalar":
+            raise NotImplementedError("noise_std_type='log' is not used by the LocoTouch cfgs")
+        if self.normalize_advantage_per_mini_batch:
+            raise NotImplementedError("per-mini-batch advantage normalisation is not used by the LocoTouch cfgs")
+        opt.refresh()
+        self._loss_accum.zero_()
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        _, world = self._world_info()
+        local_lr = adaptive and world == 1
+        off, n = ac._slices["std"]
+        for (obs, cobs, actions, values, adv, returns, logp, mu_old, sigma_old, hid, masks, _rnd) in st.recurrent_mini_batch_generator(
+                self.num_mini_batches, self.num_learning_epochs):
+            with torch.enable_grad():
+                ac.act(obs, masks=masks, hidden_states=hid[0])
+                mu = ac.action_mean                                                  # [T, n, A]
+                value = ac.evaluate(cobs, masks=masks, hidden_states=hid[1])         # [T, n, 1]
+            A = mu.shape[-1]
+            B = mu.numel() // A
+            if self._loss_bufs is None or self._loss_bufs.B != B:
+                self._loss_bufs = ops.PpoLossBuffers(B, A, self.device)
+            bufs = self._loss_bufs
+            opt.zero_grad()
+            flat = lambda x, *shape: x.detach().reshape(*shape).contiguous()  # noqa: E731
+            ops.ppo_loss(flat(mu, B, A), ac.std.detach(), flat(value, B), flat(actions, B, A), flat(logp, B), flat(mu_old, B, A), flat(sigma_old, B, A),
+                         flat(adv, B), flat(returns, B), flat(values, B), clip_param=self.clip_param, value_loss_coef=self.value_loss_coef,
+                         entropy_coef=self.entropy_coef, use_clipped_value_loss=self.use_clipped_value_loss,
+                         desired_kl=self.desired_kl if local_lr else None, lr=opt.lr_t if local_lr else None, loss_accum=self._loss_accum, buffers=bufs)
+            torch.autograd.backward([mu, value], [bufs.grad_mu.view_as(mu), bufs.grad_value.view_as(value)])
+            opt.grads[off:off + n].add_(bufs.grad_sigma)
+            if adaptive and world > 1:
+                ac.flat_grads_ext[-4:-3].copy_(bufs.out[4:5])
+            self.reduce_and_step()
+        st.clear()
 
     # ---------------------------------------------------------------------------------- K14: peer-memory gradient exchange
     def enable_peer_gradients(self, group=None) -> bool:

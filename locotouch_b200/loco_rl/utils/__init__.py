@@ -22,8 +22,27 @@ def split_and_pad_trajectories(tensor, dones):
     return ops.TrajectoryIndex(dones).split_and_pad(tensor)
 
 
+class _UnpadFn(torch.autograd.Function):
+    """Differentiable face of the un-pad kernel: the gradient of a gather of the valid rows is the zero-padded scatter of the
+    incoming gradient -- the split-and-pad kernel over the same trajectory index."""
+
+    @staticmethod
+    def forward(ctx, trajectories, masks):
+        from ... import ops
+
+        ctx.index = ops.TrajectoryIndex.from_masks(masks)
+        return ctx.index.unpad(trajectories)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ctx.index.split_and_pad(grad, want_masks=False)[0], None
+
+
 def unpad_trajectories(trajectories, masks):
-    """Inverse of split_and_pad_trajectories (reference utils.py:76-83): [T, M, D] + masks [T, M] -> [T, N, D]."""
+    """Inverse of split_and_pad_trajectories (reference utils.py:76-83): [T, M, D] + masks [T, M] -> [T, N, D].  Differentiable
+    (the recurrent PPO update back-propagates through it into the GRU outputs)."""
     from ... import ops
 
+    if torch.is_grad_enabled() and trajectories.requires_grad:
+        return _UnpadFn.apply(trajectories, masks)
     return ops.TrajectoryIndex.from_masks(masks).unpad(trajectories)

@@ -509,6 +509,81 @@ class _DummyStudent:
         self.resets += 1
 
 
+RECURRENT_PPO = dict(T=24, N=32, A=12, flat_dim=30, enc_dim=18, hidden=[32, 24], enc_hidden=[24], pre_hidden=[20, 16], pre_emb=12, emb=10,
+                     rnn_hidden=16, seed=77, num_learning_epochs=2, num_mini_batches=2)
+
+
+def recurrent_policy_kwargs(kind: str, c=RECURRENT_PPO):
+    """Constructor arguments of the two recurrent encoder policies (cfg blocks rsl_rl_ppo_cfg.py:147,181-226 at reduced widths)."""
+    obs_dim = c["flat_dim"] + c["enc_dim"]
+    kw = dict(actor_obs_dim=obs_dim, critic_obs_dim=obs_dim, num_actions=c["A"], actor_flatten_obs_end_idx=-c["enc_dim"],
+              actor_encoder_obs_start_idx=-c["enc_dim"], actor_encoder_hidden_dims=list(c["enc_hidden"]), actor_encoder_embedding_dim=c["emb"],
+              actor_hidden_dims=list(c["hidden"]), critic_flatten_obs_end_idx=-c["enc_dim"], critic_encoder_obs_start_idx=-c["enc_dim"],
+              critic_encoder_hidden_dims=list(c["enc_hidden"]), critic_encoder_embedding_dim=c["emb"], critic_hidden_dims=list(c["hidden"]),
+              encoder_rnn_type="gru", encoder_rnn_hidden_size=c["rnn_hidden"], encoder_rnn_num_layers=1, activation="elu", init_noise_std=1.0)
+    if kind == "pre_rnn":
+        kw.update(actor_pre_encoder_hidden_dims=list(c["pre_hidden"]), actor_pre_encoder_embedding_dim=c["pre_emb"],
+                  critic_pre_encoder_hidden_dims=list(c["pre_hidden"]), critic_pre_encoder_embedding_dim=c["pre_emb"])
+    return kw
+
+
+def golden_recurrent_ppo():
+    """One full PPO iteration (act x T with the hidden-state bookkeeping -> process_env_step -> compute_returns -> recurrent update) of
+    the UNMODIFIED reference with ActorCriticRNNEncoder and ActorCriticPreEncoderRNNEncoder
+    (loco_rl/modules/actor_critic_rnn_encoder.py, actor_critic_pre_encoder_rnn_encoder.py; algorithms/ppo.py:130,195-196,251-255)."""
+    import contextlib
+    import io
+
+    ref_loader.load_reference_loco_rl()
+    from loco_rl.algorithms import PPO
+    from loco_rl.modules import ActorCriticPreEncoderRNNEncoder, ActorCriticRNNEncoder
+    from torch.distributions import Normal
+
+    c = RECURRENT_PPO
+    T, N, A = c["T"], c["N"], c["A"]
+    obs_dim = c["flat_dim"] + c["enc_dim"]
+    out = {}
+    for kind, cls in (("rnn", ActorCriticRNNEncoder), ("pre_rnn", ActorCriticPreEncoderRNNEncoder)):
+        torch.manual_seed(c["seed"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            ac = cls(**recurrent_policy_kwargs(kind))
+        names = [k for k, _ in ac.named_parameters()]
+        init = torch.cat([p.detach().flatten() for p in ac.parameters()]).clone()
+        alg = PPO(ac, num_learning_epochs=c["num_learning_epochs"], num_mini_batches=c["num_mini_batches"], clip_param=0.2, gamma=0.99, lam=0.95,
+                  value_loss_coef=1.0, entropy_coef=0.01, learning_rate=1.0e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
+                  desired_kl=0.01, device="cpu")
+        alg.init_storage(N, T, [obs_dim], [obs_dim], [A])
+        r = H.make_rollout(T=T, N=N, obs_dim=obs_dim, A=A, seed=c["seed"])
+        eps = torch.randn(T, N, A, generator=torch.Generator().manual_seed(c["seed"] + 1))
+        orig_sample = Normal.sample
+        with torch.inference_mode():  # the rollout of OnPolicyRunner.learn (runners/on_policy_runner.py) runs under inference_mode
+            for t in range(T):
+                Normal.sample = lambda self, sample_shape=torch.Size(), _e=eps[t]: (self.loc + self.scale * _e).detach()
+                alg.act(r["obs"][t], r["critic_obs"][t])
+                Normal.sample = orig_sample
+                alg.process_env_step(r["rewards"][t, :, 0].clone(), r["dones"][t, :, 0].long(), {"time_outs": r["time_outs"][t, :, 0]})
+            alg.compute_returns(r["critic_obs"][-1])
+        st = alg.storage
+        out.update({f"{kind}_names": np.array(names), f"{kind}_init": init.numpy(), f"{kind}_eps": eps.numpy(), f"{kind}_actions": st.actions.numpy().copy(),
+                    f"{kind}_logp": st.actions_log_prob.numpy().copy(), f"{kind}_values": st.values.numpy().copy(),
+                    f"{kind}_returns": st.returns.numpy().copy(), f"{kind}_advantages": st.advantages.numpy().copy(),
+                    f"{kind}_hid_a": st.saved_hidden_states_a[0].numpy().copy(), f"{kind}_hid_c": st.saved_hidden_states_c[0].numpy().copy(),
+                    f"{kind}_final_hidden": ac.get_hidden_states()[0].detach().numpy().copy()})
+        lrs = []
+        orig_step = alg.optimizer.step
+
+        def step(*a, _orig=orig_step, _alg=alg, **k):
+            lrs.append(_alg.optimizer.param_groups[0]["lr"])
+            return _orig(*a, **k)
+
+        alg.optimizer.step = step
+        losses = alg.update()
+        out.update({f"{kind}_lr_sequence": np.array(lrs), f"{kind}_losses": np.array([losses[0], losses[1], losses[2]]),
+                    f"{kind}_final": torch.cat([p.detach().flatten() for p in ac.parameters()]).numpy()})
+        print(f"recurrent_ppo[{kind}]: {init.numel()} params, losses {losses[:3]}, lr {lrs}")
+    np.savez_compressed(os.path.join(OUT, "recurrent_ppo_c1.npz"), **out)
+
+
 def golden_dagger():
     """ReplayBuffer.collect_data (teacher roll-out, then a student roll-out appended to it), to_recurrent_generator and
     evaluate of the reference, driven by the deterministic tape env of tests/helpers.py."""
@@ -612,6 +687,7 @@ if __name__ == "__main__":
     golden_tactile_forces()
     golden_commands()
     golden_student_cnn()
+    golden_recurrent_ppo()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
