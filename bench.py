@@ -213,7 +213,7 @@ def run_reference(args, rank: int):
 # ------------------------------------------------------------------------------------------------------ kernel roofline
 def ncu_traffic_bytes(kernel_substr: str):
     """DRAM bytes per launch (read + write) of the committed `ncu --set full` capture, or None."""
-    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
+    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2f_ncu_full_summary.json", "r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
                  if os.path.exists(q)), None)  # newest capture first
     if path is None:
         return None
@@ -534,8 +534,9 @@ def main():
                          "alg_bytes_per_launch": nbytes})
         top = max(rows, key=lambda r: r["us_per_launch"])
         line["roofline"] = {"bound": "hbm", "achieved": top["achieved"], "peak": hbm, "unit": "GB/s", "frac": top["frac"], "traffic": ncu_traffic_bytes("mdp_step_kernel"),
-                            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1*_k1_k2_ncu_full_summary.json (one ncu --set full capture; "
-                                            "the kernel's 12.6 MB of writes are still in L2 when it ends, ncu counts 0 written)",
+                            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the newest profiles/*_ncu_full_summary.json (one ncu --set "
+                                            "full capture of this kernel, not re-measured in this run; the kernel's 12.6 MB of writes are still in L2 when it "
+                                            "ends, so ncu counts few bytes written)",
                             "kernel": top["kernel"], "us_per_launch": top["us_per_launch"], "peak_kind": kind,
                             "how": "96 launches in one CUDA graph cycling 6 state sets (> L2), CUDA events on the launch stream"}
         try:  # the small kernels of the update + GAE, timed the same way (tools/kbench.py: graph of launches over > L2 of inputs)
@@ -548,11 +549,27 @@ def main():
             extra.update(KB.bench_adam(engine.alg.optimizer.flat.numel(), 100))
             extra.update(KB.bench_k9(N * T_STEPS // 4, 80))
             extra.update(KB.bench_gather(N * T_STEPS, N * T_STEPS // 4, 20, obs_dim=engine.spec.obs_dim))
+            extra.update(KB.bench_heads(N * T_STEPS // 4, 100))
             for name, (us, nbytes) in extra.items():
                 gbs = nbytes / us / 1e3
                 rows.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "us_per_launch": us,
                              "alg_bytes_per_launch": nbytes})
+            # one row per GEMM of a mini-batch: fp32 operands make them HBM / L2 bound, so the row carries both views
+            for name, (us, nbytes, flops) in KB.bench_gemms(N * T_STEPS // 4, 30, obs_dim=engine.spec.obs_dim).items():
+                gbs = nbytes / us / 1e3
+                rows.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "us_per_launch": us,
+                             "alg_bytes_per_launch": nbytes, "tflops": flops / us / 1e6, "tf32_peak_tflops": tf / 2.0, "tensor_frac": flops / us / 1e6 / (tf / 2.0)})
             rows.extend(gemm_rows(engine, tf))
+            # the kernel with the largest share of the iteration (K12: ~50 % of the summed kernel time, profiles/r2e_launches_summary.md)
+            # next to the streaming kernel the headline fraction is quoted on
+            k12 = [r for r in rows if r["kernel"].startswith("K12 forward")]
+            if k12:
+                big = max(k12, key=lambda r: r["us_per_launch"])
+                line["roofline"]["dominant_by_share"] = {"kernel": big["kernel"], "bound": "hbm", "achieved": big["achieved"], "peak": hbm, "unit": "GB/s",
+                                                         "frac": big["frac"], "us_per_launch": big["us_per_launch"], "tflops": big["tflops"],
+                                                         "tensor_frac_of_tf32_peak": big["tensor_frac"],
+                                                         "traffic": ncu_traffic_bytes("device_kernel"),
+                                                         "note": "fp32 operands: 105 FLOP/B against a ridge of ~100 (TF32) -- HBM / L2 bound, so the fraction is of the HBM peak"}
         except Exception as exc:  # noqa: BLE001 -- the table is diagnostics; the headline numbers above do not depend on it
             line["kernels_error"] = repr(exc)
         line["kernels"] = rows

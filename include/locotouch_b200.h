@@ -496,6 +496,20 @@ int lt_dgrad_act_bwd(const float* grad_out, const float* w, const float* act_in,
 int lt_wgrad_splitk(const float* grad_out, const float* act_in, float* dw, float* dbias, int B, int n_out, int k_in, int zero_first, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * K3b  output heads of both MLPs + action sampling + log-prob, one launch per env step of the rollout
+ * replaces  the head nn.Linear of actor and critic + Normal.sample() + log_prob().sum(-1) of
+ *           loco_rl/loco_rl/modules/actor_critic.py:105-131 as PPO.act drives them (algorithms/ppo.py:129-141): a cuBLAS GEMM, a GEMV,
+ *           lt_act_sample and the value copy of round 1
+ * h_* [N,H] post-ELU activations of the last hidden layers (H % 128 == 0, H <= 256; h_critic may be NULL: actor only), heads as in
+ * K16; sigma [A] (A % 4 == 0, A <= 16); eps [N,A] explicit standard-normal draws or NULL = Philox (the stream of lt_act_sample:
+ * key (seed, offset + *offset_base), counter (env, chunk)).  Outputs: actions / mu_out / sigma_out [N,A], logp [N], values [N].
+ * ------------------------------------------------------------------------------------------------------------------ */
+int lt_act_heads(const float* h_actor, const float* h_critic, const float* w_actor, const float* b_actor, const float* w_critic,
+                 const float* b_critic, const float* sigma, const float* eps, float* actions, float* logp, float* mu_out,
+                 float* sigma_out, float* values, int N, int A, int H, uint64_t seed, uint64_t offset, const int64_t* offset_base,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * K17  tactile pre-encoder of the CNN-RNN student, forward, one kernel per batch of frames
  * replaces  loco_rl/loco_rl/models/cnn_2d.py:16-131 (CNN2dHead.forward = 3 x [Conv2d, ReLU(, MaxPool2d)] + flatten + MLP head) as
  *           built by loco_rl/loco_rl/models/model_generation.py:16-20 from locotouch/config/locotouch/agents/distillation_cfg.py:78-85

@@ -245,6 +245,7 @@ _SIGNATURES = {
     "lt_ppo_heads_loss": (C.c_int, [C.POINTER(LtPpoHeadsArgs), C.c_void_p]),
     "lt_student_cnn_forward": (C.c_int, [C.POINTER(LtStudentCnnArgs), C.c_void_p]),
     "lt_contact_sensor_update": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "lt_act_heads": (C.c_int, [C.c_void_p] * 13 + [C.c_int] * 3 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "lt_wgrad_splitk": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
     "lt_mdp_tables_len": (C.c_int, [C.POINTER(LtMdpArgs)]),
     "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),

@@ -228,6 +228,87 @@ __global__ void __launch_bounds__(kThreads, V == 1 ? 2 : 1) ppo_heads_kernel(con
   fold_and_finalize(p, s_red, s_sigma, s_log_sigma, inv_b);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// K3b: the same heads on the ROLLOUT side -- mu = h_a W_a^T + b_a, V = h_c W_c^T + b_c, a = mu + sigma * eps, log-prob -- one launch per
+// env step in place of a cuBLAS GEMM, a GEMV, the sample kernel (K3) and the value copy (reference modules/actor_critic.py:105-131 as
+// driven by algorithms/ppo.py:129-141).  Same mapping as above (warp per env, transposed butterfly); the normal draws are the Philox
+// stream of lt_act_sample (key (seed, offset), counter (env, chunk)), or explicit eps.
+struct ActHeadParams {
+  int N, A, H;
+  const float *h_actor, *h_critic, *w_actor, *b_actor, *w_critic, *b_critic, *sigma, *eps;
+  float *actions, *logp, *mu_out, *sigma_out, *values;
+  uint64_t seed, offset;
+  const int64_t* offset_base;
+};
+
+template <int V, int NA>
+__global__ void __launch_bounds__(kThreads) act_heads_kernel(const ActHeadParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int A = p.A, H = p.H;
+  const int j_own = lane >> 1;
+  const bool own = !(lane & 1) && j_own < A;
+  uint64_t offset = p.offset;
+  if (p.offset_base) offset += (uint64_t)*p.offset_base;
+  float4 wa[NA][V], wc[V];
+#pragma unroll
+  for (int j = 0; j < NA; ++j)
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      wa[j][v] = j < A ? __ldg(reinterpret_cast<const float4*>(p.w_actor + (size_t)j * H) + lane * V + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int v = 0; v < V; ++v) wc[v] = p.h_critic ? __ldg(reinterpret_cast<const float4*>(p.w_critic) + lane * V + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float bias_a = own ? __ldg(p.b_actor + j_own) : 0.f;
+  const float bias_c = p.h_critic ? __ldg(p.b_critic) : 0.f;
+  const float sig = own ? __ldg(p.sigma + j_own) : 1.f;
+  const float lsig = logf(sig);
+  for (int n = blockIdx.x * kWarps + warp; n < p.N; n += gridDim.x * kWarps) {
+    float part[kHeadA];
+    float4 ha[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) ha[v] = __ldcs(reinterpret_cast<const float4*>(p.h_actor + (size_t)n * H) + lane * V + v);
+    float vs = 0.f;
+    if (p.h_critic) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) vs = dot4(__ldcs(reinterpret_cast<const float4*>(p.h_critic + (size_t)n * H) + lane * V + v), wc[v], vs);
+    }
+#pragma unroll
+    for (int j = 0; j < kHeadA; ++j) {
+      float s = 0.f;
+      if (j < NA) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) s = dot4(ha[v], wa[j][v], s);
+      }
+      part[j] = s;
+    }
+    const float mu = transposed_reduce16(part, lane) + bias_a;
+    const float val = lt::warp_sum(vs) + bias_c;
+    float lp = 0.f;
+    if (own) {
+      const size_t o = (size_t)n * A + j_own;
+      float e;
+      if (p.eps) {
+        e = __ldcs(p.eps + o);
+      } else {
+        const uint4 r = lt::Philox::gen(p.seed, offset, (uint32_t)n, (uint32_t)(j_own >> 2));
+        const int k = j_own & 3;
+        const float2 g = k < 2 ? lt::Philox::normal2(r.x, r.y) : lt::Philox::normal2(r.z, r.w);
+        e = (k & 1) ? g.y : g.x;
+      }
+      const float a = __fadd_rn(mu, __fmul_rn(sig, e));   // torch.normal(mean, std): mean + std * eps
+      const float d = a - mu;
+      lp = -(d * d) / (2.0f * sig * sig) - lsig - kHalfLog2Pi;
+      p.actions[o] = a;
+      if (p.mu_out) p.mu_out[o] = mu;
+      if (p.sigma_out) p.sigma_out[o] = sig;
+    }
+    lp = lt::warp_sum(lp);
+    if (lane == 0) {
+      p.logp[n] = lp;
+      if (p.values) p.values[n] = val;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int64_t lt_ppo_heads_workspace_bytes(int B, int A) {
@@ -274,5 +355,31 @@ extern "C" int lt_ppo_heads_loss(const LtPpoHeadsArgs* h, void* stream) {
   LT_HEADS_CASE(1, 4) LT_HEADS_CASE(1, 8) LT_HEADS_CASE(1, 12) LT_HEADS_CASE(1, 16)
   LT_HEADS_CASE(2, 4) LT_HEADS_CASE(2, 8) LT_HEADS_CASE(2, 12) LT_HEADS_CASE(2, 16)
 #undef LT_HEADS_CASE
+  return LT_ERR_UNSUPPORTED;
+}
+
+extern "C" int lt_act_heads(const float* h_actor, const float* h_critic, const float* w_actor, const float* b_actor, const float* w_critic,
+                            const float* b_critic, const float* sigma, const float* eps, float* actions, float* logp, float* mu_out,
+                            float* sigma_out, float* values, int N, int A, int H, uint64_t seed, uint64_t offset, const int64_t* offset_base,
+                            void* stream) {
+  if (!h_actor || !w_actor || !b_actor || !sigma || !actions || !logp || N <= 0 || A <= 0) return LT_ERR_INVALID_ARG;
+  if (h_critic && (!w_critic || !b_critic || !values)) return LT_ERR_INVALID_ARG;
+  if ((A & 3) || A > kHeadA || H <= 0 || (H % 128) != 0 || H > 256) return LT_ERR_UNSUPPORTED;
+  if ((((uintptr_t)h_actor | (uintptr_t)h_critic | (uintptr_t)w_actor | (uintptr_t)w_critic) & 15) != 0) return LT_ERR_INVALID_ARG;
+  ActHeadParams p;
+  p.N = N; p.A = A; p.H = H;
+  p.h_actor = h_actor; p.h_critic = h_critic; p.w_actor = w_actor; p.b_actor = b_actor; p.w_critic = w_critic; p.b_critic = b_critic;
+  p.sigma = sigma; p.eps = eps; p.actions = actions; p.logp = logp; p.mu_out = mu_out; p.sigma_out = sigma_out; p.values = values;
+  p.seed = seed; p.offset = offset; p.offset_base = offset_base;
+  const int want = (int)lt::ceil_div(N, kWarps);
+  const int cap = 4 * lt::sm_count();
+  const int grid = want < cap ? want : cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int v = H / 128, na = A <= 4 ? 4 : (A <= 8 ? 8 : (A <= 12 ? 12 : 16));
+#define LT_ACT_CASE(V_, NA_) \
+  if (v == V_ && na == NA_) { act_heads_kernel<V_, NA_><<<grid, kThreads, 0, st>>>(p); return lt::check_launch(); }
+  LT_ACT_CASE(1, 4) LT_ACT_CASE(1, 8) LT_ACT_CASE(1, 12) LT_ACT_CASE(1, 16)
+  LT_ACT_CASE(2, 4) LT_ACT_CASE(2, 8) LT_ACT_CASE(2, 12) LT_ACT_CASE(2, 16)
+#undef LT_ACT_CASE
   return LT_ERR_UNSUPPORTED;
 }

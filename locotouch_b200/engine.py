@@ -345,6 +345,9 @@ class HotPathEngine:
         # plain launches -- so several processes capture it as ONE graph like a single process does; only the advantage-statistics
         # all-reduce of the rollout's tail stays eager.
         whole_update = self.world > 1 and self.peer_gradients and split is None and os.environ.get("LT_PEER_GRAPH", "1") != "0"
+        # ... and with the advantage statistics in symmetric memory too (barrier + peer loads instead of an NCCL all-reduce) the
+        # rollout's tail is capturable as well: the whole iteration is two graphs per rank, exactly like a single process
+        tail_in_graph = whole_update and self.alg._peer.get("adv_stats") is not None and os.environ.get("LT_PEER_STATS_GRAPH", "1") != "0"
         split = (self.world > 1) if split is None else split
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
@@ -362,7 +365,7 @@ class HotPathEngine:
             g = torch.cuda.CUDAGraph()
             with graph_capture(g):
                 self.rollout_steps(bank=bank)
-                if not split:
+                if not split or tail_in_graph:
                     self.rollout_finish()
             g_roll.append(g)
         if not split or whole_update:
@@ -370,7 +373,7 @@ class HotPathEngine:
             with graph_capture(g_upd):
                 alg.update_body(self.perm)
                 self.finish_iteration()
-            self._graphs = dict(split=False, roll=g_roll, update=g_upd, finish_eager=split)
+            self._graphs = dict(split=False, roll=g_roll, update=g_upd, finish_eager=split and not tail_in_graph)
         else:
             g_begin = torch.cuda.CUDAGraph()
             with graph_capture(g_begin):

@@ -60,8 +60,8 @@ class _FusedAdam:
             raise NotImplementedError("PPO's optimizer is torch.optim.Adam: weight_decay != 0 (L2 form) is not implemented by the fused kernel")
         return g
 
-    def use_gradient_buffer(self, buf: torch.Tensor):
-        self.grads = self.ac.rebind_gradients(buf)
+    def use_gradient_buffer(self, buf: torch.Tensor, copy: bool = True):
+        self.grads = self.ac.rebind_gradients(buf, copy=copy)
         self._peer_buf = buf
 
     def refresh(self):
@@ -200,12 +200,14 @@ class PPO:
             t.hidden_states = tuple(None if h is None else (tuple(x.clone() for x in h) if isinstance(h, tuple) else h.clone())
                                     for h in self.actor_critic.get_hidden_states())
         with torch.no_grad():
-            side = self.actor_critic.side_streams(obs.device)[0]
-            with side.forked():  # the critic runs next to the actor (two independent chains of small GEMMs)
-                values = self.actor_critic.evaluate(critic_obs)
-                slot["values"].copy_(values)  # the critic GEMM's output row is the only copy left on this path
-            t.actions = self.actor_critic.act(obs, out=slot)
-            side.join()
+            t.actions = self.actor_critic.act_evaluate_fused(obs, critic_obs, slot) if self.fused_heads else None  # K12 x 6 + K3b
+            if t.actions is None:
+                side = self.actor_critic.side_streams(obs.device)[0]
+                with side.forked():  # the critic runs next to the actor (two independent chains of small GEMMs)
+                    values = self.actor_critic.evaluate(critic_obs)
+                    slot["values"].copy_(values)  # the critic GEMM's output row is the only copy left on this path
+                t.actions = self.actor_critic.act(obs, out=slot)
+                side.join()
         t.values = slot["values"]
         t.actions_log_prob = slot["logp"]
         t.action_mean = slot["mu"]
@@ -230,8 +232,23 @@ class PPO:
 
     def compute_returns(self, last_critic_obs):
         if self.compute_returns_scan(last_critic_obs):
-            D.reduce_adv_stats_(self._adv_stats)
+            self.reduce_adv_stats()
             self.compute_returns_normalize()
+
+    def reduce_adv_stats(self):
+        """(sum, sum of squares, count) of the advantages over all ranks.  Under K14 the three doubles sit in symmetric memory: a
+        cross-GPU barrier, then every rank adds the W blocks in rank order by peer loads -- plain launches, capturable in the
+        rollout graph; otherwise one NCCL all-reduce."""
+        pr = getattr(self, "_peer", None)
+        if pr is not None and pr.get("adv_stats") is not None:
+            pr["handle"].barrier(channel=2)
+            total = pr["adv_stats"][0].clone()
+            for t in pr["adv_stats"][1:]:
+                total += t
+            self._adv_total = total
+        else:
+            D.reduce_adv_stats_(self._adv_stats)
+            self._adv_total = self._adv_stats
 
     def compute_returns_scan(self, last_critic_obs) -> bool:
         """GAE scan.  Returns True when the advantage statistics still have to be summed over the shards (env-sharded job with
@@ -250,7 +267,7 @@ class PPO:
         return True
 
     def compute_returns_normalize(self):
-        ops.adv_normalize(self.storage.advantages, self._adv_stats)
+        ops.adv_normalize(self.storage.advantages, getattr(self, "_adv_total", self._adv_stats))
 
     # ---------------------------------------------------------------------------------------------------------- update
     def update(self, indices=None):
@@ -270,6 +287,7 @@ class PPO:
             for i in range(self.num_mini_batches):
                 self.minibatch_grads(i)
                 self.reduce_and_step()
+        self.peer_update_fence()
         self.storage.clear()
 
     # The three stages below are public so that a caller can capture them separately (CUDA graphs must not contain the
@@ -295,9 +313,19 @@ class PPO:
         cobs = next(it) if has_priv else obs
         self._mb = (obs, cobs) + tuple(next(it) for _ in range(7))
 
+    def select_gradient_buffer(self):
+        """K14, double-buffered exchange: mini-batch k writes gradient buffer k % 2, so a rank may start its next backward while
+        slower ranks still read its previous buffer; the barrier in front of mini-batch k + 1's peer reads orders buffer k % 2's
+        next rewrite (mini-batch k + 2) after everybody's reads of it -- ONE cross-GPU barrier per mini-batch.  Call before
+        anything writes gradients for the next ``reduce_and_step`` (``minibatch_grads`` does)."""
+        if self.peer_gradients:
+            pr = self._peer
+            self.optimizer.use_gradient_buffer(pr["bufs"][pr["k"] % 2], copy=False)
+
     def minibatch_grads(self, i: int):
         """Forward of both MLPs on mini-batch slice ``i``, fused loss (K6), backward into the flat gradient buffer."""
         ac, opt = self.actor_critic, self.optimizer
+        self.select_gradient_buffer()
         sl = slice(i * self._mb_size, (i + 1) * self._mb_size)
         obs, cobs, actions, values, returns, logp, adv, mu_old, sigma_old = (t[sl] for t in self._mb)
         B, A = actions.shape
@@ -357,6 +385,7 @@ class PPO:
         off, n = ac._slices["std"]
         for (obs, cobs, actions, values, adv, returns, logp, mu_old, sigma_old, hid, masks, _rnd) in st.recurrent_mini_batch_generator(
                 self.num_mini_batches, self.num_learning_epochs):
+            self.select_gradient_buffer()
             with torch.enable_grad():
                 ac.act(obs, masks=masks, hidden_states=hid[0])
                 mu = ac.action_mean                                                  # [T, n, A]
@@ -377,6 +406,7 @@ class PPO:
             if adaptive and world > 1:
                 ac.flat_grads_ext[-4:-3].copy_(bufs.out[4:5])
             self.reduce_and_step()
+        self.peer_update_fence()
         st.clear()
 
     # ---------------------------------------------------------------------------------- K14: peer-memory gradient exchange
@@ -399,10 +429,21 @@ class PPO:
             ac = self.actor_critic
             ac.flatten_parameters()
             group = group if group is not None else dist.group.WORLD
-            buf = symm.empty(ac.flat_grads_ext.numel(), dtype=torch.float32, device=ac.flat_grads_ext.device)
-            hdl = symm.rendezvous(buf, group)
-            self.optimizer.use_gradient_buffer(buf)
-            self._peer = dict(handle=hdl, ptrs=[int(x) for x in hdl.buffer_ptrs], sum=torch.zeros_like(buf), buf=buf)
+            L = ac.flat_grads_ext.numel()
+            dev = ac.flat_grads_ext.device
+            # one symmetric allocation: two gradient buffers (double-buffered exchange) + 16 doubles for the advantage statistics
+            big = symm.empty(2 * L + 32, dtype=torch.float32, device=dev)
+            hdl = symm.rendezvous(big, group)
+            big.zero_()
+            bufs = [big[:L], big[L:2 * L]]
+            base = [int(x) for x in hdl.buffer_ptrs]
+            self.optimizer.use_gradient_buffer(bufs[0])
+            world = len(base)
+            stats = [hdl.get_buffer(r, (4,), torch.float64, storage_offset=(2 * L * 4) // 8) for r in range(world)] if (2 * L * 4) % 8 == 0 else None
+            self._peer = dict(handle=hdl, ptrs=[base, [b + 4 * L for b in base]], bufs=bufs, sum=torch.zeros(L, device=dev), buf=big, k=0,
+                              adv_stats=stats, rank=dist.get_rank(group))
+            if stats is not None:
+                self._adv_stats = stats[self._peer["rank"]]  # gae_scan writes the local statistics where the peers can read them
         except Exception as exc:  # noqa: BLE001 -- any failure leaves the NCCL path untouched
             self._peer = None
             self._peer_error = repr(exc)
@@ -425,12 +466,13 @@ class PPO:
         for alg in learners:
             ac = alg.actor_critic
             ac.flatten_parameters()
-            buf = torch.zeros(ac.flat_grads_ext.numel(), dtype=torch.float32, device=ac.flat_grads_ext.device)
-            alg.optimizer.use_gradient_buffer(buf)
-            bufs.append(buf)
+            pair = [torch.zeros(ac.flat_grads_ext.numel(), dtype=torch.float32, device=ac.flat_grads_ext.device) for _ in range(2)]
+            alg.optimizer.use_gradient_buffer(pair[0])
+            bufs.append(pair)
         for r, alg in enumerate(learners):
             alg._world_override = (r, W)
-            alg._peer = dict(handle=_NoBarrier(), ptrs=[b.data_ptr() for b in bufs], sum=torch.zeros_like(bufs[r]), buf=bufs[r]) if W > 1 else None
+            alg._peer = dict(handle=_NoBarrier(), ptrs=[[b[q].data_ptr() for b in bufs] for q in range(2)], bufs=bufs[r], sum=torch.zeros_like(bufs[r][0]),
+                             buf=None, k=0, adv_stats=None, rank=r) if W > 1 else None
 
     @staticmethod
     def sum_local_adv_stats(learners: "list[PPO]") -> None:
@@ -471,17 +513,24 @@ class PPO:
             pr = self._peer
             # the summed KL statistic sits behind the summed gradients: the first kernel takes the learning-rate decision
             # (every rank the same one), the second applies it
-            opt.step_peer_sum(pr["ptrs"], pr["sum"], 4, max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world,
+            opt.step_peer_sum(pr["ptrs"][pr["k"] % 2], pr["sum"], 4, max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world,
                               desired_kl=self.desired_kl if adaptive else None, kl_scale=1.0 / world)
+            pr["k"] += 1
             return
         if world > 1 and adaptive:  # every rank takes the same decision
             ops.adaptive_lr(self.actor_critic.flat_grads_ext[-4:-3], 1.0 / world, self.desired_kl, opt.lr_t)
         opt.step(max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world)
 
     def after_step_barrier(self):
-        """K14: nobody may overwrite its gradient buffer (next backward) before every rank has read it."""
+        """K14: nothing to wait for -- the gradient buffers alternate per mini-batch (see ``minibatch_grads``), so the barrier in
+        front of the NEXT mini-batch's peer reads already orders the rewrite of this one's buffer after everybody's reads."""
+
+    def peer_update_fence(self):
+        """End of an update under K14: one barrier, so that the first two mini-batches of the next update (which reuse both
+        buffers) cannot overtake a rank that is still reading in this update's last step; it also re-arms the buffer parity."""
         if self.peer_gradients:
             self._peer["handle"].barrier(channel=1)
+            self._peer["k"] = 0
 
     def update_epilogue(self):
         """The only device->host read of an update: the three logged means (reference ppo.py:361-363 reads them with

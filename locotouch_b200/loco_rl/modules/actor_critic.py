@@ -107,13 +107,17 @@ class ActorCritic(nn.Module):
         self.flat_params, self.flat_grads = flat, grads
         return flat, grads
 
-    def rebind_gradients(self, buf: torch.Tensor):
+    def rebind_gradients(self, buf: torch.Tensor, copy: bool = True):
         """Moves the flat gradient storage (and every ``p.grad`` view) into ``buf`` [total + 4] -- e.g. a buffer in NVLink-mapped
-        symmetric memory that the other ranks read directly (K14).  Call before capturing CUDA graphs."""
+        symmetric memory that the other ranks read directly (K14).  ``copy=False``: the old contents are not carried over (the
+        double-buffered exchange alternates between two such buffers, one per mini-batch; every backward rewrites all of it)."""
         self.flatten_parameters()
         if buf.numel() != self.flat_grads_ext.numel() or buf.dtype != torch.float32 or buf.device != self.flat_grads_ext.device:
             raise ValueError("gradient buffer must be float32 [total + 4] on the parameters' device")
-        buf.copy_(self.flat_grads_ext)
+        if buf.data_ptr() == self.flat_grads_ext.data_ptr():
+            return self.flat_grads
+        if copy:
+            buf.copy_(self.flat_grads_ext)
         self.flat_grads_ext = buf
         total = self.flat_params.numel()
         grads = buf[:total]
@@ -331,6 +335,52 @@ class ActorCritic(nn.Module):
                     F.elu_(out)
             h = out
         return h
+
+    def _infer_hidden(self, net, x, tag: str):
+        """The hidden layers of one MLP through K12 (bias + ELU fused) into persistent buffers; returns the last hidden activation,
+        or None when a layer is not taken by K12 (the caller then uses ``_infer``)."""
+        linears = [m for m in net if isinstance(m, nn.Linear)]
+        key = (tag, x.shape[0], str(x.device))
+        cache = self.__dict__.setdefault("_infer_bufs", {})
+        if key not in cache:
+            cache[key] = [torch.empty(x.shape[0], lin.out_features, device=x.device) for lin in linears[:-1]]
+        h = x.contiguous()
+        for lin, buf in zip(linears[:-1], cache[key]):
+            h = ops.linear_bias_act(h, lin.weight, lin.bias, out=buf, elu=True) if lin.out_features >= 64 else None
+            if h is None:
+                return None
+        return h
+
+    @torch.no_grad()
+    def act_evaluate_fused(self, observations, critic_observations, out: dict):
+        """Rollout step of BOTH networks with the heads, the action sample and the log-prob in one kernel (K3b): hidden layers
+        through K12 (critic on the side stream), then ``lt_act_heads`` writes actions / log-prob / mu / sigma / values straight into
+        the RolloutStorage slot ``out``.  Returns the actions, or None when this module / mode is not taken (fp32 parity mode,
+        non-ELU stacks, unsupported widths, recurrent subclasses): the caller then runs ``evaluate`` + ``act``."""
+        if (type(self).act is not ActorCritic.act or type(self).evaluate is not ActorCritic.evaluate or not torch.backends.cuda.matmul.allow_tf32
+                or not observations.is_cuda or observations.dim() != 2 or not self.supports_fused_heads or out is None
+                or any(out.get(k) is None for k in ("actions", "logp", "mu", "sigma", "values"))):
+            return None
+        side = self.side_streams(observations.device)[0]
+        with side.forked():
+            h_c = self._infer_hidden(self.critic, critic_observations, "critic")
+        h_a = self._infer_hidden(self.actor, observations, "actor")
+        side.join()
+        if h_a is None or h_c is None:
+            return None
+        if callable(self.rng):
+            eps = self.rng(out["mu"])
+        else:
+            eps = torch.randn_like(out["mu"]) if self.rng == "torch" else None
+        head_a, head_c = self.actor[-1], self.critic[-1]
+        actions, logp, mu, values = ops.act_heads(h_a, h_c, head_a.weight, head_a.bias, head_c.weight, head_c.bias, self._std_vector().detach().contiguous(),
+                                                  eps=eps, actions=out["actions"], logp=out["logp"], mu=out["mu"], sigma_rows=out["sigma"], values=out["values"],
+                                                  seed=self.seed, offset=self._graph_slot if self._offset_base is not None else self._draws,
+                                                  offset_base=self._offset_base)
+        self._draws += 1
+        self.distribution = _GaussianView(mu, out["sigma"])
+        self._logp, self._sampled = logp, actions
+        return actions
 
     # ---------------------------------------------------------------------------------------------- reference interface
     @staticmethod

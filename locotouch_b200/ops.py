@@ -630,3 +630,27 @@ def contact_sensor_update(forces, *, net_forces_w=None, history=None, current_ai
                                          float(force_threshold), ptr(reset_mask, torch.uint8, "reset_mask"), current_stream()),
           "lt_contact_sensor_update")
     count_launches(1)
+
+
+# ------------------------------------------------------------------------------------------------ K3b rollout heads + sampling
+def act_heads(h_actor, h_critic, w_actor, b_actor, w_critic, b_critic, sigma, *, eps=None, actions=None, logp=None, mu=None, sigma_rows=None,
+              values=None, seed: int = 0, offset: int = 0, offset_base=None):
+    """Head layers of actor (and critic) on the last hidden activations + Normal sample + log-prob in one launch (K3b).  Outputs may
+    be RolloutStorage slot rows.  Returns (actions, logp, mu, values)."""
+    N, H = h_actor.shape
+    A = w_actor.shape[0]
+    dev = h_actor.device
+    actions = actions if actions is not None else torch.empty(N, A, device=dev)
+    logp = logp if logp is not None else torch.empty(N, device=dev)
+    mu = mu if mu is not None else torch.empty(N, A, device=dev)
+    if h_critic is not None and values is None:
+        values = torch.empty(N, device=dev)
+    check(lib().lt_act_heads(ptr(h_actor, torch.float32, "h_actor"), ptr(h_critic, torch.float32, "h_critic"), ptr(w_actor, torch.float32, "w_actor"),
+                             ptr(b_actor, torch.float32), ptr(w_critic, torch.float32) if h_critic is not None else None,
+                             ptr(b_critic, torch.float32) if h_critic is not None else None, ptr(sigma, torch.float32, "sigma"),
+                             ptr(eps, torch.float32, "eps"), ptr(actions, torch.float32, "actions"), ptr(logp, torch.float32, "logp"),
+                             ptr(mu, torch.float32, "mu"), ptr(sigma_rows, torch.float32, "sigma_rows"),
+                             ptr(values.view(-1), torch.float32, "values") if values is not None else None, N, A, H, int(seed), int(offset),
+                             ptr(offset_base, torch.int64, "offset_base"), current_stream()), "lt_act_heads")
+    count_launches(1)
+    return actions, logp, mu, values

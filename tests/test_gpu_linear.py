@@ -172,3 +172,31 @@ def test_tf32_training_pass_gradients_match_autograd(cuda, lt_lib, B, hidden):
         scale = want.abs().max().item()
         err = (have - want).abs().max().item()
         assert err <= 1e-2 * scale + 1e-9, f"{name}: max abs error {err:.3e} against a largest entry of {scale:.3e}"
+
+
+@pytest.mark.parametrize("N,Hd,A,critic", [(4096, 128, 12, True), (405, 128, 12, True), (1, 128, 4, False), (4097, 256, 16, True)])
+def test_rollout_heads_kernel_matches_torch(cuda, lt_lib, N, Hd, A, critic):
+    """K3b: actor / critic head layers + Normal sample + log-prob in one launch against the torch expressions of reference
+    actor_critic.py:105-131 (explicit eps), and the Philox path against lt_act_sample's stream on the same means."""
+    from locotouch_b200 import ops
+
+    g = torch.Generator().manual_seed(N + A)
+    rn = lambda *s: torch.randn(*s, generator=g).to(cuda)  # noqa: E731
+    ha, hc = rn(N, Hd), rn(N, Hd)
+    wa, ba, wc, bc = rn(A, Hd) / Hd ** 0.5, rn(A), rn(1, Hd) / Hd ** 0.5, rn(1)
+    sigma = (0.5 + torch.rand(A, generator=g)).to(cuda)
+    eps = rn(N, A)
+    actions, logp, mu, values = ops.act_heads(ha, hc if critic else None, wa, ba, wc, bc, sigma, eps=eps)
+    mu_ref = (ha.double() @ wa.double().t() + ba.double())
+    H.assert_close(mu, mu_ref.float(), "mu", rtol=1e-5, atol=1e-5)
+    a_ref = mu_ref + sigma.double() * eps.double()
+    H.assert_close(actions, a_ref.float(), "actions", rtol=1e-5, atol=1e-5)
+    lp_ref = torch.distributions.Normal(mu_ref, sigma.double().expand_as(mu_ref)).log_prob(a_ref).sum(-1)
+    H.assert_close(logp, lp_ref.float(), "log prob", rtol=1e-5, atol=1e-4)
+    if critic:
+        H.assert_close(values.view(-1), (hc.double() @ wc.double().t() + bc.double()).view(-1).float(), "values", rtol=1e-5, atol=1e-5)
+    # Philox: the same normal stream as lt_act_sample (key (seed, offset), counter (env, chunk))
+    a2, lp2, mu2, _ = ops.act_heads(ha, None, wa, ba, None, None, sigma, seed=11, offset=5)
+    a3, lp3 = ops.act_sample(mu2.contiguous(), sigma, seed=11, offset=5)
+    H.assert_close(a2, a3, "Philox actions == lt_act_sample on the same means", rtol=0, atol=1e-6)
+    H.assert_close(lp2, lp3, "log prob == lt_act_sample", rtol=1e-5, atol=1e-4)

@@ -287,6 +287,81 @@ def bench_copy(sizes_mb, reps: int):
     return out
 
 
+def bench_heads(b: int, reps: int, A: int = 12, H: int = 128):
+    """K16: heads + loss + head dgrad.  Algorithmic bytes per sample: both hidden rows read, both gradient rows written, the 264 B
+    of rollout row, dL/dmu and dL/dV written for the head weight gradients."""
+    per = (4 * H * 4 + 264 + (A + 1) * 4) * b
+    copies = min(copies_for(per), 8)
+    sets = []
+    for i in range(copies):
+        g = torch.Generator().manual_seed(i)
+        rn = lambda *s: torch.randn(*s, generator=g).cuda()  # noqa: E731
+        sets.append((rn(b, H), rn(b, H), rn(A, H) * 0.1, rn(A), rn(1, H) * 0.1, rn(1), (0.5 + torch.rand(A, generator=g)).cuda(), rn(b, A), rn(b), rn(b, A),
+                     (0.5 + torch.rand(b, A, generator=g)).cuda(), rn(b), rn(b), rn(b), torch.empty(b, H, device="cuda"), torch.empty(b, H, device="cuda")))
+    bufs = [ops.PpoLossBuffers(b, A, "cuda") for _ in range(copies)]
+    lr = torch.tensor([1e-3], device="cuda")
+
+    def run(i):
+        ops.ppo_heads_loss(*sets[i], entropy_coef=0.01, desired_kl=0.01, lr=lr, buffers=bufs[i])
+
+    return {f"heads+loss+dgrad K16 [{b}x{H}]": (time_graph(run, copies, reps), per)}
+
+
+def bench_gemms(b: int, reps: int, obs_dim: int = 348, hidden=(512, 256, 128), A: int = 12):
+    """Per-GEMM rows of one mini-batch: K12 forward (bias + ELU fused), K12 dgrad (ELU backward fused), K15 weight + bias gradient.
+    Each row: (us, algorithmic bytes = operands read once + result written once, flops)."""
+    out = {}
+    dims = [obs_dim] + list(hidden)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    for k, n in zip(dims[:-1], dims[1:]):
+        copies = 4
+        xs = [torch.randn(b, k, device="cuda") for _ in range(copies)]
+        w, bias = torch.randn(n, k, device="cuda") / k ** 0.5, torch.randn(n, device="cuda")
+        hs = [torch.empty(b, n, device="cuda") for _ in range(copies)]
+        out[f"K12 forward {b}x{k}->{n}"] = (time_graph(lambda i: ops.linear_bias_act(xs[i], w, bias, out=hs[i], elu=True), copies, reps),
+                                            4.0 * (b * k + n * k + b * n), 2.0 * b * k * n)
+        gs = [torch.randn(b, n, device="cuda") for _ in range(copies)]
+        dw, db = torch.zeros(n, k, device="cuda"), torch.zeros(n, device="cuda")
+        out[f"K15 wgrad+bias {n}x{k} over {b}"] = (time_graph(lambda i: ops.wgrad(gs[i], xs[i], dw, db, zero_first=False), copies, reps),
+                                                   4.0 * (b * (n + k) + n * k), 2.0 * b * k * n)
+        if k != obs_dim:  # the input layer needs no dgrad
+            gin = [torch.empty(b, k, device="cuda") for _ in range(copies)]
+            out[f"K12 dgrad {b}x{n}->{k}"] = (time_graph(lambda i: ops.dgrad_act_bwd(gs[i], w, xs[i], out=gin[i]), copies, reps),
+                                              4.0 * (b * n + n * k + 2 * b * k), 2.0 * b * k * n)
+    for n in (A, 1):
+        k = hidden[-1]
+        copies = 4
+        xs = [torch.randn(b, k, device="cuda") for _ in range(copies)]
+        gs = [torch.randn(b, n, device="cuda") for _ in range(copies)]
+        dw, db = torch.zeros(n, k, device="cuda"), torch.zeros(n, device="cuda")
+        out[f"K15 head wgrad+bias {n}x{k} over {b}"] = (time_graph(lambda i: ops.wgrad(gs[i], xs[i], dw, db, zero_first=False), copies, reps),
+                                                        4.0 * (b * (n + k) + n * k), 2.0 * b * k * n)
+    return out
+
+
+def bench_student_cnn(reps: int):
+    out = {}
+    w = tuple(torch.randn(*s, device="cuda") * 0.1 for s in ((24, 2, 4, 4), (24,), (24, 24, 3, 3), (24,), (24, 24, 2, 2), (24,), (64, 192), (64,)))
+    for m in (405, 4096, 16384):
+        x = [(torch.rand(m, 442, device="cuda") < 0.1).float() for _ in range(4)]
+        o = torch.empty(m, 64, device="cuda")
+        out[f"student pre-encoder K17 [{m} frames]"] = (time_graph(lambda i: ops.student_cnn_forward(w, image=x[i], out=o), 4, reps), (442 + 64) * 4.0 * m)
+    return out
+
+
+def bench_contact_sensor(n: int, reps: int, bodies: int = 17, H: int = 3):
+    copies = 8
+    f = [torch.randn(n, bodies, 3, device="cuda") for _ in range(copies)]
+    hist = [torch.zeros(n, H, bodies, 3, device="cuda") for _ in range(copies)]
+    tm = [[torch.zeros(n, bodies, device="cuda") for _ in range(4)] for _ in range(copies)]
+
+    def run(i):
+        ops.contact_sensor_update(f[i], history=hist[i], current_air_time=tm[i][0], last_air_time=tm[i][1], current_contact_time=tm[i][2],
+                                  last_contact_time=tm[i][3], dt=0.02)
+
+    return {f"contact sensor K18 [{n}x{bodies}]": (time_graph(run, copies, reps), (12.0 * (H + 1) + 16 + 12 * H + 16) * n * bodies)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=4096)
@@ -318,6 +393,14 @@ def main():
         res.update(bench_gather(n * 24, n * 24 // 4, max(20, args.reps // 10)))
     if want("command"):
         res.update(bench_command(n, args.reps))
+    if want("heads"):
+        res.update(bench_heads(n * 24 // 4, args.reps))
+    if want("gemm"):
+        res.update({k: v[:2] for k, v in bench_gemms(n * 24 // 4, max(20, args.reps // 5)).items()})
+    if want("student"):
+        res.update(bench_student_cnn(max(20, args.reps // 5)))
+    if want("contact"):
+        res.update(bench_contact_sensor(n, args.reps))
     if want("copy"):
         res.update(bench_copy([2.47 * n / 4096, 6.49 * n / 4096, 22.85 * n / 4096, 28.34 * n / 4096, 36.21 * n / 4096], args.reps))
     rows = []

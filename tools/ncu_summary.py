@@ -22,6 +22,8 @@ KEEP = (
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+    "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
 )
 
 lines = [ln for ln in open(sys.argv[1], newline="") if not ln.startswith("==")]

@@ -46,6 +46,7 @@ for step in range(4):
     vals[-4] = 0.03 if step < 2 else 0.001  # KL statistic: first "too large" (lr / 1.5), then "too small" (lr * 1.5)
     vals[-3:] = 0
     for alg in (a, b):
+        alg.select_gradient_buffer()  # K14 alternates between two symmetric buffers, one per mini-batch
         alg.actor_critic.flat_grads_ext.copy_(vals)
         alg.reduce_and_step()
     torch.cuda.synchronize()
@@ -64,14 +65,15 @@ for step in range(4):
 
 
 def timed(alg, reps=50):
+    step = lambda: (alg.select_gradient_buffer(), alg.reduce_and_step())  # noqa: E731
     for _ in range(5):
-        alg.reduce_and_step()
+        step()
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        alg.reduce_and_step()
+        step()
     e1.record()
     e1.synchronize()
     return e0.elapsed_time(e1) * 1e3 / reps
@@ -84,7 +86,7 @@ from locotouch_b200.engine import HotPathEngine  # noqa: E402
 eng = HotPathEngine(num_envs=512, task="teacher", tactile=True, device=dev, seed=3, num_state_sets=3, hidden=(128, 64))
 assert eng.peer_gradients, "engine did not enable the peer exchange"
 eng.capture()
-assert not eng._graphs["split"] and eng._graphs.get("finish_eager"), "whole-update graph expected"
+assert not eng._graphs["split"] and not eng._graphs.get("finish_eager"), "two graphs per iteration expected (update and rollout incl. its tail)"
 p0 = eng.alg.optimizer.flat.clone()
 for _ in range(4):
     eng.replay()
@@ -106,6 +108,6 @@ if rank == 0:
 
 ta, tb = timed(a), timed(b)
 if rank == 0:
-    print(f"world={world}: NCCL all-reduce + clip + Adam {ta:.1f} us per step; barrier + peer-sum + clip + Adam + barrier {tb:.1f} us per step", flush=True)
+    print(f"world={world}: NCCL all-reduce + clip + Adam {ta:.1f} us per step; barrier + peer-sum + clip + Adam {tb:.1f} us per step", flush=True)
 dist.barrier()
 dist.destroy_process_group()

@@ -1,6 +1,7 @@
 """One launch of each streaming kernel at BASELINE size (for one `ncu --set full` capture: DRAM bytes per launch).
 
-    ncu --set full --clock-control none --import-source on -k regex:"mdp_step_kernel|taxel_kernel|ppo_loss_kernel" -c 9 -o out \
+    ncu --set full --clock-control none --import-source on \
+        -k regex:"mdp_step_kernel|taxel_kernel|ppo_loss_kernel|ppo_heads_kernel|wgrad_splitk_kernel|device_kernel" -c 21 -o out \
         python tools/prof_traffic.py        # then tools/ncu_summary.py
 """
 import os
@@ -35,5 +36,24 @@ args = dict(mu=rn(b, A), sigma=0.5 + torch.rand(A, device="cuda"), value=rn(b), 
 lr = torch.tensor([1e-3], device="cuda")
 for _ in range(3):
     ops.ppo_loss(**args, entropy_coef=0.01, desired_kl=0.01, lr=lr)
+# launches 9-11: K16 (heads + loss + head dgrad) on one mini-batch
+H = 128
+bufs = ops.PpoLossBuffers(b, A, "cuda")
+hs = [rn(b, H) for _ in range(2)]
+gh = [torch.empty(b, H, device="cuda") for _ in range(2)]
+for _ in range(3):
+    ops.ppo_heads_loss(hs[0], hs[1], rn(A, H) * 0.1, rn(A), rn(1, H) * 0.1, rn(1), args["sigma"], args["actions"], args["old_logp"], args["old_mu"],
+                       args["old_sigma"], args["advantages"], args["returns"], args["old_values"], gh[0], gh[1], entropy_coef=0.01, desired_kl=0.01, lr=lr,
+                       buffers=bufs)
+# launches 12-17: K15 weight + bias gradient of the first two layers; 18-20: K12 forward of the first layer
+torch.backends.cuda.matmul.allow_tf32 = True
+for (no, k) in ((512, 348), (256, 512)):
+    g_, x_, dw, db = rn(b, no), rn(b, k), torch.zeros(no, k, device="cuda"), torch.zeros(no, device="cuda")
+    for _ in range(3):
+        ops.wgrad(g_, x_, dw, db, zero_first=False)
+x_, w_, b_ = rn(b, 348), rn(512, 348) / 18.0, rn(512)
+o_ = torch.empty(b, 512, device="cuda")
+for _ in range(3):
+    ops.linear_bias_act(x_, w_, b_, out=o_, elu=True)
 torch.cuda.synchronize()
 print("ok")

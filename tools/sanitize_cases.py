@@ -100,6 +100,38 @@ def case_rollout(n):
     torch.cuda.synchronize()
 
 
+def case_round2(n):
+    """The kernels added in round 2: K15 (tcgen05 split-K weight + bias gradient; mbarrier pipeline, TMEM, bulk tensor reductions),
+    K16 (heads + loss + head dgrad), K12 (fused linear / dgrad), K17 (student pre-encoder), K18 (contact sensor), K10 (trajectories)."""
+    g = torch.Generator().manual_seed(n)
+    rn = lambda *s: torch.randn(*s, generator=g).cuda()  # noqa: E731
+    b = max(8, n)
+    for (no, k) in ((128, 256), (512, 348), (12, 128), (1, 128), (20, 12)):
+        ops.wgrad(rn(b, no), rn(b, k), torch.zeros(no, k, device="cuda"), torch.zeros(no, device="cuda"))
+    if torch.backends.cuda.matmul.allow_tf32 or True:
+        ops.linear_bias_act(rn(b, 348), rn(512, 348), rn(512), elu=True)
+        ops.dgrad_act_bwd(rn(b, 256), rn(256, 512), rn(b, 512))
+    A, H = 12, 128
+    bufs = ops.PpoLossBuffers(b, A, "cuda")
+    lr = torch.tensor([1e-3], device="cuda")
+    for _ in range(2):
+        ops.ppo_heads_loss(rn(b, H), rn(b, H), rn(A, H), rn(A), rn(1, H), rn(1), (0.5 + torch.rand(A, generator=g)).cuda(), rn(b, A), rn(b), rn(b, A),
+                           (0.5 + torch.rand(b, A, generator=g)).cuda(), rn(b), rn(b), rn(b), torch.empty(b, H, device="cuda"), torch.empty(b, H, device="cuda"),
+                           entropy_coef=0.01, desired_kl=0.01, lr=lr, buffers=bufs)
+    w = (rn(24, 2, 4, 4), rn(24), rn(24, 24, 3, 3), rn(24), rn(24, 24, 2, 2), rn(24), rn(64, 192), rn(64))
+    ops.student_cnn_forward(w, image=(torch.rand(n, 442, generator=g) < 0.1).float().cuda())
+    ops.student_cnn_forward(w, packed=torch.randint(0, 2 ** 31 - 1, (n, 7), generator=g, dtype=torch.int32).cuda())
+    hist, tm = torch.zeros(n, 3, 17, 3, device="cuda"), [torch.zeros(n, 17, device="cuda") for _ in range(4)]
+    for step in range(2):
+        ops.contact_sensor_update(rn(n, 17, 3), net_forces_w=torch.empty(n, 17, 3, device="cuda"), history=hist, current_air_time=tm[0], last_air_time=tm[1],
+                                  current_contact_time=tm[2], last_contact_time=tm[3], dt=0.02,
+                                  reset_mask=(torch.rand(n, generator=g) < 0.1).byte().cuda() if step else None)
+    idx = ops.TrajectoryIndex((torch.rand(24, n, 1, generator=g) < 0.1).cuda())
+    padded, masks = idx.split_and_pad(rn(24, n, 30))
+    idx.unpad(padded)
+    torch.cuda.synchronize()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--race", action="store_true")
@@ -111,6 +143,7 @@ def main():
         case_gae(n)
         case_rollout(n)
         case_update(max(4, n if args.race else n * 6))
+        case_round2(n)
         print(f"sanitize_cases: N = {n} done", flush=True)
     print("sanitize_cases: all kernels ran", flush=True)
 
