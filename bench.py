@@ -279,22 +279,20 @@ def kernel_rooflines(engine, reps: int = 96):
 
 
 def gemm_rows(engine, peak_tflops: float):
-    """The tensor-core side of one PPO mini-batch (BASELINE.md "Tensor-core side"): forward + explicit backward of both MLPs at the
-    mini-batch size through ActorCritic.train_forward / train_backward, timed as one CUDA graph; FLOPs = 6 x B x (weights of both
+    """The tensor-core side of one PPO mini-batch (BASELINE.md "Tensor-core side"): forward, heads + loss and explicit backward of both
+    MLPs at the mini-batch size exactly as PPO.minibatch_grads runs them, timed as one CUDA graph; FLOPs = 6 x B x (weights of both
     MLPs) (forward 2, dgrad 2, wgrad 2 per multiply-accumulate; the first layer has no dgrad)."""
     from locotouch_b200.streams import graph_capture
 
     ac = engine.alg.actor_critic
+    alg = engine.alg
     B = engine.N * T_STEPS // 4
-    D = engine.spec.obs_dim
-    dev = engine.device
-    obs = [torch.randn(B, D, device=dev) for _ in range(3)]
-    gmu, gv = torch.randn(B, ac.num_actions, device=dev) * 1e-4, torch.randn(B, 1, device=dev) * 1e-4
-    saved = engine.alg.optimizer.flat.clone()
+    saved, saved_lr, saved_acc = alg.optimizer.flat.clone(), alg.optimizer.lr_t.clone(), alg._loss_accum.clone()
+    if getattr(alg, "_mb", None) is None:
+        alg.update_begin(engine.perm)
 
-    def run(i):
-        ac.train_forward(obs[i % 3], obs[(i + 1) % 3])
-        ac.train_backward(gmu, gv)
+    def run(i):  # the production mini-batch pass: K12 forward x 6, K16 (heads + loss + head dgrad), K12 dgrad x 4, K15 x 8
+        alg.minibatch_grads(i % alg.num_mini_batches)
 
     for i in range(3):
         run(i)
@@ -313,7 +311,9 @@ def gemm_rows(engine, peak_tflops: float):
         e1.record()
         e1.synchronize()
         best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
-    engine.alg.optimizer.flat.copy_(saved)
+    alg.optimizer.flat.copy_(saved)
+    alg.optimizer.lr_t.copy_(saved_lr)   # the loss kernel takes the adaptive learning-rate decision on the device
+    alg._loss_accum.copy_(saved_acc)
     import torch.nn as nn
 
     macs, first = 0, 0
@@ -324,7 +324,7 @@ def gemm_rows(engine, peak_tflops: float):
     flops = 2.0 * B * (3 * macs - first)
     tfs = flops / best / 1e6
     tf32_peak = peak_tflops / 2.0  # TF32 dense = half the bf16 rate on B200 (2.25 vs 1.1 PFLOP/s nominal); measured bf16 peak / 2
-    return [{"kernel": "actor-critic MLPs fwd + bwd (one mini-batch, TF32 tcgen05 GEMMs + fused epilogues)", "bound": "tensor", "achieved": tfs, "peak": tf32_peak,
+    return [{"kernel": "actor-critic MLPs fwd + heads/loss + bwd of one mini-batch as PPO.minibatch_grads runs it (K12 + K16 + K15, TF32 tcgen05)", "bound": "tensor", "achieved": tfs, "peak": tf32_peak,
              "unit": "TFLOP/s", "frac": tfs / tf32_peak, "us_per_launch": best, "flops_per_launch": flops,
              "peak_note": "measured sustained bf16 cuBLAS peak / 2 (TF32 runs at half the bf16 rate)"}]
 

@@ -186,7 +186,8 @@ extern "C" int lt_linear_bias_act(const float* x, const float* w, const float* b
   static const int forced = [] { const char* e = getenv("LT_LINEAR_TILE"); return e ? atoi(e) : -1; }();
   // measured (B200, in-graph): 24576x348x512 33.6 us with 256x256 tiles on an SM pair (cuBLAS GEMM + ELU pass: 40.7), 24576x512x256
   // 19.7 us with 256x128 (25.0), 24576x256x128 12.8 us with 128x128 (13.2)
-  int tile = forced >= 0 ? forced : ((N >= 512 && M >= 8192) ? 3 : (N >= 256 ? 1 : 0));
+  // r2 (in-graph, us): 24576x348x512: tile 3 33.6, tile 4 32.1; 4096x348x512: tile 1 10.4, tile 7 9.6
+  int tile = forced >= 0 ? forced : ((N >= 512 && M >= 8192) ? 4 : (N >= 256 ? (M >= 8192 ? 1 : 7) : 0));
   using T0 = Shape<_128, _128, _32>;
   using T1 = Shape<_256, _128, _32>;
   using T2 = Shape<_128, _256, _32>;
@@ -194,6 +195,10 @@ extern "C" int lt_linear_bias_act(const float* x, const float* w, const float* b
   using C1 = Shape<_1, _1, _1>;
   using C2 = Shape<_2, _1, _1>;
   if (apply_elu) {
+    // cluster multicast variants: SM pairs that share an operand tile receive it by ONE multicast load (4: two pairs along N share
+    // the x tile; 7: two pairs along M share the W tile).  Measured and dropped: 256x256 with clusters 4x1 (32.7 us) and 4x2 (40.3 us).
+    if (tile == 4) return FusedLinear<Elu, T3, Shape<_2, _2, _1>>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
+    if (tile == 7) return FusedLinear<Elu, T1, Shape<_4, _1, _1>>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
     if (tile == 1) return FusedLinear<Elu, T1, C2>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
     if (tile == 2) return FusedLinear<Elu, T2, C1>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
     if (tile == 3) return FusedLinear<Elu, T3, C2>::run(x, w, bias, out, M, N, K, workspace, wsb, st);
@@ -210,7 +215,9 @@ extern "C" int lt_dgrad_act_bwd(const float* grad_out, const float* w, const flo
   cudaStream_t st = (cudaStream_t)stream;
   const size_t wsb = (size_t)workspace_bytes;
   static const int forced = [] { const char* e = getenv("LT_DGRAD_TILE"); return e ? atoi(e) : -1; }();
-  const int tile = forced >= 0 ? forced : (Kin >= 256 && M >= 8192 ? 1 : 0);
+  // r2 (in-graph, us): 24576x256->512: tile 1 25.7, tile 3 24.1, tile 6 (256x256, two pairs share the W tile) 23.8; 24576x128->256: tile 1 10.6, tile 6 13.1
+  const int tile = forced >= 0 ? forced : (Kin >= 512 && M >= 8192 ? 6 : (Kin >= 256 && M >= 8192 ? 1 : 0));
+  if (tile == 6) return FusedDgrad<Shape<_256, _256, _32>, Shape<_4, _1, _1>>::run(grad_out, w, act_in, grad_in, M, Nout, Kin, workspace, wsb, st);
   if (tile == 1) return FusedDgrad<Shape<_256, _128, _32>, Shape<_2, _1, _1>>::run(grad_out, w, act_in, grad_in, M, Nout, Kin, workspace, wsb, st);
   if (tile == 3) return FusedDgrad<Shape<_256, _256, _32>, Shape<_2, _1, _1>>::run(grad_out, w, act_in, grad_in, M, Nout, Kin, workspace, wsb, st);
   return FusedDgrad<Shape<_128, _128, _32>, Shape<_1, _1, _1>>::run(grad_out, w, act_in, grad_in, M, Nout, Kin, workspace, wsb, st);

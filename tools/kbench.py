@@ -145,7 +145,7 @@ def bench_gae(n: int, reps: int, T: int = 24):
         r, v, d, lv, ret, adv = sets[i]
         ops.gae(r, v, d, lv, 0.99, 0.95, True, ret, adv)
 
-    return {"gae+normalize (2 launches)": (time_graph(run, copies, reps), per + 8 * T * n)}
+    return {"gae+normalize (1 launch at T = 24)": (time_graph(run, copies, reps), per + 8 * T * n)}
 
 
 def bench_ppo_loss(b: int, reps: int, A: int = 12):
@@ -176,7 +176,7 @@ def bench_adam(n: int, reps: int):
         p, g, m, v = sets[i]
         ops.clip_adam(p, g, m, v, lr, step)
 
-    return {"clip+adam (2 launches)": (time_graph(run, copies, reps), per)}
+    return {"clip+adam (1 launch)": (time_graph(run, copies, reps), per)}
 
 
 def bench_k9(b: int, reps: int):

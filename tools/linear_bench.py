@@ -49,3 +49,10 @@ for (M, K, N, elu) in ((24576, 348, 512, True), (24576, 512, 256, True), (24576,
     t0 = timed(cublas)
     t1 = timed(lambda: ops.linear_bias_act(x, w, b, out=out, elu=elu))
     print(f"{M:6d} x {K:3d} x {N:3d} elu={int(elu)}: cuBLAS addmm{'+elu_' if elu else ''} {t0:7.1f} us   fused tcgen05 {t1:7.1f} us   ({2 * M * K * N / t1 / 1e6:6.1f} TFLOP/s)")
+
+# dgrad with the ELU backward fused (K12 backward)
+for (M, Nout, Kin) in ((24576, 256, 512), (24576, 128, 256)):
+    g, w, h = torch.randn(M, Nout, device="cuda"), torch.randn(Nout, Kin, device="cuda"), torch.randn(M, Kin, device="cuda")
+    out = torch.empty(M, Kin, device="cuda")
+    t1 = timed(lambda: ops.dgrad_act_bwd(g, w, h, out=out))
+    print(f"dgrad {M:6d} x {Nout:3d} -> {Kin:3d}: fused tcgen05 {t1:7.1f} us   ({2 * M * Kin * Nout / t1 / 1e6:6.1f} TFLOP/s, {4 * (M * Nout + 2 * M * Kin) / t1 / 1e3:6.0f} GB/s)")
