@@ -560,6 +560,12 @@ def main():
                 rows.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "us_per_launch": us,
                              "alg_bytes_per_launch": nbytes, "tflops": flops / us / 1e6, "tf32_peak_tflops": tf / 2.0, "tensor_frac": flops / us / 1e6 / (tf / 2.0)})
             rows.extend(gemm_rows(engine, tf))
+            # config C4 (distillation): the student's tactile pre-encoder (K17, fp32 FMA on CUDA cores: 432 kFLOP per frame) at the
+            # distillation env count, the BASELINE size and 16 384 frames; "frac" = fraction of the HBM peak its 2 KB per frame amount to
+            for name, (us, nbytes) in KB.bench_student_cnn(30).items():
+                m = nbytes / ((442 + 64) * 4.0)
+                rows.append({"kernel": name, "bound": "fp32 fma", "achieved": 2 * 216.0e3 * m / us / 1e6, "peak": None, "unit": "TFLOP/s", "frac": None,
+                             "us_per_launch": us, "alg_bytes_per_launch": nbytes, "frames_per_s": m / us * 1e6})
             # the kernel with the largest share of the iteration (K12: ~50 % of the summed kernel time, profiles/r2e_launches_summary.md)
             # next to the streaming kernel the headline fraction is quoted on
             k12 = [r for r in rows if r["kernel"].startswith("K12 forward")]

@@ -567,6 +567,18 @@ int lt_peer_sum_clip_adam(float* params, const float* const* peer_grads, int wor
                           double beta2, float eps, float weight_decay, float grad_scale, float desired_kl, float kl_scale,
                           float* grad_norm_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* K14, two-shot variant for larger worlds (W - 1 remote buffers per rank become 2 (W - 1) / W):
+ * lt_peer_reduce_scatter: rank `rank` adds slice `rank` (ceil(n / 4 / world) float4 each, the last slice takes the rest) of all W
+ * buffers in rank order and writes the sum over that slice of ITS OWN buffer peer_grads[rank]; then a cross-GPU barrier; then
+ * lt_peer_gather_clip_adam (same arguments as lt_peer_sum_clip_adam) reads slice q from rank q instead of summing W buffers.  The tail
+ * statistics are still summed directly.  Results are bit-identical to the one-shot exchange (same summation order per element).
+ * LT_ERR_UNSUPPORTED when n exceeds what the one-launch optimizer kernel holds (use the one-shot call). */
+int lt_peer_reduce_scatter(const float* const* peer_grads, int world, int rank, int64_t n, void* stream);
+int lt_peer_gather_clip_adam(float* params, const float* const* peer_grads, int world, float* grad_sum, int tail, float* exp_avg,
+                          float* exp_avg_sq, int64_t n, float* lr, float* step_inout, float max_grad_norm, double beta1,
+                          double beta2, float eps, float weight_decay, float grad_scale, float desired_kl, float kl_scale,
+                          float* grad_norm_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * K13  velocity command term + reward-driven velocity curriculum, device resident
  * replaces  locotouch/mdp/commands.py:379-576  UniformVelocityCommandGaitLoggingMultiSampling (reset / compute / set_ranges,

@@ -227,6 +227,9 @@ _SIGNATURES = {
     "lt_clip_adam": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int64, f32p, f32p, C.c_float, C.c_double, C.c_double, C.c_float, C.c_float, C.c_float, f32p, C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_peer_sum_clip_adam": (C.c_int, [f32p, C.POINTER(C.c_void_p), C.c_int, f32p, C.c_int, f32p, f32p, C.c_int64, f32p, f32p, C.c_float, C.c_double,
                                         C.c_double, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, f32p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "lt_peer_gather_clip_adam": (C.c_int, [f32p, C.POINTER(C.c_void_p), C.c_int, f32p, C.c_int, f32p, f32p, C.c_int64, f32p, f32p, C.c_float, C.c_double,
+                                        C.c_double, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, f32p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "lt_peer_reduce_scatter": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_void_p]),
     "lt_bias_act_bwd_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "lt_bias_act_bwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     "lt_taxel_synth": (C.c_int, [C.POINTER(LtTaxelArgs), C.c_void_p]),

@@ -113,7 +113,7 @@ struct PeerPtrs {
 
 template <bool kPeer>
 __global__ void __launch_bounds__(kThreads, kFusedBlocksPerSm)
-clip_adam_fused_kernel(float* __restrict__ p, const float* __restrict__ g, const __grid_constant__ PeerPtrs peer, int world, int tail,
+clip_adam_fused_kernel(float* __restrict__ p, const float* __restrict__ g, const __grid_constant__ PeerPtrs peer, int world, int tail, int64_t gather_slice4,
                        float* __restrict__ m, float* __restrict__ v, int64_t n, float* lr_ptr, float* step_ptr, float max_norm,
                        double b1d, double b2d, float eps, float wd, float grad_scale, float desired_kl, float kl_scale,
                        double* __restrict__ partial, FusedWs* ws, float* grad_norm_out, float* __restrict__ gsum_tail) {
@@ -131,11 +131,25 @@ clip_adam_fused_kernel(float* __restrict__ p, const float* __restrict__ g, const
     if (i < n4) {
       if constexpr (kPeer) {  // rank order 0..W-1 on every rank: bit-identical sums, replicas stay replicas
         float4 s;
+        if (gather_slice4 > 0) {  // two-shot exchange, second half: slice q of the sum was reduced by rank q into ITS buffer
+          const int64_t owner = min(i / gather_slice4, (int64_t)world - 1);
+          asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s.x), "=f"(s.y), "=f"(s.z), "=f"(s.w) : "l"(peer.p[owner] + 4 * i));
+          gg[k] = s;
+          const float a = s.x * grad_scale, b = s.y * grad_scale, c = s.z * grad_scale, d = s.w * grad_scale;
+          acc += (double)(a * a + b * b) + (double)(c * c + d * d);
+          continue;
+        }
         asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s.x), "=f"(s.y), "=f"(s.z), "=f"(s.w) : "l"(peer.p[0] + 4 * i));
-        for (int r = 1; r < world; ++r) {
-          float4 t;
-          asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(peer.p[r] + 4 * i));
-          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        // the remote loads go out four at a time (one NVLink round trip per group instead of one per rank); the additions keep rank order
+        for (int r0 = 1; r0 < world; r0 += 4) {
+          float4 t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (r0 + u < world)
+              asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[u].x), "=f"(t[u].y), "=f"(t[u].z), "=f"(t[u].w) : "l"(peer.p[r0 + u] + 4 * i));
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (r0 + u < world) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
         }
         gg[k] = s;
       } else {
@@ -297,6 +311,24 @@ peer_sum_sqnorm_kernel(const PeerPtrs peers, int world, int64_t n, int tail, flo
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+// Two-shot exchange, first half (reduce-scatter by peer loads): rank q adds slice q of all W buffers in rank order and writes the sum
+// over slice q of its OWN buffer (nobody else reads that slice in this phase).  After a cross-GPU barrier the gather mode of the
+// fused kernel reads slice q from rank q: 2 (W - 1) / W buffers cross NVLink per rank instead of W - 1.
+__global__ void __launch_bounds__(kThreads)
+peer_reduce_slice_kernel(const PeerPtrs peers, int world, int rank, int64_t lo4, int64_t hi4) {
+  for (int64_t i = lo4 + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * kThreads) {
+    float4 t[LT_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < LT_MAX_PEERS; ++r)
+      if (r < world) t[r] = ld_peer4(peers.p[r] + 4 * i);   // all W loads in flight together
+    float4 s = t[0];
+#pragma unroll
+    for (int r = 1; r < LT_MAX_PEERS; ++r)
+      if (r < world) { s.x += t[r].x; s.y += t[r].y; s.z += t[r].z; s.w += t[r].w; }
+    reinterpret_cast<float4*>(const_cast<float*>(peers.p[rank]))[i] = s;
+  }
+}
+
 int grid_for(int64_t n) {
   const int64_t want = lt::ceil_div(lt::ceil_div(n, 4), (int64_t)kThreads * kVecPerThread);
   int64_t cap = 8LL * lt::sm_count();
@@ -325,7 +357,7 @@ extern "C" int lt_clip_adam(float* params, float* grads, float* exp_avg, float* 
   const int fgrid = fused_grid_for(n);
   if (fgrid > 0 && workspace_bytes >= 1024 * (int64_t)sizeof(double) + (int64_t)sizeof(FusedWs)) {
     FusedWs* fws = (FusedWs*)((char*)workspace + 1024 * sizeof(double));
-    clip_adam_fused_kernel<false><<<fgrid, kThreads, 0, st>>>(params, grads, PeerPtrs{}, 1, 0, exp_avg, exp_avg_sq, n, const_cast<float*>(lr), step_inout,
+    clip_adam_fused_kernel<false><<<fgrid, kThreads, 0, st>>>(params, grads, PeerPtrs{}, 1, 0, 0, exp_avg, exp_avg_sq, n, const_cast<float*>(lr), step_inout,
                                                               max_grad_norm, beta1, beta2, eps, weight_decay, grad_scale, 0.f, 1.f, partial, fws,
                                                               grad_norm_out, nullptr);
     return lt::check_launch();
@@ -338,10 +370,29 @@ extern "C" int lt_clip_adam(float* params, float* grads, float* exp_avg, float* 
   return lt::check_launch();
 }
 
-extern "C" int lt_peer_sum_clip_adam(float* params, const float* const* peer_grads, int world, float* grad_sum, int tail, float* exp_avg,
-                                     float* exp_avg_sq, int64_t n, float* lr, float* step_inout, float max_grad_norm, double beta1,
-                                     double beta2, float eps, float weight_decay, float grad_scale, float desired_kl, float kl_scale,
-                                     float* grad_norm_out, void* workspace, int64_t workspace_bytes, void* stream) {
+static int64_t peer_slice4(int64_t n, int world) { return lt::ceil_div(n >> 2, (int64_t)world); }
+
+extern "C" int lt_peer_reduce_scatter(const float* const* peer_grads, int world, int rank, int64_t n, void* stream) {
+  if (!peer_grads || world < 1 || world > LT_MAX_PEERS || rank < 0 || rank >= world || n <= 0 || (n & 3)) return LT_ERR_INVALID_ARG;
+  PeerPtrs peers;
+  for (int r = 0; r < LT_MAX_PEERS; ++r) {
+    peers.p[r] = r < world ? peer_grads[r] : nullptr;
+    if (r < world && (!peer_grads[r] || ((uintptr_t)peer_grads[r] & 15))) return LT_ERR_INVALID_ARG;
+  }
+  const int64_t slice4 = peer_slice4(n, world), n4 = n >> 2;
+  const int64_t lo = slice4 * rank < n4 ? slice4 * rank : n4, hi = (rank == world - 1) ? n4 : (slice4 * (rank + 1) < n4 ? slice4 * (rank + 1) : n4);
+  if (hi <= lo) return LT_OK;
+  int64_t blocks = lt::ceil_div(hi - lo, (int64_t)kThreads);
+  const int64_t cap = 4LL * lt::sm_count();
+  if (blocks > cap) blocks = cap;
+  peer_reduce_slice_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(peers, world, rank, lo, hi);
+  return lt::check_launch();
+}
+
+static int peer_clip_adam_impl(bool gather, float* params, const float* const* peer_grads, int world, float* grad_sum, int tail, float* exp_avg,
+                               float* exp_avg_sq, int64_t n, float* lr, float* step_inout, float max_grad_norm, double beta1,
+                               double beta2, float eps, float weight_decay, float grad_scale, float desired_kl, float kl_scale,
+                               float* grad_norm_out, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!params || !peer_grads || !grad_sum || !exp_avg || !exp_avg_sq || !lr || !step_inout || !workspace || n <= 0 || (n & 3)) return LT_ERR_INVALID_ARG;
   if (world < 1 || world > LT_MAX_PEERS || tail < 0 || tail > 16) return LT_ERR_INVALID_ARG;
   PeerPtrs peers;
@@ -362,15 +413,32 @@ extern "C" int lt_peer_sum_clip_adam(float* params, const float* const* peer_gra
   if (fgrid > 0 && workspace_bytes >= 1024 * (int64_t)sizeof(double) + (int64_t)sizeof(FusedWs)) {
     // one launch: peer sums stay in registers across the grid barrier (grad_sum only receives the summed tail statistics)
     FusedWs* fws = (FusedWs*)((char*)workspace + 1024 * sizeof(double));
-    clip_adam_fused_kernel<true><<<fgrid, kThreads, 0, st>>>(params, nullptr, peers, world, tail, exp_avg, exp_avg_sq, n, lr, step_inout, max_grad_norm,
+    clip_adam_fused_kernel<true><<<fgrid, kThreads, 0, st>>>(params, nullptr, peers, world, tail, gather ? peer_slice4(n, world) : 0, exp_avg, exp_avg_sq, n, lr, step_inout, max_grad_norm,
                                                              beta1, beta2, eps, weight_decay, grad_scale, desired_kl, kl_scale, partial, fws,
                                                              grad_norm_out, grad_sum + n);
     return lt::check_launch();
   }
+  if (gather) return LT_ERR_UNSUPPORTED;  // the gather mode exists in the one-launch kernel only (parameter counts beyond it: one-shot)
   peer_sum_sqnorm_kernel<<<grid, kThreads, 0, st>>>(peers, world, n, tail, grad_scale, grad_sum, partial, step_inout, desired_kl, kl_scale, lr);
   int rc = lt::check_launch();
   if (rc != LT_OK) return rc;
   clip_adam_kernel<<<grid, kThreads, 0, st>>>(params, grad_sum, exp_avg, exp_avg_sq, n, lr, step_inout, max_grad_norm, beta1, beta2, eps,
                                               weight_decay, grad_scale, partial, grid, grad_norm_out);
   return lt::check_launch();
+}
+
+extern "C" int lt_peer_sum_clip_adam(float* params, const float* const* peer_grads, int world, float* grad_sum, int tail, float* exp_avg,
+                                     float* exp_avg_sq, int64_t n, float* lr, float* step_inout, float max_grad_norm, double beta1,
+                                     double beta2, float eps, float weight_decay, float grad_scale, float desired_kl, float kl_scale,
+                                     float* grad_norm_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  return peer_clip_adam_impl(false, params, peer_grads, world, grad_sum, tail, exp_avg, exp_avg_sq, n, lr, step_inout, max_grad_norm, beta1, beta2, eps,
+                             weight_decay, grad_scale, desired_kl, kl_scale, grad_norm_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lt_peer_gather_clip_adam(float* params, const float* const* peer_grads, int world, float* grad_sum, int tail, float* exp_avg,
+                                        float* exp_avg_sq, int64_t n, float* lr, float* step_inout, float max_grad_norm, double beta1,
+                                        double beta2, float eps, float weight_decay, float grad_scale, float desired_kl, float kl_scale,
+                                        float* grad_norm_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  return peer_clip_adam_impl(true, params, peer_grads, world, grad_sum, tail, exp_avg, exp_avg_sq, n, lr, step_inout, max_grad_norm, beta1, beta2, eps,
+                             weight_decay, grad_scale, desired_kl, kl_scale, grad_norm_out, workspace, workspace_bytes, stream);
 }

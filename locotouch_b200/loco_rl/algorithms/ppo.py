@@ -82,12 +82,12 @@ class _FusedAdam:
             self.grads = self.ac.rebind_gradients(buf)
         return True
 
-    def step_peer_sum(self, peer_ptrs, grad_sum, tail: int, max_grad_norm=None, grad_scale: float = 1.0, desired_kl=None, kl_scale=1.0):
+    def step_peer_sum(self, peer_ptrs, grad_sum, tail: int, max_grad_norm=None, grad_scale: float = 1.0, desired_kl=None, kl_scale=1.0, gather=False):
         """K14: sum of the ranks' gradient buffers (peer loads, rank order) + learning-rate decision + clip + Adam."""
         g = self._check_group()
         ops.peer_sum_clip_adam(self.flat, peer_ptrs, grad_sum, tail, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t,
                                max_grad_norm=max_grad_norm, betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"],
-                               grad_scale=grad_scale, desired_kl=desired_kl, kl_scale=kl_scale, grad_norm_out=self.grad_norm)
+                               grad_scale=grad_scale, desired_kl=desired_kl, kl_scale=kl_scale, grad_norm_out=self.grad_norm, gather=gather)
 
     def sync_lr_to_device(self):
         lr = self.param_groups[0]["lr"]
@@ -440,8 +440,10 @@ class PPO:
             self.optimizer.use_gradient_buffer(bufs[0])
             world = len(base)
             stats = [hdl.get_buffer(r, (4,), torch.float64, storage_offset=(2 * L * 4) // 8) for r in range(world)] if (2 * L * 4) % 8 == 0 else None
+            mode = os.environ.get("LT_PEER_TWO_SHOT", "auto")
             self._peer = dict(handle=hdl, ptrs=[base, [b + 4 * L for b in base]], bufs=bufs, sum=torch.zeros(L, device=dev), buf=big, k=0,
-                              adv_stats=stats, rank=dist.get_rank(group))
+                              adv_stats=stats, rank=dist.get_rank(group),
+                              two_shot=(mode == "1") or (mode == "auto" and world > 4 and ops._adam_launches(L - 4, dev) == 1))
             if stats is not None:
                 self._adv_stats = stats[self._peer["rank"]]  # gae_scan writes the local statistics where the peers can read them
         except Exception as exc:  # noqa: BLE001 -- any failure leaves the NCCL path untouched
@@ -513,8 +515,15 @@ class PPO:
             pr = self._peer
             # the summed KL statistic sits behind the summed gradients: the first kernel takes the learning-rate decision
             # (every rank the same one), the second applies it
-            opt.step_peer_sum(pr["ptrs"][pr["k"] % 2], pr["sum"], 4, max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world,
-                              desired_kl=self.desired_kl if adaptive else None, kl_scale=1.0 / world)
+            ptrs = pr["ptrs"][pr["k"] % 2]
+            two_shot = pr.get("two_shot", False)
+            if two_shot:
+                # larger worlds: every rank first reduces ITS slice of the W buffers in place (W - 1 remote slices), a second
+                # barrier, then the optimizer kernel gathers the W reduced slices: 2 (W - 1) / W buffers per rank instead of W - 1
+                ops.peer_reduce_scatter(ptrs, pr["rank"], opt.flat.numel())
+                pr["handle"].barrier(channel=3)
+            opt.step_peer_sum(ptrs, pr["sum"], 4, max_grad_norm=self.max_grad_norm, grad_scale=1.0 / world,
+                              desired_kl=self.desired_kl if adaptive else None, kl_scale=1.0 / world, gather=two_shot)
             pr["k"] += 1
             return
         if world > 1 and adaptive:  # every rank takes the same decision

@@ -263,22 +263,31 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0
 
 
 def peer_sum_clip_adam(params, peer_ptrs, grad_sum, tail, exp_avg, exp_avg_sq, lr, step, *, max_grad_norm=1.0, betas=(0.9, 0.999), eps=1e-8,
-                       weight_decay=0.0, grad_scale=1.0, desired_kl=None, kl_scale=1.0, grad_norm_out=None):
+                       weight_decay=0.0, grad_scale=1.0, desired_kl=None, kl_scale=1.0, grad_norm_out=None, gather: bool = False):
     """K14: grad_sum = sum over ranks of the flat gradient buffers at ``peer_ptrs`` (raw device-visible addresses, rank order), then
     (``desired_kl``: adaptive learning-rate decision from the summed KL statistic in the tail) clip_grad_norm_ + Adam on
     grad_sum * grad_scale.  The caller has put a cross-GPU barrier between the ranks' gradient writes and
-    this call."""
+    this call.  ``gather``: second half of the two-shot exchange (slice q of the sum is read from rank q, which reduced it with
+    ``peer_reduce_scatter``; a second cross-GPU barrier separates the two)."""
     n = params.numel()
     nbytes = lib().lt_clip_adam_workspace_bytes(n)
     ws = _workspace("adam", nbytes, params.device)
     arr = (C.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
-    check(lib().lt_peer_sum_clip_adam(ptr(params, torch.float32, "params"), arr, len(peer_ptrs), ptr(grad_sum, torch.float32, "grad_sum"), int(tail),
-                                      ptr(exp_avg, torch.float32), ptr(exp_avg_sq, torch.float32), n, ptr(lr, torch.float32, "lr"),
-                                      ptr(step, torch.float32, "step"), float(max_grad_norm if max_grad_norm is not None else 0.0), betas[0], betas[1],
-                                      eps, weight_decay, grad_scale, float(desired_kl) if desired_kl else 0.0, float(kl_scale),
-                                      ptr(grad_norm_out, torch.float32), ptr(ws), nbytes, current_stream()),
-          "lt_peer_sum_clip_adam")
+    fn = lib().lt_peer_gather_clip_adam if gather else lib().lt_peer_sum_clip_adam
+    check(fn(ptr(params, torch.float32, "params"), arr, len(peer_ptrs), ptr(grad_sum, torch.float32, "grad_sum"), int(tail),
+             ptr(exp_avg, torch.float32), ptr(exp_avg_sq, torch.float32), n, ptr(lr, torch.float32, "lr"),
+             ptr(step, torch.float32, "step"), float(max_grad_norm if max_grad_norm is not None else 0.0), betas[0], betas[1],
+             eps, weight_decay, grad_scale, float(desired_kl) if desired_kl else 0.0, float(kl_scale),
+             ptr(grad_norm_out, torch.float32), ptr(ws), nbytes, current_stream()),
+          "lt_peer_gather_clip_adam" if gather else "lt_peer_sum_clip_adam")
     count_launches(_adam_launches(n, params.device))
+
+
+def peer_reduce_scatter(peer_ptrs, rank: int, n: int):
+    """K14 two-shot, first half: this rank sums ITS slice of all ranks' gradient buffers (peer loads, rank order) in place."""
+    arr = (C.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
+    check(lib().lt_peer_reduce_scatter(arr, len(peer_ptrs), int(rank), int(n), current_stream()), "lt_peer_reduce_scatter")
+    count_launches(1)
 
 
 # ------------------------------------------------------------------------------------------------- K9 MLP backward helper

@@ -39,13 +39,17 @@ if not ok:
     print(f"[rank {rank}] symmetric memory unavailable: {getattr(b, '_peer_error', '?')}", flush=True)
     dist.destroy_process_group()
     sys.exit(3)
+os.environ["LT_PEER_TWO_SHOT"] = "1"  # third learner: the two-shot exchange (reduce-scatter by peer loads, barrier, gather) forced on
+c = learner()
+assert c.enable_peer_gradients() and c._peer["two_shot"]
+os.environ["LT_PEER_TWO_SHOT"] = "auto"
 n = a.actor_critic.flat_grads_ext.numel()
 for step in range(4):
     g = torch.Generator(device="cpu").manual_seed(100 * step + rank)
     vals = (torch.randn(n, generator=g) * (0.05 if step else 5.0)).to(dev)  # step 0: the clip is active
     vals[-4] = 0.03 if step < 2 else 0.001  # KL statistic: first "too large" (lr / 1.5), then "too small" (lr * 1.5)
     vals[-3:] = 0
-    for alg in (a, b):
+    for alg in (a, b, c):
         alg.select_gradient_buffer()  # K14 alternates between two symmetric buffers, one per mini-batch
         alg.actor_critic.flat_grads_ext.copy_(vals)
         alg.reduce_and_step()
@@ -56,6 +60,9 @@ for step in range(4):
                        ("lr", a.optimizer.lr_t, b.optimizer.lr_t), ("grad_norm", a.optimizer.grad_norm, b.optimizer.grad_norm)):
         err = (x - y).abs().max().item()
         assert err <= tol * max(1.0, y.abs().max().item()), f"step {step} {name}: NCCL vs peer-sum differ by {err}"
+    for name, x, y in (("params", c.optimizer.flat, pb), ("exp_avg_sq", c.optimizer.exp_avg_sq, b.optimizer.exp_avg_sq), ("lr", c.optimizer.lr_t, b.optimizer.lr_t),
+                       ("grad_norm", c.optimizer.grad_norm, b.optimizer.grad_norm)):
+        assert torch.equal(x, y), f"step {step} {name}: two-shot exchange differs from the one-shot exchange"
     lo, hi = pb.clone(), pb.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -106,8 +113,9 @@ assert torch.equal(lr_lo, lr_hi)
 if rank == 0:
     print(f"graph replay: 4 iterations x 20 mini-batch exchanges, replicas bit-identical (lr {float(lr):.6g})", flush=True)
 
-ta, tb = timed(a), timed(b)
+ta, tb, tc = timed(a), timed(b), timed(c)
 if rank == 0:
-    print(f"world={world}: NCCL all-reduce + clip + Adam {ta:.1f} us per step; barrier + peer-sum + clip + Adam {tb:.1f} us per step", flush=True)
+    print(f"world={world}: NCCL all-reduce + clip + Adam {ta:.1f} us per step; barrier + peer-sum + clip + Adam {tb:.1f} us per step; "
+          f"two-shot (barrier + reduce-scatter + barrier + gather + clip + Adam) {tc:.1f} us per step", flush=True)
 dist.barrier()
 dist.destroy_process_group()
