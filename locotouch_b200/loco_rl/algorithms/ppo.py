@@ -311,6 +311,12 @@ class PPO:
         it = iter(bufs)
         obs = next(it)
         cobs = next(it) if has_priv else obs
+        if (obs.shape[1] & 3) and torch.backends.cuda.matmul.allow_tf32 and ac.supports_explicit_backward:
+            # observation widths that are not a multiple of 4 (locomotion: 270) reach the tcgen05 kernels through zero-padded rows
+            # (TMA needs a 16-byte pitch): pad the gathered rollout ONCE per update instead of every mini-batch slice
+            obs_p = self._padded_obs(obs, 0)
+            cobs = self._padded_obs(cobs, 1) if has_priv else obs_p
+            obs = obs_p
         self._mb = (obs, cobs) + tuple(next(it) for _ in range(7))
 
     def select_gradient_buffer(self):
@@ -321,6 +327,15 @@ class PPO:
         if self.peer_gradients:
             pr = self._peer
             self.optimizer.use_gradient_buffer(pr["bufs"][pr["k"] % 2], copy=False)
+
+    def _padded_obs(self, x, slot: int):
+        kp = (x.shape[1] + 3) // 4 * 4
+        bufs = self.__dict__.setdefault("_obs_pad", {})
+        key = (slot, x.shape[0], kp)
+        if key not in bufs:
+            bufs[key] = torch.zeros(x.shape[0], kp, device=x.device)
+        bufs[key][:, :x.shape[1]].copy_(x)
+        return bufs[key]
 
     def minibatch_grads(self, i: int):
         """Forward of both MLPs on mini-batch slice ``i``, fused loss (K6), backward into the flat gradient buffer."""

@@ -13,6 +13,7 @@ In TF32 mode (allowed exactly like reference locotouch/scripts/train.py:66-69) t
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -186,6 +187,28 @@ class ActorCritic(nn.Module):
         lc = [m for m in self.critic if isinstance(m, nn.Linear)]
         return len(la) >= 2 and len(lc) >= 2 and ops.ppo_heads_supported(self.num_actions, la[-1].in_features, lc[-1].in_features)
 
+    def _pad4(self, t, tag: str):
+        """[rows, k] -> a persistent [rows, ceil4(k)] copy with zero tail columns (None when k is already a multiple of 4).  TMA needs a
+        16-byte row pitch: the locomotion task's 270-wide observations / first-layer weights reach K12 / K15 through this copy (one
+        strided-copy launch) instead of falling back to cuBLAS + ELU + split-K + K9."""
+        k = t.shape[1]
+        kp = (k + 3) // 4 * 4
+        if kp == k:
+            return None
+        if os.environ.get("LT_PAD_K", "1") == "0":  # measurement knob: keep the cuBLAS path of round 1 for unaligned K
+            return t
+        if tag is None:  # one-off copy owned by the caller
+            out = torch.zeros(t.shape[0], kp, device=t.device)
+            out[:, :k].copy_(t)
+            return out
+        cache = self.__dict__.setdefault("_pad_bufs", {})
+        key = (tag, t.shape[0], kp, str(t.device))
+        buf = cache.get(key)
+        if buf is None:
+            buf = cache[key] = torch.zeros(t.shape[0], kp, device=t.device)
+        buf[:, :k].copy_(t)
+        return buf
+
     @torch.no_grad()
     def train_forward(self, observations, critic_observations, heads: bool = True):
         """Forward of both MLPs keeping the post-activation tensors (K12: tcgen05 GEMM with bias + ELU in its epilogue; fp32 mode:
@@ -198,7 +221,7 @@ class ActorCritic(nn.Module):
 
         fused = torch.backends.cuda.matmul.allow_tf32  # K12 computes in TF32, like cuBLAS does under the reference's train.py:66-69
 
-        def chain(linears, hs, x):
+        def chain(linears, hs, x, tag):
             acts, h = [x], x
             for i, lin in enumerate(linears):
                 hidden = i < len(linears) - 1
@@ -206,7 +229,12 @@ class ActorCritic(nn.Module):
                     break
                 out = None
                 if fused and lin.out_features >= 64:  # one tcgen05 GEMM with bias + ELU in the epilogue (K12)
-                    out = ops.linear_bias_act(h, lin.weight, lin.bias, out=hs[i], elu=hidden)
+                    w = lin.weight
+                    if i == 0 and (lin.in_features & 3):  # e.g. K = 270: zero-padded copies with a 16-byte row pitch
+                        if h.shape[1] == lin.in_features:  # (PPO pads the gathered rollout once per update: nothing to copy then)
+                            h = acts[0] = self._pad4(h, "x" + tag)
+                        w = self._pad4(w, "w" + tag)
+                    out = ops.linear_bias_act(h, w, lin.bias, out=hs[i], elu=hidden)
                 if out is None:  # fp32 mode, narrow output layers, unaligned K: cuBLAS GEMM with fused bias, ELU in place
                     out = torch.addmm(lin.bias, h, lin.weight.t(), out=hs[i])
                     if hidden:
@@ -220,10 +248,10 @@ class ActorCritic(nn.Module):
         side = self.side_streams(observations.device)[0]
         for k, ((linears, hs, gs), x) in enumerate(zip(bufs, (observations, critic_observations))):
             if k == 0:
-                acts = chain(linears, hs, x)
+                acts = chain(linears, hs, x, "a")
             else:
                 with side.forked():
-                    acts = chain(linears, hs, x)
+                    acts = chain(linears, hs, x, "c")
             self._saved.append((linears, acts, gs))
             outs.append(acts[-1])
         side.join()
@@ -293,8 +321,19 @@ class ActorCritic(nn.Module):
         """Weight gradient of ``lin`` on the trailing stream.  Returns True when the same kernel also produced the bias gradient
         (K15, TF32 mode, ``with_bias``)."""
         with wstream.forked():
-            if torch.backends.cuda.matmul.allow_tf32 and ops.wgrad(g, x, lin.weight.grad, lin.bias.grad if with_bias else None, zero_first=False) is not None:
-                return with_bias  # K15: one tcgen05 kernel, in-kernel split-K, dW and db
+            if torch.backends.cuda.matmul.allow_tf32:
+                if x.shape[1] != lin.in_features:  # zero-padded input (K % 4 != 0): K15 into a padded scratch, valid columns copied out
+                    cache = self.__dict__.setdefault("_pad_bufs", {})
+                    key = ("dw", lin.out_features, x.shape[1], str(x.device), id(lin))
+                    dwp = cache.get(key)
+                    if dwp is None:
+                        dwp = cache[key] = torch.empty(lin.out_features, x.shape[1], device=x.device)
+                    if ops.wgrad(g, x, dwp, lin.bias.grad if with_bias else None, zero_first=True) is not None:
+                        lin.weight.grad.copy_(dwp[:, :lin.in_features])
+                        return with_bias
+                    x = x[:, :lin.in_features].contiguous()
+                elif ops.wgrad(g, x, lin.weight.grad, lin.bias.grad if with_bias else None, zero_first=False) is not None:
+                    return with_bias  # K15: one tcgen05 kernel, in-kernel split-K, dW and db
             self._wgrad(g, x, lin.weight.grad, lin._wgrad_part)
         return False
 
@@ -328,7 +367,10 @@ class ActorCritic(nn.Module):
             hidden = i < len(linears) - 1
             out = None
             if hidden and lin.out_features >= 64:
-                out = ops.linear_bias_act(h, lin.weight, lin.bias, out=hs[i], elu=True)
+                w = lin.weight
+                if i == 0 and (lin.in_features & 3):
+                    h, w = self._pad4(h, "ix" + tag), self._pad4(w, "iw" + tag)
+                out = ops.linear_bias_act(h, w, lin.bias, out=hs[i], elu=True)
             if out is None:
                 out = torch.addmm(lin.bias, h, lin.weight.t(), out=hs[i] if hidden else None)
                 if hidden:
@@ -345,8 +387,11 @@ class ActorCritic(nn.Module):
         if key not in cache:
             cache[key] = [torch.empty(x.shape[0], lin.out_features, device=x.device) for lin in linears[:-1]]
         h = x.contiguous()
-        for lin, buf in zip(linears[:-1], cache[key]):
-            h = ops.linear_bias_act(h, lin.weight, lin.bias, out=buf, elu=True) if lin.out_features >= 64 else None
+        for i, (lin, buf) in enumerate(zip(linears[:-1], cache[key])):
+            w = lin.weight
+            if i == 0 and (lin.in_features & 3):
+                h, w = self._pad4(h, "ix" + tag), self._pad4(w, "iw" + tag)
+            h = ops.linear_bias_act(h, w, lin.bias, out=buf, elu=True) if lin.out_features >= 64 else None
             if h is None:
                 return None
         return h

@@ -102,3 +102,43 @@ def test_full_size_c1_update_matches_oracle(cuda, lt_lib):
     assert float((err > tol).float().mean()) <= 1e-4, f"{int((err > tol).sum())} of {err.numel()} parameters beyond rtol 1e-4 / atol 3e-5"
     assert float(err.max()) <= 5e-4, f"largest parameter difference {float(err.max()):.3g}"
     assert float((after - flat0).abs().max()) > 1e-3
+
+
+def test_unaligned_observation_width_takes_the_tensor_core_path(cuda, lt_lib):
+    """Locomotion observations are 270 wide (not a multiple of 4: no TMA row pitch).  In TF32 mode PPO pads the gathered rollout once
+    per update and the first-layer weights per step so that K12 / K15 take the layer; the update must agree with the fp32-mode update
+    (cuBLAS first layer) within TF32 tolerance, launch only library kernels for the MLPs, and leave no trace of the padding columns."""
+    from locotouch_b200 import _C
+    from locotouch_b200.loco_rl import PPO, ActorCritic
+
+    T, N, A, D, hidden = 24, 512, 12, 270, [128, 128]
+    r = H.make_rollout(T=T, N=N, obs_dim=D, A=A, seed=3)
+    eps = torch.randn(T, N, A, generator=torch.Generator().manual_seed(4)).to(cuda)
+    perm = torch.randperm(T * N, generator=torch.Generator().manual_seed(5)).to(cuda)
+    results = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            torch.manual_seed(0)
+            ac = ActorCritic(D, D, A, hidden, hidden, "elu", 1.0)
+            alg = PPO(ac, num_learning_epochs=1, num_mini_batches=2, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0, entropy_coef=0.01,
+                      learning_rate=1.0e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="fixed", device="cuda:0")
+            alg.init_storage(N, T, [D], [D], [A])
+            for t in range(T):
+                ac.rng = lambda mean, _e=eps[t]: _e
+                alg.act(r["obs"][t].to(cuda), r["critic_obs"][t].to(cuda))
+                alg.process_env_step(r["rewards"][t, :, 0].to(cuda), r["dones"][t, :, 0].long().to(cuda), {"time_outs": r["time_outs"][t, :, 0].to(cuda)})
+            alg.compute_returns(r["critic_obs"][-1].to(cuda))
+            n0 = _C.launch_count
+            losses = alg.update(indices=perm)
+            results[tf32] = (torch.cat([p.detach().flatten() for p in ac.parameters()]).cpu(), losses[:3], _C.launch_count - n0)
+            if tf32:
+                assert alg._mb[0].shape[1] == 272 and float(alg._mb[0][:, 270:].abs().max()) == 0.0
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = False
+    p32, l32, _ = results[False]
+    ptf, ltf, launches = results[True]
+    assert launches >= 2 * (2 * 2 + 1 + 2 * 3 + 1), launches   # per mini-batch: 4 fused forward layers, K16, 6 K15, clip + Adam (+ dgrad)
+    H.assert_close(torch.tensor(ltf), torch.tensor(l32), "mean losses, TF32 (padded K12 / K15 first layer) vs fp32", rtol=5e-3, atol=1e-4)
+    err = (ptf - p32).abs()
+    assert float((err > 2e-3).float().mean()) < 1e-3 and float(err.max()) < 5e-3, f"parameters differ: max {float(err.max()):.3g}"
