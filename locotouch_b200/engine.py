@@ -4,13 +4,14 @@ Sequence of reference ``OnPolicyRunner.learn`` (loco_rl/loco_rl/runners/on_polic
 PhysX stepping replaced by pre-generated synthetic state sets (BASELINE.json north_star):
 
     for t in range(num_steps_per_env):                       HOT LOOP A
-        actions = alg.act(obs, critic_obs)                   cuBLAS MLPs + K3 act epilogue -> rollout slot t
+        actions = alg.act(obs, critic_obs)                   K12 hidden layers + K3b heads / sample -> rollout slot t
         [ env.step(actions) ]                                K0 action pre-processing, synthetic state set t % K,
                                                              K1 fused MDP step (obs written straight into slot t+1),
                                                              K2 binary taxels + packed delay line
         alg.process_env_step(rewards, dones, infos)          K3 store (time-out bootstrap fused)
     alg.compute_returns(critic_obs)                          K4 GAE + advantage normalisation
-    alg.update()                                             HOT LOOP B: K5 gather, cuBLAS MLPs, K6 loss, K7 clip+Adam
+    alg.update()                                             HOT LOOP B: K5 gather, K12 fwd / dgrad, K16 heads + loss,
+                                                             K15 weight gradients, K7 clip+Adam (K14 across GPUs)
 
 ``iteration()`` runs it through the public drop-in classes (PPO / RolloutStorage / ActorCritic / FusedMdp);
 ``capture()`` records the same calls into CUDA graphs so that ``replay()`` has no Python or launch overhead.

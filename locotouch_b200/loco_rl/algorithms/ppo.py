@@ -8,12 +8,15 @@ What changed below the interface:
 * ``act`` writes actions / log-prob / mu / sigma / values directly into the RolloutStorage slot (K3);
 * ``process_env_step`` fuses the time-out bootstrap into the store kernel (K3);
 * ``compute_returns`` is the GAE kernel pair (K4);
-* ``update``: one fused gather of the permuted rollout (K5); per mini-batch the cuBLAS MLP forward, ONE fused loss
-  kernel (K6: log-prob, entropy, KL, adaptive learning rate on the device, clipped surrogate + value loss and their
-  analytic gradients), autograd only through the two MLPs, ONE fused clip + Adam over the flat parameter buffer (K7).
-  No ``.item()`` inside the loop: the learning rate lives on the device and the three logged means are accumulated on
-  the device and read back once per update.  With ``torch.distributed`` initialised, gradients are all-reduced as one
-  flat NCCL buffer and the KL statistic is all-reduced before the learning-rate decision.
+* ``update``: one fused gather of the permuted rollout (K5); per mini-batch the hidden layers of both MLPs as tcgen05 GEMMs with
+  bias + ELU in their epilogue (K12; fp32 parity mode: cuBLAS), ONE kernel for the head layers + the loss (log-prob, entropy, KL,
+  adaptive learning rate on the device, clipped surrogate + value loss and their analytic gradients) + the head dgrad (K16), an
+  explicit backward (K12 dgrad with the ELU backward fused, K15 weight + bias gradients into the flat gradient buffer), ONE fused
+  clip + Adam over the flat parameter buffer (K7).  No ``.item()`` inside the loop: the learning rate lives on the device and the
+  three logged means are accumulated on the device and read back once per update.  Recurrent policies take ``update_recurrent``
+  (K10 trajectories, cuDNN GRU under autograd, K6, K7).  With ``torch.distributed`` initialised, gradients are exchanged by peer loads
+  inside the optimizer kernel (K14; NCCL all-reduce of one flat buffer as fallback) with the KL statistic in the buffer's tail
+  (SURVEY.md 8e).
 RND and symmetry augmentation (unused by every LocoTouch runner cfg) are not part of the hot path and raise.
 """
 from __future__ import annotations
