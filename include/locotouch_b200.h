@@ -32,7 +32,7 @@ const char* lt_error_string(int status);
 /* Text of the last CUDA error seen by this thread inside the library ("" if none). */
 const char* lt_last_cuda_error(void);
 /* sizeof() of the argument structs as compiled, so that a foreign-language binding can verify its own layout:
- * which = 10 LtPpoHeadsArgs, 11 LtStudentCnnArgs, 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams, 6 LtTaxelForceArgs,
+ * which = 10 LtPpoHeadsArgs, 11 LtStudentCnnArgs, 12 LtMlp3Net, 0 LtGatherArgs, 1 LtPpoLossArgs, 2 LtTaxelArgs, 3 LtMdpArgs, 4 LtGaitState, 5 LtGaitParams, 6 LtTaxelForceArgs,
  * 7 LtCommandRanges, 8 LtCommandArgs, 9 LtVelCurriculumArgs; -1 otherwise. */
 int64_t lt_struct_size(int which);
 
@@ -494,6 +494,27 @@ int lt_dgrad_act_bwd(const float* grad_out, const float* w, const float* act_in,
  * Wider layers need n_out % 4 == 0, k_in % 4 == 0 and 16-byte aligned pointers (LT_ERR_UNSUPPORTED otherwise or in a stub build).
  * Summation order over the batch slices is not fixed (fp32 atomics): results are reproducible to rounding, not bit for bit. */
 int lt_wgrad_splitk(const float* grad_out, const float* act_in, float* dw, float* dbias, int B, int n_out, int k_in, int zero_first, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K19  the three hidden layers (k0 -> 512 -> 256 -> 128, bias + ELU each) of up to two MLPs in ONE persistent tcgen05 kernel
+ * replaces  the three nn.Linear + nn.ELU pairs of actor and critic (loco_rl/loco_rl/modules/actor_critic.py:33-56) as `act` /
+ *           `evaluate` run them per env step (actor_critic.py:105-131 from algorithms/ppo.py:129-141) and per mini-batch
+ *           (algorithms/ppo.py:264-281): six K12 launches (reference: six cuBLAS GEMMs + six ELU launches)
+ * A CTA carries a 128-row slab of one network through all three layers: x slab resident in shared memory, weight tiles streamed
+ * by TMA, accumulators in TMEM, bias + ELU written back to TMEM in place where they are the A operand of the next layer
+ * (kind::tf32, like the reference's TF32 training configuration).  h3 [B,128] is always written; h1 [B,512] / h2 [B,256] only when
+ * not NULL (the training pass keeps them for the backward).  Both nets must share k0; k0 % 4 == 0, k0 <= 352 (row pitch of x and
+ * w1), all pointers 16-byte aligned; LT_ERR_UNSUPPORTED otherwise (callers keep the per-layer K12 path).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct LtMlp3Net {
+  const float* x;              /* [B, k0] */
+  int k0;
+  const float *w1, *b1;        /* [512, k0], [512] */
+  const float *w2, *b2;        /* [256, 512], [256] */
+  const float *w3, *b3;        /* [128, 256], [128] */
+  float *h1, *h2, *h3;         /* post-ELU activations; h1 / h2 may be NULL */
+} LtMlp3Net;
+int lt_mlp3_forward(const LtMlp3Net* nets, int n_nets, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * K3b  output heads of both MLPs + action sampling + log-prob, one launch per env step of the rollout

@@ -70,6 +70,14 @@ class LtStudentCnnArgs(C.Structure):
     ]
 
 
+class LtMlp3Net(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("k0", C.c_int),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("h1", C.c_void_p), ("h2", C.c_void_p), ("h3", C.c_void_p),
+    ]
+
+
 class LtTaxelArgs(C.Structure):
     _fields_ = [
         ("N", C.c_int), ("T", C.c_int),
@@ -250,6 +258,7 @@ _SIGNATURES = {
     "lt_contact_sensor_update": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "lt_act_heads": (C.c_int, [C.c_void_p] * 13 + [C.c_int] * 3 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "lt_wgrad_splitk": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
+    "lt_mlp3_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lt_mdp_tables_len": (C.c_int, [C.POINTER(LtMdpArgs)]),
     "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),
     "lt_mdp_reset": (C.c_int, [C.POINTER(LtGaitState), f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
@@ -292,7 +301,7 @@ def lib() -> C.CDLL:
     if handle.lt_abi_version() != 1:
         raise LocoTouchLibraryError("ABI version mismatch between _C.py and liblocotouch_b200.so")
     for which, struct in enumerate((LtGatherArgs, LtPpoLossArgs, LtTaxelArgs, LtMdpArgs, LtGaitState, LtGaitParams, LtTaxelForceArgs,
-                                    LtCommandRanges, LtCommandArgs, LtVelCurriculumArgs, LtPpoHeadsArgs, LtStudentCnnArgs)):
+                                    LtCommandRanges, LtCommandArgs, LtVelCurriculumArgs, LtPpoHeadsArgs, LtStudentCnnArgs, LtMlp3Net)):
         if handle.lt_struct_size(which) != C.sizeof(struct):
             raise LocoTouchLibraryError(
                 f"struct layout mismatch for {struct.__name__}: C {handle.lt_struct_size(which)} vs ctypes {C.sizeof(struct)}")

@@ -90,7 +90,7 @@ def _build(force: bool, verbose: bool, variant: str | None) -> str:
         if (not force or (variant and not knobbed)) and os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))):
             continue
         extra = [f"-D{k}={v}" for k, v in os.environ.items() if k.startswith(("LT_MDP_", "LT_TAXEL_"))] if (knobbed or not variant) else []  # tuning knobs
-        if os.path.basename(src) in ("gemm_fused.cu", "wgrad_tc.cu"):
+        if os.path.basename(src) in ("gemm_fused.cu", "wgrad_tc.cu", "mlp_fused.cu"):
             dirs = cutlass_include_dirs()
             extra += ["--expt-extended-lambda", "-DLT_HAVE_CUTLASS=1"] + [x for d in dirs for x in ("-I", d)] if dirs else ["-DLT_HAVE_CUTLASS=0"]
         cmd = [nvcc, *NVCC_FLAGS, *PER_FILE_FLAGS.get(os.path.basename(src), []), *extra, "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]

@@ -55,6 +55,7 @@ extern "C" int64_t lt_struct_size(int which) {
     case 9: return (int64_t)sizeof(LtVelCurriculumArgs);
     case 10: return (int64_t)sizeof(LtPpoHeadsArgs);
     case 11: return (int64_t)sizeof(LtStudentCnnArgs);
+    case 12: return (int64_t)sizeof(LtMlp3Net);
     default: return -1;
   }
 }

@@ -221,9 +221,12 @@ class ActorCritic(nn.Module):
 
         fused = torch.backends.cuda.matmul.allow_tf32  # K12 computes in TF32, like cuBLAS does under the reference's train.py:66-69
 
-        def chain(linears, hs, x, tag):
-            acts, h = [x], x
+        def chain(linears, hs, x, tag, acts=None):
+            acts = [x] if acts is None else acts
+            h, first = acts[-1], len(acts) - 1  # K19 may already have produced the first three hidden layers
             for i, lin in enumerate(linears):
+                if i < first:
+                    continue
                 hidden = i < len(linears) - 1
                 if not hidden and not heads:
                     break
@@ -246,16 +249,43 @@ class ActorCritic(nn.Module):
         # the critic chain runs on a side stream next to the actor chain (eagerly and as a parallel branch of a captured graph):
         # the GEMMs of one network overlap the memory-bound ELU passes of the other
         side = self.side_streams(observations.device)[0]
+        pre = self._mlp3_hidden([(bufs[0][0], observations, "a", bufs[0][1]), (bufs[1][0], critic_observations, "c", bufs[1][1])], keep=True) if fused else None
         for k, ((linears, hs, gs), x) in enumerate(zip(bufs, (observations, critic_observations))):
             if k == 0:
-                acts = chain(linears, hs, x, "a")
+                acts = chain(linears, hs, x, "a", pre[0] if pre else None)
+            elif pre and (not heads or len(linears) == 4):  # nothing (or one small head GEMM) left: not worth a forked branch
+                acts = chain(linears, hs, x, "c", pre[1])
             else:
                 with side.forked():
-                    acts = chain(linears, hs, x, "c")
+                    acts = chain(linears, hs, x, "c", pre[1] if pre else None)
+                side.join()
             self._saved.append((linears, acts, gs))
             outs.append(acts[-1])
-        side.join()
         return outs[0], outs[1]
+
+    def _mlp3_hidden(self, nets, keep: bool):
+        """K19: the three hidden layers [512, 256, 128] of actor AND critic in one persistent tcgen05 kernel (x slab resident in shared
+        memory, activations handed from layer to layer inside TMEM).  ``nets`` = [(linears, x, tag, hs)] with ``hs`` the [B, 512] /
+        [B, 256] / [B, 128] buffers; ``keep`` stores h1 / h2 as well (the training pass needs them).  Returns per net the list
+        [x (padded to a multiple of 4 columns if need be), h1, h2, h3], or None when a stack is not taken (callers keep K12 per layer)."""
+        args, outs = [], []
+        for linears, x, tag, hs in nets:
+            if len(linears) < 4 or x.dim() != 2 or not x.is_cuda or x.dtype != torch.float32:  # three hidden layers + a head
+                return None
+            lin1, w1 = linears[0], linears[0].weight
+            if lin1.in_features & 3:  # e.g. K = 270: zero-padded copies with a 16-byte row pitch (like the per-layer path)
+                if x.shape[1] == lin1.in_features:
+                    x = self._pad4(x, "x" + tag)
+                w1 = self._pad4(w1, "w" + tag)
+            if not ops.mlp3_supported(linears, x.shape[1]) or w1.shape[1] != x.shape[1]:
+                return None
+            x = x.contiguous()
+            args.append((x, (w1, lin1.bias, linears[1].weight, linears[1].bias, linears[2].weight, linears[2].bias),
+                         (hs[0] if keep else None, hs[1] if keep else None, hs[2])))
+            outs.append([x, hs[0], hs[1], hs[2]])
+        if len({a[0].shape for a in args}) != 1:  # the two networks share one launch only when their inputs have the same shape
+            return None
+        return outs if ops.mlp3_forward(args) is not None else None
 
     def hidden_grad_buffers(self):
         """(g_h_actor, g_h_critic): where the gradient w.r.t. the pre-activation of the last hidden layers goes (K16 output)."""
@@ -378,6 +408,13 @@ class ActorCritic(nn.Module):
             h = out
         return h
 
+    def _infer_buffers(self, linears, tag: str, x):
+        key = (tag, x.shape[0], str(x.device))
+        cache = self.__dict__.setdefault("_infer_bufs", {})
+        if key not in cache:
+            cache[key] = [torch.empty(x.shape[0], lin.out_features, device=x.device) for lin in linears[:-1]]
+        return cache[key]
+
     def _infer_hidden(self, net, x, tag: str):
         """The hidden layers of one MLP through K12 (bias + ELU fused) into persistent buffers; returns the last hidden activation,
         or None when a layer is not taken by K12 (the caller then uses ``_infer``)."""
@@ -406,11 +443,20 @@ class ActorCritic(nn.Module):
                 or not observations.is_cuda or observations.dim() != 2 or not self.supports_fused_heads or out is None
                 or any(out.get(k) is None for k in ("actions", "logp", "mu", "sigma", "values"))):
             return None
-        side = self.side_streams(observations.device)[0]
-        with side.forked():
-            h_c = self._infer_hidden(self.critic, critic_observations, "critic")
-        h_a = self._infer_hidden(self.actor, observations, "actor")
-        side.join()
+        h_a = h_c = None
+        la = [m for m in self.actor if isinstance(m, nn.Linear)]
+        lc = [m for m in self.critic if isinstance(m, nn.Linear)]
+        if len(la) == 4 and len(lc) == 4 and observations.shape == critic_observations.shape:  # K19: both networks, one launch
+            bufs = self._infer_buffers(la, "actor", observations), self._infer_buffers(lc, "critic", critic_observations)
+            pre = self._mlp3_hidden([(la, observations, "iactor", bufs[0]), (lc, critic_observations, "icritic", bufs[1])], keep=False)
+            if pre is not None:
+                h_a, h_c = pre[0][-1], pre[1][-1]
+        if h_a is None:
+            side = self.side_streams(observations.device)[0]
+            with side.forked():
+                h_c = self._infer_hidden(self.critic, critic_observations, "critic")
+            h_a = self._infer_hidden(self.actor, observations, "actor")
+            side.join()
         if h_a is None or h_c is None:
             return None
         if callable(self.rng):

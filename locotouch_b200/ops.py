@@ -7,6 +7,7 @@ classes that mirror the reference interfaces (``locotouch_b200.loco_rl``, ``loco
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -559,6 +560,49 @@ def dgrad_act_bwd(grad_out, weight, act_in, out=None):
     check(rc, "lt_dgrad_act_bwd")
     count_launches(1)
     return out
+
+
+# ------------------------------------------------------------------------------------------- K19 fused three-layer MLP forward
+MLP3_HIDDEN = (512, 256, 128)
+
+
+def mlp3_supported(linears, k_in: int) -> bool:
+    """The stacks K19 takes: three hidden layers [512, 256, 128] over an input width that is a multiple of 4 and <= 352."""
+    return (len(linears) >= 3 and tuple(lin.out_features for lin in linears[:3]) == MLP3_HIDDEN and linears[0].in_features <= k_in
+            and (k_in & 3) == 0 and k_in <= 352 and os.environ.get("LT_MLP3", "1") != "0")
+
+
+def mlp3_forward(nets):
+    """K19: the three hidden Linear + ELU layers of one or two MLPs in ONE persistent tcgen05 kernel.  ``nets`` = list of
+    ``(x, (w1, b1, w2, b2, w3, b3), (h1, h2, h3))`` with x [B, k0], w1 [512, k0] (k0 % 4 == 0: zero-padded copies for other
+    widths), h3 [B, 128] and h1 [B, 512] / h2 [B, 256] or None (rollout: only h3 is needed).  Returns the h3 tensors, or None
+    when the shapes / alignment are not taken (callers keep the per-layer K12 path)."""
+    if not 1 <= len(nets) <= 2:
+        return None
+    arr = (_C.LtMlp3Net * len(nets))()
+    B, k0 = nets[0][0].shape
+    for a, (x, params, hs) in zip(arr, nets):
+        w1, b1, w2, b2, w3, b3 = params
+        h1, h2, h3 = hs
+        if (tuple(x.shape) != (B, k0) or tuple(w1.shape) != (512, k0) or tuple(w2.shape) != (256, 512) or tuple(w3.shape) != (128, 256)
+                or (k0 & 3) or k0 > 352 or tuple(h3.shape) != (B, 128)):
+            return None
+        ts = [x, w1, b1, w2, b2, w3, b3, h3] + [h for h in (h1, h2) if h is not None]
+        if any((not t.is_contiguous()) or (t.data_ptr() & 15) or t.dtype != torch.float32 for t in ts) or any(h is not None and (h.data_ptr() & 31) for h in hs):
+            return None
+        if (h1 is not None and tuple(h1.shape) != (B, 512)) or (h2 is not None and tuple(h2.shape) != (B, 256)):
+            return None
+        a.x, a.k0 = ptr(x, torch.float32, "x"), k0
+        a.w1, a.b1, a.w2, a.b2, a.w3, a.b3 = (ptr(t, torch.float32, "param") for t in params)
+        a.h1 = ptr(h1, torch.float32, "h1") if h1 is not None else None
+        a.h2 = ptr(h2, torch.float32, "h2") if h2 is not None else None
+        a.h3 = ptr(h3, torch.float32, "h3")
+    rc = lib().lt_mlp3_forward(arr, len(nets), B, current_stream())
+    if rc == _C.LT_ERR_UNSUPPORTED:
+        return None
+    check(rc, "lt_mlp3_forward")
+    count_launches(1)
+    return [hs[2] for (_, _, hs) in nets]
 
 
 # ------------------------------------------------------------------------------------------- K15 split-K weight gradient

@@ -35,7 +35,7 @@ def test_struct_layouts_match(lt_lib):
     from locotouch_b200 import _C
 
     for which, struct in enumerate((_C.LtGatherArgs, _C.LtPpoLossArgs, _C.LtTaxelArgs, _C.LtMdpArgs, _C.LtGaitState, _C.LtGaitParams, _C.LtTaxelForceArgs,
-                                    _C.LtCommandRanges, _C.LtCommandArgs, _C.LtVelCurriculumArgs, _C.LtPpoHeadsArgs, _C.LtStudentCnnArgs)):
+                                    _C.LtCommandRanges, _C.LtCommandArgs, _C.LtVelCurriculumArgs, _C.LtPpoHeadsArgs, _C.LtStudentCnnArgs, _C.LtMlp3Net)):
         assert lt_lib.lt_struct_size(which) == ctypes.sizeof(struct), struct.__name__
     assert lt_lib.lt_struct_size(99) == -1
 

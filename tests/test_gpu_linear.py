@@ -158,8 +158,10 @@ def test_tf32_training_pass_gradients_match_autograd(cuda, lt_lib, B, hidden, OB
         own = _C.launch_count - n0
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    # library launches only: per network 3 fused forward layers, 2 fused dgrad layers and one K15 per Linear (heads included)
-    assert own >= 2 * (len(hidden) + (len(hidden) - 1) + len(hidden) + 1), own
+    # library launches only: per network 2 fused dgrad layers and one K15 per Linear (heads included), plus the forward: ONE K19
+    # launch for both networks at the [512, 256, 128] stack, otherwise one K12 per hidden layer and network
+    fwd = 1 if list(hidden) == [512, 256, 128] else 2 * len(hidden)
+    assert own >= fwd + 2 * ((len(hidden) - 1) + len(hidden) + 1), own
     mu64, v64 = ref.actor(obs.double()), ref.critic(cobs.double())
     H.assert_close(mu, mu64.float(), "mu (TF32 forward)", rtol=2e-2, atol=2e-2)
     torch.autograd.backward([mu64, v64], [g_mu.double(), g_v.double()])
