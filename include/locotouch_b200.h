@@ -226,6 +226,8 @@ typedef struct {
   const int64_t* delay_steps; /* [N] slot to read */
   int max_delay;
   float* delayed_signal;      /* [N, 2T] */
+  const uint8_t* delay_reset; /* [N] or NULL: envs reset since the previous frame (the dones of the previous env step, e.g. a row of
+                                 RolloutStorage.dones): treated like delay_first, read only -- saves the separate flag |= dones pass */
 } LtTaxelArgs;
 int lt_taxel_synth(const LtTaxelArgs* args, void* stream);
 /* Force-valued tactile encodings (reference locotouch/mdp/observations.py:166-237; classes NormalizedTactileSignals,
@@ -494,6 +496,11 @@ int lt_dgrad_act_bwd(const float* grad_out, const float* w, const float* act_in,
  * Wider layers need n_out % 4 == 0, k_in % 4 == 0 and 16-byte aligned pointers (LT_ERR_UNSUPPORTED otherwise or in a stub build).
  * Summation order over the batch slices is not fixed (fp32 atomics): results are reproducible to rounding, not bit for bit. */
 int lt_wgrad_splitk(const float* grad_out, const float* act_in, float* dw, float* dbias, int B, int n_out, int k_in, int zero_first, void* stream);
+/* Two layers of identical shape (layer i of the actor and of the critic) in ONE launch: the CTAs are divided between the two problems, the
+ * fixed cost of a launch is paid once.  Outputs are accumulated into (the caller cleared them); dbias0 / dbias1 both NULL or both set;
+ * n_out > 16 only.  LT_ERR_UNSUPPORTED under the alignment rules of lt_wgrad_splitk. */
+int lt_wgrad_splitk_pair(const float* grad_out0, const float* act_in0, float* dw0, float* dbias0, const float* grad_out1, const float* act_in1,
+                         float* dw1, float* dbias1, int B, int n_out, int k_in, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * K19  the three hidden layers (k0 -> 512 -> 256 -> 128, bias + ELU each) of up to two MLPs in ONE persistent tcgen05 kernel

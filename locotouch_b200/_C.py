@@ -87,7 +87,7 @@ class LtTaxelArgs(C.Structure):
         ("seed", C.c_uint64), ("offset", C.c_uint64), ("offset_base", C.c_void_p),
         ("signal", C.c_void_p), ("packed", C.c_void_p), ("normal_forces", C.c_void_p), ("original_contact", C.c_void_p),
         ("delay_ring", C.c_void_p), ("delay_first", C.c_void_p), ("delay_steps", C.c_void_p), ("max_delay", C.c_int),
-        ("delayed_signal", C.c_void_p),
+        ("delayed_signal", C.c_void_p), ("delay_reset", C.c_void_p),
     ]
 
 
@@ -259,6 +259,7 @@ _SIGNATURES = {
     "lt_act_heads": (C.c_int, [C.c_void_p] * 13 + [C.c_int] * 3 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "lt_wgrad_splitk": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
     "lt_mlp3_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "lt_wgrad_splitk_pair": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 3 + [C.c_void_p]),
     "lt_mdp_tables_len": (C.c_int, [C.POINTER(LtMdpArgs)]),
     "lt_mdp_build_tables": (C.c_int, [C.POINTER(LtMdpArgs), C.POINTER(C.c_int32), C.c_int]),
     "lt_mdp_reset": (C.c_int, [C.POINTER(LtGaitState), f32p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) taxel_kernel(const LtTaxe
     const uint32_t* ring = a.delay_ring + (size_t)n * a.max_delay * words;
 #pragma unroll
     for (int k = 0; k < kMaxDelay - 1; ++k) old_ring[k] = (k < a.max_delay - 1 && lane < words) ? ring[k * words + lane] : 0u;
-    first = a.delay_first[n] != 0;
+    first = a.delay_first[n] != 0 || (a.delay_reset != nullptr && a.delay_reset[n] != 0);
     slot = (int)a.delay_steps[n];
   }
   const uint64_t rng_offset = a.offset + (a.offset_base ? (uint64_t)*a.offset_base : 0ull);

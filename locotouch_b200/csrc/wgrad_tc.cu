@@ -87,16 +87,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t& bar) {
 
 template <int BNH, int NH, class TmaA, class TmaB, class TmaD, class TensorA, class TensorB, class TensorD>
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_splitk_kernel(TensorA mA, TensorB mB, TensorD mD, float* __restrict__ dw, float* __restrict__ dbias, int n_out, int k_in, int k_tiles,
-                    int k_tiles_per_split, int bulk_reduce, CUTE_GRID_CONSTANT TmaA const tma_a, CUTE_GRID_CONSTANT TmaB const tma_b,
-                    CUTE_GRID_CONSTANT TmaD const tma_d) {
+wgrad_splitk_kernel(TensorA mA, TensorB mB, TensorD mD, float* __restrict__ dw_0, float* __restrict__ dbias_0, int n_out, int k_in, int k_tiles,
+                    int k_tiles_per_split, int bulk_reduce, CUTE_GRID_CONSTANT TmaA const tma_a0, CUTE_GRID_CONSTANT TmaB const tma_b0,
+                    CUTE_GRID_CONSTANT TmaD const tma_d0, int splits, float* __restrict__ dw_1, float* __restrict__ dbias_1,
+                    CUTE_GRID_CONSTANT TmaA const tma_a1, CUTE_GRID_CONSTANT TmaB const tma_b1, CUTE_GRID_CONSTANT TmaD const tma_d1) {
   using C = Cfg<BNH, NH>;
   constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   typename C::Storage& ss = *reinterpret_cast<typename C::Storage*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
+  // two problems of the same shape (the actor's and the critic's layer) share one launch: blockIdx.z >= splits works on the second
+  const bool second = (int)blockIdx.z >= splits;
+  const int zsplit = (int)blockIdx.z - (second ? splits : 0);
+  TmaA const& tma_a = second ? tma_a1 : tma_a0;
+  TmaB const& tma_b = second ? tma_b1 : tma_b0;
+  TmaD const& tma_d = second ? tma_d1 : tma_d0;
+  float* __restrict__ dw = second ? dw_1 : dw_0;
+  float* __restrict__ dbias = second ? dbias_1 : dbias_0;
+
   const int warp = threadIdx.x >> 5;
-  const int kt0 = blockIdx.z * k_tiles_per_split;
+  const int kt0 = zsplit * k_tiles_per_split;
   const int nkt = min(k_tiles, kt0 + k_tiles_per_split) - kt0;
   if (nkt <= 0) return;  // uniform per CTA (only when splits * per_split overshoots)
   const bool fold_bias = dbias != nullptr && blockIdx.y == 0;  // uniform per CTA
@@ -207,7 +217,7 @@ wgrad_splitk_kernel(TensorA mA, TensorB mB, TensorD mD, float* __restrict__ dw, 
     int issued = 0;
 #pragma unroll 1
     for (int cc = 0; cc < kBlocks; ++cc) {
-      const int cb = (cc + (int)blockIdx.z) % kBlocks;  // staggered start: the splits of one slab hit different lines
+      const int cb = (cc + zsplit) % kBlocks;  // staggered start: the splits of one slab hit different lines
       const int c = cb * 32;
       if (col0 + c >= k_in) continue;            // uniform over the CTA
       uint32_t r[32];
@@ -254,8 +264,10 @@ wgrad_splitk_kernel(TensorA mA, TensorB mB, TensorD mD, float* __restrict__ dw, 
 }
 
 template <int BNH, int NH>
-int launch(const float* g, const float* x, float* dw, float* dbias, int B, int n_out, int k_in, int sms, int bulk_reduce, cudaStream_t st) {
+int launch(const float* g, const float* x, float* dw, float* dbias, int B, int n_out, int k_in, int sms, int bulk_reduce, cudaStream_t st,
+           const float* g1 = nullptr, const float* x1 = nullptr, float* dw1 = nullptr, float* dbias1 = nullptr) {
   using C = Cfg<BNH, NH>;
+  const int nprob = g1 ? 2 : 1;
   static_assert(C::kNT % 32 == 0 && C::kNT <= 512 && C::kStages >= 3, "tile configuration");
   // (MN, K) views with the MN mode contiguous: exactly the row-major [B, n] / [B, k] tensors
   Tensor mA = make_tensor(make_gmem_ptr(reinterpret_cast<TF const*>(g)), make_layout(make_shape(n_out, B), make_stride(Int<1>{}, n_out)));
@@ -272,7 +284,7 @@ int launch(const float* g, const float* x, float* dw, float* dbias, int B, int n
   Tensor cD = tma_d.get_tma_tensor(shape(mD));
   const int tiles_m = (n_out + kBM - 1) / kBM, tiles_n = (k_in + C::kNT - 1) / C::kNT;
   const int k_tiles = (B + kBK - 1) / kBK;
-  int splits = sms / (tiles_m * tiles_n);
+  int splits = sms / (tiles_m * tiles_n * nprob);
   if (splits < 1) splits = 1;
   if (splits > k_tiles) splits = k_tiles;
   const int per = (k_tiles + splits - 1) / splits;
@@ -283,8 +295,19 @@ int launch(const float* g, const float* x, float* dw, float* dbias, int B, int n
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) != cudaSuccess) return LT_ERR_CUDA;
     attr_set = true;
   }
-  dim3 grid(tiles_m, tiles_n, splits);
-  kern<<<grid, kThreads, C::kSmemBytes, st>>>(cA, cB, cD, dw, dbias, n_out, k_in, k_tiles, per, bulk_reduce, tma_a, tma_b, tma_d);
+  dim3 grid(tiles_m, tiles_n, splits * nprob);
+  if (nprob == 2) {
+    Tensor mA1 = make_tensor(make_gmem_ptr(reinterpret_cast<TF const*>(g1)), make_layout(make_shape(n_out, B), make_stride(Int<1>{}, n_out)));
+    Tensor mB1 = make_tensor(make_gmem_ptr(reinterpret_cast<TF const*>(x1)), make_layout(make_shape(k_in, B), make_stride(Int<1>{}, k_in)));
+    Tensor mD1 = make_tensor(make_gmem_ptr(dw1), make_layout(make_shape(n_out, k_in), make_stride(k_in, Int<1>{})));
+    auto tma_a1 = make_tma_atom(SM90_TMA_LOAD{}, mA1, sa(_, _, _, Int<0>{}), make_shape(Int<kBM>{}, Int<kBK>{}));
+    auto tma_b1 = make_tma_atom(SM90_TMA_LOAD{}, mB1, sb(_, _, _, Int<0>{}), make_shape(Int<BNH>{}, Int<kBK>{}));
+    auto tma_d1 = make_tma_atom(SM90_TMA_REDUCE_ADD{}, mD1, sd(_, _, Int<0>{}), make_shape(Int<kBM>{}, Int<32>{}));
+    kern<<<grid, kThreads, C::kSmemBytes, st>>>(cA, cB, cD, dw, dbias, n_out, k_in, k_tiles, per, bulk_reduce, tma_a, tma_b, tma_d, splits, dw1, dbias1, tma_a1, tma_b1,
+                                                tma_d1);
+  } else {
+    kern<<<grid, kThreads, C::kSmemBytes, st>>>(cA, cB, cD, dw, dbias, n_out, k_in, k_tiles, per, bulk_reduce, tma_a, tma_b, tma_d, splits, dw, dbias, tma_a, tma_b, tma_d);
+  }
   return lt::check_launch();
 }
 
@@ -419,8 +442,30 @@ extern "C" int lt_wgrad_splitk(const float* grad_out, const float* act_in, float
   return launch<64, 1>(grad_out, act_in, dw, dbias, B, n_out, k_in, sms, bulk, st);
 }
 
+// The same for TWO layers of identical shape (the actor's and the critic's layer i) in ONE launch: the CTAs are divided between the two
+// problems, so the fixed cost of a launch (prologue, pipeline fill, the flush of the 128-row accumulator slabs) is paid once and every
+// CTA accumulates twice as many batch rows before it adds its slab into dW.  Outputs must have been cleared by the caller.
+extern "C" int lt_wgrad_splitk_pair(const float* grad_out0, const float* act_in0, float* dw0, float* dbias0, const float* grad_out1, const float* act_in1, float* dw1,
+                                    float* dbias1, int B, int n_out, int k_in, void* stream) {
+  if (!grad_out0 || !act_in0 || !dw0 || !grad_out1 || !act_in1 || !dw1 || B <= 0 || n_out <= 0 || k_in <= 0 || (dbias0 == nullptr) != (dbias1 == nullptr))
+    return LT_ERR_INVALID_ARG;
+  if (n_out <= 16 || (n_out & 3) || (k_in & 3) ||
+      (((uintptr_t)grad_out0 | (uintptr_t)act_in0 | (uintptr_t)dw0 | (uintptr_t)grad_out1 | (uintptr_t)act_in1 | (uintptr_t)dw1) & 15))
+    return LT_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = lt::sm_count();
+  if (k_in > 384) return launch<256, 2>(grad_out0, act_in0, dw0, dbias0, B, n_out, k_in, sms, 1, st, grad_out1, act_in1, dw1, dbias1);
+  if (k_in > 256) return launch<192, 2>(grad_out0, act_in0, dw0, dbias0, B, n_out, k_in, sms, 1, st, grad_out1, act_in1, dw1, dbias1);
+  if (k_in > 128) return launch<256, 1>(grad_out0, act_in0, dw0, dbias0, B, n_out, k_in, sms, 1, st, grad_out1, act_in1, dw1, dbias1);
+  if (k_in > 64) return launch<128, 1>(grad_out0, act_in0, dw0, dbias0, B, n_out, k_in, sms, 1, st, grad_out1, act_in1, dw1, dbias1);
+  return launch<64, 1>(grad_out0, act_in0, dw0, dbias0, B, n_out, k_in, sms, 1, st, grad_out1, act_in1, dw1, dbias1);
+}
+
 #else  // !LT_HAVE_CUTLASS
 
+extern "C" int lt_wgrad_splitk_pair(const float*, const float*, float*, float*, const float*, const float*, float*, float*, int, int, int, void*) {
+  return LT_ERR_UNSUPPORTED;
+}
 extern "C" int lt_wgrad_splitk(const float*, const float*, float*, float*, int, int, int, int, void*) { return LT_ERR_UNSUPPORTED; }
 
 #endif

@@ -282,7 +282,10 @@ class HotPathEngine:
                                 self.taxel_thr, quat_body_offset=synth.NUM_ROBOT_BODIES, p_drop=0.005, p_add=0.005, seed=self.taxel_seed,
                                 offset=t, offset_base=self.step_counter, signal=None, want_signal=False, packed=self.taxel_packed,
                                 delay_ring=self.taxel_ring, delay_first=self.taxel_first, delay_steps=self.taxel_delay,
-                                delayed_signal=self.tactile_obs)
+                                delayed_signal=self.tactile_obs,
+                                # envs that were reset start a fresh delay line (reference replay_buffer.py:61 -> tactile_recorder.py:18-22):
+                                # the dones of the previous env step, read from their RolloutStorage row (no flag |= dones launch)
+                                delay_reset=st.dones[(t - 1) % self.T].view(-1))
         ops.process_actions(actions, a.raw_actions, a.prev_raw_actions, a.prev_prev_raw_actions, a.processed_actions,
                             clip=ACTION_CLIP, raw_scale=ACTION_RAW_SCALE, scale=1.0, offset=self.default_joint_pos)
         self._bind(k)
@@ -290,8 +293,6 @@ class HotPathEngine:
                       critic_out=st._priv_buf[t + 1], step_offset=t, offset_base=self.step_counter)
         if self.tactile:
             self._taxel_stream.join()
-            # envs that were reset start a fresh delay line (reference replay_buffer.py:61 -> tactile_recorder.py:18-22)
-            torch.logical_or(self.taxel_first, self.mdp.dones, out=self.taxel_first.view(torch.bool))
         return st._obs_buf[t + 1], self.mdp.reward_buf, self.mdp.dones, {"time_outs": self.mdp.time_outs, "observations": {"critic": st._priv_buf[t + 1]}}
 
     def rollout_steps(self, upload: bool = False, bank: int = 0):

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ... import ops
+from ... import _C, ops
 from ...streams import SideStream
 from ..utils import resolve_nn_activation
 
@@ -329,6 +329,10 @@ class ActorCritic(nn.Module):
                         have_bias = True
                     g = out
 
+        if fused and self._train_backward_paired(grad_mu, grad_value, from_hidden):
+            self._saved = None
+            return
+
         side, w_actor, w_critic = self.side_streams(grad_mu.device)
         for k, ((linears, acts, gs), g) in enumerate(zip(self._saved, (grad_mu, grad_value))):
             if k == 0:
@@ -340,6 +344,59 @@ class ActorCritic(nn.Module):
         w_actor.join()
         side.join()
         self._saved = None
+
+    def _train_backward_paired(self, grad_mu, grad_value, from_hidden: bool) -> bool:
+        """TF32 backward of two networks with identical hidden stacks: layer i of actor and critic share ONE K15 launch
+        (``ops.wgrad_pair``: the CTAs are divided between the two problems, the fixed cost of a launch is paid once) on the trailing
+        stream; the dgrad GEMMs (K12, ELU backward in the epilogue) run actor on the caller's stream, critic on the side stream.
+        Returns False (nothing launched) when the stacks differ or an input is a zero-padded copy -- the per-network path then runs."""
+        (la, acts_a, gs_a), (lc, acts_c, gs_c) = self._saved
+        if len(la) != len(lc) or len(la) < 2 or os.environ.get("LT_WGRAD_PAIR", "1") == "0" or _C.gemm_backend() == "stub":
+            return False
+        for a, c in zip(la[:-1], lc[:-1]):
+            if (a.in_features, a.out_features) != (c.in_features, c.out_features) or a.out_features < 64:
+                return False
+        if acts_a[0].shape[1] != la[0].in_features or acts_c[0].shape[1] != lc[0].in_features or (la[0].in_features & 3):
+            return False
+        side, wstream, _ = self.side_streams(grad_mu.device)
+        ga, gc = grad_mu, grad_value
+        last = len(la) - 1
+        have_bias = False  # bias gradients of layer i already written (by the K9 pass below the narrow head layers)
+        for i in range(last, -1, -1):
+            with wstream.forked():  # ordered after everything enqueued so far on this stream (both g of this layer)
+                done = None
+                if i < last:
+                    done = ops.wgrad_pair(ga, acts_a[i], la[i].weight.grad, None if have_bias else la[i].bias.grad, gc, acts_c[i], lc[i].weight.grad,
+                                          None if have_bias else lc[i].bias.grad)
+                if done is None:  # the narrow head layers (CUDA-core kernels) and anything the pair launch does not take
+                    for g, x, lin in ((ga, acts_a[i], la[i]), (gc, acts_c[i], lc[i])):
+                        if ops.wgrad(g, x, lin.weight.grad, None if have_bias else lin.bias.grad, zero_first=False) is None:
+                            self._wgrad(g, x, lin.weight.grad, lin._wgrad_part)
+                            if not have_bias:
+                                ops.bias_act_bwd(g, None, lin.bias.grad)
+            have_bias = False
+            if i == last and from_hidden:  # K16 already produced the gradients below the heads
+                ga, gc = gs_a[i], gs_c[i]
+                continue
+            if i == last:  # narrow head layers (n = 12 / 1): cuBLAS dgrad, then K9 = ELU backward in place + bias gradient of the layer below
+                with side.forked():
+                    gc = torch.mm(gc, lc[i].weight, out=gs_c[i])
+                    ops.bias_act_bwd(gc, acts_c[i], lc[i - 1].bias.grad)
+                ga = torch.mm(ga, la[i].weight, out=gs_a[i])
+                ops.bias_act_bwd(ga, acts_a[i], la[i - 1].bias.grad)
+                side.join()
+                have_bias = True
+                continue
+            if i > 0:
+                with side.forked():
+                    out_c = ops.dgrad_act_bwd(gc, lc[i].weight, acts_c[i], out=gs_c[i])
+                out_a = ops.dgrad_act_bwd(ga, la[i].weight, acts_a[i], out=gs_a[i])
+                side.join()
+                if out_a is None or out_c is None:  # shapes were checked above: only a misaligned buffer gets here
+                    raise _C.LocoTouchLibraryError("K12 dgrad rejected a layer of the paired backward (misaligned activation buffer?)")
+                ga, gc = out_a, out_c
+        wstream.join()
+        return True
 
     _WGRAD_SPLIT = 8
 

@@ -308,7 +308,7 @@ def bias_act_bwd(grad_out, act_out, bias_grad, grad_pre=None, alpha: float = 1.0
 # ----------------------------------------------------------------------------------------------------------- K2 taxels
 def taxel_synth(body_quat_w, net_forces_w, thresholds, *, quat_body_offset=0, u_drop=None, u_add=None, p_drop=0.005, p_add=0.005,
                 seed=0, offset=0, offset_base=None, signal=None, packed=None, normal_forces=None, original_contact=None, delay_ring=None,
-                delay_first=None, delay_steps=None, delayed_signal=None, want_signal=True, want_packed=True):
+                delay_first=None, delay_steps=None, delayed_signal=None, want_signal=True, want_packed=True, delay_reset=None):
     """Binary taxel bitmap from contact forces (reference observations.py:154-199, 281-308)."""
     N, T = net_forces_w.shape[0], net_forces_w.shape[1]
     dev = net_forces_w.device
@@ -338,6 +338,8 @@ def taxel_synth(body_quat_w, net_forces_w, thresholds, *, quat_body_offset=0, u_
         a.delay_steps = ptr(delay_steps, torch.int64)
         a.max_delay = delay_ring.shape[1]
         a.delayed_signal = ptr(delayed_signal, torch.float32)
+        if delay_reset is not None:  # [N] bytes: envs reset since the previous frame (read only)
+            a.delay_reset = ptr(delay_reset.view(torch.uint8) if delay_reset.dtype == torch.bool else delay_reset, torch.uint8)
     check(lib().lt_taxel_synth(C.byref(a), current_stream()), "lt_taxel_synth")
     count_launches(1)
     return signal, packed
@@ -626,6 +628,27 @@ def wgrad(grad_out, act_in, out, bias_out=None, zero_first: bool = True):
     check(rc, "lt_wgrad_splitk")
     count_launches(1)
     return out
+
+
+def wgrad_pair(grad_out0, act_in0, out0, bias_out0, grad_out1, act_in1, out1, bias_out1):
+    """K15 for two layers of the same shape (actor and critic) in ONE launch; outputs are accumulated into (cleared by the caller).
+    Returns None when the shapes / alignment are not taken (the caller launches them one by one)."""
+    B, n = grad_out0.shape
+    k = act_in0.shape[1]
+    if (tuple(grad_out1.shape) != (B, n) or tuple(act_in1.shape) != (B, k) or tuple(out0.shape) != (n, k) or tuple(out1.shape) != (n, k) or n <= 16 or (n & 3) or (k & 3)
+            or os.environ.get("LT_WGRAD_PAIR", "1") == "0"):
+        return None
+    ts = [grad_out0, act_in0, out0, grad_out1, act_in1, out1]
+    if any((not t.is_contiguous()) or (t.data_ptr() & 15) for t in ts) or (bias_out0 is None) != (bias_out1 is None):
+        return None
+    rc = lib().lt_wgrad_splitk_pair(ptr(grad_out0, torch.float32), ptr(act_in0, torch.float32), ptr(out0, torch.float32),
+                                    ptr(bias_out0, torch.float32) if bias_out0 is not None else None, ptr(grad_out1, torch.float32), ptr(act_in1, torch.float32),
+                                    ptr(out1, torch.float32), ptr(bias_out1, torch.float32) if bias_out1 is not None else None, B, n, k, current_stream())
+    if rc == _C.LT_ERR_UNSUPPORTED:
+        return None
+    check(rc, "lt_wgrad_splitk_pair")
+    count_launches(1)
+    return out0, out1
 
 
 # ------------------------------------------------------------------------------------------- K17 student tactile pre-encoder

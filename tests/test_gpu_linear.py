@@ -161,7 +161,10 @@ def test_tf32_training_pass_gradients_match_autograd(cuda, lt_lib, B, hidden, OB
     # library launches only: per network 2 fused dgrad layers and one K15 per Linear (heads included), plus the forward: ONE K19
     # launch for both networks at the [512, 256, 128] stack, otherwise one K12 per hidden layer and network
     fwd = 1 if list(hidden) == [512, 256, 128] else 2 * len(hidden)
-    assert own >= fwd + 2 * ((len(hidden) - 1) + len(hidden) + 1), own
+    if OBS % 4 == 0:  # paired backward: one K15 launch per hidden layer for BOTH networks, two head wgrads, two K9 below the heads, dgrads
+        assert own >= fwd + len(hidden) + 2 + 2 + 2 * (len(hidden) - 1), own
+    else:
+        assert own >= fwd + 2 * ((len(hidden) - 1) + len(hidden) + 1), own
     mu64, v64 = ref.actor(obs.double()), ref.critic(cobs.double())
     H.assert_close(mu, mu64.float(), "mu (TF32 forward)", rtol=2e-2, atol=2e-2)
     torch.autograd.backward([mu64, v64], [g_mu.double(), g_v.double()])
@@ -204,3 +207,66 @@ def test_rollout_heads_kernel_matches_torch(cuda, lt_lib, N, Hd, A, critic):
     a3, lp3 = ops.act_sample(mu2.contiguous(), sigma, seed=11, offset=5)
     H.assert_close(a2, a3, "Philox actions == lt_act_sample on the same means", rtol=0, atol=1e-6)
     H.assert_close(lp2, lp3, "log prob == lt_act_sample", rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,n,k", [(24576, 512, 348), (24576, 256, 512), (24576, 128, 256), (1000, 132, 100), (37, 64, 64)])
+def test_wgrad_pair_matches_two_single_launches(cuda, lt_lib, B, n, k):
+    """K15 with two problems of one shape (actor and critic layer) in ONE launch against the fp64 products; bias both set / both None."""
+    from locotouch_b200 import ops
+
+    gen = torch.Generator().manual_seed(B + n + k + 1)
+    gs = [(torch.randn(B, n, generator=gen) / B ** 0.5).to(cuda) for _ in range(2)]
+    xs = [torch.randn(B, k, generator=gen).to(cuda) for _ in range(2)]
+    outs = [torch.zeros(n, k, device=cuda) for _ in range(2)]
+    dbs = [torch.zeros(n, device=cuda) for _ in range(2)]
+    assert ops.wgrad_pair(gs[0], xs[0], outs[0], dbs[0], gs[1], xs[1], outs[1], dbs[1]) is not None
+    for g, x, out, db in zip(gs, xs, outs, dbs):
+        assert (out.double() - g.double().t() @ x.double()).abs().max().item() < 4e-3
+        assert (db.double() - g.double().sum(0)).abs().max().item() < 2e-3
+    outs2 = [torch.zeros(n, k, device=cuda) for _ in range(2)]
+    assert ops.wgrad_pair(gs[0], xs[0], outs2[0], None, gs[1], xs[1], outs2[1], None) is not None
+    for a, b in zip(outs, outs2):
+        H.assert_close(a, b, "pair launch with / without bias outputs", rtol=1e-3, atol=1e-3)
+    assert ops.wgrad_pair(gs[0], xs[0], outs[0], dbs[0], gs[1], xs[1], outs[1], None) is None  # bias outputs: both or none
+
+
+@pytest.mark.parametrize("B", [24576, 1000])
+def test_tf32_production_backward_from_hidden_matches_autograd(cuda, lt_lib, B):
+    """The backward exactly as PPO.minibatch_grads drives it: K19 forward without heads, the gradients below the heads handed over in
+    ``hidden_grad_buffers()`` (what K16 writes), then ``train_backward(from_hidden=True)`` = paired K15 launches + K12 dgrads; against
+    float64 autograd of the reference modules (actor_critic.py:33-56 under loss.backward())."""
+    import copy
+
+    from locotouch_b200.loco_rl.modules.actor_critic import ActorCritic
+
+    torch.manual_seed(B + 3)
+    A, OBS, hidden = 12, 348, [512, 256, 128]
+    ac = ActorCritic(OBS, OBS, A, actor_hidden_dims=hidden, critic_hidden_dims=hidden, activation="elu").to(cuda)
+    ref = copy.deepcopy(ac).double()
+    ac.flatten_parameters()
+    obs, cobs = torch.randn(B, OBS, device=cuda), torch.randn(B, OBS, device=cuda)
+    g_mu, g_v = torch.randn(B, A, device=cuda) / B, torch.randn(B, 1, device=cuda) / B
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        h_a, h_c = ac.train_forward(obs, cobs, heads=False)
+        assert tuple(h_a.shape) == (B, 128) and tuple(h_c.shape) == (B, 128)
+        gh_a, gh_c = ac.hidden_grad_buffers()
+        with torch.no_grad():  # dL/d(pre-activation of the last hidden layer) = (g W_head) * elu'(h), elu' through the stored activation
+            gh_a.copy_(((g_mu.double() @ ac.actor[-1].weight.double()) * torch.where(h_a > 0, 1.0, h_a.double() + 1.0)).float())
+            gh_c.copy_(((g_v.double() @ ac.critic[-1].weight.double()) * torch.where(h_c > 0, 1.0, h_c.double() + 1.0)).float())
+        ac.train_backward(g_mu, g_v, from_hidden=True)
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    mu64, v64 = ref.actor(obs.double()), ref.critic(cobs.double())
+    torch.autograd.backward([mu64, v64], [g_mu.double(), g_v.double()])
+    got = dict(ac.named_parameters())
+    for name, p in ref.named_parameters():
+        if name in ("std", "log_std"):
+            continue
+        want, have = p.grad, got[name].grad.double()
+        scale = want.abs().max().item()
+        err = (have - want).abs().max().item()
+        tol = 3e-2 if name.endswith("bias") else 1e-2
+        assert err <= tol * scale + 1e-9, f"{name}: max abs error {err:.3e} against a largest entry of {scale:.3e}"
