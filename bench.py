@@ -213,7 +213,7 @@ def run_reference(args, rank: int):
 # ------------------------------------------------------------------------------------------------------ kernel roofline
 def ncu_traffic_bytes(kernel_substr: str):
     """DRAM bytes per launch (read + write) of the committed `ncu --set full` capture, or None."""
-    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2f_ncu_full_summary.json", "r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
+    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2o_ncu_full_summary.json", "r2f_ncu_full_summary.json", "r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
                  if os.path.exists(q)), None)  # newest capture first
     if path is None:
         return None
@@ -291,7 +291,7 @@ def gemm_rows(engine, peak_tflops: float):
     if getattr(alg, "_mb", None) is None:
         alg.update_begin(engine.perm)
 
-    def run(i):  # the production mini-batch pass: K12 forward x 6, K16 (heads + loss + head dgrad), K12 dgrad x 4, K15 x 8
+    def run(i):  # the production mini-batch pass: K19 (forward of both MLPs), K16 (heads + loss + head dgrad), K12 dgrad x 4, K15 pair x 3 + 2 heads
         alg.minibatch_grads(i % alg.num_mini_batches)
 
     for i in range(3):
@@ -324,7 +324,7 @@ def gemm_rows(engine, peak_tflops: float):
     flops = 2.0 * B * (3 * macs - first)
     tfs = flops / best / 1e6
     tf32_peak = peak_tflops / 2.0  # TF32 dense = half the bf16 rate on B200 (2.25 vs 1.1 PFLOP/s nominal); measured bf16 peak / 2
-    return [{"kernel": "actor-critic MLPs fwd + heads/loss + bwd of one mini-batch as PPO.minibatch_grads runs it (K12 + K16 + K15, TF32 tcgen05)", "bound": "tensor", "achieved": tfs, "peak": tf32_peak,
+    return [{"kernel": "actor-critic MLPs fwd + heads/loss + bwd of one mini-batch as PPO.minibatch_grads runs it (K19 + K16 + K12 dgrad + K15, TF32 tcgen05)", "bound": "tensor", "achieved": tfs, "peak": tf32_peak,
              "unit": "TFLOP/s", "frac": tfs / tf32_peak, "us_per_launch": best, "flops_per_launch": flops,
              "peak_note": "measured sustained bf16 cuBLAS peak / 2 (TF32 runs at half the bf16 rate)"}]
 
@@ -559,6 +559,12 @@ def main():
                 gbs = nbytes / us / 1e3
                 rows.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "us_per_launch": us,
                              "alg_bytes_per_launch": nbytes, "tflops": flops / us / 1e6, "tf32_peak_tflops": tf / 2.0, "tensor_frac": flops / us / 1e6 / (tf / 2.0)})
+            # K19 (both MLPs' hidden layers in one persistent kernel: rollout step and mini-batch forward) and the K15 pair launches
+            for name, (us, nbytes, flops) in KB.bench_mlp3(N, N * T_STEPS // 4, 30, obs_dim=engine.spec.obs_dim).items():
+                gbs = nbytes / us / 1e3
+                rows.append({"kernel": name, "bound": "tensor" if name.startswith("K19") else "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                             "us_per_launch": us, "alg_bytes_per_launch": nbytes, "tflops": flops / us / 1e6, "tf32_peak_tflops": tf / 2.0,
+                             "tensor_frac": flops / us / 1e6 / (tf / 2.0)})
             rows.extend(gemm_rows(engine, tf))
             # config C4 (distillation): the student's tactile pre-encoder (K17, fp32 FMA on CUDA cores: 432 kFLOP per frame) at the
             # distillation env count, the BASELINE size and 16 384 frames; "frac" = fraction of the HBM peak its 2 KB per frame amount to
@@ -566,16 +572,21 @@ def main():
                 m = nbytes / ((442 + 64) * 4.0)
                 rows.append({"kernel": name, "bound": "fp32 fma", "achieved": 2 * 216.0e3 * m / us / 1e6, "peak": None, "unit": "TFLOP/s", "frac": None,
                              "us_per_launch": us, "alg_bytes_per_launch": nbytes, "frames_per_s": m / us * 1e6})
-            # the kernel with the largest share of the iteration (K12: ~50 % of the summed kernel time, profiles/r2e_launches_summary.md)
-            # next to the streaming kernel the headline fraction is quoted on
-            k12 = [r for r in rows if r["kernel"].startswith("K12 forward")]
+            # the kernel with the largest share of the iteration (K19: ~35 % of the summed kernel time, profiles/r2m_launches_summary.md) next
+            # to the streaming kernel the headline fraction is quoted on; without K19 (other widths) the largest K12 forward layer
+            k19 = [r for r in rows if r["kernel"].startswith("K19") and "mini-batch" in r["kernel"]]
+            k12 = k19 or [r for r in rows if r["kernel"].startswith("K12 forward")]
             if k12:
                 big = max(k12, key=lambda r: r["us_per_launch"])
-                line["roofline"]["dominant_by_share"] = {"kernel": big["kernel"], "bound": "hbm", "achieved": big["achieved"], "peak": hbm, "unit": "GB/s",
-                                                         "frac": big["frac"], "us_per_launch": big["us_per_launch"], "tflops": big["tflops"],
-                                                         "tensor_frac_of_tf32_peak": big["tensor_frac"],
-                                                         "traffic": ncu_traffic_bytes("device_kernel"),
-                                                         "note": "fp32 operands: 105 FLOP/B against a ridge of ~100 (TF32) -- HBM / L2 bound, so the fraction is of the HBM peak"}
+                line["roofline"]["dominant_by_share"] = {"kernel": big["kernel"], "bound": "tensor" if k19 else "hbm", "achieved": big["tflops"] if k19 else big["achieved"],
+                                                         "peak": tf / 2.0 if k19 else hbm, "unit": "TFLOP/s" if k19 else "GB/s",
+                                                         "frac": big["tensor_frac"] if k19 else big["frac"], "us_per_launch": big["us_per_launch"], "tflops": big["tflops"],
+                                                         "tensor_frac_of_tf32_peak": big["tensor_frac"], "hbm_gbs": big["achieved"], "hbm_frac": big["frac"],
+                                                         "traffic": ncu_traffic_bytes("mlp3_forward" if k19 else "device_kernel"),
+                                                         "note": ("persistent fused MLP: activations stay in TMEM, so the algorithmic HBM bytes (x once, h1 / h2 / h3 once) are 0.36 of "
+                                                                  "what three GEMM launches move and the kernel is bound by the TF32 tensor pipe + the shared-memory fill of the "
+                                                                  "weight tiles; peak = measured bf16 cuBLAS peak / 2") if k19 else
+                                                                 "fp32 operands: 105 FLOP/B against a ridge of ~100 (TF32) -- HBM / L2 bound, so the fraction is of the HBM peak"}
         except Exception as exc:  # noqa: BLE001 -- the table is diagnostics; the headline numbers above do not depend on it
             line["kernels_error"] = repr(exc)
         line["kernels"] = rows

@@ -190,14 +190,20 @@ wgrad_splitk_kernel(TensorA mA, TensorB mB, TensorD mD, float* __restrict__ dw_0
       for (int i = 0; i < nkt; ++i) {
         const int s = i % S;
         cute::wait_barrier(ss.full[s], (i / S) & 1);
+        asm volatile("" ::: "memory");  // cute::wait_barrier carries no memory clobber: keep the plain shared-memory loads below it
         CUTE_UNROLL
         for (int kb = 0; kb < size<2>(sA); ++kb) {
           CUTE_UNROLL
-          for (int k8 = 0; k8 < 8; ++k8) {
-            const TF v = sA(make_coord(m_local, k8), 0, kb, s);
-            bsum += reinterpret_cast<const float&>(v);
+          for (int k8 = 0; k8 < 8; ++k8) {  // explicit ld.shared: a generic LD.E is not ordered with the mbarrier unit at all
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(cute::cast_smem_ptr_to_uint(raw_pointer_cast(&sA(make_coord(m_local, k8), 0, kb, s)))) : "memory");
+            bsum += v;
           }
         }
+        // The loads above are asynchronous and nothing in the arrive below waits for them: without a consumer in front of it the stage is
+        // released -- and refilled by TMA -- while rows of it are still being fetched (seen as a few rows of the NEXT batch slice in the
+        // column sums whenever TMA is fast: aligned row pitches, warm L2).  The sum is made a control dependency of the release.
+        if (__float_as_uint(bsum) == 0x7fc0beefu) asm volatile("trap;");  // a real consumer of every load in front of the release (never taken)
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(ss.empty[s]);
       }
@@ -205,6 +211,9 @@ wgrad_splitk_kernel(TensorA mA, TensorB mB, TensorD mD, float* __restrict__ dw_0
     }
     cute::wait_barrier(ss.acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // the staging boxes below alias the operand ring: the MMAs are done with it (acc_full), but a slower bias-folding warp may still be
+    // adding up the g rows of the last stages -- all four warps must have left the fold loop before the first box is written
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int col0 = blockIdx.y * C::kNT;
     float* out = dw + (size_t)row * k_in + col0;
     constexpr int kBlocks = C::kBlocks;

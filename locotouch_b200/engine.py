@@ -270,12 +270,13 @@ class HotPathEngine:
             ev.record(cs)
         self._upload_done[bank] = ev
 
-    def env_step(self, t: int, actions: torch.Tensor, bank: int = 0):
-        """Stand-in for ``env.step(actions)``: everything IsaacLab's managers would compute around PhysX."""
+    def taxel_step(self, t: int, bank: int = 0):
+        """K2 of env step ``t`` on the taxel stream.  It reads nothing the policy or the MDP step of this env step writes (sensor state
+        of step t, the dones of step t - 1), so ``rollout_steps`` forks it BEFORE the policy: K19 occupies 64 of the 148 SMs at 4096
+        envs and the taxel kernel fills the rest, instead of competing with the MDP step (one 1024-thread block per SM) afterwards."""
         k = self.set_index(t, bank)
         st = self.alg.storage
-        a = self.action_term
-        if self.tactile:  # the taxel kernel reads nothing the policy or the MDP step writes: it runs next to them
+        if self.tactile:
             with self._taxel_stream.forked():
                 env = self.envs[k]
                 ops.taxel_synth(env.scene["robot"].data.body_quat_w, env.scene.sensors["tactile_contact_sensor"].data.net_forces_w,
@@ -286,6 +287,14 @@ class HotPathEngine:
                                 # envs that were reset start a fresh delay line (reference replay_buffer.py:61 -> tactile_recorder.py:18-22):
                                 # the dones of the previous env step, read from their RolloutStorage row (no flag |= dones launch)
                                 delay_reset=st.dones[(t - 1) % self.T].view(-1))
+
+    def env_step(self, t: int, actions: torch.Tensor, bank: int = 0, taxels_launched: bool = False):
+        """Stand-in for ``env.step(actions)``: everything IsaacLab's managers would compute around PhysX."""
+        k = self.set_index(t, bank)
+        st = self.alg.storage
+        a = self.action_term
+        if not taxels_launched:
+            self.taxel_step(t, bank)
         ops.process_actions(actions, a.raw_actions, a.prev_raw_actions, a.prev_prev_raw_actions, a.processed_actions,
                             clip=ACTION_CLIP, raw_scale=ACTION_RAW_SCALE, scale=1.0, offset=self.default_joint_pos)
         self._bind(k)
@@ -304,8 +313,9 @@ class HotPathEngine:
             if upload:
                 self.upload_state(self.set_index(t, bank))
             ac._graph_slot = t
+            self.taxel_step(t, bank)
             actions = alg.act(st._obs_buf[t], st._priv_buf[t])
-            obs, rewards, dones, infos = self.env_step(t, actions, bank)
+            obs, rewards, dones, infos = self.env_step(t, actions, bank, taxels_launched=True)
             alg.process_env_step(rewards, dones, infos)
         ops.counter_add(self.step_counter, self.T)
 

@@ -270,3 +270,26 @@ def test_tf32_production_backward_from_hidden_matches_autograd(cuda, lt_lib, B):
         err = (have - want).abs().max().item()
         tol = 3e-2 if name.endswith("bias") else 1e-2
         assert err <= tol * scale + 1e-9, f"{name}: max abs error {err:.3e} against a largest entry of {scale:.3e}"
+
+
+@pytest.mark.parametrize("n,k,pair", [(512, 352, False), (512, 320, False), (128, 256, True), (512, 348, True)])
+def test_wgrad_bias_fold_is_repeatable_with_warm_l2(cuda, lt_lib, n, k, pair):
+    """Regression: K15's bias-folding warps released a pipeline stage while their shared-memory loads of it were still in flight (generic
+    LD.E is not ordered with the mbarrier unit), so with fast TMA (128-byte-aligned row pitch, warm L2, the longer slices of the pair
+    launch) a few rows of the NEXT batch slice leaked into the column sums: errors of 5-10 % that no single cold launch shows."""
+    from locotouch_b200 import ops
+
+    B = 24576
+    gen = torch.Generator().manual_seed(n * k)
+    g = (torch.randn(B, n, generator=gen) / B ** 0.5).to(cuda)
+    x = torch.randn(B, k, generator=gen).to(cuda)
+    ref = g.double().sum(0)
+    for _ in range(12):
+        out, db = torch.zeros(n, k, device=cuda), torch.zeros(n, device=cuda)
+        if pair:
+            out2, db2 = torch.zeros(n, k, device=cuda), torch.zeros(n, device=cuda)
+            assert ops.wgrad_pair(g, x, out, db, g, x, out2, db2) is not None
+            assert (db2.double() - ref).abs().max().item() < 2e-3
+        else:
+            assert ops.wgrad(g, x, out, db, zero_first=False) is not None
+        assert (db.double() - ref).abs().max().item() < 2e-3

@@ -339,6 +339,42 @@ def bench_gemms(b: int, reps: int, obs_dim: int = 348, hidden=(512, 256, 128), A
     return out
 
 
+def bench_mlp3(n_envs: int, b: int, reps: int, obs_dim: int = 348):
+    """K19: the three hidden layers of actor AND critic in one persistent tcgen05 kernel, at the rollout batch (one env step, h3 only)
+    and at the mini-batch size (h1 / h2 stored for the backward); next to it the K15 pair launches (layer i of both networks).
+    Each row: (us, algorithmic bytes = x read once + weights + stored activations, flops)."""
+    out = {}
+    if obs_dim & 3 or obs_dim > 352:
+        return out
+    macs = obs_dim * 512 + 512 * 256 + 256 * 128
+    wbytes = 4.0 * (macs + 512 + 256 + 128)
+    for rows_, keep, tag in ((n_envs, False, "rollout step"), (b, True, "mini-batch forward")):
+        copies = 4
+        sets = []
+        for _ in range(copies):
+            pair = []
+            for _ in range(2):
+                x = torch.randn(rows_, obs_dim, device="cuda")
+                ps = []
+                for (n, k) in ((512, obs_dim), (256, 512), (128, 256)):
+                    ps += [torch.randn(n, k, device="cuda") / k ** 0.5, torch.randn(n, device="cuda")]
+                hs = (torch.empty(rows_, 512, device="cuda") if keep else None, torch.empty(rows_, 256, device="cuda") if keep else None,
+                      torch.empty(rows_, 128, device="cuda"))
+                pair.append((x, tuple(ps), hs))
+            sets.append(pair)
+        nbytes = 2 * (4.0 * rows_ * (obs_dim + 128 + ((512 + 256) if keep else 0)) + wbytes)
+        out[f"K19 fused MLP x2 [{rows_}x{obs_dim}->512->256->128] {tag}"] = (time_graph(lambda i: ops.mlp3_forward(sets[i]), copies, reps), nbytes, 2.0 * 2 * rows_ * macs)
+    for k, n in ((obs_dim, 512), (512, 256), (256, 128)):
+        copies = 4
+        xs = [[torch.randn(b, k, device="cuda") for _ in range(2)] for _ in range(copies)]
+        gs = [[torch.randn(b, n, device="cuda") for _ in range(2)] for _ in range(copies)]
+        dws, dbs = [torch.zeros(n, k, device="cuda") for _ in range(2)], [torch.zeros(n, device="cuda") for _ in range(2)]
+        out[f"K15 pair wgrad+bias 2 x {n}x{k} over {b}"] = (
+            time_graph(lambda i: ops.wgrad_pair(gs[i][0], xs[i][0], dws[0], dbs[0], gs[i][1], xs[i][1], dws[1], dbs[1]), copies, reps),
+            2 * 4.0 * (b * (n + k) + n * k), 2 * 2.0 * b * k * n)
+    return out
+
+
 def bench_student_cnn(reps: int):
     out = {}
     w = tuple(torch.randn(*s, device="cuda") * 0.1 for s in ((24, 2, 4, 4), (24,), (24, 24, 3, 3), (24,), (24, 24, 2, 2), (24,), (64, 192), (64,)))
@@ -397,6 +433,8 @@ def main():
         res.update(bench_heads(n * 24 // 4, args.reps))
     if want("gemm"):
         res.update({k: v[:2] for k, v in bench_gemms(n * 24 // 4, max(20, args.reps // 5)).items()})
+    if want("mlp3"):
+        res.update({k: v[:2] for k, v in bench_mlp3(n, n * 24 // 4, max(20, args.reps // 5)).items()})
     if want("student"):
         res.update(bench_student_cnn(max(20, args.reps // 5)))
     if want("contact"):

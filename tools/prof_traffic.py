@@ -1,7 +1,7 @@
 """One launch of each streaming kernel at BASELINE size (for one `ncu --set full` capture: DRAM bytes per launch).
 
     ncu --set full --clock-control none --import-source on \
-        -k regex:"mdp_step_kernel|taxel_kernel|ppo_loss_kernel|ppo_heads_kernel|wgrad_splitk_kernel|device_kernel" -c 21 -o out \
+        -k regex:"mdp_step_kernel|taxel_kernel|ppo_loss_kernel|ppo_heads_kernel|wgrad_splitk_kernel|device_kernel|mlp3_forward_kernel" -c 30 -o out \
         python tools/prof_traffic.py        # then tools/ncu_summary.py
 """
 import os
@@ -55,5 +55,21 @@ x_, w_, b_ = rn(b, 348), rn(512, 348) / 18.0, rn(512)
 o_ = torch.empty(b, 512, device="cuda")
 for _ in range(3):
     ops.linear_bias_act(x_, w_, b_, out=o_, elu=True)
+# K19 (three hidden layers of both MLPs in one persistent kernel): 3 launches at the mini-batch size (h1 / h2 stored), 3 at the rollout size
+for rows_, keep in ((b, True), (n, False)):
+    nets = []
+    for _ in range(2):
+        ps = []
+        for (no, k) in ((512, 348), (256, 512), (128, 256)):
+            ps += [rn(no, k) / k ** 0.5, rn(no)]
+        nets.append((rn(rows_, 348), tuple(ps), (torch.empty(rows_, 512, device="cuda") if keep else None, torch.empty(rows_, 256, device="cuda") if keep else None,
+                                                  torch.empty(rows_, 128, device="cuda"))))
+    for _ in range(3):
+        ops.mlp3_forward(nets)
+# K15 pair launch (layer 1 of actor and critic)
+g2, x2 = [rn(b, 512) for _ in range(2)], [rn(b, 348) for _ in range(2)]
+dw2, db2 = [torch.zeros(512, 348, device="cuda") for _ in range(2)], [torch.zeros(512, device="cuda") for _ in range(2)]
+for _ in range(3):
+    ops.wgrad_pair(g2[0], x2[0], dw2[0], db2[0], g2[1], x2[1], dw2[1], db2[1])
 torch.cuda.synchronize()
 print("ok")

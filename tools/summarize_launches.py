@@ -41,7 +41,7 @@ for k, us in rows:
 total = sum(a[1] for a in agg.values())
 mine = ("mdp_step", "taxel", "gae_scan", "adv_normalize", "ppo_loss", "clip_adam", "grad_sqnorm", "act_sample", "store_scalars", "gather_rows",
         "process_actions", "counter_add", "bias_act_bwd", "copy4", "copy1", "any_nonzero", "adaptive_lr", "masked_mse", "pad_traj", "tactile_delay",
-        "command_step", "vel_curriculum", "lt_wgrad::", "ppo_heads", "gae_fused", "peer_sum", "contact_time", "student_", "policy_",
+        "command_step", "vel_curriculum", "lt_wgrad::", "lt_mlp3::", "act_heads", "ppo_heads", "gae_fused", "peer_sum", "contact_time", "student_", "policy_",
         # K12 (gemm_fused.cu): our translation unit built from the CUTLASS sm100 collective builders; cuBLAS's own kernels are
         # named cutlass3x_* / cutlass::Kernel2<cutlass_80_*> and are NOT ours
         "cutlass::device_kernel<")
