@@ -50,7 +50,8 @@ constexpr int kTile = kRows * kBK * 4;  // 16 KB: one [128 x 32] fp32 box
 constexpr int kMaxKB0 = 11;          // k0 <= 352
 constexpr int kWK = 32;              // fp32 columns of one weight tile: [128 x 32], 128-byte rows (SW128), 16 KB
 constexpr int kWTile = kRows * kWK * 4;
-constexpr int kSlots = 3;            // weight-tile ring
+constexpr int kSlots = 3;            // weight-tile ring (one CTA per slab)
+constexpr int kSlotsPair = 6;        // pair mode: a CTA holds half of every weight tile (64 rows, 8 KB), so the same 48 KB are six slots
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + 32 * kEpiWarps;  // warp 0 weight producer, 1 MMA issuer, 2 x producer, 3 idle, 4-19 epilogue
 constexpr uint32_t kColD1 = 0;       // two chunk buffers: columns 0-127, 128-255
@@ -60,8 +61,8 @@ constexpr uint32_t kColD3 = 128;     // over chunk buffer 1
 struct Bars {
   uint64_t x_full[kMaxKB0];
   uint64_t x_empty;
-  uint64_t ring_full[kSlots];
-  uint64_t ring_empty[kSlots];
+  uint64_t ring_full[kSlotsPair];
+  uint64_t ring_empty[kSlotsPair];
   uint64_t d1_full[4];
   uint64_t a2_ready[4];
   uint64_t d2_full, a3_ready, d3_full, d3_empty;
@@ -81,7 +82,7 @@ struct NetArgs {
 struct alignas(64) Params {
   CUtensorMap x[2], w1[2], w2[2], w3[2];
   NetArgs net[2];
-  int n_nets, B, nkb0, slabs;
+  int n_nets, B, nkb0, slabs, pairs_per_net;
   unsigned long long* dbg;  // LT_MLP3_DBG: per-CTA wait-cycle attribution (debug builds of the launcher only)
 };
 
@@ -166,6 +167,59 @@ __device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
 
+// ---- pair mode (cta_group::2): two CTAs of a cluster carry two adjacent slabs of one network; every weight tile is split between
+// their shared memories (64 of its 128 rows each), the leader CTA issues M = 256 MMAs for both.
+constexpr uint32_t kIdescPair = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared-memory address: the same offset in the leader CTA
+__device__ __forceinline__ void mma2_ss_lo(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %6};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, p;\n\t}" ::"r"(d),
+      "r"(a_lo), "r"(b_lo), "r"(kIdescPair), "r"(acc), "r"(kDescHiSW128), "r"(kDescHiW)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_ts_lo(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], db, %3, p;\n\t}" ::"r"(d),
+      "r"(a_tmem), "r"(b_lo), "r"(kIdescPair), "r"(acc), "r"(kDescHiW)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit2_a(uint32_t bar_addr) {  // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_a(uint32_t bar_addr, uint32_t parity) {  // arrivals may come from the peer CTA
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar_addr, bool remote) {  // arrive on the LEADER's barrier at this offset
+  if (remote) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar_addr) : "memory");
+  } else {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void tma_load_t(const CUtensorMap* map, uint32_t bar_addr, uint32_t dst_addr, int c0, int c1, uint64_t hint) {
+  if constexpr (kPair) {  // both CTAs load; the bytes are counted on the leader's barrier
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_addr),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr & kPeerMask), "r"(c0), "r"(c1), "l"(hint)
+                 : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_addr),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1), "l"(hint)
+                 : "memory");
+  }
+}
+
 #define LT_TMEM_LD32(r, taddr)                                                                                                                         \
   asm volatile(                                                                                                                                        \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                                                        \
@@ -194,10 +248,12 @@ __device__ __forceinline__ float elu1(float v) {
 }
 
 // One 32-column block of an accumulator: TMEM -> registers, + bias, ELU, optionally back to TMEM in place and / or to global memory.
-__device__ __forceinline__ void epi_block(uint32_t taddr, const float* __restrict__ bias, float* __restrict__ out_row, bool write_back) {
+__device__ __forceinline__ void epi_block(uint32_t taddr, const float* __restrict__ bias, float* __restrict__ out_row, bool write_back, long long* prof = nullptr) {
   uint32_t r[32];
+  const long long t0 = prof ? clock64() : 0;
   LT_TMEM_LD32(r, taddr);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  const long long t1 = prof ? clock64() : 0;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + j));
@@ -205,6 +261,11 @@ __device__ __forceinline__ void epi_block(uint32_t taddr, const float* __restric
     r[j + 1] = __float_as_uint(elu1(__uint_as_float(r[j + 1]) + b.y));
     r[j + 2] = __float_as_uint(elu1(__uint_as_float(r[j + 2]) + b.z));
     r[j + 3] = __float_as_uint(elu1(__uint_as_float(r[j + 3]) + b.w));
+  }
+  long long t2 = 0;
+  if (prof) {
+    asm volatile("" ::"r"(r[0]), "r"(r[7]), "r"(r[15]), "r"(r[23]), "r"(r[31]) : "memory");
+    t2 = clock64();
   }
   if (write_back) LT_TMEM_ST32(r, taddr);
   if (out_row != nullptr) {  // 32-byte stores: every lane writes whole sectors of its own row (rows are 128-byte aligned)
@@ -214,11 +275,19 @@ __device__ __forceinline__ void epi_block(uint32_t taddr, const float* __restric
                    "r"(r[j + 5]), "r"(r[j + 6]), "r"(r[j + 7])
                    : "memory");
   }
+  if (prof) {
+    if (write_back) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    const long long t3 = clock64();
+    prof[1] += t1 - t0;
+    prof[2] += t2 - t1;
+    prof[3] += t3 - t2;
+  }
 }
 
 // epilogue of `nblk` 32-column blocks of one accumulator for this thread's row
+template <bool kPair>
 __device__ __forceinline__ void epi_job(uint32_t wait_bar, uint32_t par, uint32_t taddr, const float* bias, float* out, int nblk, bool write_back, uint32_t arrive_bar,
-                                     long long* wait_cycles) {
+                                        long long* wait_cycles, bool remote) {
   {
     const long long t0 = wait_cycles ? clock64() : 0;
     mbar_wait_a(wait_bar, par);
@@ -226,47 +295,68 @@ __device__ __forceinline__ void epi_job(uint32_t wait_bar, uint32_t par, uint32_
   }
   fence_after();
 #pragma unroll 1
-  for (int blk = 0; blk < nblk; ++blk) epi_block(taddr + blk * 32, bias + blk * 32, out ? out + blk * 32 : nullptr, write_back);
+  for (int blk = 0; blk < nblk; ++blk) epi_block(taddr + blk * 32, bias + blk * 32, out ? out + blk * 32 : nullptr, write_back, wait_cycles);
   if (write_back) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   fence_before();
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(arrive_bar) : "memory");
+  if ((threadIdx.x & 31) == 0) {
+    if constexpr (kPair)
+      mbar_arrive_leader(arrive_bar, remote);
+    else
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(arrive_bar) : "memory");
+  }
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_constant__ Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xs = base;                               // [kb][128 x 32] SW128 boxes of the x slab
-  uint8_t* ring = base + kMaxKB0 * kTile;           // [128 x 32] SW128 weight tiles
+  uint8_t* ring = base + kMaxKB0 * kTile;           // SW128 weight tiles: [128 x 32], or this CTA's [64 x 32] half in pair mode
   Bars& bars = *reinterpret_cast<Bars*>(ring + kSlots * kWTile);
+  constexpr uint32_t NS = kPair ? kSlotsPair : kSlots;            // ring slots
+  constexpr uint32_t kSlotBytes = kPair ? kWTile / 2 : kWTile;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tasks = P.n_nets * P.slabs;
+  uint32_t rank = 0;
+  if constexpr (kPair) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool leader = rank == 0;
+  // tasks of this CTA: slab `slab_of(task)` of network `net_of(task)`; in pair mode a task is two adjacent slabs (one per CTA)
+  const int first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tasks = kPair ? P.n_nets * P.pairs_per_net : P.n_nets * P.slabs;
+  auto net_of = [&](int task) { return kPair ? task / P.pairs_per_net : task / P.slabs; };
+  auto slab_of = [&](int task) { return kPair ? 2 * (task % P.pairs_per_net) + (int)rank : task % P.slabs; };
   const int nkb0 = P.nkb0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxKB0; ++i) mbar_init(&bars.x_full[i], 1);
     mbar_init(&bars.x_empty, 1);
-    for (int i = 0; i < kSlots; ++i) {
+    for (int i = 0; i < (int)NS; ++i) {
       mbar_init(&bars.ring_full[i], 1);
       mbar_init(&bars.ring_empty[i], 1);
     }
+    constexpr int kEpiArrivals = kPair ? 2 * kEpiWarps : kEpiWarps;  // pair mode: the leader's MMA warp waits for the epilogues of both CTAs
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bars.d1_full[i], 1);
-      mbar_init(&bars.a2_ready[i], kEpiWarps);
+      mbar_init(&bars.a2_ready[i], kEpiArrivals);
     }
     mbar_init(&bars.d2_full, 1);
-    mbar_init(&bars.a3_ready, kEpiWarps);
+    mbar_init(&bars.a3_ready, kEpiArrivals);
     mbar_init(&bars.d3_full, 1);
-    mbar_init(&bars.d3_empty, kEpiWarps);
+    mbar_init(&bars.d3_empty, kEpiArrivals);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars.tmem_base)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars.tmem_base)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars.tmem_base)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   fence_after();
   const uint32_t tmem = bars.tmem_base;
   const uint32_t full0 = smem_u32(&bars.ring_full[0]), empty0 = smem_u32(&bars.ring_empty[0]);
@@ -285,14 +375,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
         if (wrapped) mbar_wait_a(empty0 + slot * 8, phase ^ 1);
         if (cute::elect_one_sync()) {
           const uint32_t bar = full0 + slot * 8;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kWTile) : "memory");
-          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-                           ring_addr + slot * kWTile),
-                       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(col0 + t * kWK), "r"(row), "l"(keep)
-                       : "memory");
+          // the whole tile (both halves in pair mode) is counted on the leader's barrier
+          if (leader) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kWTile) : "memory");
+          tma_load_t<kPair>(map, bar, ring_addr + slot * kSlotBytes, col0 + t * kWK, row + (kPair ? (int)rank * 64 : 0), keep);
         }
         __syncwarp();
-        if (++slot == kSlots) {
+        if (++slot == NS) {
           slot = 0;
           phase ^= 1;
           wrapped = 1;
@@ -300,9 +388,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
       }
     };
 #pragma unroll 1
-    for (int task = blockIdx.x; task < tasks; task += gridDim.x) {
-      const int net = task / P.slabs;
-      if (task == (int)blockIdx.x) tiles(&P.w1[net], 0, 0, nkb0);
+    for (int task = first; task < tasks; task += stride) {
+      const int net = net_of(task);
+      if (task == first) tiles(&P.w1[net], 0, 0, nkb0);
       tiles(&P.w1[net], 0, 128, nkb0);
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {  // layer-2 part j (two N halves), then layer-1 chunk j + 2: the order of the MMA warp
@@ -310,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
         tiles(&P.w2[net], j * 128, 128, 128 / kWK);
         if (j < 2) tiles(&P.w1[net], 0, (j + 2) * 128, nkb0);
       }
-      if (task + (int)gridDim.x < tasks) tiles(&P.w1[(task + gridDim.x) / P.slabs], 0, 0, nkb0);  // chunk 0 of the next slab runs ahead of layer 3
+      if (task + stride < tasks) tiles(&P.w1[net_of(task + stride)], 0, 0, nkb0);  // chunk 0 of the next slab runs ahead of layer 3
       tiles(&P.w3[net], 0, 0, 256 / kWK);
     }
   } else if (warp == 2) {
@@ -318,20 +406,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
     const uint64_t once = (uint64_t)TMA::CacheHintSm90::EVICT_FIRST;
     int it = 0;
 #pragma unroll 1
-    for (int task = blockIdx.x; task < tasks; task += gridDim.x, ++it) {
-      const int net = task / P.slabs, row0 = (task % P.slabs) * kRows;
+    for (int task = first; task < tasks; task += stride, ++it) {
+      const int net = net_of(task), row0 = slab_of(task) * kRows;  // a padding slab (row0 >= B) reads zeros
       if (it > 0) mbar_wait(&bars.x_empty, (it - 1) & 1);
       if (cute::elect_one_sync()) {
 #pragma unroll 1
         for (int kb = 0; kb < nkb0; ++kb) {
-          mbar_expect_tx(&bars.x_full[kb], kTile);
-          tma_load(&P.x[net], &bars.x_full[kb], xs + kb * kTile, kb * kBK, row0, once);
+          if (leader) mbar_expect_tx(&bars.x_full[kb], kPair ? 2 * kTile : kTile);  // pair mode: the boxes of both CTAs, counted on the leader
+          tma_load_t<kPair>(&P.x[net], smem_u32(&bars.x_full[kb]), smem_u32(xs + kb * kTile), kb * kBK, row0, once);
         }
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (pair mode: the leader CTA issues for both)
     const uint32_t xs_lo = smem_u32(xs) >> 4, ring_lo = smem_u32(ring) >> 4;
     const uint32_t xfull0 = smem_u32(&bars.x_full[0]);
     const uint32_t d1f0 = smem_u32(&bars.d1_full[0]), a2r0 = smem_u32(&bars.a2_ready[0]);
@@ -342,13 +430,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
     const long long t_begin = clock64();
     uint32_t slot = 0, phase = 0;
     auto wait_t = [&](uint32_t bar, uint32_t parity, long long& acc) {
-      if (dbg) {
-        const long long t0 = clock64();
-        mbar_wait_a(bar, parity);
-        acc += clock64() - t0;
-      } else {
-        mbar_wait_a(bar, parity);
-      }
+      const long long t0 = dbg ? clock64() : 0;
+      if constexpr (kPair) mbar_wait_cluster_a(bar, parity); else mbar_wait_a(bar, parity);
+      if (dbg) acc += clock64() - t0;
+    };
+    auto commit = [&](uint32_t bar) {
+      if constexpr (kPair) umma_commit2_a(bar); else umma_commit_a(bar);
     };
     // `ntiles` weight tiles of one accumulation chain; a = low descriptor word of the first x box (SS) or TMEM address of the first A
     // column (TS); commits c1 / c2 (0: none) follow the last tile
@@ -358,9 +445,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
         if (xbar) wait_t(xbar + t * 8, xpar, w_x);
         wait_t(full0 + slot * 8, phase, w_ring);
         fence_after();
-        const uint32_t b = ring_lo + slot * (kWTile >> 4);
+        const uint32_t b = ring_lo + slot * (kSlotBytes >> 4);
         if (cute::elect_one_sync()) {
-          if (is_ts) {
+          if constexpr (kPair) {
+            if (is_ts) {
+              mma2_ts_lo(d, a, b, acc);
+              mma2_ts_lo(d, a + 8, b + 2, 1);
+              mma2_ts_lo(d, a + 16, b + 4, 1);
+              mma2_ts_lo(d, a + 24, b + 6, 1);
+            } else {
+              mma2_ss_lo(d, a, b, acc);
+              mma2_ss_lo(d, a + 2, b + 2, 1);
+              mma2_ss_lo(d, a + 4, b + 4, 1);
+              mma2_ss_lo(d, a + 6, b + 6, 1);
+            }
+          } else if (is_ts) {
             mma_ts_lo(d, a, b, acc);
             mma_ts_lo(d, a + 8, b + 2, 1);
             mma_ts_lo(d, a + 16, b + 4, 1);
@@ -371,14 +470,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
             mma_ss_lo(d, a + 4, b + 4, 1);
             mma_ss_lo(d, a + 6, b + 6, 1);
           }
-          umma_commit_a(empty0 + slot * 8);
+          commit(empty0 + slot * 8);
           if (t + 1 == ntiles) {
-            if (c1) umma_commit_a(c1);
-            if (c2) umma_commit_a(c2);
+            if (c1) commit(c1);
+            if (c2) commit(c2);
           }
         }
         __syncwarp();
-        if (++slot == kSlots) {
+        if (++slot == NS) {
           slot = 0;
           phase ^= 1;
         }
@@ -403,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
     };
     int it = 0;
 #pragma unroll 1
-    for (int task = blockIdx.x; task < tasks; task += gridDim.x, ++it) {
+    for (int task = first; task < tasks; task += stride, ++it) {
       const uint32_t par = it & 1;
       if (it == 0) layer1_chunk(0, 0);
       layer1_chunk(1, it);
@@ -413,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
       layer1_chunk(3, it);
       layer2_part(2, par);
       layer2_part(3, par);
-      if (task + (int)gridDim.x < tasks) layer1_chunk(0, it + 1);  // keeps the tensor pipe busy while the epilogue turns D2 into A3
+      if (task + stride < tasks) layer1_chunk(0, it + 1);  // keeps the tensor pipe busy while the epilogue turns D2 into A3
       wait_t(b_a3_ready, par, w_epi);
       fence_after();
       run(true, 256 / kWK, tmem + kColD2, 32, tmem + kColD3, 0, 0, 0, b_d3_full, 0);
@@ -434,35 +533,43 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
     const int r_local = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t d1f0 = smem_u32(&bars.d1_full[0]), a2r0 = smem_u32(&bars.a2_ready[0]);
-    long long w_mma = 0;
-    long long* wp = P.dbg ? &w_mma : nullptr;
+    long long w_prof[4] = {0, 0, 0, 0};  // wait for the MMA warp, TMEM load, bias + ELU, TMEM store + global stores
+    long long& w_mma = w_prof[0];
+    long long* wp = P.dbg ? w_prof : nullptr;
     const long long t_begin = clock64();
     int it = 0;
 #pragma unroll 1
-    for (int task = blockIdx.x; task < tasks; task += gridDim.x, ++it) {
+    const bool remote = kPair && !leader;
+    for (int task = first; task < tasks; task += stride, ++it) {
       const uint32_t par = it & 1;
-      const int net = task / P.slabs, row = (task % P.slabs) * kRows + r_local;
+      const int net = net_of(task), row = slab_of(task) * kRows + r_local;
       const NetArgs& na = P.net[net];
       const bool live = row < P.B;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int col = c * 128 + part * 32;
-        epi_job(d1f0 + c * 8, par, lane_addr + kColD1 + (c & 1) * 128 + part * 32, na.b1 + col, (na.h1 != nullptr && live) ? na.h1 + (size_t)row * kH1 + col : nullptr, 1,
-                true, a2r0 + c * 8, wp);
+        epi_job<kPair>(d1f0 + c * 8, par, lane_addr + kColD1 + (c & 1) * 128 + part * 32, na.b1 + col,
+                       (na.h1 != nullptr && live) ? na.h1 + (size_t)row * kH1 + col : nullptr, 1, true, a2r0 + c * 8, wp, remote);
       }
-      epi_job(smem_u32(&bars.d2_full), par, lane_addr + kColD2 + part * 64, na.b2 + part * 64,
-              (na.h2 != nullptr && live) ? na.h2 + (size_t)row * kH2 + part * 64 : nullptr, 2, true, smem_u32(&bars.a3_ready), wp);
-      epi_job(smem_u32(&bars.d3_full), par, lane_addr + kColD3 + part * 32, na.b3 + part * 32, live ? na.h3 + (size_t)row * kH3 + part * 32 : nullptr, 1, false,
-              smem_u32(&bars.d3_empty), wp);
+      epi_job<kPair>(smem_u32(&bars.d2_full), par, lane_addr + kColD2 + part * 64, na.b2 + part * 64,
+                     (na.h2 != nullptr && live) ? na.h2 + (size_t)row * kH2 + part * 64 : nullptr, 2, true, smem_u32(&bars.a3_ready), wp, remote);
+      epi_job<kPair>(smem_u32(&bars.d3_full), par, lane_addr + kColD3 + part * 32, na.b3 + part * 32, live ? na.h3 + (size_t)row * kH3 + part * 32 : nullptr, 1, false,
+                     smem_u32(&bars.d3_empty), wp, remote);
     }
     if (P.dbg && warp == 4 && lane == 0) {
       P.dbg[8 * blockIdx.x + 5] = (unsigned long long)(clock64() - t_begin);
       P.dbg[8 * blockIdx.x + 6] = (unsigned long long)w_mma;
+      P.dbg[8 * blockIdx.x + 7] = (unsigned long long)w_prof[1] | ((unsigned long long)w_prof[2] << 20) | ((unsigned long long)w_prof[3] << 40);
     }
   }
   fence_before();
-  __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  if constexpr (kPair) {  // the peer's shared memory, TMEM and barriers are in use until the leader's last MMA has completed
+    cluster_sync_all();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  } else {
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
 }
 
 
@@ -527,13 +634,13 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(unsigned long long* ou
 }
 
 // K-major [rows, k] fp32 tensor -> tensor map with [128 x 32] SW128 boxes (rows / columns beyond the tensor read as zero)
-template <int BK>
+template <int BK, int ROWS = kRows>
 static bool make_map(CUtensorMap* out, const float* ptr, int rows, int k) {
   using TF = cute::tfloat32_t;
   using Atom = cute::conditional_t<BK == 32, UMMA::Layout_K_SW128_Atom<TF>, UMMA::Layout_K_SW64_Atom<TF>>;
   Tensor g = make_tensor(make_gmem_ptr(reinterpret_cast<TF const*>(ptr)), make_layout(make_shape(rows, k), make_stride(k, Int<1>{})));
-  auto sl = tile_to_shape(Atom{}, make_shape(Int<kRows>{}, Int<BK>{}));
-  auto atom = make_tma_atom(SM90_TMA_LOAD{}, g, sl, make_shape(Int<kRows>{}, Int<BK>{}));
+  auto sl = tile_to_shape(Atom{}, make_shape(Int<ROWS>{}, Int<BK>{}));
+  auto atom = make_tma_atom(SM90_TMA_LOAD{}, g, sl, make_shape(Int<ROWS>{}, Int<BK>{}));
   static_assert(sizeof(*atom.get_tma_descriptor()) == sizeof(CUtensorMap), "descriptor size");
   memcpy(out, atom.get_tma_descriptor(), sizeof(CUtensorMap));
   return true;
@@ -546,6 +653,7 @@ extern "C" int lt_mlp3_forward(const LtMlp3Net* nets, int n_nets, int B, void* s
   if (!nets || n_nets < 1 || n_nets > 2 || B <= 0) return LT_ERR_INVALID_ARG;
   const int k0 = nets[0].k0;
   if (k0 <= 0 || (k0 & 3) || k0 > kMaxKB0 * kBK) return LT_ERR_UNSUPPORTED;
+  static const bool pair = !(getenv("LT_MLP3_PAIR") && atoi(getenv("LT_MLP3_PAIR")) == 0);  // cta_group::2 pairs (default) / one CTA per slab
   Params P;
   memset(&P, 0, sizeof(P));
   for (int i = 0; i < n_nets; ++i) {
@@ -556,23 +664,60 @@ extern "C" int lt_mlp3_forward(const LtMlp3Net* nets, int n_nets, int B, void* s
                          (uintptr_t)n.h1 | (uintptr_t)n.h2 | (uintptr_t)n.h3;
     if ((al & 15) || (((uintptr_t)n.h1 | (uintptr_t)n.h2 | (uintptr_t)n.h3) & 31)) return LT_ERR_UNSUPPORTED;  // TMA: 16 bytes; 32-byte stores of the rows
     make_map<kBK>(&P.x[i], n.x, B, k0);
-    make_map<kWK>(&P.w1[i], n.w1, kH1, k0);
-    make_map<kWK>(&P.w2[i], n.w2, kH2, kH1);
-    make_map<kWK>(&P.w3[i], n.w3, kH3, kH2);
+    if (pair) {  // a CTA loads its 64-row half of every weight tile
+      make_map<kWK, 64>(&P.w1[i], n.w1, kH1, k0);
+      make_map<kWK, 64>(&P.w2[i], n.w2, kH2, kH1);
+      make_map<kWK, 64>(&P.w3[i], n.w3, kH3, kH2);
+    } else {
+      make_map<kWK>(&P.w1[i], n.w1, kH1, k0);
+      make_map<kWK>(&P.w2[i], n.w2, kH2, kH1);
+      make_map<kWK>(&P.w3[i], n.w3, kH3, kH2);
+    }
     P.net[i] = NetArgs{n.b1, n.b2, n.b3, n.h1, n.h2, n.h3};
   }
   P.n_nets = n_nets;
   P.B = B;
   P.nkb0 = (k0 + kBK - 1) / kBK;
   P.slabs = (B + kRows - 1) / kRows;
+  P.pairs_per_net = (P.slabs + 1) / 2;  // an odd slab count is padded with an all-zero slab that stores nothing
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(mlp3_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); });
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(mlp3_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(mlp3_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  });
   if (attr_err != cudaSuccess) return LT_ERR_CUDA;
   static const int knob_ctas = getenv("LT_MLP3_CTAS") ? atoi(getenv("LT_MLP3_CTAS")) : 0;
-  const int tasks = n_nets * P.slabs;
+  const int tasks = pair ? n_nets * P.pairs_per_net : n_nets * P.slabs;
   int grid = knob_ctas > 0 ? knob_ctas : lt::sm_count();
+  if (pair) grid /= 2;                 // clusters
   if (grid > tasks) grid = tasks;
+  if (grid < 1) grid = 1;
+  if (pair) grid *= 2;
+  auto launch = [&]() -> int {
+    if (!pair) {
+      mlp3_forward_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+      return lt::check_launch();
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, mlp3_forward_kernel<true>, P) != cudaSuccess) {
+      lt::set_last_cuda_error(cudaGetLastError());
+      return LT_ERR_CUDA;
+    }
+    return lt::check_launch();
+  };
   if (getenv("LT_MLP3_RATE")) {
     unsigned long long* d = nullptr;
     unsigned long long h[8];
@@ -594,21 +739,25 @@ extern "C" int lt_mlp3_forward(const LtMlp3Net* nets, int n_nets, int B, void* s
     if (!dbuf) cudaMalloc(&dbuf, 8 * sizeof(unsigned long long) * 1024);
     cudaMemset(dbuf, 0, 8 * sizeof(unsigned long long) * 1024);
     P.dbg = dbuf;
-    mlp3_forward_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    const int rc = launch();
     cudaDeviceSynchronize();
     static unsigned long long host[8 * 1024];
     cudaMemcpy(host, dbuf, sizeof(unsigned long long) * 8 * grid, cudaMemcpyDeviceToHost);
-    double tot = 0, ring = 0, xw = 0, epi = 0, slabs = 0, etot = 0, ewait = 0;
+    double tot = 0, ring = 0, xw = 0, epi = 0, slabs = 0, etot = 0, ewait = 0, eld = 0, emath = 0, est = 0;
+    int issuers = 0;
     for (int i = 0; i < grid; ++i) {
+      if (host[8 * i]) ++issuers;  // pair mode: only the leader CTAs issue MMAs
       tot += host[8 * i]; ring += host[8 * i + 1]; xw += host[8 * i + 2]; epi += host[8 * i + 3]; slabs += host[8 * i + 4];
       etot += host[8 * i + 5]; ewait += host[8 * i + 6];
+      eld += host[8 * i + 7] & 0xFFFFF; emath += (host[8 * i + 7] >> 20) & 0xFFFFF; est += (host[8 * i + 7] >> 40) & 0xFFFFF;
     }
-    fprintf(stderr, "[mlp3 dbg] B=%d grid=%d slabs/CTA=%.2f  MMA thread cycles per CTA: total %.0f  wait ring %.0f  wait x %.0f  wait epilogue %.0f | "
-            "epilogue warp: total %.0f  wait MMA %.0f\n", B, grid, slabs / grid, tot / grid, ring / grid, xw / grid, epi / grid, etot / grid, ewait / grid);
-    return lt::check_launch();
+    if (issuers < 1) issuers = 1;
+    fprintf(stderr, "[mlp3 dbg] B=%d grid=%d pair=%d tasks/issuer=%.2f  MMA warp cycles per issuing CTA: total %.0f  wait ring %.0f  wait x %.0f  wait epilogue %.0f | "
+            "epilogue warp (per CTA): total %.0f  wait MMA %.0f  TMEM ld %.0f  bias+ELU %.0f  TMEM st + global st %.0f\n", B, grid, (int)pair, slabs / issuers, tot / issuers,
+            ring / issuers, xw / issuers, epi / issuers, etot / grid, ewait / grid, eld / grid, emath / grid, est / grid);
+    return rc;
   }
-  mlp3_forward_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
-  return lt::check_launch();
+  return launch();
 }
 
 #else  // !LT_HAVE_CUTLASS
