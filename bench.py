@@ -213,7 +213,7 @@ def run_reference(args, rank: int):
 # ------------------------------------------------------------------------------------------------------ kernel roofline
 def ncu_traffic_bytes(kernel_substr: str):
     """DRAM bytes per launch (read + write) of the committed `ncu --set full` capture, or None."""
-    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2o_ncu_full_summary.json", "r2f_ncu_full_summary.json", "r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
+    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2u_ncu_full_summary.json", "r2f_ncu_full_summary.json", "r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
                  if os.path.exists(q)), None)  # newest capture first
     if path is None:
         return None

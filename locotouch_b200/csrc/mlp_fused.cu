@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
     const uint32_t b_x_empty = smem_u32(&bars.x_empty), b_d3_empty = smem_u32(&bars.d3_empty), b_d2_full = smem_u32(&bars.d2_full),
                    b_a3_ready = smem_u32(&bars.a3_ready), b_d3_full = smem_u32(&bars.d3_full);
     const bool dbg = P.dbg != nullptr;
-    long long w_ring = 0, w_x = 0, w_epi = 0;
+    long long w_ring = 0, w_ring_ts = 0, w_x = 0, w_epi = 0;
     const long long t_begin = clock64();
     uint32_t slot = 0, phase = 0;
     auto wait_t = [&](uint32_t bar, uint32_t parity, long long& acc) {
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
 #pragma unroll 1
       for (uint32_t t = 0; t < ntiles; ++t) {
         if (xbar) wait_t(xbar + t * 8, xpar, w_x);
-        wait_t(full0 + slot * 8, phase, w_ring);
+        wait_t(full0 + slot * 8, phase, is_ts ? w_ring_ts : w_ring);
         fence_after();
         const uint32_t b = ring_lo + slot * (kSlotBytes >> 4);
         if (cute::elect_one_sync()) {
@@ -520,7 +520,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
     if (dbg && lane == 0) {
       unsigned long long* d = P.dbg + 8 * blockIdx.x;
       d[0] = (unsigned long long)(clock64() - t_begin);
-      d[1] = (unsigned long long)w_ring;
+      d[1] = (unsigned long long)(w_ring + w_ring_ts);
+      P.dbg[8 * (blockIdx.x + 1) + 0] = (unsigned long long)w_ring_ts;  // pair mode only: the peer CTA's row is otherwise unused
       d[2] = (unsigned long long)w_x;
       d[3] = (unsigned long long)w_epi;
       d[4] = (unsigned long long)it;
@@ -743,18 +744,19 @@ extern "C" int lt_mlp3_forward(const LtMlp3Net* nets, int n_nets, int B, void* s
     cudaDeviceSynchronize();
     static unsigned long long host[8 * 1024];
     cudaMemcpy(host, dbuf, sizeof(unsigned long long) * 8 * grid, cudaMemcpyDeviceToHost);
-    double tot = 0, ring = 0, xw = 0, epi = 0, slabs = 0, etot = 0, ewait = 0, eld = 0, emath = 0, est = 0;
+    double tot = 0, ring = 0, ring_ts = 0, xw = 0, epi = 0, slabs = 0, etot = 0, ewait = 0, eld = 0, emath = 0, est = 0;
     int issuers = 0;
     for (int i = 0; i < grid; ++i) {
+      if (pair && (i & 1)) { ring_ts += host[8 * i]; host[8 * i] = 0; }
       if (host[8 * i]) ++issuers;  // pair mode: only the leader CTAs issue MMAs
       tot += host[8 * i]; ring += host[8 * i + 1]; xw += host[8 * i + 2]; epi += host[8 * i + 3]; slabs += host[8 * i + 4];
       etot += host[8 * i + 5]; ewait += host[8 * i + 6];
       eld += host[8 * i + 7] & 0xFFFFF; emath += (host[8 * i + 7] >> 20) & 0xFFFFF; est += (host[8 * i + 7] >> 40) & 0xFFFFF;
     }
     if (issuers < 1) issuers = 1;
-    fprintf(stderr, "[mlp3 dbg] B=%d grid=%d pair=%d tasks/issuer=%.2f  MMA warp cycles per issuing CTA: total %.0f  wait ring %.0f  wait x %.0f  wait epilogue %.0f | "
+    fprintf(stderr, "[mlp3 dbg] B=%d grid=%d pair=%d tasks/issuer=%.2f  MMA warp cycles per issuing CTA: total %.0f  wait ring %.0f (layers 2-3: %.0f)  wait x %.0f  wait epilogue %.0f | "
             "epilogue warp (per CTA): total %.0f  wait MMA %.0f  TMEM ld %.0f  bias+ELU %.0f  TMEM st + global st %.0f\n", B, grid, (int)pair, slabs / issuers, tot / issuers,
-            ring / issuers, xw / issuers, epi / issuers, etot / grid, ewait / grid, eld / grid, emath / grid, est / grid);
+            ring / issuers, ring_ts / issuers, xw / issuers, epi / issuers, etot / grid, ewait / grid, eld / grid, emath / grid, est / grid);
     return rc;
   }
   return launch();

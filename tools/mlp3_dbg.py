@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 from locotouch_b200 import ops  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-keep = B > 8192
+keep = (B > 8192) if os.environ.get("KEEP") is None else os.environ["KEEP"] == "1"
 nets = []
 for _ in range(2):
     x = torch.randn(B, 348, device="cuda")
