@@ -13,14 +13,19 @@
 //   * layer 2: D2 (256 TMEM columns, two N halves) += A2 chunk (TMEM) . W2[:, chunk]^T as soon as a chunk is ready, interleaved with the
 //     layer-1 MMAs of the next chunk, so the tensor pipe runs while the epilogue warps work;
 //   * layer 3: D3 (128 columns, over the idle chunk buffer) = ELU(D2 + b2) (in place, TMEM) . W3^T; its epilogue writes h3.
-// TMEM: 2 x 128 (D1 chunks / A2 / D3) + 256 (D2 / A3) = 512 columns.  Shared memory: x slab 11 x 16 KB + a 3-slot ring of [128 x 32]
-// weight tiles (16 KB each, 84 tiles per slab in the fixed order the MMA warp consumes them) -- the weights (1.37 MB per network) are
+// TMEM: 2 x 128 (D1 chunks / A2 / D3) + 256 (D2 / A3) = 512 columns.  Shared memory: x slab 11 x 16 KB + a 48 KB ring of [128 x 32]
+// weight tiles (84 tiles per slab in the fixed order the MMA warp consumes them) -- the weights (1.37 MB per network) are
 // L2 resident and are the only operand that streams.  Per-SM fill is 1.55 MB per slab against 2.1 MB (x re-read per column tile) for
 // three separate GEMMs, and the per-layer launch tails, the activation round trips (write h, re-read h) and the non-overlapped
 // epilogues of the per-layer kernels are gone.  Training mode additionally stores h1 / h2 (the backward pass needs them) straight
 // from the epilogue registers.
-// Warp roles: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warps 2-9 = epilogue (TMEM lane quarter = warp % 4,
-// two warps per quarter split the columns).
+// Warp roles (20 warps): warp 0 = weight-tile producer, warp 1 = MMA issuer, warp 2 = x producer, warp 3 idle, warps 4-19 = epilogue
+// (TMEM lane quarter = warp % 4, four warps per quarter split a chunk's columns).  Producer and MMA roles run warp-uniform with only the
+// TMA / MMA / commit instructions under elect_one (a single diverged lane pays a register -> uniform-register move per MMA operand).
+// Pair mode (template parameter, the default): the two CTAs of a cluster carry two adjacent slabs of one network; every weight tile is
+// split between their shared memories (64 of its 128 rows each: six ring slots instead of three, half the weight traffic per SM), the
+// leader CTA issues cta_group::2 MMAs (M = 256) for both, the TMA bytes of both halves are counted on the leader's barriers, commits are
+// multicast to both CTAs and the peer's epilogue warps arrive remotely on the leader's barriers.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -1,4 +1,4 @@
-"""Where the rollout graph's time goes: 24 x policy step (K12 x 6 + K3b) and 24 x env step (K0 + K1 || K2 + store) captured as separate
+"""Where the rollout graph's time goes: 24 x policy step (K19 + K3b) and 24 x env step (K0 + K1 || K2 + store) captured as separate
 CUDA graphs next to the full rollout graph.    python tools/rollout_split.py"""
 import os
 import sys
@@ -35,7 +35,7 @@ with graph_capture(g_pol):
         st.step = t
         alg.act(st._obs_buf[t], st._priv_buf[t])
 st.step = 0
-print(f"24 x policy step (hidden layers K12 x 6, heads + sample K3b): {timed(g_pol):.3f} ms = {timed(g_pol) / 24 * 1e3:.1f} us per step")
+print(f"24 x policy step (hidden layers K19, heads + sample K3b): {timed(g_pol):.3f} ms = {timed(g_pol) / 24 * 1e3:.1f} us per step")
 actions = st.actions[0]
 g_env = torch.cuda.CUDAGraph()
 with graph_capture(g_env):
