@@ -71,6 +71,9 @@ class ActorCritic(nn.Module):
         else:
             raise ValueError(f"Unknown standard deviation type: {self.noise_std_type}. Should be 'scalar' or 'log'")
         self.num_actions = num_actions
+        if num_actions % 4 or num_actions > 64:  # lt_act_sample / lt_ppo_loss / K16 move one float4 of every [A] row per lane
+            raise ValueError(f"locotouch_b200.ActorCritic: num_actions = {num_actions} is not supported by the sampling / PPO-loss kernels "
+                             "(a multiple of 4, at most 64; the LocoTouch tasks use 12)")
         self.distribution = None
         self.flat_params = None
         self.flat_grads = None

@@ -129,3 +129,16 @@ def test_mdp_lookup_tables_are_built_on_the_host(lt_lib):
     assert as_float(par[TS.RK_TRACK_LIN_VEL_XY * 6]) == 0.25
     assert abs(as_float(par[TS.RK_BASE_HEIGHT * 6]) - 0.42) < 1e-7
     assert as_float(par[TS.RK_FOOT_SLIP * 6]) == 0.0
+
+
+def test_actor_critic_rejects_action_widths_the_kernels_do_not_take():
+    """ADVICE (round 1): lt_act_sample / lt_ppo_loss need num_actions % 4 == 0 and <= 64 -- fail at construction with a clear message,
+    not at the first act() with LT_ERR_INVALID_ARG."""
+    import pytest
+
+    from locotouch_b200.loco_rl import ActorCritic
+
+    for bad in (6, 13, 68):
+        with pytest.raises(ValueError, match="num_actions"):
+            ActorCritic(8, 8, bad, [8], [8])
+    ActorCritic(8, 8, 12, [8], [8])
