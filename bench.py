@@ -211,8 +211,9 @@ def run_reference(args, rank: int):
 
 
 # ------------------------------------------------------------------------------------------------------ kernel roofline
-def ncu_traffic_bytes(kernel_substr: str):
-    """DRAM bytes per launch (read + write) of the committed `ncu --set full` capture, or None."""
+def ncu_traffic_bytes(kernel_substr: str, largest: int = 0):
+    """DRAM bytes per launch (read + write) of the committed `ncu --set full` capture, or None.  ``largest`` > 0: mean over the
+    launches with the most traffic only (a capture that holds the same kernel at two problem sizes: the larger one)."""
     path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2u_ncu_full_summary.json", "r2f_ncu_full_summary.json", "r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
                  if os.path.exists(q)), None)  # newest capture first
     if path is None:
@@ -226,6 +227,8 @@ def ncu_traffic_bytes(kernel_substr: str):
                 v, u = rec[key].split()
                 tot += float(v) * unit[u]
             vals.append(tot)
+    if largest > 0:
+        vals = sorted(vals)[-largest:]
     return sum(vals) / len(vals) if vals else None
 
 
@@ -582,7 +585,7 @@ def main():
                                                          "peak": tf / 2.0 if k19 else hbm, "unit": "TFLOP/s" if k19 else "GB/s",
                                                          "frac": big["tensor_frac"] if k19 else big["frac"], "us_per_launch": big["us_per_launch"], "tflops": big["tflops"],
                                                          "tensor_frac_of_tf32_peak": big["tensor_frac"], "hbm_gbs": big["achieved"], "hbm_frac": big["frac"],
-                                                         "traffic": ncu_traffic_bytes("mlp3_forward" if k19 else "device_kernel"),
+                                                         "traffic": ncu_traffic_bytes("mlp3_forward", largest=3) if k19 else ncu_traffic_bytes("device_kernel"),
                                                          "note": ("persistent fused MLP: activations stay in TMEM, so the algorithmic HBM bytes (x once, h1 / h2 / h3 once) are 0.36 of "
                                                                   "what three GEMM launches move and the kernel is bound by the TF32 tensor pipe + the shared-memory fill of the "
                                                                   "weight tiles; peak = measured bf16 cuBLAS peak / 2") if k19 else

@@ -335,17 +335,13 @@ wgrad_narrow_kernel(const float* __restrict__ g, const float* __restrict__ x, fl
   const int b0 = blockIdx.x * rows_per_block;
   const int b1 = min(B, b0 + rows_per_block);
   float4 acc[NMAX];
+  float bacc[NMAX];  // bias gradient = column sums of g: the first quad of every row group adds up the g values it loads anyway
 #pragma unroll
-  for (int j = 0; j < NMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (dbias != nullptr && (threadIdx.x >> 5) == 7) {  // bias gradient = column sums of g: the last warp, before it joins the others
-    const int lane = threadIdx.x & 31;
-    for (int j = 0; j < n_out; ++j) {
-      float t = 0.0f;
-      for (int r = b0 + lane; r < b1; r += 32) t += __ldg(g + (size_t)r * n_out + j);
-      t = lt::warp_sum(t);
-      if (lane == 0) atomicAdd(dbias + j, t);
-    }
+  for (int j = 0; j < NMAX; ++j) {
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bacc[j] = 0.0f;
   }
+  const bool fold_bias = dbias != nullptr && cq == 0;
   if (live) {
 #pragma unroll 4
     for (int r = b0 + rg; r < b1; r += groups) {
@@ -359,7 +355,21 @@ wgrad_narrow_kernel(const float* __restrict__ g, const float* __restrict__ x, fl
           acc[j].y = fmaf(gv, xv.y, acc[j].y);
           acc[j].z = fmaf(gv, xv.z, acc[j].z);
           acc[j].w = fmaf(gv, xv.w, acc[j].w);
+          if (fold_bias) bacc[j] += gv;
         }
+    }
+  }
+  if (dbias != nullptr) {  // fold the row groups of the block in shared memory: one atomic per block and output
+    __shared__ float bfold[64][NMAX];  // groups <= 256 / 4
+    if (live && cq == 0) {
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j) bfold[rg][j] = bacc[j];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n_out) {
+      float t = 0.0f;
+      for (int q = 0; q < groups; ++q) t += bfold[q][threadIdx.x];
+      atomicAdd(dbias + threadIdx.x, t);
     }
   }
 #pragma unroll
