@@ -403,6 +403,15 @@ typedef struct {
   int* any_flag_ws;              /* [2] device ints, zero-initialised once; used for the cross-env any() */
   const int32_t* tables;         /* optional DEVICE copy (16-byte aligned) of lt_mdp_build_tables() output for this term
                                     configuration; NULL: every block rebuilds the tables in shared memory */
+  /* Optional fused action term (K0 inside K1; act_new == NULL: off).  JointPositionActionPrevPrev.process_actions (locotouch/mdp/actions.py:30-44,
+   * = lt_process_actions, bit for bit) is applied to the action-term state of every env before any term of this launch reads it:
+   *   prev_prev_raw = prev_raw ; prev_raw = raw ; raw = clamp(act_new, -clip, clip) * raw_scale ; processed = raw * scale + offset.
+   * raw_actions / prev_raw_actions above must be the PRE-update state and are rewritten in place (the launch needs LT_PHASE_REWARDS). */
+  const float* act_new;          /* [N,J] the policy's actions of this env step */
+  float* act_prev_prev_raw;      /* [N,J] or NULL */
+  float* act_processed;          /* [N,J] or NULL */
+  const float* act_offset;       /* [N,J] or NULL (default joint positions) */
+  float act_clip, act_raw_scale, act_scale;
 } LtMdpArgs;
 int lt_mdp_step(const LtMdpArgs* args, void* stream);
 /* Launch-constant lookup tables (observation column map, per-value term info, reward kind -> slot); host-side, no CUDA call.

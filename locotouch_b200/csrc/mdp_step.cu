@@ -490,8 +490,27 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
       s_of[12 * kEnvs + e] = qr.w; s_of[13 * kEnvs + e] = qr.x; s_of[14 * kEnvs + e] = qr.y; s_of[15 * kEnvs + e] = qr.z;
     }
   }
+  // Fused action term (K0 inside K1): JointPositionActionPrevPrev.process_actions on the staged action-term state of the block's envs,
+  // the arithmetic of lt_process_actions bit for bit (explicitly rounded multiply / add); the tasks below read the updated rows.
+  if (A.act_new) {
+#pragma unroll 1
+    for (int i = tid; i < nvalid * J; i += kThreads) {
+      const int ee = i / J, c = i - ee * J;
+      const size_t g = (size_t)(e0 + ee) * J + c;
+      const float old_raw = sm[L.act + ee * sJ + c], old_prev = sm[L.pact + ee * sJ + c];
+      float a = A.act_new[g];
+      if (A.act_clip > 0.f) a = fminf(fmaxf(a, -A.act_clip), A.act_clip);
+      a = __fmul_rn(a, A.act_raw_scale);
+      if (A.act_prev_prev_raw) A.act_prev_prev_raw[g] = old_prev;
+      const_cast<float*>(A.prev_raw_actions)[g] = old_raw;
+      const_cast<float*>(A.raw_actions)[g] = a;
+      if (A.act_processed) A.act_processed[g] = __fadd_rn(__fmul_rn(a, A.act_scale), A.act_offset ? A.act_offset[g] : 0.f);
+      sm[L.act + ee * sJ + c] = a;
+      sm[L.pact + ee * sJ + c] = old_raw;
+    }
+  }
   PROF_STAMP(21);
-  if (do_rew || has_obj) __syncthreads();
+  if (do_rew || has_obj || A.act_new) __syncthreads();
 
   // ------------------------------------------------------------------------------------------------ stage 1: tasks
   float* s_raw = sm + L.raw;  // [LT_RK_COUNT][kEnvs]: unweighted value of every reward kind (stage 2a picks the task's terms)
@@ -1186,6 +1205,7 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   const bool do_rew = a->phases & LT_PHASE_REWARDS, do_obs = a->phases & LT_PHASE_OBS;
   const bool has_obj = a->obj_root_pos_w != nullptr;
   if (a->J <= 0 || a->J > kMaxJ) return LT_ERR_INVALID_ARG;
+  if (a->act_new && !do_rew) return LT_ERR_INVALID_ARG;  // the fused action term belongs to the reward pass (the previous raw actions are staged there)
   if (!a->command || !a->root_pos_w || !a->root_ang_vel_b || !a->projected_gravity_b || !a->joint_pos || !a->joint_vel ||
       !a->default_joint_pos || !a->raw_actions)
     return LT_ERR_INVALID_ARG;

@@ -255,7 +255,7 @@ class FusedMdp:
     # --------------------------------------------------------------------------------------------------------- launch
     def step(self, rewards: bool = True, observations: bool = True, *, auto_reset: bool = True, u_obs=None, u_obj_euler=None,
              policy_out=None, critic_out=None, policy_in=None, critic_in=None, any_nonzero_cmd: bool | None = None,
-             step_offset: int | None = None, offset_base: torch.Tensor | None = None):
+             step_offset: int | None = None, offset_base: torch.Tensor | None = None, actions=None, action_term=None):
         """One fused pass.  ``rewards``: terminations + rewards (+ reset of done envs when ``auto_reset``);
         ``observations``: policy / critic observation rows (history source ``*_in`` defaults to this object's buffers,
         destination ``*_out`` likewise; they may alias, or point into RolloutStorage slots for a zero-copy rollout).
@@ -264,6 +264,20 @@ class FusedMdp:
         guarantees that the previous step's observation pass ran with the same counter."""
         self.bind()
         a = self._args
+        # ``actions`` + ``action_term`` (dict: prev_prev_raw, processed, offset tensors or None; clip, raw_scale, scale): the action term's
+        # process_actions (reference mdp/actions.py:30-44 = K0) runs INSIDE this launch on the bound raw / prev_raw tensors, before any
+        # term reads them -- one launch less per env step for a caller that owns the step loop
+        if actions is not None:
+            if not rewards:
+                raise _C.LocoTouchLibraryError("FusedMdp.step(actions=...): the fused action term needs the reward pass")
+            t = action_term or {}
+            a.act_new = _C.ptr(actions, torch.float32, "actions")
+            a.act_prev_prev_raw = _C.ptr(t.get("prev_prev_raw"), torch.float32)
+            a.act_processed = _C.ptr(t.get("processed"), torch.float32)
+            a.act_offset = _C.ptr(t.get("offset"), torch.float32)
+            a.act_clip, a.act_raw_scale, a.act_scale = float(t.get("clip", 0.0)), float(t.get("raw_scale", 1.0)), float(t.get("scale", 1.0))
+        else:
+            a.act_new = None
         a.phases = (_C.LT_PHASE_REWARDS if rewards else 0) | (_C.LT_PHASE_OBS if observations else 0)
         a.auto_reset = int(auto_reset)
         # an observation-only pass belongs to the step whose reward pass already ran (IsaacLab order: rewards -> reset -> obs)

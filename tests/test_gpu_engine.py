@@ -76,3 +76,26 @@ def test_prefetched_upload_replay_matches_eager_iteration(cuda, lt_lib):
     torch.cuda.synchronize()
     H.assert_close(_params(b), _params(a), "parameters after 5 iterations (prefetched uploads vs eager)", rtol=1e-4, atol=1e-5)
     H.assert_equal(b.step_counter, a.step_counter, "device step counter")
+
+
+def test_fused_action_term_matches_separate_launch(cuda, lt_lib):
+    """K0 inside K1 (``FusedMdp.step(actions=...)``): the action-term state, rewards, dones and both observation groups of a rollout are
+    bit-identical to ``lt_process_actions`` followed by ``lt_mdp_step`` (reference mdp/actions.py:30-44 runs before the managers)."""
+    from locotouch_b200.engine import HotPathEngine
+
+    cfg = dict(num_envs=300, task="teacher", tactile=True, device=cuda, seed=11, num_state_sets=3, hidden=(64, 32), tf32=False)
+    a = HotPathEngine(**cfg)
+    b = HotPathEngine(**cfg)
+    a.fuse_action_term, b.fuse_action_term = True, False
+    for eng in (a, b):
+        torch.manual_seed(7)
+        eng.rollout()
+    torch.cuda.synchronize()
+    sa, sb = a.alg.storage, b.alg.storage
+    H.assert_equal(sa.actions, sb.actions, "actions (same policy, same draws)")
+    for name in ("raw_actions", "prev_raw_actions", "prev_prev_raw_actions", "processed_actions"):
+        H.assert_equal(getattr(a.action_term, name), getattr(b.action_term, name), name)
+    H.assert_equal(sa.rewards, sb.rewards, "rewards")
+    H.assert_equal(sa.dones, sb.dones, "dones")
+    H.assert_equal(sa._obs_buf, sb._obs_buf, "policy observations")
+    H.assert_equal(sa._priv_buf, sb._priv_buf, "critic observations")
