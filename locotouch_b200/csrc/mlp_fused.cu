@@ -252,9 +252,8 @@ __device__ __forceinline__ float elu1(float v) {
   return v > 0.0f ? v : t - 1.0f;
 }
 
-// One 32-column block of an accumulator: TMEM -> registers, + bias, ELU, optionally back to TMEM in place and / or to global memory.
-__device__ __forceinline__ void epi_block(uint32_t taddr, const float* __restrict__ bias, float* __restrict__ out_row, bool write_back, long long* prof = nullptr) {
-  uint32_t r[32];
+// One 32-column block of an accumulator: TMEM -> registers, + bias, ELU (in r), optionally back to TMEM in place.
+__device__ __forceinline__ void epi_compute(uint32_t (&r)[32], uint32_t taddr, const float* __restrict__ bias, bool write_back, long long* prof) {
   const long long t0 = prof ? clock64() : 0;
   LT_TMEM_LD32(r, taddr);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -267,29 +266,27 @@ __device__ __forceinline__ void epi_block(uint32_t taddr, const float* __restric
     r[j + 2] = __float_as_uint(elu1(__uint_as_float(r[j + 2]) + b.z));
     r[j + 3] = __float_as_uint(elu1(__uint_as_float(r[j + 3]) + b.w));
   }
-  long long t2 = 0;
   if (prof) {
     asm volatile("" ::"r"(r[0]), "r"(r[7]), "r"(r[15]), "r"(r[23]), "r"(r[31]) : "memory");
-    t2 = clock64();
+    prof[1] += t1 - t0;
+    prof[2] += clock64() - t1;
   }
   if (write_back) LT_TMEM_ST32(r, taddr);
-  if (out_row != nullptr) {  // 32-byte stores: every lane writes whole sectors of its own row (rows are 128-byte aligned)
-#pragma unroll
-    for (int j = 0; j < 32; j += 8)
-      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_row + j), "r"(r[j]), "r"(r[j + 1]), "r"(r[j + 2]), "r"(r[j + 3]), "r"(r[j + 4]),
-                   "r"(r[j + 5]), "r"(r[j + 6]), "r"(r[j + 7])
-                   : "memory");
-  }
-  if (prof) {
-    if (write_back) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    const long long t3 = clock64();
-    prof[1] += t1 - t0;
-    prof[2] += t2 - t1;
-    prof[3] += t3 - t2;
-  }
 }
 
-// epilogue of `nblk` 32-column blocks of one accumulator for this thread's row
+// the block's row to global memory: 32-byte stores, every lane writes whole sectors of its own row (rows are 128-byte aligned)
+__device__ __forceinline__ void epi_store(const uint32_t (&r)[32], float* __restrict__ out_row, long long* prof) {
+  const long long t0 = prof ? clock64() : 0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8)
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_row + j), "r"(r[j]), "r"(r[j + 1]), "r"(r[j + 2]), "r"(r[j + 3]), "r"(r[j + 4]),
+                 "r"(r[j + 5]), "r"(r[j + 6]), "r"(r[j + 7])
+                 : "memory");
+  if (prof) prof[3] += clock64() - t0;
+}
+
+// epilogue of `nblk` 32-column blocks of one accumulator for this thread's row.  The hand-over to the MMA warp (the accumulator is
+// written back / drained) comes BEFORE the global stores of the last block: a full store queue then holds up this warp, not the tensor pipe.
 template <bool kPair>
 __device__ __forceinline__ void epi_job(uint32_t wait_bar, uint32_t par, uint32_t taddr, const float* bias, float* out, int nblk, bool write_back, uint32_t arrive_bar,
                                         long long* wait_cycles, bool remote) {
@@ -299,8 +296,14 @@ __device__ __forceinline__ void epi_job(uint32_t wait_bar, uint32_t par, uint32_
     if (wait_cycles) *wait_cycles += clock64() - t0;
   }
   fence_after();
+  uint32_t r[32];
 #pragma unroll 1
-  for (int blk = 0; blk < nblk; ++blk) epi_block(taddr + blk * 32, bias + blk * 32, out ? out + blk * 32 : nullptr, write_back, wait_cycles);
+  for (int blk = 0; blk + 1 < nblk; ++blk) {
+    epi_compute(r, taddr + blk * 32, bias + blk * 32, write_back, wait_cycles);
+    if (out) epi_store(r, out + blk * 32, wait_cycles);
+  }
+  const int last = nblk - 1;
+  epi_compute(r, taddr + last * 32, bias + last * 32, write_back, wait_cycles);
   if (write_back) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   fence_before();
   __syncwarp();
@@ -310,6 +313,7 @@ __device__ __forceinline__ void epi_job(uint32_t wait_bar, uint32_t par, uint32_
     else
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(arrive_bar) : "memory");
   }
+  if (out) epi_store(r, out + last * 32, wait_cycles);
 }
 
 template <bool kPair>
@@ -544,8 +548,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
     long long* wp = P.dbg ? w_prof : nullptr;
     const long long t_begin = clock64();
     int it = 0;
-#pragma unroll 1
     const bool remote = kPair && !leader;
+#pragma unroll 1
     for (int task = first; task < tasks; task += stride, ++it) {
       const uint32_t par = it & 1;
       const int net = net_of(task), row = slab_of(task) * kRows + r_local;
