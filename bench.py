@@ -214,7 +214,7 @@ def run_reference(args, rank: int):
 def ncu_traffic_bytes(kernel_substr: str, largest: int = 0):
     """DRAM bytes per launch (read + write) of the committed `ncu --set full` capture, or None.  ``largest`` > 0: mean over the
     launches with the most traffic only (a capture that holds the same kernel at two problem sizes: the larger one)."""
-    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2u_ncu_full_summary.json", "r2f_ncu_full_summary.json", "r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
+    path = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2x_ncu_full_summary.json", "r2f_ncu_full_summary.json", "r1c_k1_k2_ncu_full_summary.json", "r1_k1_k2_ncu_full_summary.json"))
                  if os.path.exists(q)), None)  # newest capture first
     if path is None:
         return None
