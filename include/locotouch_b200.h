@@ -412,6 +412,12 @@ typedef struct {
   float* act_processed;          /* [N,J] or NULL */
   const float* act_offset;       /* [N,J] or NULL (default joint positions) */
   float act_clip, act_raw_scale, act_scale;
+  /* ActionManager.reset(env_ids) inside the launch (IsaacLab's ManagerBasedRLEnv.step order: rewards -> reset -> observations; reference
+   * JointPositionActionPrevPrev.reset, locotouch/mdp/actions.py:46-52): with auto_reset and LT_PHASE_REWARDS, raw_actions / prev_raw_actions /
+   * act_prev_prev_raw of every env this launch resets are zeroed in place (processed keeps raw * scale + offset of the pre-reset action) and,
+   * with LT_PHASE_OBS, the last_action values of its post-reset observation are built from the zeroed row.  0: the action term is left to the
+   * caller (the split-phase order compute_rewards -> term.reset(env_ids) -> compute_observations gives the same result). */
+  int act_reset_on_done;
 } LtMdpArgs;
 int lt_mdp_step(const LtMdpArgs* args, void* stream);
 /* Launch-constant lookup tables (observation column map, per-value term info, reward kind -> slot); host-side, no CUDA call.

@@ -172,7 +172,7 @@ class LtMdpArgs(C.Structure):
         ("os_non_contact", C.c_float * 13), ("os_last_contact_thr", C.c_float), ("os_current_contact_thr", C.c_float),
         ("any_flag_ws", C.c_void_p), ("tables", C.c_void_p),
         ("act_new", C.c_void_p), ("act_prev_prev_raw", C.c_void_p), ("act_processed", C.c_void_p), ("act_offset", C.c_void_p),
-        ("act_clip", C.c_float), ("act_raw_scale", C.c_float), ("act_scale", C.c_float),
+        ("act_clip", C.c_float), ("act_raw_scale", C.c_float), ("act_scale", C.c_float), ("act_reset_on_done", C.c_int),
     ]
 
 

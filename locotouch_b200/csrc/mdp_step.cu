@@ -988,6 +988,47 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
   }
 #endif
   PROF_STAMP(4);
+  // ActionManager.reset(env_ids) of IsaacLab's step order (rewards -> reset -> observations; reference mdp/actions.py:46-52 and the
+  // [IL] ActionTerm.reset behind it): the action history of an env that this launch resets is zeroed BEFORE its post-reset observation
+  // is built.  processed_actions keeps raw * scale + offset of the pre-reset raw action (actions.py:49 runs before the base class
+  // zeroes raw).  The new last_action values were computed by the task phase from the pre-reset row, so they are redone here for
+  // the (few) done envs with raw = 0 and the same uniform of the same Philox word / u_obs column.
+  if (A.act_reset_on_done && A.auto_reset && do_rew) {
+    __syncthreads();  // s_done of every env of the block is final; nobody reads the staged action rows any more
+#pragma unroll 1
+    for (int i = tid; i < nvalid * J; i += kThreads) {
+      const int ee = i / J, c = i - ee * J;
+      if (!s_done[ee]) continue;
+      const size_t g = (size_t)(e0 + ee) * J + c;
+      const_cast<float*>(A.raw_actions)[g] = 0.f;
+      const_cast<float*>(A.prev_raw_actions)[g] = 0.f;
+      if (A.act_prev_prev_raw) A.act_prev_prev_raw[g] = 0.f;
+      if (!do_obs) continue;
+      int jb = 0;
+#pragma unroll 1
+      for (int t = 0; t < A.num_obs_terms; ++t) {
+        const LtObsTerm& ot = A.obs_terms[t];
+        if (ot.kind == LT_OK_LAST_ACTION) {
+          const int j = jb + c;
+          float noisy = 0.f;
+          if (ot.noisy) {
+            float u;
+            if (A.u_obs) {
+              u = __ldcs(A.u_obs + (size_t)(e0 + ee) * dps + j);
+            } else {
+              const uint4 r4 = philox4(A.seed, rng_offset, (uint32_t)(e0 + ee), (uint32_t)(j >> 2));
+              const int w = j & 3;
+              u = lt::Philox::u01(w == 0 ? r4.x : (w == 1 ? r4.y : (w == 2 ? r4.z : r4.w)));
+            }
+            noisy = (0.f + u * (ot.n_max - ot.n_min)) + ot.n_min;
+          }
+          nv[(0 * kEnvs + ee) * sNew + j] = noisy * ot.scale;
+          nv[(1 * kEnvs + ee) * sNew + j] = 0.f * ot.scale;
+        }
+        jb += ot.dim;
+      }
+    }
+  }
   if (do_obs) {
     __pipeline_wait_prior(0);
     if (bulk_hist) mbar_wait(&s_bar[1], 0);

@@ -216,6 +216,8 @@ class HotPathEngine:
         ac.seed = stream_seed(seed, drank, 0)
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int64)  # device-resident env-step index
         self.fuse_action_term = os.environ.get("LT_FUSE_K0", "1") != "0"
+        # ActionManager.reset(env_ids) of the envs a step resets, inside the MDP launch (IsaacLab's order: rewards -> reset -> observations)
+        self.reset_action_term = os.environ.get("LT_ACTION_RESET", "1") != "0"
         # ---- fused MDP: one instance, re-bound to the state set of each step
         self.mdp = FusedMdp(self.envs[0], self.spec, seed=stream_seed(seed, drank, 1))
         self.taxel_seed = stream_seed(seed, drank, 2)
@@ -301,12 +303,14 @@ class HotPathEngine:
             self.mdp.step(True, True, policy_in=st._obs_buf[t], critic_in=st._priv_buf[t], policy_out=st._obs_buf[t + 1],
                           critic_out=st._priv_buf[t + 1], step_offset=t, offset_base=self.step_counter, actions=actions,
                           action_term=dict(prev_prev_raw=a.prev_prev_raw_actions, processed=a.processed_actions, offset=self.default_joint_pos,
-                                           clip=ACTION_CLIP, raw_scale=ACTION_RAW_SCALE, scale=1.0))
+                                           clip=ACTION_CLIP, raw_scale=ACTION_RAW_SCALE, scale=1.0),
+                          reset_action_term=self.reset_action_term)
         else:
             ops.process_actions(actions, a.raw_actions, a.prev_raw_actions, a.prev_prev_raw_actions, a.processed_actions,
                                 clip=ACTION_CLIP, raw_scale=ACTION_RAW_SCALE, scale=1.0, offset=self.default_joint_pos)
             self.mdp.step(True, True, policy_in=st._obs_buf[t], critic_in=st._priv_buf[t], policy_out=st._obs_buf[t + 1],
-                          critic_out=st._priv_buf[t + 1], step_offset=t, offset_base=self.step_counter)
+                          critic_out=st._priv_buf[t + 1], step_offset=t, offset_base=self.step_counter,
+                          action_term=dict(prev_prev_raw=a.prev_prev_raw_actions), reset_action_term=self.reset_action_term)
         if self.tactile:
             self._taxel_stream.join()
         return st._obs_buf[t + 1], self.mdp.reward_buf, self.mdp.dones, {"time_outs": self.mdp.time_outs, "observations": {"critic": st._priv_buf[t + 1]}}

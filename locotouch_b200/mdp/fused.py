@@ -255,7 +255,8 @@ class FusedMdp:
     # --------------------------------------------------------------------------------------------------------- launch
     def step(self, rewards: bool = True, observations: bool = True, *, auto_reset: bool = True, u_obs=None, u_obj_euler=None,
              policy_out=None, critic_out=None, policy_in=None, critic_in=None, any_nonzero_cmd: bool | None = None,
-             step_offset: int | None = None, offset_base: torch.Tensor | None = None, actions=None, action_term=None):
+             step_offset: int | None = None, offset_base: torch.Tensor | None = None, actions=None, action_term=None,
+             reset_action_term: bool = False):
         """One fused pass.  ``rewards``: terminations + rewards (+ reset of done envs when ``auto_reset``);
         ``observations``: policy / critic observation rows (history source ``*_in`` defaults to this object's buffers,
         destination ``*_out`` likewise; they may alias, or point into RolloutStorage slots for a zero-copy rollout).
@@ -278,6 +279,11 @@ class FusedMdp:
             a.act_clip, a.act_raw_scale, a.act_scale = float(t.get("clip", 0.0)), float(t.get("raw_scale", 1.0)), float(t.get("scale", 1.0))
         else:
             a.act_new = None
+            a.act_prev_prev_raw = _C.ptr((action_term or {}).get("prev_prev_raw"), torch.float32)
+        # ``reset_action_term``: IsaacLab's ActionManager.reset(env_ids) (reference mdp/actions.py:46-52) for the envs this launch resets,
+        # between the reward and the observation pass as ManagerBasedRLEnv.step orders them: raw / prev_raw (/ prev_prev_raw when given
+        # in ``action_term``) zeroed in place, the post-reset last_action observation built from the zeroed row
+        a.act_reset_on_done = int(bool(reset_action_term and auto_reset and rewards))
         a.phases = (_C.LT_PHASE_REWARDS if rewards else 0) | (_C.LT_PHASE_OBS if observations else 0)
         a.auto_reset = int(auto_reset)
         # an observation-only pass belongs to the step whose reward pass already ran (IsaacLab order: rewards -> reset -> obs)

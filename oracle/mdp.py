@@ -344,6 +344,37 @@ def object_state_in_robot_frame(env, os_cfg, noisy, u_state=None, u_euler=None):
     return torch.where(never.unsqueeze(-1), const, state)
 
 
+def action_term_process(term, actions, clip, raw_scale, scale, offset):
+    """JointPositionActionPrevPrev.process_actions (reference locotouch/mdp/actions.py:30-44) over [IL] JointAction.process_actions
+    (raw[:] = actions; processed = raw * scale + offset): the histories shift first, then clamp (``clip`` None: off), raw scale."""
+    term.prev_prev_raw_actions[:] = term.prev_raw_actions.clone()
+    term.prev_raw_actions[:] = term.raw_actions.clone()
+    if getattr(term, "prev_processed_actions", None) is not None:
+        term.prev_prev_processed_actions[:] = term.prev_processed_actions.clone()
+        term.prev_processed_actions[:] = term.processed_actions.clone()
+    if clip is not None:
+        actions = torch.clamp(actions, -clip, clip)
+    actions = actions * raw_scale
+    term.raw_actions[:] = actions
+    term.processed_actions[:] = term.raw_actions * scale + offset
+
+
+def action_term_reset(term, env_ids, scale=None, offset=None):
+    """JointPositionActionPrevPrev.reset (reference locotouch/mdp/actions.py:46-52) on the state block the hot path reads:
+    prev / prev_prev raw actions zeroed, processed = raw * scale + offset of the PRE-reset raw action (line 49 runs before the base
+    class), then [IL] ActionTerm.reset zeroes raw_actions of those envs.  ``scale`` / ``offset`` None: processed_actions is left as
+    process_actions wrote it (the same value by construction)."""
+    term.prev_raw_actions[env_ids] = 0.0
+    if getattr(term, "prev_prev_raw_actions", None) is not None:
+        term.prev_prev_raw_actions[env_ids] = 0.0
+    if scale is not None and getattr(term, "processed_actions", None) is not None:
+        term.processed_actions[env_ids] = (term.raw_actions * scale + (0.0 if offset is None else offset))[env_ids]
+    if getattr(term, "prev_processed_actions", None) is not None:
+        term.prev_processed_actions[env_ids] = term.processed_actions[env_ids].clone()
+        term.prev_prev_processed_actions[env_ids] = term.processed_actions[env_ids].clone()
+    term.raw_actions[env_ids] = 0.0
+
+
 class MdpOracle:
     """Managers + terms for one task: ``step(env)`` = terminations -> rewards -> (auto reset) ; ``observe(env)``."""
 
@@ -404,7 +435,10 @@ class MdpOracle:
             self.step_reward[:, i] = value / dt
         return raw, self.reward_buf
 
-    def step(self, env, auto_reset=True):
+    def step(self, env, auto_reset=True, reset_action_term=False):
+        """``reset_action_term``: [IL] ManagerBasedRLEnv.step also runs ActionManager.reset(env_ids) between the reward and the
+        observation pass; for the LocoTouch action term that is JointPositionActionPrevPrev.reset (reference locotouch/mdp/actions.py:46-52)
+        followed by [IL] ActionTerm.reset (raw_actions[env_ids] = 0)."""
         masks, terminated, time_outs = self.terminations(env)
         raw, reward = self.rewards(env)
         reward = reward.clone()
@@ -415,6 +449,8 @@ class MdpOracle:
                 self.gait.reset(ids)
                 self.episode_sums[:, ids] = 0.0
                 self.needs_fill[ids] = True
+                if reset_action_term:
+                    action_term_reset(env.action_manager.get_term("joint_pos"), ids)
         return dict(masks=masks, terminated=terminated, time_outs=time_outs, raw=raw, reward=reward, done=done)
 
     # -- [IL] ObservationManager.compute for the policy (noisy) and critic (clean) groups

@@ -14,6 +14,7 @@ Fixtures (all < 1 MB):
                                         learning-rate, parameters after the update) from the reference ``loco_rl``.
   commands_c3.npz                       velocity command term (multi-sampling bins, zero-command steps, gait logging metrics) and the
                                         reward-driven velocity curriculum over 70 steps of a reset tape, torch global RNG seeded.
+  action_term_c0.npz                    JointPositionActionPrevPrev state after every process_actions / reset(env_ids) of a seeded tape.
   tactile_c4.npz                        BinaryTactileSignals bitmaps (explicit dropout / addition uniforms) and
                                         TactileRecorder outputs across resets.
 """
@@ -674,6 +675,53 @@ def golden_commands():
     np.savez_compressed(os.path.join(OUT, "commands_c3.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------ action term (mdp/actions.py)
+ACTION_STATE = ("raw_actions", "prev_raw_actions", "prev_prev_raw_actions", "processed_actions", "prev_processed_actions",
+                "prev_prev_processed_actions")
+
+
+def golden_action_term():
+    """The reference ``JointPositionActionPrevPrev`` (locotouch/mdp/actions.py:13-69, unmodified) over a restated [IL] base: IsaacLab's
+    JointAction keeps ``_raw_actions`` / ``_processed_actions``, ``process_actions`` stores the actions and applies scale + offset,
+    ``reset`` zeroes the raw actions of the given envs.  State after every process_actions call and after every reset(env_ids)."""
+    _, _, _, actions_mod = ref_loader.load_reference_mdp()
+    base = sys.modules["isaaclab.envs.mdp.actions"].JointPositionAction
+    c = H.ACTION_TERM
+
+    def il_init(self, cfg, env):  # [IL] JointAction.__init__ / JointPositionAction.__init__ (use_default_offset: default joint positions)
+        self.cfg, self._env = cfg, env
+        self._raw_actions = torch.zeros(env.num_envs, cfg.action_dim)
+        self._processed_actions = torch.zeros_like(self._raw_actions)
+        self._scale, self._offset = cfg.scale, cfg.offset
+
+    def il_process(self, actions):  # [IL] JointAction.process_actions
+        self._raw_actions[:] = actions
+        self._processed_actions = self._raw_actions * self._scale + self._offset
+
+    def il_reset(self, env_ids=None):  # [IL] JointAction.reset
+        self._raw_actions[env_ids] = 0.0
+
+    base.__init__, base.process_actions, base.reset = il_init, il_process, il_reset
+    base.raw_actions = property(lambda self: self._raw_actions)
+    base.processed_actions = property(lambda self: self._processed_actions)
+    acts, offset, resets = H.action_term_tape()
+    from types import SimpleNamespace
+
+    cfg = SimpleNamespace(clip_raw_actions=True, raw_action_clip_value=c["clip"], raw_action_scale=c["raw_scale"], scale=c["scale"],
+                          offset=offset, action_dim=c["J"])
+    term = actions_mod.JointPositionActionPrevPrev(cfg, SimpleNamespace(num_envs=c["n"]))
+    out = {f"{k}_{when}": [] for k in ACTION_STATE for when in ("processed", "reset")}
+    for s in range(c["steps"]):
+        term.process_actions(acts[s])
+        for k in ACTION_STATE:
+            out[f"{k}_processed"].append(getattr(term, k).clone().numpy())
+        term.reset(resets[s])
+        for k in ACTION_STATE:
+            out[f"{k}_reset"].append(getattr(term, k).clone().numpy())
+    np.savez_compressed(os.path.join(OUT, "action_term_c0.npz"), input_checksum=np.float64(float(acts.double().sum() + offset.double().sum())),
+                        num_reset=np.array([len(r) for r in resets]), **{k: np.stack(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     assert ref_loader.reference_available(), "the reference is not mounted"
     torch.set_num_threads(1)
@@ -688,6 +736,7 @@ if __name__ == "__main__":
     golden_commands()
     golden_student_cnn()
     golden_recurrent_ppo()
+    golden_action_term()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

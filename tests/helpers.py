@@ -74,6 +74,31 @@ def assert_equal(actual, expected, what=""):
     assert not bool(neq.any()), f"{what}: {int(neq.sum())}/{neq.numel()} elements differ (bit-exact comparison)"
 
 
+ACTION_TERM = dict(n=37, J=12, steps=10, seed=23, clip=100.0, raw_scale=0.25, scale=0.5)
+
+
+def action_term_tape(c=ACTION_TERM):
+    """Seeded inputs of the action-term fixture: per-step policy actions (one step far outside the clip range), the per-env joint
+    offsets and the env ids reset after each step (none on some steps, a single env, a random subset, all)."""
+    g = torch.Generator().manual_seed(c["seed"])
+    n, J, steps = c["n"], c["J"], c["steps"]
+    actions = torch.randn(steps, n, J, generator=g)
+    actions[3] *= 300.0
+    offset = torch.randn(n, J, generator=g)
+    resets = []
+    for s in range(steps):
+        if s % 4 == 0:
+            ids = torch.zeros(0, dtype=torch.long)
+        elif s == 5:
+            ids = torch.tensor([n - 1])
+        elif s == 7:
+            ids = torch.arange(n)
+        else:
+            ids = (torch.rand(n, generator=g) < 0.3).nonzero().flatten()
+        resets.append(ids)
+    return actions, offset, resets
+
+
 # ----------------------------------------------------------------------------------------------------- C1: loco_rl PPO
 def make_rollout(T=24, N=64, obs_dim=270, A=12, seed=0):
     """Synthetic rollout tensors of config C1."""

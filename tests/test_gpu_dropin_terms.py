@@ -159,3 +159,23 @@ def test_student_batch_helpers(cuda, lt_lib):
     loss.backward()
     H.assert_close(loss, loss_ref.detach(), "masked MSE")
     H.assert_close(sd.grad, s.grad, "masked MSE gradient", rtol=1e-5, atol=1e-8)
+
+
+def test_action_term_matches_reference_golden(cuda, lt_lib):
+    """The drop-in JointPositionActionPrevPrev (K0 kernel + reset) vs the reference class (tests/golden/action_term_c0.npz, generated
+    from locotouch/mdp/actions.py:13-69): all six state tensors after every process_actions and every reset(env_ids), bit-exact."""
+    from locotouch_b200.mdp.actions import JointPositionActionPrevPrev
+
+    gold = H.load_golden("action_term_c0.npz")
+    c = H.ACTION_TERM
+    acts, offset, resets = H.action_term_tape()
+    term = JointPositionActionPrevPrev(c["n"], c["J"], cuda, scale=c["scale"], offset=offset.to(cuda), clip_raw_actions=True,
+                                       raw_action_clip_value=c["clip"], raw_action_scale=c["raw_scale"])
+    names = ("raw_actions", "prev_raw_actions", "prev_prev_raw_actions", "processed_actions", "prev_processed_actions", "prev_prev_processed_actions")
+    for s in range(c["steps"]):
+        term.process_actions(acts[s].to(cuda))
+        for k in names:
+            H.assert_equal(getattr(term, k), gold[f"{k}_processed"][s], f"step {s} {k} after process_actions")
+        term.reset(resets[s].to(cuda))
+        for k in names:
+            H.assert_equal(getattr(term, k), gold[f"{k}_reset"][s], f"step {s} {k} after reset")

@@ -139,3 +139,89 @@ def test_ragged_env_counts_and_rng_mode(cuda, lt_lib, n):
         col += w
     if n > 1000:
         assert float(diff[:, 18:36].mean()) > 0.01  # noise is actually there (projected gravity columns)
+
+
+def _last_action_columns(spec):
+    col = 0
+    for t in spec.obs_terms:
+        w = t.dim * spec.history_length
+        if t.name == "last_action":
+            return col, w, t
+        col += w
+    raise AssertionError("no last_action term")
+
+
+@pytest.mark.parametrize("scenario", ["locomotion", "teacher"])
+def test_action_term_reset_inside_the_step(cuda, lt_lib, scenario):
+    """``reset_action_term``: IsaacLab's step order (rewards -> ActionManager.reset(env_ids) -> observations; reference
+    mdp/actions.py:46-52) inside ONE launch.  36 chained steps vs the oracle with the same order: action-term state bit-exact, both
+    observation groups (explicit uniforms), and the post-reset rows carry a zero last_action in every history slot of the critic."""
+    from locotouch_b200.mdp.fused import FusedMdp
+    from oracle.mdp import MdpOracle
+
+    spec, env, steps = H.make_mdp_env(scenario)
+    oracle = MdpOracle(env, spec)
+    mdp, seen = None, 0
+    col, width, _ = _last_action_columns(spec)
+    for step in range(steps):
+        denv = env.to(cuda)  # pre-reset copy: the launch resets its own action term
+        before = env.action_manager.get_term("joint_pos").raw_actions.clone()
+        out = oracle.step(env, auto_reset=True, reset_action_term=True)
+        u_obs, u_euler = H.mdp_noise(scenario, step, env.num_envs, spec.obs_dim_per_step)
+        pol, cri = oracle.observe(env, u_noise=u_obs, u_obj_euler=u_euler)
+        if mdp is None:
+            mdp = FusedMdp(denv, spec)
+        mdp.env, mdp._bound_ptrs = denv, None
+        dterm = denv.action_manager.get_term("joint_pos")
+        mdp.step(True, True, u_obs=u_obs.to(cuda), u_obj_euler=u_euler.to(cuda), reset_action_term=True,
+                 action_term=dict(prev_prev_raw=dterm.prev_prev_raw_actions))
+        torch.cuda.synchronize()
+        H.assert_equal(mdp.dones, out["done"], f"step {step} dones")
+        oterm = env.action_manager.get_term("joint_pos")
+        for k in ("raw_actions", "prev_raw_actions", "prev_prev_raw_actions"):
+            H.assert_equal(getattr(dterm, k), getattr(oterm, k), f"step {step} {k}")
+        H.assert_close(mdp.policy_obs, pol, f"step {step} policy obs")
+        H.assert_close(mdp.critic_obs, cri, f"step {step} critic obs")
+        ids = out["done"].nonzero().flatten()
+        if len(ids):
+            seen += int((before[ids].abs().sum(dim=1) > 0).sum())
+            assert float(mdp.critic_obs[ids.to(cuda), col:col + width].abs().max()) == 0.0
+            assert float(dterm.raw_actions[ids.to(cuda)].abs().max()) == 0.0
+        H.advance_mdp_env(env, step)
+    assert seen > 0, "no env with a non-zero action was reset: the scenario does not exercise the path"
+
+
+def test_action_term_reset_fused_equals_split_phases(cuda, lt_lib):
+    """Production mode (in-kernel Philox noise, ragged env count): the in-launch reset == compute_rewards -> term.reset(env_ids) ->
+    compute_observations, bit for bit (the re-drawn last_action noise uses the same Philox words); and a rewards-only launch with the
+    flag zeroes the action term for the observation pass that follows."""
+    from locotouch_b200.mdp import task_spec as TS
+    from locotouch_b200.mdp.fused import FusedMdp
+
+    spec = TS.teacher_spec()
+    env = synth.make_env(4097, seed=321, with_object=True)
+    envs = [env.to(cuda) for _ in range(3)]
+    mdps = [FusedMdp(e, spec, seed=9) for e in envs]
+    terms = [e.action_manager.get_term("joint_pos") for e in envs]
+    kw = [dict(reset_action_term=True, action_term=dict(prev_prev_raw=t.prev_prev_raw_actions)) for t in terms]
+    mdps[0].step(True, True, **kw[0])
+    mdps[1].compute_rewards()
+    ids = mdps[1].dones.nonzero().flatten()
+    assert 0 < len(ids) < 4097
+    for name in ("raw_actions", "prev_raw_actions", "prev_prev_raw_actions"):
+        getattr(terms[1], name)[ids] = 0.0
+    mdps[1].compute_observations()
+    mdps[2].compute_rewards(**kw[2])
+    mdps[2].compute_observations()
+    torch.cuda.synchronize()
+    for m, t, what in ((mdps[1], terms[1], "split phases + host reset"), (mdps[2], terms[2], "rewards-only launch with the flag")):
+        H.assert_equal(mdps[0].dones, m.dones, f"dones ({what})")
+        H.assert_equal(mdps[0].policy_obs, m.policy_obs, f"policy obs ({what})")
+        H.assert_equal(mdps[0].critic_obs, m.critic_obs, f"critic obs ({what})")
+        for name in ("raw_actions", "prev_raw_actions", "prev_prev_raw_actions"):
+            H.assert_equal(getattr(terms[0], name), getattr(t, name), f"{name} ({what})")
+    # without the flag the post-reset row still shows the pre-reset action (the documented default of the read-only launch)
+    plain = FusedMdp(env.to(cuda), spec, seed=9).step(True, True)
+    col, width, _ = _last_action_columns(spec)
+    assert float(plain.critic_obs[ids, col:col + width].abs().max()) > 0.0
+    assert float(mdps[0].critic_obs[ids, col:col + width].abs().max()) == 0.0
