@@ -120,11 +120,12 @@ class CpuReference:
     def __init__(self, envs: int = ENVS_PER_GPU, threads: int | None = None):
         from oracle import ppo as OP
         from oracle import tactile as OT
+        from oracle import mdp as OM
         from oracle.mdp import MdpOracle
         from locotouch_b200.mdp import task_spec as TS
         from locotouch_b200.sim import synth
 
-        self.OP, self.OT = OP, OT
+        self.OP, self.OT, self.OM = OP, OT, OM
         self.threads = threads or os.cpu_count() or 1
         torch.set_num_threads(self.threads)
         self.envs = envs
@@ -158,7 +159,11 @@ class CpuReference:
                 values = OP.mlp_forward(self.cobs, cw, cb)
                 st["obs"][t], st["critic_obs"][t], st["actions"][t], st["values"][t] = self.obs, self.cobs, actions, values
                 st["logp"][t, :, 0], st["mu"][t], st["sigma"][t] = logp, mu, params["std"].expand_as(mu)
-                out = self.oracle.step(env)
+                # the action term of the env step (reference mdp/actions.py:30-52: process_actions ahead of the managers, reset(env_ids) of the
+                # done envs between the reward and the observation pass) -- the work K0 / act_reset_on_done do inside K1 on the GPU arm
+                term = env.action_manager.get_term("joint_pos")
+                self.OM.action_term_process(term, actions, 100.0, 0.25, 1.0, env.scene["robot"].data.default_joint_pos)
+                out = self.oracle.step(env, auto_reset=True, reset_action_term=True)
                 self.obs, self.cobs = self.oracle.observe(env, u_noise=torch.rand(N, spec.obs_dim_per_step, generator=g), u_obj_euler=torch.rand(N, 3, generator=g))
                 tac = OT.binary_taxels(env.scene["robot"].data.body_quat_w[:, 17:], env.scene.sensors["tactile_contact_sensor"].data.net_forces_w, self.thr,
                                        torch.rand(N, 221, generator=g), torch.rand(N, 221, generator=g))
