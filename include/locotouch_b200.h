@@ -418,6 +418,14 @@ typedef struct {
    * with LT_PHASE_OBS, the last_action values of its post-reset observation are built from the zeroed row.  0: the action term is left to the
    * caller (the split-phase order compute_rewards -> term.reset(env_ids) -> compute_observations gives the same result). */
   int act_reset_on_done;
+  /* Optional fused rollout store (K3 inside K1; store_rewards == NULL: off; needs LT_PHASE_REWARDS).  PPO.process_env_step's time-out bootstrap
+   * + the scalar part of RolloutStorage.add_transitions (loco_rl/algorithms/ppo.py:162-165, storage/rollout_storage.py:86-88, = lt_store_step
+   * bit for bit): store_rewards[n] = reward[n] + store_gamma * (store_values[n] * time_outs[n]) ; store_dones[n] = dones[n], written straight
+   * into the rollout slot of this env step (store_values == NULL: no bootstrap). */
+  float* store_rewards;          /* [N] RolloutStorage.rewards[step] */
+  uint8_t* store_dones;          /* [N] RolloutStorage.dones[step] or NULL */
+  const float* store_values;     /* [N] the critic's values of this step (RolloutStorage.values[step]) or NULL */
+  float store_gamma;
 } LtMdpArgs;
 int lt_mdp_step(const LtMdpArgs* args, void* stream);
 /* Launch-constant lookup tables (observation column map, per-value term info, reward kind -> slot); host-side, no CUDA call.

@@ -173,6 +173,7 @@ class LtMdpArgs(C.Structure):
         ("any_flag_ws", C.c_void_p), ("tables", C.c_void_p),
         ("act_new", C.c_void_p), ("act_prev_prev_raw", C.c_void_p), ("act_processed", C.c_void_p), ("act_offset", C.c_void_p),
         ("act_clip", C.c_float), ("act_raw_scale", C.c_float), ("act_scale", C.c_float), ("act_reset_on_done", C.c_int),
+        ("store_rewards", C.c_void_p), ("store_dones", C.c_void_p), ("store_values", C.c_void_p), ("store_gamma", C.c_float),
     ]
 
 

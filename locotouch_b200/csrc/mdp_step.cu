@@ -288,7 +288,7 @@ __device__ __forceinline__ float body_force_max(const float* force_env, int H, i
 // latency-bound copy loop earlier (14.3 vs 13.9 us).  What did pay: see the reward sum in stage 2a.
 __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A, const Layout L, const StageTable ST) {
   extern __shared__ __align__(16) float sm[];
-  __shared__ unsigned char s_done[kEnvs], s_fill[kEnvs], s_tflag[kEnvs];
+  __shared__ unsigned char s_done[kEnvs], s_fill[kEnvs], s_tflag[kEnvs], s_tout[kEnvs];
   __shared__ int s_step, s_any_nz, s_next_task;
   __shared__ __align__(8) unsigned long long s_bar[2];  // mbarriers: [0] state tensors + tables, [1] observation history
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
     const int i = tid - 160;
     s_fill[i] = (i < nvalid && do_obs && A.obs_fill) ? A.obs_fill[e0 + i] : 0;
     s_done[i] = 0;
+    s_tout[i] = 0;
   }
   PROF_STAMP(18);
   if (!A.tables) {
@@ -838,6 +839,7 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
           timed_out = timed_out || (other & 2);
           const bool done = terminated || timed_out;
           s_done[e] = done;
+          s_tout[e] = timed_out;
           A.terminated[n] = terminated;
           A.time_outs[n] = timed_out;
           A.dones[n] = done;
@@ -1092,6 +1094,12 @@ __global__ void __launch_bounds__(kThreads, 1) mdp_step_kernel(const LtMdpArgs A
         reward = reward + (w != 0.f ? (raw * w) * dt : 0.f);
       }
       A.reward[n] = reward;
+      if (A.store_rewards) {  // K3 inside K1: time-out bootstrap (ppo.py:162-165) + the scalar rollout store, lt_store_step bit for bit
+        float r = reward;
+        if (A.store_values) r = __fadd_rn(r, __fmul_rn(A.store_gamma, __fmul_rn(A.store_values[n], s_tout[e] ? 1.f : 0.f)));
+        A.store_rewards[n] = r;
+        if (A.store_dones) A.store_dones[n] = s_done[e] ? 1 : 0;
+      }
       if (A.auto_reset && s_done[e] && A.episode_log_sums) atomicAdd(A.episode_log_sums + T, 1.0f);
     }
     PROF_STAMP(20);
@@ -1247,6 +1255,7 @@ extern "C" int lt_mdp_step(const LtMdpArgs* a, void* stream) {
   const bool has_obj = a->obj_root_pos_w != nullptr;
   if (a->J <= 0 || a->J > kMaxJ) return LT_ERR_INVALID_ARG;
   if (a->act_new && !do_rew) return LT_ERR_INVALID_ARG;  // the fused action term belongs to the reward pass (the previous raw actions are staged there)
+  if (a->store_rewards && !do_rew) return LT_ERR_INVALID_ARG;  // the fused rollout store writes what the reward pass computes
   if (!a->command || !a->root_pos_w || !a->root_ang_vel_b || !a->projected_gravity_b || !a->joint_pos || !a->joint_vel ||
       !a->default_joint_pos || !a->raw_actions)
     return LT_ERR_INVALID_ARG;

@@ -216,6 +216,7 @@ class HotPathEngine:
         ac.seed = stream_seed(seed, drank, 0)
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int64)  # device-resident env-step index
         self.fuse_action_term = os.environ.get("LT_FUSE_K0", "1") != "0"
+        self.fuse_store = os.environ.get("LT_FUSE_K3", "1") != "0"
         # ActionManager.reset(env_ids) of the envs a step resets, inside the MDP launch (IsaacLab's order: rewards -> reset -> observations)
         self.reset_action_term = os.environ.get("LT_ACTION_RESET", "1") != "0"
         # ---- fused MDP: one instance, re-bound to the state set of each step
@@ -299,8 +300,12 @@ class HotPathEngine:
         if not taxels_launched:
             self.taxel_step(t, bank)
         self._bind(k)
+        # K3 inside K1: the time-out bootstrap + scalar rollout store of process_env_step written by the MDP launch into row t
+        store = None
+        if self.fuse_store:
+            store = dict(rewards=st.rewards[t].view(-1), dones=st.dones[t].view(-1), values=st.values[t].view(-1), gamma=self.alg.gamma)
         if self.fuse_action_term:  # K0 inside K1: the action term's process_actions runs in the MDP launch, before any term reads it
-            self.mdp.step(True, True, policy_in=st._obs_buf[t], critic_in=st._priv_buf[t], policy_out=st._obs_buf[t + 1],
+            self.mdp.step(True, True, policy_in=st._obs_buf[t], critic_in=st._priv_buf[t], policy_out=st._obs_buf[t + 1], store=store,
                           critic_out=st._priv_buf[t + 1], step_offset=t, offset_base=self.step_counter, actions=actions,
                           action_term=dict(prev_prev_raw=a.prev_prev_raw_actions, processed=a.processed_actions, offset=self.default_joint_pos,
                                            clip=ACTION_CLIP, raw_scale=ACTION_RAW_SCALE, scale=1.0),
@@ -309,10 +314,12 @@ class HotPathEngine:
             ops.process_actions(actions, a.raw_actions, a.prev_raw_actions, a.prev_prev_raw_actions, a.processed_actions,
                                 clip=ACTION_CLIP, raw_scale=ACTION_RAW_SCALE, scale=1.0, offset=self.default_joint_pos)
             self.mdp.step(True, True, policy_in=st._obs_buf[t], critic_in=st._priv_buf[t], policy_out=st._obs_buf[t + 1],
-                          critic_out=st._priv_buf[t + 1], step_offset=t, offset_base=self.step_counter,
+                          critic_out=st._priv_buf[t + 1], step_offset=t, offset_base=self.step_counter, store=store,
                           action_term=dict(prev_prev_raw=a.prev_prev_raw_actions), reset_action_term=self.reset_action_term)
         if self.tactile:
             self._taxel_stream.join()
+        if store is not None:  # rewards (bootstrapped) and dones already sit in their RolloutStorage row: process_env_step has nothing to launch
+            return st._obs_buf[t + 1], store["rewards"], store["dones"], {"observations": {"critic": st._priv_buf[t + 1]}}
         return st._obs_buf[t + 1], self.mdp.reward_buf, self.mdp.dones, {"time_outs": self.mdp.time_outs, "observations": {"critic": st._priv_buf[t + 1]}}
 
     def rollout_steps(self, upload: bool = False, bank: int = 0):

@@ -95,10 +95,16 @@ class RolloutStorage:
         s = self.step
         t = transition
         obs, cobs = t.observations, t.critic_observations
-        ops.store_step(
-            t.rewards.view(-1), t.dones.view(-1), time_outs, t.values.view(-1) if t.values is not None else None, gamma,
-            self.rewards[s].view(-1), self.dones[s].view(-1),
-            obs, self._obs_buf[s], cobs if self._priv_buf is not None else None, self._priv_buf[s] if self._priv_buf is not None else None)
+        # everything already in its row (a caller that let the MDP launch write rewards + dones into the slot -- K3 inside K1 -- and built the
+        # observations in place): nothing to launch
+        in_place = (time_outs is None and t.rewards.data_ptr() == self.rewards[s].data_ptr() and t.dones.data_ptr() == self.dones[s].data_ptr()
+                    and t.dones.dtype == torch.uint8 and obs.data_ptr() == self._obs_buf[s].data_ptr()
+                    and (self._priv_buf is None or cobs is None or cobs.data_ptr() == self._priv_buf[s].data_ptr()))
+        if not in_place:
+            ops.store_step(
+                t.rewards.view(-1), t.dones.view(-1), time_outs, t.values.view(-1) if t.values is not None else None, gamma,
+                self.rewards[s].view(-1), self.dones[s].view(-1),
+                obs, self._obs_buf[s], cobs if self._priv_buf is not None else None, self._priv_buf[s] if self._priv_buf is not None else None)
         self._copy_if_needed(self.actions[s], t.actions)
         self._copy_if_needed(self.values[s], t.values)
         self._copy_if_needed(self.actions_log_prob[s], t.actions_log_prob)

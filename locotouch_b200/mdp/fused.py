@@ -256,7 +256,7 @@ class FusedMdp:
     def step(self, rewards: bool = True, observations: bool = True, *, auto_reset: bool = True, u_obs=None, u_obj_euler=None,
              policy_out=None, critic_out=None, policy_in=None, critic_in=None, any_nonzero_cmd: bool | None = None,
              step_offset: int | None = None, offset_base: torch.Tensor | None = None, actions=None, action_term=None,
-             reset_action_term: bool = False):
+             reset_action_term: bool = False, store=None):
         """One fused pass.  ``rewards``: terminations + rewards (+ reset of done envs when ``auto_reset``);
         ``observations``: policy / critic observation rows (history source ``*_in`` defaults to this object's buffers,
         destination ``*_out`` likewise; they may alias, or point into RolloutStorage slots for a zero-copy rollout).
@@ -284,6 +284,21 @@ class FusedMdp:
         # between the reward and the observation pass as ManagerBasedRLEnv.step orders them: raw / prev_raw (/ prev_prev_raw when given
         # in ``action_term``) zeroed in place, the post-reset last_action observation built from the zeroed row
         a.act_reset_on_done = int(bool(reset_action_term and auto_reset and rewards))
+        # ``store`` (dict: rewards [N] float slot, dones [N] uint8 slot or None, values [N] or None, gamma): K3 inside this launch -- the
+        # time-out bootstrap of PPO.process_env_step and the scalar rollout store (reference ppo.py:162-165, rollout_storage.py:86-88)
+        # written straight into the RolloutStorage row of this env step
+        if store is not None:
+            if not rewards:
+                raise _C.LocoTouchLibraryError("FusedMdp.step(store=...): the fused rollout store needs the reward pass")
+            a.store_rewards = _C.ptr(store["rewards"], torch.float32, "store rewards")
+            a.store_dones = _C.ptr(store.get("dones"), torch.uint8)
+            a.store_values = _C.ptr(store.get("values"), torch.float32)
+            a.store_gamma = float(store.get("gamma", 0.0))
+            for k in ("rewards", "dones", "values"):
+                if store.get(k) is not None and store[k].numel() != self.N:
+                    raise _C.LocoTouchLibraryError(f"FusedMdp.step(store=...): {k} must hold one element per env")
+        else:
+            a.store_rewards = None
         a.phases = (_C.LT_PHASE_REWARDS if rewards else 0) | (_C.LT_PHASE_OBS if observations else 0)
         a.auto_reset = int(auto_reset)
         # an observation-only pass belongs to the step whose reward pass already ran (IsaacLab order: rewards -> reset -> obs)

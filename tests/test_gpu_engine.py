@@ -99,3 +99,33 @@ def test_fused_action_term_matches_separate_launch(cuda, lt_lib):
     H.assert_equal(sa.dones, sb.dones, "dones")
     H.assert_equal(sa._obs_buf, sb._obs_buf, "policy observations")
     H.assert_equal(sa._priv_buf, sb._priv_buf, "critic observations")
+
+
+def test_fused_rollout_store_matches_separate_launch(cuda, lt_lib):
+    """K3 inside K1 (``FusedMdp.step(store=...)``): the bootstrapped rewards and the dones of every rollout row are bit-identical to
+    ``lt_store_step`` after ``lt_mdp_step`` (reference ppo.py:162-165 + rollout_storage.py:86-88), time-outs included, at a ragged env
+    count; and the step needs one launch less."""
+    from locotouch_b200 import _C
+    from locotouch_b200.engine import HotPathEngine
+
+    cfg = dict(num_envs=301, task="teacher", tactile=True, device=cuda, seed=13, num_state_sets=3, hidden=(64, 32), tf32=False)
+    a = HotPathEngine(**cfg)
+    b = HotPathEngine(**cfg)
+    a.fuse_store, b.fuse_store = True, False
+    launches = []
+    for eng in (a, b):
+        torch.manual_seed(9)
+        n0 = _C.launch_count
+        eng.rollout()
+        launches.append(_C.launch_count - n0)
+    torch.cuda.synchronize()
+    sa, sb = a.alg.storage, b.alg.storage
+    assert int(sb.dones.sum()) > 0, "the rollout must contain resets"
+    H.assert_equal(sa.actions, sb.actions, "actions (same policy, same draws)")
+    H.assert_equal(sa.rewards, sb.rewards, "stored (bootstrapped) rewards")
+    H.assert_equal(sa.dones, sb.dones, "stored dones")
+    H.assert_equal(sa.values, sb.values, "values")
+    H.assert_equal(sa.returns, sb.returns, "returns")
+    H.assert_equal(sa.advantages, sb.advantages, "advantages")
+    H.assert_equal(sa._obs_buf, sb._obs_buf, "policy observations")
+    assert launches[1] - launches[0] == a.T, launches
