@@ -41,7 +41,7 @@ g_env = torch.cuda.CUDAGraph()
 with graph_capture(g_env):
     for t in range(eng.T):
         eng.env_step(t, actions, 0)
-print(f"24 x env step (K0, K1 || K2, delay-line bookkeeping): {timed(g_env):.3f} ms = {timed(g_env) / 24 * 1e3:.1f} us per step")
+print(f"24 x env step (K0 + K1 + K3 store in one launch || K2, delay-line bookkeeping; LT_FUSE_K3=0: K3 separate, below): {timed(g_env):.3f} ms = {timed(g_env) / 24 * 1e3:.1f} us per step")
 g_store = torch.cuda.CUDAGraph()
 rew, dn, inf = eng.mdp.reward_buf, eng.mdp.dones, {"time_outs": eng.mdp.time_outs}
 with graph_capture(g_store):
@@ -52,4 +52,4 @@ with graph_capture(g_store):
         alg.transition.actions_log_prob, alg.transition.action_mean, alg.transition.action_sigma = st.actions_log_prob[t], st.mu[t], st.sigma[t]
         alg.process_env_step(rew, dn, inf)
 st.step = 0
-print(f"24 x process_env_step (K3 store): {timed(g_store):.3f} ms = {timed(g_store) / 24 * 1e3:.1f} us per step")
+print(f"24 x process_env_step as a separate K3 launch (not part of the rollout graph when K3 is fused into K1): {timed(g_store):.3f} ms = {timed(g_store) / 24 * 1e3:.1f} us per step")
