@@ -217,6 +217,7 @@ class HotPathEngine:
         self.step_counter = torch.zeros(1, device=self.device, dtype=torch.int64)  # device-resident env-step index
         self.fuse_action_term = os.environ.get("LT_FUSE_K0", "1") != "0"
         self.fuse_store = os.environ.get("LT_FUSE_K3", "1") != "0"
+        self.taxel_after_policy = os.environ.get("LT_TAXEL_AFTER_POLICY", "1") != "0"
         # ActionManager.reset(env_ids) of the envs a step resets, inside the MDP launch (IsaacLab's order: rewards -> reset -> observations)
         self.reset_action_term = os.environ.get("LT_ACTION_RESET", "1") != "0"
         # ---- fused MDP: one instance, re-bound to the state set of each step
@@ -274,14 +275,14 @@ class HotPathEngine:
             ev.record(cs)
         self._upload_done[bank] = ev
 
-    def taxel_step(self, t: int, bank: int = 0):
+    def taxel_step(self, t: int, bank: int = 0, after=None):
         """K2 of env step ``t`` on the taxel stream.  It reads nothing the policy or the MDP step of this env step writes (sensor state
         of step t, the dones of step t - 1), so ``rollout_steps`` forks it BEFORE the policy: K19 occupies 64 of the 148 SMs at 4096
         envs and the taxel kernel fills the rest, instead of competing with the MDP step (one 1024-thread block per SM) afterwards."""
         k = self.set_index(t, bank)
         st = self.alg.storage
         if self.tactile:
-            with self._taxel_stream.forked():
+            with self._taxel_stream.forked(after=after):
                 env = self.envs[k]
                 ops.taxel_synth(env.scene["robot"].data.body_quat_w, env.scene.sensors["tactile_contact_sensor"].data.net_forces_w,
                                 self.taxel_thr, quat_body_offset=synth.NUM_ROBOT_BODIES, p_drop=0.005, p_add=0.005, seed=self.taxel_seed,
@@ -331,8 +332,16 @@ class HotPathEngine:
             if upload:
                 self.upload_state(self.set_index(t, bank))
             ac._graph_slot = t
-            self.taxel_step(t, bank)
-            actions = alg.act(st._obs_buf[t], st._priv_buf[t])
+            if self.taxel_after_policy and self.tactile:
+                # K2 depends on nothing of this env step, but it is ENQUEUED behind the policy kernels: the block scheduler serves grids in
+                # launch order, so K19's 64 one-per-SM CTAs are resident before the 1024 taxel blocks arrive and the taxel kernel fills the
+                # remaining SMs, instead of K19's CTAs waiting for a first wave of taxel blocks to leave the SMs they need whole
+                mark = self._taxel_stream.mark()
+                actions = alg.act(st._obs_buf[t], st._priv_buf[t])
+                self.taxel_step(t, bank, after=mark)
+            else:
+                self.taxel_step(t, bank)
+                actions = alg.act(st._obs_buf[t], st._priv_buf[t])
             obs, rewards, dones, infos = self.env_step(t, actions, bank, taxels_launched=True)
             alg.process_env_step(rewards, dones, infos)
         ops.counter_add(self.step_counter, self.T)

@@ -37,15 +37,27 @@ class SideStream:
         enabled = os.environ.get("LT_SIDE_STREAMS", "1") != "0"  # LT_SIDE_STREAMS=0: everything on the caller's stream
         self.stream = torch.cuda.Stream(device=self.device) if (self.device.type == "cuda" and enabled) else None
 
+    def mark(self):
+        """A fork point on the current stream for a LATER ``forked(after=mark)``: the body then depends only on what was enqueued up to
+        here, although it is enqueued (launched, or created as a graph node) after whatever the current stream received in between."""
+        if self.stream is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
     @contextlib.contextmanager
-    def forked(self):
+    def forked(self, after=None):
         """``with side.forked(): ...`` enqueues the body on the side stream, ordered after everything already enqueued on the
-        current stream.  Call ``join()`` before the current stream consumes what the body produced."""
+        current stream (``after``: only after that earlier ``mark()``).  Call ``join()`` before the current stream consumes what the
+        body produced."""
         if self.stream is None:
             yield
             return
-        ev = torch.cuda.Event()
-        ev.record()
+        ev = after
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record()
         self.stream.wait_event(ev)
         with torch.cuda.stream(self.stream):
             yield
