@@ -4,11 +4,12 @@ Sequence of reference ``OnPolicyRunner.learn`` (loco_rl/loco_rl/runners/on_polic
 PhysX stepping replaced by pre-generated synthetic state sets (BASELINE.json north_star):
 
     for t in range(num_steps_per_env):                       HOT LOOP A
-        actions = alg.act(obs, critic_obs)                   K12 hidden layers + K3b heads / sample -> rollout slot t
-        [ env.step(actions) ]                                K0 action pre-processing, synthetic state set t % K,
-                                                             K1 fused MDP step (obs written straight into slot t+1),
-                                                             K2 binary taxels + packed delay line
-        alg.process_env_step(rewards, dones, infos)          K3 store (time-out bootstrap fused)
+        actions = alg.act(obs, critic_obs)                   K19 hidden layers + K3b heads / sample -> rollout slot t
+                                                             (K2 binary taxels + packed delay line of this step run beside it)
+        [ env.step(actions) ]                                synthetic state set t % K; ONE launch: K0 action term (+ its reset of done
+                                                             envs), K1 fused MDP step (obs written straight into slot t+1) and the K3
+                                                             scalar store (bootstrapped reward + done flag into rollout row t)
+        alg.process_env_step(rewards, dones, infos)          finds everything in its row: nothing to launch (LT_FUSE_K3=0: K3 store)
     alg.compute_returns(critic_obs)                          K4 GAE + advantage normalisation
     alg.update()                                             HOT LOOP B: K5 gather, K12 fwd / dgrad, K16 heads + loss,
                                                              K15 weight gradients, K7 clip+Adam (K14 across GPUs)
